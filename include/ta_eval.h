@@ -1,0 +1,165 @@
+/*
+ * ta_eval.h — C ABI of the B200-native TAO-Amodal evaluation hot path.
+ *
+ * The reference (WesleyHsieh0806/TAO-Amodal) has no FFI for this path: its hot
+ * loops are Python methods.  Each entry point below replaces the Python
+ * function(s) named in its comment (paths relative to the reference root); a
+ * maintainer binds them with ctypes from those methods.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ / torch types.
+ *   - every function returns 0 on success or a negative ta_status; the message
+ *     of the last failure on the calling thread is ta_last_error().
+ *   - the caller owns every buffer; the library never frees or retains a
+ *     pointer after the call returns (device calls are asynchronous on
+ *     `stream`, so buffers must outlive the stream work).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - all offsets arrays are exclusive prefix sums with n+1 entries (CSR).
+ *   - boxes are fp64 [x, y, w, h]; scores fp64; ids int64; arithmetic is IEEE
+ *     fp64 without FMA contraction, bit-compatible with the reference's
+ *     bb_intersect_union (tao_amodal/evaluation/tao_amodal/eval.py:15-48).
+ *   - pointers are DEVICE pointers unless the function name ends in _host.
+ */
+#ifndef TA_EVAL_H
+#define TA_EVAL_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TA_ABI_VERSION 1
+#define TA_MAX_THRS 16   /* IoU thresholds packed as 16 TP bits + 16 FP bits per detection */
+
+typedef enum ta_status {
+    TA_OK = 0,
+    TA_ERR_INVALID = -1,     /* bad argument */
+    TA_ERR_CUDA = -2,        /* CUDA runtime error (message has the detail) */
+    TA_ERR_TOO_LARGE = -3,   /* a group exceeds the on-chip capacity of the kernel */
+    TA_ERR_ASSERT = -4,      /* the reference would have raised AssertionError (eval.py:95) */
+    TA_ERR_NCCL = -5
+} ta_status;
+
+/* 3-D IoU flavours of TaoEval (Params.iou_3d_type, eval.py:753-757) */
+typedef enum ta_iou_mode {
+    TA_IOU_3D = 0,           /* sum_t I / sum_t U, tiled kernel (eval.py:73-96) */
+    TA_IOU_AVG = 1,          /* mean_t (I/U)                     (eval.py:99-117) */
+    TA_IOU_IMAGENETVID = 2,  /* frac of frames with I > 0.5 U    (eval.py:51-70) */
+    TA_IOU_3D_SEQ = 3        /* as TA_IOU_3D, one thread per track pair, terms added
+                                sequentially in ascending frame order */
+} ta_iou_mode;
+
+/* One (area, duration) cell of TaoEval.Params (eval.py:735-744) or one visibility range
+ * of LVISEval.Params (lvis_amodal/eval.py:567-575).  A ground-truth entity is ignored
+ * when  flag&1  ||  a<gt_a_lo || a>gt_a_hi  ||  b<gt_b_lo || b>gt_b_hi
+ *       ||  hp < gt_hp_min  ||  (gt_need_oof && !(flag&2)).
+ * An UNMATCHED detection is ignored when
+ *       a<dt_a_lo || a>dt_a_hi || b<dt_b_lo || b>dt_b_hi || flag&1.               */
+typedef struct ta_range_cfg {
+    double gt_a_lo, gt_a_hi, gt_b_lo, gt_b_hi;
+    double dt_a_lo, dt_a_hi, dt_b_lo, dt_b_hi;
+    int32_t gt_hp_min;      /* INT32_MIN disables the rule */
+    int32_t gt_need_oof;
+} ta_range_cfg;
+
+typedef struct ta_ctx ta_ctx;
+
+int         ta_abi_version(void);
+const char* ta_last_error(void);
+int         ta_ctx_create(int device, ta_ctx** out);
+int         ta_ctx_destroy(ta_ctx* ctx);
+int         ta_ctx_sm_count(const ta_ctx* ctx);
+
+/* Spatio-temporal IoU of every (predicted track, GT track) pair of every (video, category)
+ * group.  Replaces TaoEval.compute_iou + compute_track_box_iou / compute_avg_track_iou /
+ * compute_imagenetvid_iou + bb_intersect_union (tao_amodal/evaluation/tao_amodal/
+ * eval.py:306-335, :51-117, :15-48).
+ * Tracks of group g are [grp_dt_off[g], grp_dt_off[g+1]) (descending score) and
+ * [grp_gt_off[g], grp_gt_off[g+1]); boxes of track t are [trk_off[t], trk_off[t+1]) sorted
+ * by `slot` (dense frame index inside the video, one box per slot).  Writes the row-major
+ * [D,G] matrix of group g at iou_out + iou_off[g].  n_slots_max bounds slot+1.       */
+int ta_track_iou(ta_ctx* ctx, void* stream, int mode, int64_t n_groups,
+                 const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+                 const int64_t* dt_trk_off, const double* dt_box, const int32_t* dt_slot,
+                 const int64_t* gt_trk_off, const double* gt_box, const int32_t* gt_slot,
+                 int32_t n_slots_max, const int64_t* iou_off, double* iou_out);
+
+/* Per-(image, category) box IoU.  Replaces LVISEval.compute_iou -> pycocotools.mask.iou
+ * -> bbIou (lvis_amodal/eval.py:168-192; maskApi.c:109-120 in-tree copy), iscrowd = 0. */
+int ta_box_iou(ta_ctx* ctx, void* stream, int64_t n_groups,
+               const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+               const double* dt_box, const double* gt_box,
+               const int64_t* iou_off, double* iou_out);
+
+/* COCO-style sequential greedy assignment for every group x range cfg x IoU threshold.
+ * Replaces TaoEval.evaluate_vid (eval.py:337-457) and LVISEval.evaluate_img
+ * (lvis_amodal/eval.py:194-303).  `sentinel` is the "unmatched" id value of the
+ * reference's match arrays (-1 for TaoEval, 0 for LVISEval): a detection whose matched GT
+ * id equals it counts as unmatched, and a GT is locked only by a detection id > 0.
+ * g_max bounds the number of GT entities of any group (sizes the shared-memory state).
+ * Outputs:
+ *   dt_tpfp  uint32 [n_cfg][n_dt]  bit t = TP at threshold t, bit 16+t = FP (neither: ignored)
+ *   num_gt   int32  [n_cat][n_cfg] non-ignored GT count, ACCUMULATED (caller zeroes)
+ *   dt_match_gt (optional, may be NULL) int32 [n_cfg][n_thr][n_dt] matched GT position
+ *            inside its group (original order) or -1
+ *   gt_ignore_out (optional) uint8 [n_cfg][n_gt]                                       */
+int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
+                    const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+                    const int32_t* grp_cat, const int64_t* iou_off, const double* iou,
+                    int32_t n_thr, const double* iou_thrs,
+                    int32_t n_cfg, const ta_range_cfg* cfgs,
+                    int64_t n_dt, const double* dt_attr_a, const double* dt_attr_b,
+                    const uint8_t* dt_flag, const int64_t* dt_id,
+                    int64_t n_gt, const double* gt_attr_a, const double* gt_attr_b,
+                    const int32_t* gt_hp, const uint8_t* gt_flag, const int64_t* gt_id,
+                    int64_t sentinel, int32_t g_max,
+                    uint32_t* dt_tpfp, int32_t* num_gt,
+                    int32_t* dt_match_gt, uint8_t* gt_ignore_out);
+
+/* Precision / recall accumulation.  Replaces TaoEval.accumulate (eval.py:459-584) and
+ * LVISEval.accumulate (lvis_amodal/eval.py:305-426).  acc_perm lists, category by
+ * category (cat_dt_off), the detection indices in stable descending-score order.
+ * Outputs (reference tensor layouts, -1 where the reference leaves -1):
+ *   precision f64 [n_thr][n_rec][n_cat][n_cfg], recall f64 [n_thr][n_cat][n_cfg],
+ *   tp_cnt / fp_cnt int64 [n_thr][n_cat][n_cfg] (may be NULL).                       */
+int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
+                     const int32_t* acc_perm, int64_t n_dt, const uint32_t* dt_tpfp,
+                     const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                     int32_t n_rec, const double* rec_thrs,
+                     double* precision, double* recall, int64_t* tp_cnt, int64_t* fp_cnt);
+
+/* Whole evaluation of one prepared plan from HOST buffers: copies the plan to the device,
+ * runs IoU -> match -> accumulate on ctx's stream, copies precision / recall / counts
+ * back, and returns when they are valid.  This is the call the reference-side
+ * TaoEval.run()/LVISEval.run() replacement makes (evaluate + accumulate, eval.py:662-665).
+ * Track path when the *_trk_off pointers are non-NULL, frame path otherwise.          */
+typedef struct ta_plan_host {
+    int64_t n_groups, n_dt, n_gt, n_dt_boxes, n_gt_boxes;
+    int32_t n_cat, n_cfg, n_thr, n_rec, n_slots_max, g_max, iou_mode;
+    int64_t sentinel;
+    const int64_t *grp_dt_off, *grp_gt_off, *iou_off, *cat_dt_off;
+    const int32_t *grp_cat, *acc_perm;
+    const double  *dt_box, *gt_box;
+    const int64_t *dt_trk_off, *gt_trk_off;   /* NULL on the frame path */
+    const int32_t *dt_slot, *gt_slot;         /* NULL on the frame path */
+    const double  *dt_attr_a, *dt_attr_b, *gt_attr_a, *gt_attr_b;
+    const uint8_t *dt_flag, *gt_flag;
+    const int32_t *gt_hp;
+    const int64_t *dt_id, *gt_id;
+    const double  *iou_thrs, *rec_thrs;
+    const ta_range_cfg* cfgs;
+} ta_plan_host;
+
+int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* plan,
+                      double* precision, double* recall,
+                      int64_t* tp_cnt, int64_t* fp_cnt, int32_t* num_gt,
+                      int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* Number of kernel launches issued through this context since creation. */
+int64_t ta_ctx_launch_count(const ta_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TA_EVAL_H */

@@ -1,0 +1,142 @@
+// ta_device_fns.cuh — per-thread arithmetic shared by the kernels of ta_eval.cu.
+//
+// Everything here is scalar IEEE fp64 / integer code, written so that it also compiles as
+// plain C++ (TA_HD expands to nothing under g++): tests/hostsim builds these exact functions
+// for the host to check the kernel logic against the oracle without a GPU.  That build is a
+// test artefact only; the product library has no CPU path.
+#ifndef TA_DEVICE_FNS_CUH
+#define TA_DEVICE_FNS_CUH
+
+#include <stdint.h>
+#include "ta_eval.h"
+
+#ifdef __CUDACC__
+#define TA_HD __host__ __device__ __forceinline__
+#else
+#define TA_HD inline
+#endif
+
+// Intersection area of a detection and a GT box given as corners.
+// tao_amodal/evaluation/tao_amodal/eval.py:38-46 with Python's max/min tie rules:
+//   max(dx, gx) keeps dx unless gx > dx; min(a, b) keeps a unless b < a;
+//   max(w, 0) yields 0 only when 0 > w.
+TA_HD double ta_inter_corners(double dx, double dy, double dx2, double dy2,
+                              double gx, double gy, double gx2, double gy2) {
+    const double left = (gx > dx) ? gx : dx;
+    const double right = (gx2 < dx2) ? gx2 : dx2;
+    const double top = (gy > dy) ? gy : dy;
+    const double bottom = (gy2 < dy2) ? gy2 : dy2;
+    const double w = right - left;
+    const double h = bottom - top;
+    const double ii = w * h;
+    return ((0.0 > w) || (0.0 > h)) ? 0.0 : ii;
+}
+
+// pycocotools bbIou, iscrowd = 0 (in-tree copy: visualization/tao/third_party/pysot/
+// training_dataset/coco/pycocotools/common/maskApi.c:109-120).
+TA_HD double ta_bb_iou(double dx, double dy, double dw, double dh,
+                       double gx, double gy, double gw, double gh) {
+    const double da = dw * dh, ga = gw * gh;
+    const double r0 = dw + dx, r1 = gw + gx;
+    const double w = ((r0 < r1) ? r0 : r1) - ((dx > gx) ? dx : gx);
+    if (w <= 0.0) return 0.0;
+    const double b0 = dh + dy, b1 = gh + gy;
+    const double h = ((b0 < b1) ? b0 : b1) - ((dy > gy) ? dy : gy);
+    if (h <= 0.0) return 0.0;
+    const double i = w * h;
+    const double u = da + ga - i;
+    return i / u;
+}
+
+// One (predicted track, GT track) pair by a sequential merge of the two slot-sorted box
+// lists — the term structure of eval.py:83-96 (3D), :99-117 (avg), :51-70 (imagenetvid),
+// terms taken in ascending frame order.
+TA_HD double ta_pair_iou_merge(const double* db, const int32_t* ds, int nd,
+                               const double* gb, const int32_t* gs, int ng,
+                               int mode, int* assert_failed) {
+    int a = 0, b = 0;
+    double i = 0.0, u = 0.0, ratio_sum = 0.0;
+    long long total = 0, matched = 0;
+    while (a < nd || b < ng) {
+        const int sa = (a < nd) ? ds[a] : 0x7fffffff;
+        const int sb = (b < ng) ? gs[b] : 0x7fffffff;
+        if (sa == sb) {
+            const double* d = db + 4 * a;
+            const double* g = gb + 4 * b;
+            const double da = d[2] * d[3], ga = g[2] * g[3];
+            const double ii = ta_inter_corners(d[0], d[1], d[0] + d[2], d[1] + d[3],
+                                               g[0], g[1], g[0] + g[2], g[1] + g[3]);
+            const double uu = da + ga - ii;
+            i += ii;
+            u += uu;
+            ratio_sum += (uu > 0.0) ? ii / uu : 0.0;
+            if (ii > 0.5 * uu) matched++;
+            ++a; ++b;
+        } else if (sa < sb) {
+            u += db[4 * a + 2] * db[4 * a + 3];
+            ++a;
+        } else {
+            u += gb[4 * b + 2] * gb[4 * b + 3];
+            ++b;
+        }
+        ++total;
+    }
+    if (mode == TA_IOU_AVG) return total ? ratio_sum / (double)total : 0.0;
+    if (mode == TA_IOU_IMAGENETVID) return total ? (double)matched / (double)total : 0.0;
+    if (!(i <= u)) *assert_failed = 1;            // eval.py:95
+    return (u > 0.0) ? i / u : 0.0;
+}
+
+// eval.py:349-368 (TaoEval) / lvis_amodal/eval.py:202-217: GT `_ignore` flag of one range cfg.
+TA_HD uint8_t ta_gt_ignored(const ta_range_cfg& c, double a, double b, int32_t hp, uint8_t flag) {
+    const bool ig = (flag & 1) || (a < c.gt_a_lo) || (a > c.gt_a_hi) || (b < c.gt_b_lo) ||
+                    (b > c.gt_b_hi) || (hp < c.gt_hp_min) || (c.gt_need_oof && !(flag & 2));
+    return ig ? 1 : 0;
+}
+
+// eval.py:432-439 / lvis_amodal/eval.py:281-286: mask applied to UNMATCHED detections.
+TA_HD bool ta_dt_unmatched_ignored(const ta_range_cfg& c, double a, double b, uint8_t flag) {
+    return (a < c.dt_a_lo) || (a > c.dt_a_hi) || (b < c.dt_b_lo) || (b > c.dt_b_hi) || (flag & 1);
+}
+
+// Best GT for one detection under one matcher state (eval.py:400-417).  The reference walks
+// GTs sorted "ignored last" (stable) and stops at the first free ignored GT once a regular
+// GT is held; that is two passes over the original order: regular GTs, then — only if none
+// matched — ignored GTs.  Later GTs win IoU ties (`<` at :413).
+TA_HD int ta_match_one(const double* iou_row, int G, const uint8_t* gt_ig,
+                       const uint32_t* taken, int taken_stride, double thr) {
+    double best = (thr < 1.0 - 1e-10) ? thr : 1.0 - 1e-10;   // min([iou_thr, 1 - 1e-10])
+    int m = -1;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int g = 0; g < G; ++g) {
+            if (gt_ig[g] != pass) continue;
+            if (taken[(g >> 5) * taken_stride] & (1u << (g & 31))) continue;
+            const double v = iou_row[g];
+            if (v < best) continue;
+            best = v;
+            m = g;
+        }
+        if (m >= 0) break;
+    }
+    return m;
+}
+
+// Smallest TP count t in [0, ngt] with t / ngt >= r (fp64 division as in eval.py:543,561);
+// ngt + 1 when no count reaches r.
+TA_HD int64_t ta_min_tp_for_recall(double r, int32_t ngt) {
+    const double n = (double)ngt;
+    double g = r * n;
+    int64_t t = (g <= 0.0) ? 0 : ((g >= n + 1.0) ? (int64_t)ngt + 1 : (int64_t)g);
+    if (t > (int64_t)ngt + 1) t = (int64_t)ngt + 1;
+    while (t > 0 && ((double)(t - 1) / n) >= r) --t;
+    while (t <= (int64_t)ngt && ((double)t / n) < r) ++t;
+    return t;
+}
+
+// eval.py:550: tp / (fp + tp + np.spacing(1))
+TA_HD double ta_precision_at(int64_t tp, int64_t fp) {
+    const double t = (double)tp, f = (double)fp;
+    return t / ((f + t) + 2.220446049250313e-16);
+}
+
+#endif  // TA_DEVICE_FNS_CUH

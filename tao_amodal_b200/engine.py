@@ -1,0 +1,263 @@
+"""Device engine: runs an ``EvalPlan`` (prep.py) through the C ABI of include/ta_eval.h.
+
+Two entry levels, mirroring how the reference is used:
+
+* ``Engine.evaluate_host(plan)`` — ONE C call (``ta_eval_plan_host``) that takes the plan
+  from host memory, runs IoU -> greedy match -> PR accumulation on the GPU and returns the
+  reference's ``eval['precision']`` / ``eval['recall']`` tensors.  This is what
+  ``TaoEval.run()`` / ``LVISEval.run()`` of this repo call (reference:
+  tao_amodal/evaluation/tao_amodal/eval.py:662-666, lvis_amodal/eval.py:501-505).
+* ``Engine.upload(plan)`` + ``Engine.evaluate_device(dev, detail=...)`` — the three
+  stage entry points (``ta_track_iou``/``ta_box_iou``, ``ta_match_greedy``,
+  ``ta_pr_accumulate``) on device-resident buffers; torch tensors are used purely as
+  device-memory containers.  ``detail=True`` also returns the IoU matrices, the matched GT
+  per (range, threshold, detection) and the GT ignore flags, from which the reference's
+  ``ious`` / ``eval_vids`` / ``eval_imgs`` structures are rebuilt lazily (materialize.py).
+
+No CPU fallback exists: every method raises if libta_eval.so is missing or a call fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from .prep import EvalPlan
+
+IOU_THRS = np.linspace(0.5, 0.95, int(np.round((0.95 - 0.5) / 0.05)) + 1, endpoint=True)
+REC_THRS = np.linspace(0.0, 1.00, int(np.round((1.00 - 0.0) / 0.01)) + 1, endpoint=True)
+
+
+@dataclass
+class EvalOutput:
+    """Accumulated tensors in the reference's layouts (eval.py:474-484, lvis eval.py:320-326):
+    precision [T,R,C,n_cfg], recall [T,C,n_cfg] (−1 where the reference leaves −1), the
+    TP / FP totals per cell and the non-ignored GT count per (category, cfg)."""
+    precision: np.ndarray
+    recall: np.ndarray
+    tp_cnt: np.ndarray
+    fp_cnt: np.ndarray
+    num_gt: np.ndarray
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+    # detail (optional)
+    iou: Optional[np.ndarray] = None          # f64 [sum D*G], group g at plan.iou_off[g]
+    dt_tpfp: Optional[np.ndarray] = None      # u32 [n_cfg, n_dt]
+    dt_match_gt: Optional[np.ndarray] = None  # i32 [n_cfg, n_thr, n_dt]
+    gt_ignore: Optional[np.ndarray] = None    # u8  [n_cfg, n_gt]
+
+
+def plan_limits(plan: EvalPlan):
+    """(g_max, n_slots_max) of a plan: the largest GT count of a group and 1 + the largest
+    frame slot (0 on the frame path)."""
+    g_cnt = np.diff(plan.grp_gt_off)
+    g_max = int(g_cnt.max()) if g_cnt.size else 0
+    n_slots = 0
+    if plan.kind == "tao":
+        for s in (plan.dt_box_slot, plan.gt_box_slot):
+            if s is not None and s.size:
+                n_slots = max(n_slots, int(s.max()) + 1)
+    return g_max, n_slots
+
+
+def _ptr(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "plan arrays must be contiguous"
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One ta_ctx on one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        if self.lib.ta_abi_version() != 1:
+            raise RuntimeError("libta_eval.so ABI version mismatch")
+        self.device = int(device)
+        h = C.c_void_p()
+        _lib.check(self.lib.ta_ctx_create(self.device, C.byref(h)))
+        self._ctx = h
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.ta_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.ta_ctx_launch_count(self._ctx))
+
+    @property
+    def sm_count(self) -> int:
+        return int(self.lib.ta_ctx_sm_count(self._ctx))
+
+    # ------------------------------------------------------------------ host-buffer call
+    def evaluate_host(self, plan: EvalPlan, iou_mode: str = "3d_iou",
+                      iou_thrs: np.ndarray = IOU_THRS, rec_thrs: np.ndarray = REC_THRS,
+                      out: Optional[EvalOutput] = None) -> EvalOutput:
+        n_thr, n_rec, n_cfg, n_cat = len(iou_thrs), len(rec_thrs), plan.n_cfg, len(plan.cat_ids)
+        g_max, n_slots = plan_limits(plan)
+        iou_thrs = np.ascontiguousarray(iou_thrs, dtype=np.float64)
+        rec_thrs = np.ascontiguousarray(rec_thrs, dtype=np.float64)
+        track = plan.kind == "tao"
+        ph = _lib.PlanHost()
+        ph.n_groups, ph.n_dt, ph.n_gt = plan.n_groups, plan.n_dt, plan.n_gt
+        ph.n_dt_boxes, ph.n_gt_boxes = plan.dt_box.shape[0], plan.gt_box.shape[0]
+        ph.n_cat, ph.n_cfg, ph.n_thr, ph.n_rec = n_cat, n_cfg, n_thr, n_rec
+        ph.n_slots_max, ph.g_max = n_slots, g_max
+        ph.iou_mode = _lib.IOU_MODES[iou_mode]
+        ph.sentinel = plan.sentinel
+        keep = dict(
+            grp_dt_off=plan.grp_dt_off, grp_gt_off=plan.grp_gt_off, iou_off=plan.iou_off,
+            cat_dt_off=plan.cat_dt_off, grp_cat=plan.grp_cat, acc_perm=plan.acc_perm,
+            dt_box=plan.dt_box, gt_box=plan.gt_box,
+            dt_trk_off=plan.dt_trk_box_off if track else None,
+            gt_trk_off=plan.gt_trk_box_off if track else None,
+            dt_slot=plan.dt_box_slot if track else None,
+            gt_slot=plan.gt_box_slot if track else None,
+            dt_attr_a=plan.dt_attr_a, dt_attr_b=plan.dt_attr_b,
+            gt_attr_a=plan.gt_attr_a, gt_attr_b=plan.gt_attr_b,
+            dt_flag=plan.dt_flag, gt_flag=plan.gt_flag, gt_hp=plan.gt_hp,
+            dt_id=plan.dt_id, gt_id=plan.gt_id, iou_thrs=iou_thrs, rec_thrs=rec_thrs,
+            cfgs=plan.range_cfgs)
+        for k, v in keep.items():
+            setattr(ph, k, _ptr(v))
+        if out is None:
+            out = EvalOutput(
+                precision=np.empty((n_thr, n_rec, n_cat, n_cfg), dtype=np.float64),
+                recall=np.empty((n_thr, n_cat, n_cfg), dtype=np.float64),
+                tp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64),
+                fp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64),
+                num_gt=np.empty((n_cat, n_cfg), dtype=np.int32))
+        h2d, d2h = C.c_int64(0), C.c_int64(0)
+        _lib.check(self.lib.ta_eval_plan_host(
+            self._ctx, C.byref(ph), _ptr(out.precision), _ptr(out.recall), _ptr(out.tp_cnt),
+            _ptr(out.fp_cnt), _ptr(out.num_gt), C.byref(h2d), C.byref(d2h)))
+        out.h2d_bytes, out.d2h_bytes = int(h2d.value), int(d2h.value)
+        return out
+
+    # ------------------------------------------------------------------ device-resident path
+    def upload(self, plan: EvalPlan, iou_thrs: np.ndarray = IOU_THRS,
+               rec_thrs: np.ndarray = REC_THRS) -> "DevicePlan":
+        return DevicePlan(self, plan, iou_thrs, rec_thrs)
+
+    def evaluate_device(self, dev: "DevicePlan", detail: bool = False,
+                        iou_mode: str = "3d_iou", fetch: bool = True):
+        """IoU -> match -> accumulate on dev's buffers (asynchronous on torch's current
+        stream until results are fetched).  Returns EvalOutput (fetch=True) or None."""
+        import torch
+        lib, ctx = self.lib, self._ctx
+        p = dev.ptr
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        plan = dev.plan
+        if plan.kind == "tao":
+            _lib.check(lib.ta_track_iou(
+                ctx, st, _lib.IOU_MODES[iou_mode], plan.n_groups, p["grp_dt_off"], p["grp_gt_off"],
+                p["dt_trk_off"], p["dt_box"], p["dt_slot"], p["gt_trk_off"], p["gt_box"],
+                p["gt_slot"], dev.n_slots, p["iou_off"], p["iou"]))
+        else:
+            _lib.check(lib.ta_box_iou(
+                ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["dt_box"],
+                p["gt_box"], p["iou_off"], p["iou"]))
+        dev.t["num_gt"].zero_()
+        if detail:
+            dev.ensure_detail()
+            p = dev.ptr
+        _lib.check(lib.ta_match_greedy(
+            ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["grp_cat"], p["iou_off"],
+            p["iou"], dev.n_thr, p["iou_thrs"], plan.n_cfg, p["cfgs"],
+            plan.n_dt, p["dt_attr_a"], p["dt_attr_b"], p["dt_flag"], p["dt_id"],
+            plan.n_gt, p["gt_attr_a"], p["gt_attr_b"], p["gt_hp"], p["gt_flag"], p["gt_id"],
+            plan.sentinel, dev.g_max, p["dt_tpfp"], p["num_gt"],
+            p["dt_match_gt"] if detail else None, p["gt_ignore"] if detail else None))
+        _lib.check(lib.ta_pr_accumulate(
+            ctx, st, dev.n_cat, p["cat_dt_off"], p["acc_perm"], plan.n_dt, p["dt_tpfp"],
+            p["num_gt"], dev.n_thr, plan.n_cfg, dev.n_rec, p["rec_thrs"],
+            p["precision"], p["recall"], p["tp_cnt"], p["fp_cnt"]))
+        if not fetch:
+            return None
+        t = dev.t
+        out = EvalOutput(
+            precision=t["precision"].cpu().numpy(), recall=t["recall"].cpu().numpy(),
+            tp_cnt=t["tp_cnt"].cpu().numpy(), fp_cnt=t["fp_cnt"].cpu().numpy(),
+            num_gt=t["num_gt"].cpu().numpy())
+        if detail:
+            n_iou = int(plan.iou_off[-1]) if plan.iou_off.size else 0
+            out.iou = t["iou"].cpu().numpy()[:n_iou]
+            out.dt_tpfp = (t["dt_tpfp"].cpu().numpy().view(np.uint32)[:plan.n_cfg * plan.n_dt]
+                           .reshape(plan.n_cfg, plan.n_dt))
+            out.dt_match_gt = t["dt_match_gt"].cpu().numpy()[:, :, :plan.n_dt]
+            out.gt_ignore = t["gt_ignore"].cpu().numpy()[:, :plan.n_gt]
+        return out
+
+
+class DevicePlan:
+    """A plan resident in HBM: one torch tensor per column (device-memory containers only)."""
+
+    def __init__(self, eng: Engine, plan: EvalPlan, iou_thrs, rec_thrs):
+        import torch
+        self.plan = plan
+        self.eng = eng
+        dev = torch.device("cuda", eng.device)
+        self.dev = dev
+        self.g_max, self.n_slots = plan_limits(plan)
+        self.n_thr, self.n_rec, self.n_cat = len(iou_thrs), len(rec_thrs), len(plan.cat_ids)
+        n_cfg = plan.n_cfg
+        track = plan.kind == "tao"
+        host: Dict[str, np.ndarray] = dict(
+            grp_dt_off=plan.grp_dt_off, grp_gt_off=plan.grp_gt_off, iou_off=plan.iou_off,
+            cat_dt_off=plan.cat_dt_off, grp_cat=plan.grp_cat, acc_perm=plan.acc_perm,
+            dt_box=plan.dt_box, gt_box=plan.gt_box,
+            dt_attr_a=plan.dt_attr_a, dt_attr_b=plan.dt_attr_b,
+            gt_attr_a=plan.gt_attr_a, gt_attr_b=plan.gt_attr_b,
+            dt_flag=plan.dt_flag, gt_flag=plan.gt_flag, gt_hp=plan.gt_hp,
+            dt_id=plan.dt_id, gt_id=plan.gt_id,
+            iou_thrs=np.ascontiguousarray(iou_thrs, dtype=np.float64),
+            rec_thrs=np.ascontiguousarray(rec_thrs, dtype=np.float64),
+            cfgs=plan.range_cfgs.view(np.uint8))
+        if track:
+            host.update(dt_trk_off=plan.dt_trk_box_off, gt_trk_off=plan.gt_trk_box_off,
+                        dt_slot=plan.dt_box_slot, gt_slot=plan.gt_box_slot)
+        self.t = {}
+        self.input_bytes = 0
+        for k, v in host.items():
+            v = np.ascontiguousarray(v)
+            self.input_bytes += v.nbytes
+            if v.size == 0:
+                self.t[k] = torch.zeros(16, dtype=torch.uint8, device=dev)
+            else:
+                self.t[k] = torch.from_numpy(v).to(dev)
+        n_iou = int(plan.iou_off[-1]) if plan.iou_off.size else 0
+        C_, T, R = self.n_cat, self.n_thr, self.n_rec
+        self.t["iou"] = torch.empty(max(n_iou, 1), dtype=torch.float64, device=dev)
+        self.t["dt_tpfp"] = torch.zeros(max(n_cfg * plan.n_dt, 1), dtype=torch.int32, device=dev)
+        self.t["num_gt"] = torch.zeros((C_, n_cfg), dtype=torch.int32, device=dev)
+        self.t["precision"] = torch.empty((T, R, C_, n_cfg), dtype=torch.float64, device=dev)
+        self.t["recall"] = torch.empty((T, C_, n_cfg), dtype=torch.float64, device=dev)
+        self.t["tp_cnt"] = torch.empty((T, C_, n_cfg), dtype=torch.int64, device=dev)
+        self.t["fp_cnt"] = torch.empty((T, C_, n_cfg), dtype=torch.int64, device=dev)
+        self._refresh()
+
+    def ensure_detail(self):
+        import torch
+        if "dt_match_gt" in self.t:
+            return
+        plan = self.plan
+        self.t["dt_match_gt"] = torch.empty(
+            (plan.n_cfg, self.n_thr, max(plan.n_dt, 1)), dtype=torch.int32, device=self.dev)
+        self.t["gt_ignore"] = torch.empty(
+            (plan.n_cfg, max(plan.n_gt, 1)), dtype=torch.uint8, device=self.dev)
+        self._refresh()
+
+    def _refresh(self):
+        self.ptr = {k: C.c_void_p(v.data_ptr()) for k, v in self.t.items()}

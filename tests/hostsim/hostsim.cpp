@@ -1,0 +1,163 @@
+// TEST ARTEFACT — host build of the per-thread kernel arithmetic (csrc/ta_device_fns.cuh).
+//
+// Serial loops that mirror the work decomposition of the kernels in csrc/ta_eval.cu so the
+// algorithms (two-pass greedy matching, union re-association, bucketed PR interpolation) can
+// be checked against the oracle and the reference goldens on a machine without a GPU.
+// Never linked into, loaded by, or shipped with the product library.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+#include <algorithm>
+#include "ta_device_fns.cuh"
+
+extern "C" {
+
+int hs_track_iou(int mode, int64_t n_groups, const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+                 const int64_t* dt_off, const double* dt_box, const int32_t* dt_slot,
+                 const int64_t* gt_off, const double* gt_box, const int32_t* gt_slot,
+                 const int64_t* iou_off, double* iou) {
+    int bad_total = 0;
+    for (int64_t grp = 0; grp < n_groups; ++grp) {
+        const int64_t d0 = grp_dt_off[grp], g0 = grp_gt_off[grp];
+        const int D = (int)(grp_dt_off[grp + 1] - d0), G = (int)(grp_gt_off[grp + 1] - g0);
+        double* out = iou + iou_off[grp];
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < G; ++j) {
+                const int64_t db0 = dt_off[d0 + i], db1 = dt_off[d0 + i + 1];
+                const int64_t gb0 = gt_off[g0 + j], gb1 = gt_off[g0 + j + 1];
+                if (mode == TA_IOU_3D) {
+                    // k_track_iou_tiled: I over common slots, U = DA + GA - I
+                    double da = 0, ga = 0, inter = 0;
+                    for (int64_t k = db0; k < db1; ++k) da += dt_box[4 * k + 2] * dt_box[4 * k + 3];
+                    for (int64_t k = gb0; k < gb1; ++k) ga += gt_box[4 * k + 2] * gt_box[4 * k + 3];
+                    int64_t a = db0, b = gb0;
+                    while (a < db1 && b < gb1) {
+                        if (dt_slot[a] == gt_slot[b]) {
+                            const double* d = dt_box + 4 * a; const double* g = gt_box + 4 * b;
+                            inter += ta_inter_corners(d[0], d[1], d[0] + d[2], d[1] + d[3],
+                                                      g[0], g[1], g[0] + g[2], g[1] + g[3]);
+                            ++a; ++b;
+                        } else if (dt_slot[a] < gt_slot[b]) ++a; else ++b;
+                    }
+                    const double uni = (da + ga) - inter;
+                    out[(int64_t)i * G + j] = uni > 0.0 ? inter / uni : 0.0;
+                } else {
+                    int bad = 0;
+                    out[(int64_t)i * G + j] = ta_pair_iou_merge(
+                        dt_box + 4 * db0, dt_slot + db0, (int)(db1 - db0),
+                        gt_box + 4 * gb0, gt_slot + gb0, (int)(gb1 - gb0), mode, &bad);
+                    bad_total += bad;
+                }
+            }
+    }
+    return bad_total;
+}
+
+int hs_box_iou(int64_t n_groups, const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+               const double* dt_box, const double* gt_box, const int64_t* iou_off, double* iou) {
+    for (int64_t grp = 0; grp < n_groups; ++grp) {
+        const int64_t d0 = grp_dt_off[grp], g0 = grp_gt_off[grp];
+        const int D = (int)(grp_dt_off[grp + 1] - d0), G = (int)(grp_gt_off[grp + 1] - g0);
+        double* out = iou + iou_off[grp];
+        for (int d = 0; d < D; ++d)
+            for (int g = 0; g < G; ++g) {
+                const double* a = dt_box + 4 * (d0 + d); const double* b = gt_box + 4 * (g0 + g);
+                out[(int64_t)d * G + g] = ta_bb_iou(a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]);
+            }
+    }
+    return 0;
+}
+
+int hs_match_greedy(int64_t n_groups, const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+                    const int32_t* grp_cat, const int64_t* iou_off, const double* iou,
+                    int32_t n_thr, const double* thrs, int32_t n_cfg, const ta_range_cfg* cfgs,
+                    int64_t n_dt, const double* dt_a, const double* dt_b, const uint8_t* dt_flag,
+                    const int64_t* dt_id, int64_t n_gt, const double* gt_a, const double* gt_b,
+                    const int32_t* gt_hp, const uint8_t* gt_flag, const int64_t* gt_id,
+                    int64_t sentinel, int32_t g_max, uint32_t* dt_tpfp, int32_t* num_gt,
+                    int32_t* dt_match_gt, uint8_t* gt_ignore_out) {
+    (void)g_max;
+    for (int64_t grp = 0; grp < n_groups; ++grp) {
+        const int64_t d0 = grp_dt_off[grp], g0 = grp_gt_off[grp];
+        const int D = (int)(grp_dt_off[grp + 1] - d0), G = (int)(grp_gt_off[grp + 1] - g0);
+        if (D == 0 && G == 0) continue;
+        const int words = (G + 31) / 32;
+        for (int c = 0; c < n_cfg; ++c) {
+            std::vector<uint8_t> ig(G);
+            int cnt = 0;
+            for (int g = 0; g < G; ++g) {
+                ig[g] = ta_gt_ignored(cfgs[c], gt_a[g0 + g], gt_b[g0 + g], gt_hp[g0 + g], gt_flag[g0 + g]);
+                cnt += ig[g] == 0;
+                if (gt_ignore_out) gt_ignore_out[(int64_t)c * n_gt + g0 + g] = ig[g];
+            }
+            num_gt[(int64_t)grp_cat[grp] * n_cfg + c] += cnt;
+            for (int d = 0; d < D; ++d) dt_tpfp[(int64_t)c * n_dt + d0 + d] = 0;
+            for (int t = 0; t < n_thr; ++t) {
+                std::vector<uint32_t> taken(words ? words : 1, 0u);
+                for (int d = 0; d < D; ++d) {
+                    int m = -1;
+                    if (G > 0) m = ta_match_one(iou + iou_off[grp] + (int64_t)d * G, G, ig.data(),
+                                                taken.data(), 1, thrs[t]);
+                    const int64_t did = dt_id[d0 + d];
+                    bool unmatched = true, ign = false;
+                    if (m >= 0) {
+                        if (did > 0) taken[m >> 5] |= 1u << (m & 31);
+                        unmatched = gt_id[g0 + m] == sentinel;
+                        ign = ig[m] != 0;
+                    }
+                    if (unmatched && !ign)
+                        ign = ta_dt_unmatched_ignored(cfgs[c], dt_a[d0 + d], dt_b[d0 + d], dt_flag[d0 + d]);
+                    if (!ign) dt_tpfp[(int64_t)c * n_dt + d0 + d] |= unmatched ? (1u << (16 + t)) : (1u << t);
+                    if (dt_match_gt) dt_match_gt[((int64_t)c * n_thr + t) * n_dt + d0 + d] = m;
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+int hs_pr_accumulate(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
+                     const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                     int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
+                     int64_t* tp_cnt, int64_t* fp_cnt) {
+    std::vector<int64_t> tk(n_rec);
+    std::vector<double> bucket(n_rec);
+    for (int c = 0; c < n_cat; ++c)
+        for (int cfg = 0; cfg < n_cfg; ++cfg)
+            for (int t = 0; t < n_thr; ++t) {
+                const int ngt = num_gt[(int64_t)c * n_cfg + cfg];
+                const int64_t cell = ((int64_t)t * n_cat + c) * n_cfg + cfg;
+                if (ngt == 0) {
+                    for (int k = 0; k < n_rec; ++k)
+                        precision[(((int64_t)t * n_rec + k) * n_cat + c) * n_cfg + cfg] = -1.0;
+                    recall[cell] = -1.0;
+                    if (tp_cnt) tp_cnt[cell] = 0;
+                    if (fp_cnt) fp_cnt[cell] = 0;
+                    continue;
+                }
+                for (int k = 0; k < n_rec; ++k) { tk[k] = ta_min_tp_for_recall(rec_thrs[k], ngt); bucket[k] = 0.0; }
+                int64_t tp = 0, fp = 0;
+                for (int64_t p = cat_dt_off[c]; p < cat_dt_off[c + 1]; ++p) {
+                    const uint32_t w = dt_tpfp[(int64_t)cfg * n_dt + acc_perm[p]];
+                    if ((w >> t) & 1u) {
+                        ++tp;
+                        const double pr = ta_precision_at(tp, fp);
+                        const int lo = (int)(std::upper_bound(tk.begin(), tk.end(), tp) - tk.begin());
+                        if (lo > 0 && pr > bucket[lo - 1]) bucket[lo - 1] = pr;
+                    } else if ((w >> (16 + t)) & 1u) {
+                        ++fp;
+                    }
+                }
+                double best = 0.0;
+                for (int k = n_rec - 1; k >= 0; --k) {
+                    if (bucket[k] > best) best = bucket[k];
+                    precision[(((int64_t)t * n_rec + k) * n_cat + c) * n_cfg + cfg] = best;
+                }
+                recall[cell] = (cat_dt_off[c + 1] > cat_dt_off[c]) ? (double)tp / (double)ngt : 0.0;
+                if (tp_cnt) tp_cnt[cell] = tp;
+                if (fp_cnt) fp_cnt[cell] = fp;
+            }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+"""Parity of the CUDA path (through the C ABI) with the unmodified reference's goldens and
+with the CPU oracle.  Needs a B200; run with ``pytest -m gpu``."""
+import numpy as np
+import pytest
+
+from conftest import golden_inputs
+from plan_backends import compare_with_golden, plans_from_json, run_hostsim
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from tao_amodal_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def test_tao_golden_device_path(golden, eng):
+    gt, res = golden_inputs(golden)
+    plan, _ = plans_from_json(gt, res)
+    out = eng.evaluate_device(eng.upload(plan), detail=True)
+    off_grid = golden["_name"] == "small_float"
+    compare_with_golden(golden, "tao_", plan, out, exact_iou=not off_grid, iou_atol=1e-12)
+
+
+def test_lvis_golden_device_path(golden, eng):
+    gt, res = golden_inputs(golden)
+    _, plan = plans_from_json(gt, res)
+    out = eng.evaluate_device(eng.upload(plan), detail=True)
+    compare_with_golden(golden, "lvis_", plan, out, exact_iou=True)
+
+
+def test_host_buffer_call_matches_golden(golden, eng):
+    """ta_eval_plan_host: the single C call the drop-in evaluators make."""
+    gt, res = golden_inputs(golden)
+    tao_plan, lvis_plan = plans_from_json(gt, res)
+    o = eng.evaluate_host(tao_plan)
+    assert np.array_equal(golden["tao_precision"], o.precision.reshape(golden["tao_precision"].shape))
+    assert np.array_equal(golden["tao_recall"], o.recall.reshape(golden["tao_recall"].shape))
+    assert np.array_equal(golden["tao_tp_cnt"], o.tp_cnt.reshape(golden["tao_tp_cnt"].shape))
+    assert np.array_equal(golden["tao_fp_cnt"], o.fp_cnt.reshape(golden["tao_fp_cnt"].shape))
+    assert o.h2d_bytes > 0 and o.d2h_bytes > 0
+    o = eng.evaluate_host(lvis_plan)
+    assert np.array_equal(golden["lvis_precision"], o.precision)
+    assert np.array_equal(golden["lvis_recall"], o.recall)
+    assert np.array_equal(golden["lvis_tp_cnt"], o.tp_cnt)
+    assert np.array_equal(golden["lvis_fp_cnt"], o.fp_cnt)
+
+
+@pytest.mark.parametrize("mode", ["3d_iou_seq", "avg_iou", "imagenetvid"])
+def test_alt_iou_modes_match_host_arithmetic(mode, eng):
+    """The pairwise kernel (alternative Params.iou_3d_type values, eval.py:51-117) against the
+    same per-thread function compiled for the host."""
+    from conftest import load_golden
+    g = load_golden("small")
+    gt, res = golden_inputs(g)
+    plan, _ = plans_from_json(gt, res)
+    out = eng.evaluate_device(eng.upload(plan), detail=True, iou_mode=mode)
+    ref = run_hostsim(plan, mode)
+    assert np.array_equal(out.iou, ref.iou)
+    assert np.array_equal(out.dt_match_gt, ref.dt_match_gt)
+    assert np.array_equal(out.precision, ref.precision)
+
+
+def test_cfg2_sized_synthetic_matches_oracle(eng):
+    """A BASELINE configs[1]-shaped set, reduced in videos so the pure-Python oracle finishes
+    in seconds; integer decisions and AP compared bit for bit."""
+    from oracle import lvis_frame, tao_track
+    from tao_amodal_b200 import synth
+    import copy
+    gtc, dtc = synth.generate_named("cfg2", videos=2, frames=120, seed=4242)
+    gt, res = gtc.to_dict(), dtc.to_list()
+    tao_plan, lvis_plan = plans_from_json(copy.deepcopy(gt), copy.deepcopy(res))
+    o_t = eng.evaluate_host(tao_plan)
+    o_l = eng.evaluate_host(lvis_plan)
+    res2 = copy.deepcopy(res)
+    tao_track.uniquify_track_ids(res2)
+    ref_t = tao_track.evaluate_tao(copy.deepcopy(gt), res2, keep_cells=False)
+    ref_l = lvis_frame.evaluate_lvis(copy.deepcopy(gt), copy.deepcopy(res), keep_cells=False)
+    assert np.array_equal(ref_t["precision"], o_t.precision.reshape(ref_t["precision"].shape))
+    assert np.array_equal(ref_t["tp_cnt"], o_t.tp_cnt.reshape(ref_t["tp_cnt"].shape))
+    assert np.array_equal(ref_t["fp_cnt"], o_t.fp_cnt.reshape(ref_t["fp_cnt"].shape))
+    assert np.array_equal(ref_t["num_gt"], o_t.num_gt.reshape(ref_t["num_gt"].shape))
+    assert np.array_equal(ref_l["precision"], o_l.precision)
+    assert np.array_equal(ref_l["tp_cnt"], o_l.tp_cnt)
+    assert np.array_equal(ref_l["fp_cnt"], o_l.fp_cnt)
+    assert np.array_equal(ref_l["num_gt"], o_l.num_gt)
