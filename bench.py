@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""Benchmark of the TAO-Amodal evaluation hot path on B200 (contract: see DESIGN.md §Measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3]
+
+A *step* is one pass of the whole hot path — track-AP (3-D IoU -> greedy match -> PR
+accumulate) and visibility-split frame-AP (box IoU -> greedy match -> PR accumulate) — over
+one synthetic prediction + annotation set of BASELINE.json's configs[2] shape
+(500 videos x 300 frames, 200 predicted / 30 GT tracks per video, 1203 categories), per GPU.
+``value`` = box-pairs / s with the prepared columns resident in HBM; ``e2e`` = the same metric
+through ``ta_eval_plan_host`` (host buffers in pinned memory, H2D + D2H inside the timed
+region).  With N > 1 (torchrun) every rank evaluates its own 500-video shard of an N x 500
+video set ("weak" scaling) and the per-detection records are exchanged over NCCL for the
+category-sharded PR accumulation (parallel.py).
+
+``--impl reference`` times the CPU implementation of the same path (the oracle port of the
+reference, oracle/; the Python reference itself cannot travel to the GPU box) on all host
+cores over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "box_pairs_per_s"
+UNIT = "box-pairs/s"
+
+
+# ------------------------------------------------------------------------------ workload
+def make_workload(name: str, rank: int, videos: int = 0):
+    from tao_amodal_b200 import prep, synth
+    over = {"seed": synth.CONFIGS[name].seed + 7919 * rank}
+    if videos:
+        over["videos"] = videos
+    gt, dt = synth.generate_named(name, **over)
+    lvis_plan = prep.prepare_lvis(gt, dt)
+    dt2 = dt.copy()
+    prep.make_track_ids_unique(dt2)
+    tao_plan = prep.prepare_tao(gt, dt2)
+    return gt, dt, tao_plan, lvis_plan
+
+
+def algorithmic_bytes(plan) -> dict:
+    """Per-launch algorithmic HBM bytes of each kernel."""
+    nd_box, ng_box = plan.dt_box.shape[0], plan.gt_box.shape[0]
+    n_iou = int(plan.iou_off[-1])
+    n_cfg, n_dt, n_gt = plan.n_cfg, plan.n_dt, plan.n_gt
+    per_box = 36 if plan.kind == "tao" else 32
+    n_cat = len(plan.cat_ids)
+    return {
+        "iou": per_box * (nd_box + ng_box) + 8 * n_iou,
+        "match": 8 * n_iou + 25 * n_dt + 29 * n_gt + 4 * n_cfg * n_dt,
+        "accumulate": n_dt * (4 + 4 * n_cfg) + 8 * 10 * 101 * n_cat * n_cfg,
+    }
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), 0
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": float(self.max_mhz) if self.max_mhz else None,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ CPU legs
+def _cpu_sample_worker(args):
+    """One bounded sample: the oracle port of the reference on one video's sub-dataset."""
+    gt_dict, res_list = args
+    import copy
+    from oracle import lvis_frame, tao_track
+    t0 = time.perf_counter()
+    o_l = lvis_frame.evaluate_lvis(copy.deepcopy(gt_dict), copy.deepcopy(res_list), keep_cells=False)
+    res2 = copy.deepcopy(res_list)
+    tao_track.uniquify_track_ids(res2)
+    o_t = tao_track.evaluate_tao(gt_dict, res2, keep_cells=False)
+    return o_t["box_pair_visits"] + o_l["box_pairs"], time.perf_counter() - t0
+
+
+def cpu_samples(gt, dt, n_samples: int, frames: int):
+    """n one-video samples (first `frames` frames of each) in the reference's JSON structures."""
+    from tao_amodal_b200.columnar import subset_videos
+    out = []
+    vids = np.unique(gt.vid_id)[:n_samples]
+    for v in vids:
+        g, d = subset_videos(gt, dt, [int(v)])
+        gd, dl = g.to_dict(), d.to_list()
+        if frames:
+            keep = {im["id"] for im in gd["images"] if im["frame_index"] < frames}
+            gd["images"] = [im for im in gd["images"] if im["id"] in keep]
+            gd["annotations"] = [a for a in gd["annotations"] if a["image_id"] in keep]
+            live = {a["track_id"] for a in gd["annotations"]}
+            gd["tracks"] = [t for t in gd["tracks"] if t["id"] in live]
+            dl = [r for r in dl if r["image_id"] in keep]
+        out.append((gd, dl))
+    return out
+
+
+def run_cpu_port(samples, cores: int):
+    """All samples through a process pool of `cores` workers; returns (pairs, wall seconds)."""
+    t0 = time.perf_counter()
+    if cores <= 1:
+        res = [_cpu_sample_worker(s) for s in samples]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_sample_worker, samples)
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall
+
+
+CPU_SAMPLE_FRAMES = 0     # 0 = whole videos (cfg3 videos have 300 frames)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from tao_amodal_b200 import synth
+    cores = os.cpu_count() or 1
+    cfg = synth.CONFIGS[args.workload]
+    gt, dt = synth.generate_named(args.workload, videos=max(cores, 2), seed=cfg.seed)
+    # size the per-step sample so that K steps end within ~2.5 minutes: calibrate on the first
+    # 60 frames, then take the largest prefix of frames whose projected cost fits
+    t_cal = run_cpu_port(cpu_samples(gt, dt, cores, 60), cores)[1]
+    frames = 0
+    for cand in (300, 200, 150, 100, 60):
+        if args.steps * t_cal * (cand / 60.0) ** 1.5 <= 150.0 or cand == 60:
+            frames = 0 if cand >= cfg.frames else cand
+            break
+    samples = cpu_samples(gt, dt, cores, frames)
+    for _ in range(min(args.warmup, 1)):
+        run_cpu_port(samples, cores)
+    pairs, wall = 0, 0.0
+    for _ in range(args.steps):
+        p, w = run_cpu_port(samples, cores)
+        pairs += p
+        wall += w
+    value = pairs / wall
+    sample = "%d one-video samples per step (first %d of %d frames of %s-shaped videos), one per core" % (
+        len(samples), frames or cfg.frames, cfg.frames, args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, world):
+    from tao_amodal_b200 import synth
+    c = synth.CONFIGS[args.workload]
+    return {"workload": "%s: %d videos x %d frames, %d predicted + %d GT tracks per video, %d "
+                        "categories, 10 IoU thresholds; track-AP + frame-AP paths per step"
+                        % (args.workload, args.videos or c.videos, c.frames, c.pred_tracks,
+                           c.gt_tracks, c.categories),
+            "per_gpu_videos": args.videos or c.videos, "world": world,
+            "l2": "inputs (>0.6 GB per step) exceed the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------ main arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--videos", type=int, default=0, help="override videos per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from tao_amodal_b200.engine import Engine
+    from tao_amodal_b200 import prep
+    t_prep = time.perf_counter()
+    gt, dt, tao_plan, lvis_plan = make_workload(args.workload, rank, args.videos)
+    pairs_trk = prep.count_box_pair_visits(tao_plan)
+    pairs_img = prep.count_box_pair_visits(lvis_plan)
+    pairs_local = pairs_trk + pairs_img
+    t_prep = time.perf_counter() - t_prep
+
+    eng = Engine(local)
+    d_tao, d_lvis = eng.upload(tao_plan), eng.upload(lvis_plan)
+    exch = None
+    if world > 1:
+        from tao_amodal_b200 import parallel
+        exch = parallel.Exchange(eng, [d_tao, d_lvis], rank, world)
+
+    stage_names = ["tao_iou", "tao_match", "tao_acc", "lvis_iou", "lvis_match", "lvis_acc"]
+    ev = None
+
+    def step(record=None):
+        k = 0
+        for dev in (d_tao, d_lvis):
+            for fn in (eng.stage_iou, eng.stage_match):
+                if record is not None:
+                    record[k][0].record()
+                fn(dev)
+                if record is not None:
+                    record[k][1].record()
+                k += 1
+            if record is not None:
+                record[k][0].record()
+            if exch is None:
+                eng.stage_accumulate(dev)
+            else:
+                exch.accumulate(dev)
+            if record is not None:
+                record[k][1].record()
+            k += 1
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [[[torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+           for _ in stage_names] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launches
+    e0.record()
+    for s in range(args.steps):
+        step(ev[s])
+    e1.record()
+    sync()
+    clocks = sampler.stop()
+    launches = eng.launches - l0
+    dev_ms = e0.elapsed_time(e1)
+    stage_ms = {n: float(np.mean([ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)]))
+                for i, n in enumerate(stage_names)}
+
+    # ---- e2e: host buffers (pinned) through the single C call, H2D + D2H inside the region
+    def pin(plan):
+        import dataclasses
+        rep = {}
+        for f in dataclasses.fields(plan):
+            v = getattr(plan, f.name)
+            if isinstance(v, np.ndarray) and v.size:
+                if v.dtype.fields is not None:
+                    raw = torch.from_numpy(np.ascontiguousarray(v).view(np.uint8)).pin_memory()
+                    rep[f.name] = raw.numpy().view(v.dtype)
+                else:
+                    rep[f.name] = torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
+        return dataclasses.replace(plan, **rep)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    p_tao, p_lvis = pin(tao_plan), pin(lvis_plan)
+    outs = [None, None]
+    for _ in range(2):
+        outs[0] = eng.evaluate_host(p_tao, out=outs[0])
+        outs[1] = eng.evaluate_host(p_lvis, out=outs[1])
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        outs[0] = eng.evaluate_host(p_tao, out=outs[0])
+        outs[1] = eng.evaluate_host(p_lvis, out=outs[1])
+    e2e_s = time.perf_counter() - t0
+    h2d = outs[0].h2d_bytes + outs[1].h2d_bytes
+    d2h = outs[0].d2h_bytes + outs[1].d2h_bytes
+
+    # ---- reduce over ranks: max time, sum units
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+        u = torch.tensor([pairs_local], device="cuda", dtype=torch.int64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        pairs_total = int(u[0])
+    else:
+        pairs_total = pairs_local
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    ms_per_step = dev_ms / args.steps
+    value = pairs_total / (ms_per_step * 1e-3)
+    e2e_value = pairs_total / (e2e_s / e2e_steps)
+
+    # ---- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    bytes_by_stage = {}
+    for pre, plan in (("tao", tao_plan), ("lvis", lvis_plan)):
+        ab = algorithmic_bytes(plan)
+        bytes_by_stage[pre + "_iou"] = ab["iou"]
+        bytes_by_stage[pre + "_match"] = ab["match"]
+        bytes_by_stage[pre + "_acc"] = ab["accumulate"]
+    dom = max(stage_ms, key=stage_ms.get)
+    kernel_names = {"tao_iou": "k_track_iou_tiled", "lvis_iou": "k_box_iou",
+                    "tao_match": "k_match_greedy", "lvis_match": "k_match_greedy",
+                    "tao_acc": "k_pr_accumulate", "lvis_acc": "k_pr_accumulate"}
+    per_stage = {n: {"ms": stage_ms[n], "alg_bytes": bytes_by_stage[n],
+                     "gbs": bytes_by_stage[n] / (stage_ms[n] * 1e-3) / 1e9 if stage_ms[n] > 0 else None}
+                 for n in stage_names}
+    achieved = per_stage[dom]["gbs"]
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get(kernel_names[dom])
+    roofline = {"bound": "hbm", "kernel": kernel_names[dom], "stage": dom, "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "stages": per_stage}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "box_pairs_per_step": pairs_total, "box_pairs_track_path": pairs_trk,
+        "box_pairs_frame_path": pairs_img,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                "api": "ta_eval_plan_host (pinned host plan -> precision/recall on host)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "host_prep_s": t_prep,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        samples = cpu_samples(gt, dt, cores, CPU_SAMPLE_FRAMES)
+        pairs, wall = run_cpu_port(samples, cores)
+        line["cpu_baseline"] = {
+            "value": pairs / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d one-video samples (first %d frames each) of the same workload, one per "
+                      "core, %.1f s wall" % (len(samples), CPU_SAMPLE_FRAMES, wall)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -296,3 +296,43 @@ class DtColumns:
 
     def copy(self) -> "DtColumns":
         return DtColumns(**{f.name: getattr(self, f.name).copy() for f in fields(self)})
+
+
+def _ragged_take(r: Ragged, rows: np.ndarray) -> Ragged:
+    off, vals = r
+    lens = (off[1:] - off[:-1])[rows]
+    new_off = np.zeros(rows.size + 1, dtype=np.int64)
+    np.cumsum(lens, out=new_off[1:])
+    idx = (np.arange(int(new_off[-1]), dtype=np.int64) - np.repeat(new_off[:-1], lens)
+           + np.repeat(off[:-1][rows], lens))
+    return new_off, vals[idx] if vals.size else vals
+
+
+def subset_videos(gt: GtColumns, dt: DtColumns, video_ids) -> Tuple[GtColumns, DtColumns]:
+    """The annotation / prediction columns restricted to some videos (categories are kept
+    whole).  Used to shard a dataset across GPUs and to cut bounded CPU-baseline samples."""
+    vids = np.unique(np.asarray(video_ids, dtype=np.int64))
+    vrow = np.nonzero(np.isin(gt.vid_id, vids))[0]
+    irow = np.nonzero(np.isin(gt.img_video_id, vids))[0]
+    trow = np.nonzero(np.isin(gt.trk_video_id, vids))[0]
+    arow = np.nonzero(np.isin(gt.ann_image_id, gt.img_id[irow]))[0]
+    g = GtColumns(
+        img_id=gt.img_id[irow], img_video_id=gt.img_video_id[irow],
+        img_frame_index=gt.img_frame_index[irow],
+        img_neg=_ragged_take(gt.img_neg, irow), img_nel=_ragged_take(gt.img_nel, irow),
+        vid_id=gt.vid_id[vrow], vid_neg=_ragged_take(gt.vid_neg, vrow),
+        vid_nel=_ragged_take(gt.vid_nel, vrow),
+        trk_id=gt.trk_id[trow], trk_category_id=gt.trk_category_id[trow],
+        trk_video_id=gt.trk_video_id[trow], trk_ignore=gt.trk_ignore[trow],
+        cat_id=gt.cat_id, cat_freq=gt.cat_freq, merge_map=dict(gt.merge_map),
+        ann_id=gt.ann_id[arow], ann_image_id=gt.ann_image_id[arow],
+        ann_track_id=gt.ann_track_id[arow], ann_category_id=gt.ann_category_id[arow],
+        ann_bbox=np.ascontiguousarray(gt.ann_bbox[arow]), ann_area=gt.ann_area[arow],
+        ann_visibility=gt.ann_visibility[arow], ann_oof=gt.ann_oof[arow],
+        ann_ignore=gt.ann_ignore[arow],
+        has_image_lists=gt.has_image_lists, has_video_lists=gt.has_video_lists)
+    drow = np.nonzero(np.isin(dt.video_id, vids))[0]
+    d = DtColumns(image_id=dt.image_id[drow], track_id=dt.track_id[drow],
+                  category_id=dt.category_id[drow], video_id=dt.video_id[drow],
+                  bbox=np.ascontiguousarray(dt.bbox[drow]), score=dt.score[drow])
+    return g, d

@@ -151,39 +151,57 @@ class Engine:
                rec_thrs: np.ndarray = REC_THRS) -> "DevicePlan":
         return DevicePlan(self, plan, iou_thrs, rec_thrs)
 
-    def evaluate_device(self, dev: "DevicePlan", detail: bool = False,
-                        iou_mode: str = "3d_iou", fetch: bool = True):
-        """IoU -> match -> accumulate on dev's buffers (asynchronous on torch's current
-        stream until results are fetched).  Returns EvalOutput (fetch=True) or None."""
+    def stage_iou(self, dev: "DevicePlan", iou_mode: str = "3d_iou"):
+        """compute_iou of every group (eval.py:306-335 / lvis eval.py:168-192)."""
         import torch
-        lib, ctx = self.lib, self._ctx
-        p = dev.ptr
+        p, plan = dev.ptr, dev.plan
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        plan = dev.plan
         if plan.kind == "tao":
-            _lib.check(lib.ta_track_iou(
-                ctx, st, _lib.IOU_MODES[iou_mode], plan.n_groups, p["grp_dt_off"], p["grp_gt_off"],
-                p["dt_trk_off"], p["dt_box"], p["dt_slot"], p["gt_trk_off"], p["gt_box"],
-                p["gt_slot"], dev.n_slots, p["iou_off"], p["iou"]))
+            _lib.check(self.lib.ta_track_iou(
+                self._ctx, st, _lib.IOU_MODES[iou_mode], plan.n_groups, p["grp_dt_off"],
+                p["grp_gt_off"], p["dt_trk_off"], p["dt_box"], p["dt_slot"], p["gt_trk_off"],
+                p["gt_box"], p["gt_slot"], dev.n_slots, p["iou_off"], p["iou"]))
         else:
-            _lib.check(lib.ta_box_iou(
-                ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["dt_box"],
+            _lib.check(self.lib.ta_box_iou(
+                self._ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["dt_box"],
                 p["gt_box"], p["iou_off"], p["iou"]))
+
+    def stage_match(self, dev: "DevicePlan", detail: bool = False):
+        """evaluate_vid / evaluate_img of every group x range x threshold
+        (eval.py:337-457 / lvis eval.py:194-303)."""
+        import torch
+        plan = dev.plan
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         dev.t["num_gt"].zero_()
         if detail:
             dev.ensure_detail()
-            p = dev.ptr
-        _lib.check(lib.ta_match_greedy(
-            ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["grp_cat"], p["iou_off"],
-            p["iou"], dev.n_thr, p["iou_thrs"], plan.n_cfg, p["cfgs"],
+        p = dev.ptr
+        _lib.check(self.lib.ta_match_greedy(
+            self._ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["grp_cat"],
+            p["iou_off"], p["iou"], dev.n_thr, p["iou_thrs"], plan.n_cfg, p["cfgs"],
             plan.n_dt, p["dt_attr_a"], p["dt_attr_b"], p["dt_flag"], p["dt_id"],
             plan.n_gt, p["gt_attr_a"], p["gt_attr_b"], p["gt_hp"], p["gt_flag"], p["gt_id"],
             plan.sentinel, dev.g_max, p["dt_tpfp"], p["num_gt"],
             p["dt_match_gt"] if detail else None, p["gt_ignore"] if detail else None))
-        _lib.check(lib.ta_pr_accumulate(
-            ctx, st, dev.n_cat, p["cat_dt_off"], p["acc_perm"], plan.n_dt, p["dt_tpfp"],
+
+    def stage_accumulate(self, dev: "DevicePlan"):
+        """accumulate (eval.py:459-584 / lvis eval.py:305-426)."""
+        import torch
+        p, plan = dev.ptr, dev.plan
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(self.lib.ta_pr_accumulate(
+            self._ctx, st, dev.n_cat, p["cat_dt_off"], p["acc_perm"], plan.n_dt, p["dt_tpfp"],
             p["num_gt"], dev.n_thr, plan.n_cfg, dev.n_rec, p["rec_thrs"],
             p["precision"], p["recall"], p["tp_cnt"], p["fp_cnt"]))
+
+    def evaluate_device(self, dev: "DevicePlan", detail: bool = False,
+                        iou_mode: str = "3d_iou", fetch: bool = True):
+        """IoU -> match -> accumulate on dev's buffers (asynchronous on torch's current
+        stream until results are fetched).  Returns EvalOutput (fetch=True) or None."""
+        plan = dev.plan
+        self.stage_iou(dev, iou_mode)
+        self.stage_match(dev, detail)
+        self.stage_accumulate(dev)
         if not fetch:
             return None
         t = dev.t

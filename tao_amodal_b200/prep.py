@@ -623,3 +623,30 @@ def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
     plan.stats["n_gt_boxes"] = float(g_sel.size)
     plan.stats["box_pairs"] = float(iou_off[-1])
     return plan
+
+
+# ---- workload accounting -----------------------------------------------------------------
+def count_box_pair_visits(plan: EvalPlan) -> int:
+    """The metric's unit.  Track path: one iteration of the reference's
+    per-frame loop (tao_amodal/evaluation/tao_amodal/eval.py:83-84), i.e. the sum over all
+    (dt track, gt track) pairs of a group of |F_d ∪ F_g|.  Frame path: sum of D*G."""
+    if plan.kind != "tao":
+        return int(plan.iou_off[-1])
+    total = 0
+    n_slots = 1 + max(int(plan.dt_box_slot.max()) if plan.dt_box_slot.size else 0,
+                      int(plan.gt_box_slot.max()) if plan.gt_box_slot.size else 0)
+    d_len = np.diff(plan.dt_trk_box_off)
+    g_len = np.diff(plan.gt_trk_box_off)
+    for g in np.nonzero(np.diff(plan.iou_off) > 0)[0]:
+        d0, d1 = int(plan.grp_dt_off[g]), int(plan.grp_dt_off[g + 1])
+        g0, g1 = int(plan.grp_gt_off[g]), int(plan.grp_gt_off[g + 1])
+        D, G = d1 - d0, g1 - g0
+        pd = np.zeros((D, n_slots), dtype=np.float32)
+        pg = np.zeros((G, n_slots), dtype=np.float32)
+        b0, b1 = int(plan.dt_trk_box_off[d0]), int(plan.dt_trk_box_off[d1])
+        pd[np.repeat(np.arange(D), d_len[d0:d1]), plan.dt_box_slot[b0:b1]] = 1.0
+        b0, b1 = int(plan.gt_trk_box_off[g0]), int(plan.gt_trk_box_off[g1])
+        pg[np.repeat(np.arange(G), g_len[g0:g1]), plan.gt_box_slot[b0:b1]] = 1.0
+        common = int(round(float((pd @ pg.T).sum())))
+        total += int(d_len[d0:d1].sum()) * G + int(g_len[g0:g1].sum()) * D - common
+    return total
