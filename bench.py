@@ -59,8 +59,13 @@ def algorithmic_bytes(plan) -> dict:
     n_cat = len(plan.cat_ids)
     return {
         "iou": per_box * (nd_box + ng_box) + 8 * n_iou,
-        "match": 8 * n_iou + 25 * n_dt + 29 * n_gt + 4 * n_cfg * n_dt,
-        "accumulate": n_dt * (4 + 4 * n_cfg) + 8 * 10 * 101 * n_cat * n_cfg,
+        # IoU matrix + dt (area, n_anns, flag) + gt (attr a, b, hp, flag) read, TP/FP words written
+        "match": 8 * n_iou + 17 * n_dt + 21 * n_gt + 4 * n_cfg * n_dt,
+        # fused frame kernel: boxes + flags + visibility + group table read, TP/FP words written
+        "frame_eval": 32 * (nd_box + ng_box) + n_dt + 9 * n_gt + 20 * plan.n_groups
+                      + 4 * n_cfg * n_dt,
+        # permutation + TP/FP words read twice (count, bucket), precision tensor written
+        "accumulate": 2 * n_dt * (4 + 4 * n_cfg) + 8 * 10 * 101 * n_cat * n_cfg,
     }
 
 
@@ -257,28 +262,25 @@ def main():
         from tao_amodal_b200 import parallel
         exch = parallel.Exchange(eng, [d_tao, d_lvis], rank, world)
 
-    stage_names = ["tao_iou", "tao_match", "tao_acc", "lvis_iou", "lvis_match", "lvis_acc"]
+    stage_names = ["tao_iou", "tao_match", "tao_acc", "lvis_eval", "lvis_acc"]
     ev = None
 
+    def acc(dev):
+        if exch is None:
+            eng.stage_accumulate(dev)
+        else:
+            exch.accumulate(dev)
+
+    stages = [lambda: eng.stage_iou(d_tao), lambda: eng.stage_match(d_tao), lambda: acc(d_tao),
+              lambda: eng.stage_frame_eval(d_lvis), lambda: acc(d_lvis)]
+
     def step(record=None):
-        k = 0
-        for dev in (d_tao, d_lvis):
-            for fn in (eng.stage_iou, eng.stage_match):
-                if record is not None:
-                    record[k][0].record()
-                fn(dev)
-                if record is not None:
-                    record[k][1].record()
-                k += 1
+        for k, fn in enumerate(stages):
             if record is not None:
                 record[k][0].record()
-            if exch is None:
-                eng.stage_accumulate(dev)
-            else:
-                exch.accumulate(dev)
+            fn()
             if record is not None:
                 record[k][1].record()
-            k += 1
 
     def sync():
         torch.cuda.synchronize()
@@ -361,15 +363,14 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     bytes_by_stage = {}
-    for pre, plan in (("tao", tao_plan), ("lvis", lvis_plan)):
-        ab = algorithmic_bytes(plan)
-        bytes_by_stage[pre + "_iou"] = ab["iou"]
-        bytes_by_stage[pre + "_match"] = ab["match"]
-        bytes_by_stage[pre + "_acc"] = ab["accumulate"]
+    ab_t, ab_l = algorithmic_bytes(tao_plan), algorithmic_bytes(lvis_plan)
+    bytes_by_stage = {"tao_iou": ab_t["iou"], "tao_match": ab_t["match"],
+                      "tao_acc": ab_t["accumulate"], "lvis_eval": ab_l["frame_eval"],
+                      "lvis_acc": ab_l["accumulate"]}
     dom = max(stage_ms, key=stage_ms.get)
-    kernel_names = {"tao_iou": "k_track_iou_tiled", "lvis_iou": "k_box_iou",
-                    "tao_match": "k_match_greedy", "lvis_match": "k_match_greedy",
-                    "tao_acc": "k_pr_accumulate", "lvis_acc": "k_pr_accumulate"}
+    kernel_names = {"tao_iou": "k_track_iou_tiled", "tao_match": "k_match_greedy",
+                    "lvis_eval": "k_frame_eval", "tao_acc": "k_pr_bucket",
+                    "lvis_acc": "k_pr_bucket"}
     per_stage = {n: {"ms": stage_ms[n], "alg_bytes": bytes_by_stage[n],
                      "gbs": bytes_by_stage[n] / (stage_ms[n] * 1e-3) / 1e9 if stage_ms[n] > 0 else None}
                  for n in stage_names}

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 1
+#define TA_ABI_VERSION 2
 #define TA_MAX_THRS 16   /* IoU thresholds packed as 16 TP bits + 16 FP bits per detection */
 
 typedef enum ta_status {
@@ -86,43 +86,77 @@ int ta_track_iou(ta_ctx* ctx, void* stream, int mode, int64_t n_groups,
                  int32_t n_slots_max, const int64_t* iou_off, double* iou_out);
 
 /* Per-(image, category) box IoU.  Replaces LVISEval.compute_iou -> pycocotools.mask.iou
- * -> bbIou (lvis_amodal/eval.py:168-192; maskApi.c:109-120 in-tree copy), iscrowd = 0. */
+ * -> bbIou (lvis_amodal/eval.py:168-192; maskApi.c:109-120 in-tree copy), iscrowd = 0.
+ * grp_list (optional, n_list entries) restricts the call to those groups.            */
 int ta_box_iou(ta_ctx* ctx, void* stream, int64_t n_groups,
+               const int32_t* grp_list, int64_t n_list,
                const int64_t* grp_dt_off, const int64_t* grp_gt_off,
                const double* dt_box, const double* gt_box,
                const int64_t* iou_off, double* iou_out);
 
 /* COCO-style sequential greedy assignment for every group x range cfg x IoU threshold.
  * Replaces TaoEval.evaluate_vid (eval.py:337-457) and LVISEval.evaluate_img
- * (lvis_amodal/eval.py:194-303).  `sentinel` is the "unmatched" id value of the
- * reference's match arrays (-1 for TaoEval, 0 for LVISEval): a detection whose matched GT
- * id equals it counts as unmatched, and a GT is locked only by a detection id > 0.
- * g_max bounds the number of GT entities of any group (sizes the shared-memory state).
+ * (lvis_amodal/eval.py:194-303).  The reference's id tests are carried by flag bits so the
+ * kernels never read 64-bit ids:
+ *   dt_flag bit0  the detection's category is not exhaustively annotated in its video/image
+ *                 (eval.py:437-439 / lvis :284-286)
+ *           bit1  the detection LOCKS the GT it matches: the reference marks a GT taken with
+ *                 `gt_m > 0` on the stored detection id (eval.py:407, lvis :248), so only
+ *                 ids > 0 lock
+ *   gt_flag bit0  "ignore" key of the GT, bit1 out_of_frame, bit2 the GT's id EQUALS the
+ *                 evaluator's "unmatched" value (-1 TaoEval eval.py:390, 0 LVISEval :239):
+ *                 a detection matched to it still counts as unmatched (eval.py:527-528)
+ * grp_list (optional, n_list entries) restricts the call to those groups; NULL = all.
+ * g_max bounds the number of GT entities of any processed group.
  * Outputs:
- *   dt_tpfp  uint32 [n_cfg][n_dt]  bit t = TP at threshold t, bit 16+t = FP (neither: ignored)
+ *   dt_tpfp  uint32 [n_dt][n_cfg]  bit t = TP at threshold t, bit 16+t = FP (neither: ignored)
  *   num_gt   int32  [n_cat][n_cfg] non-ignored GT count, ACCUMULATED (caller zeroes)
  *   dt_match_gt (optional, may be NULL) int32 [n_cfg][n_thr][n_dt] matched GT position
  *            inside its group (original order) or -1
  *   gt_ignore_out (optional) uint8 [n_cfg][n_gt]                                       */
 int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
+                    const int32_t* grp_list, int64_t n_list,
                     const int64_t* grp_dt_off, const int64_t* grp_gt_off,
                     const int32_t* grp_cat, const int64_t* iou_off, const double* iou,
                     int32_t n_thr, const double* iou_thrs,
                     int32_t n_cfg, const ta_range_cfg* cfgs,
                     int64_t n_dt, const double* dt_attr_a, const double* dt_attr_b,
-                    const uint8_t* dt_flag, const int64_t* dt_id,
+                    const uint8_t* dt_flag,
                     int64_t n_gt, const double* gt_attr_a, const double* gt_attr_b,
-                    const int32_t* gt_hp, const uint8_t* gt_flag, const int64_t* gt_id,
-                    int64_t sentinel, int32_t g_max,
+                    const int32_t* gt_hp, const uint8_t* gt_flag, int32_t g_max,
                     uint32_t* dt_tpfp, int32_t* num_gt,
                     int32_t* dt_match_gt, uint8_t* gt_ignore_out);
+
+/* Fused frame path: box IoU + greedy assignment of every (image, category) group in ONE
+ * kernel — LVISEval.compute_iou + evaluate_img (lvis_amodal/eval.py:168-303) — with the
+ * group's GT boxes staged in shared memory and its IoU tile kept on chip.  Detection area
+ * (the unmatched-ignore test of :281-283) is w*h of the box, as lvis_amodal/results.py:56
+ * defines it.  Groups with more than ta_frame_eval_max_gt() GT boxes or more than
+ * ta_frame_eval_max_pairs() box pairs must be listed in big_list: they are routed through
+ * ta_box_iou + ta_match_greedy using `iou` (sized by iou_off) as their IoU storage.  With
+ * write_iou != 0 every group's IoU matrix is also written to `iou`.
+ * gt_attr_a is the GT visibility.  Outputs as in ta_match_greedy.                       */
+int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
+                  const int64_t* grp_dt_off, const int64_t* grp_gt_off, const int32_t* grp_cat,
+                  const double* dt_box, const double* gt_box,
+                  int32_t n_thr, const double* iou_thrs, int32_t n_cfg, const ta_range_cfg* cfgs,
+                  int64_t n_dt, const uint8_t* dt_flag,
+                  int64_t n_gt, const double* gt_attr_a, const uint8_t* gt_flag,
+                  int64_t n_big, const int32_t* big_list, int32_t g_max_big,
+                  const int64_t* iou_off, double* iou, int32_t write_iou,
+                  uint32_t* dt_tpfp, int32_t* num_gt,
+                  int32_t* dt_match_gt, uint8_t* gt_ignore_out);
+int ta_frame_eval_max_gt(void);
+int ta_frame_eval_max_pairs(void);
 
 /* Precision / recall accumulation.  Replaces TaoEval.accumulate (eval.py:459-584) and
  * LVISEval.accumulate (lvis_amodal/eval.py:305-426).  acc_perm lists, category by
  * category (cat_dt_off), the detection indices in stable descending-score order.
+ * dt_tpfp is the [n_dt][n_cfg] output of the matchers.
  * Outputs (reference tensor layouts, -1 where the reference leaves -1):
  *   precision f64 [n_thr][n_rec][n_cat][n_cfg], recall f64 [n_thr][n_cat][n_cfg],
- *   tp_cnt / fp_cnt int64 [n_thr][n_cat][n_cfg] (may be NULL).                       */
+ *   tp_cnt / fp_cnt int64 [n_thr][n_cat][n_cfg] (may be NULL).
+ * Scratch (chunk counters) lives in the context and grows on demand.                   */
 int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
                      const int32_t* acc_perm, int64_t n_dt, const uint32_t* dt_tpfp,
                      const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
@@ -133,20 +167,18 @@ int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* ca
  * runs IoU -> match -> accumulate on ctx's stream, copies precision / recall / counts
  * back, and returns when they are valid.  This is the call the reference-side
  * TaoEval.run()/LVISEval.run() replacement makes (evaluate + accumulate, eval.py:662-665).
- * Track path when the *_trk_off pointers are non-NULL, frame path otherwise.          */
+ * Track path when the *_trk_off pointers are non-NULL, frame path (fused) otherwise.   */
 typedef struct ta_plan_host {
-    int64_t n_groups, n_dt, n_gt, n_dt_boxes, n_gt_boxes;
-    int32_t n_cat, n_cfg, n_thr, n_rec, n_slots_max, g_max, iou_mode;
-    int64_t sentinel;
+    int64_t n_groups, n_dt, n_gt, n_dt_boxes, n_gt_boxes, n_big;
+    int32_t n_cat, n_cfg, n_thr, n_rec, n_slots_max, g_max, iou_mode, reserved;
     const int64_t *grp_dt_off, *grp_gt_off, *iou_off, *cat_dt_off;
-    const int32_t *grp_cat, *acc_perm;
+    const int32_t *grp_cat, *acc_perm, *big_list;
     const double  *dt_box, *gt_box;
     const int64_t *dt_trk_off, *gt_trk_off;   /* NULL on the frame path */
     const int32_t *dt_slot, *gt_slot;         /* NULL on the frame path */
     const double  *dt_attr_a, *dt_attr_b, *gt_attr_a, *gt_attr_b;
     const uint8_t *dt_flag, *gt_flag;
     const int32_t *gt_hp;
-    const int64_t *dt_id, *gt_id;
     const double  *iou_thrs, *rec_thrs;
     const ta_range_cfg* cfgs;
 } ta_plan_host;

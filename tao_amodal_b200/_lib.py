@@ -25,8 +25,8 @@ IOU_MODES = {"3d_iou": 0, "avg_iou": 1, "imagenetvid": 2, "3d_iou_seq": 3}
 
 EXPORTS = [
     "ta_abi_version", "ta_last_error", "ta_ctx_create", "ta_ctx_destroy", "ta_ctx_sm_count",
-    "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_pr_accumulate",
-    "ta_eval_plan_host",
+    "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
+    "ta_frame_eval_max_gt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
 ]
 
 
@@ -44,15 +44,15 @@ class RangeCfg(C.Structure):
 class PlanHost(C.Structure):
     """struct ta_plan_host."""
     _fields_ = (
-        [(n, C.c_int64) for n in ("n_groups", "n_dt", "n_gt", "n_dt_boxes", "n_gt_boxes")]
+        [(n, C.c_int64) for n in ("n_groups", "n_dt", "n_gt", "n_dt_boxes", "n_gt_boxes",
+                                  "n_big")]
         + [(n, C.c_int32) for n in ("n_cat", "n_cfg", "n_thr", "n_rec", "n_slots_max", "g_max",
-                                    "iou_mode")]
-        + [("sentinel", C.c_int64)]
+                                    "iou_mode", "reserved")]
         + [(n, C.c_void_p) for n in (
-            "grp_dt_off", "grp_gt_off", "iou_off", "cat_dt_off", "grp_cat", "acc_perm",
+            "grp_dt_off", "grp_gt_off", "iou_off", "cat_dt_off", "grp_cat", "acc_perm", "big_list",
             "dt_box", "gt_box", "dt_trk_off", "gt_trk_off", "dt_slot", "gt_slot",
             "dt_attr_a", "dt_attr_b", "gt_attr_a", "gt_attr_b", "dt_flag", "gt_flag",
-            "gt_hp", "dt_id", "gt_id", "iou_thrs", "rec_thrs", "cfgs")]
+            "gt_hp", "iou_thrs", "rec_thrs", "cfgs")]
     )
 
 
@@ -88,10 +88,12 @@ def load() -> C.CDLL:
     lib.ta_ctx_launch_count.argtypes = [P]
     lib.ta_ctx_launch_count.restype = I64
     lib.ta_track_iou.argtypes = [P, P, C.c_int, I64, P, P, P, P, P, P, P, P, I32, P, P]
-    lib.ta_box_iou.argtypes = [P, P, I64, P, P, P, P, P, P]
-    lib.ta_match_greedy.argtypes = ([P, P, I64, P, P, P, P, P, I32, P, I32, P,
-                                     I64, P, P, P, P, I64, P, P, P, P, P, I64, I32,
+    lib.ta_box_iou.argtypes = [P, P, I64, P, I64, P, P, P, P, P, P]
+    lib.ta_match_greedy.argtypes = ([P, P, I64, P, I64, P, P, P, P, P, I32, P, I32, P,
+                                     I64, P, P, P, I64, P, P, P, P, I32,
                                      P, P, P, P])
+    lib.ta_frame_eval.argtypes = ([P, P, I64, P, P, P, P, P, I32, P, I32, P, I64, P,
+                                   I64, P, P, I64, P, I32, P, P, I32, P, P, P, P])
     lib.ta_pr_accumulate.argtypes = [P, P, I32, P, P, I64, P, P, I32, I32, I32, P, P, P, P, P]
     lib.ta_eval_plan_host.argtypes = [P, C.POINTER(PlanHost), P, P, P, P, P,
                                       C.POINTER(I64), C.POINTER(I64)]

@@ -1,0 +1,43 @@
+// ta_internal.h — context, error plumbing and launch helpers shared by the .cu files of
+// libta_eval.so.  Not part of the public C ABI (include/ta_eval.h).
+#ifndef TA_INTERNAL_H
+#define TA_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ta_eval.h"
+
+struct ta_ctx {
+    int device;
+    int sm_count;
+    int smem_optin;        // max dynamic shared memory per block (opt-in)
+    int64_t launches;      // kernels launched through this context
+    int* d_flags;          // [0]: "intersection > union" counter (eval.py:95)
+    cudaStream_t own_stream;
+    // stream-ordered scratch of ta_pr_accumulate, grown on demand
+    void* ws;
+    size_t ws_bytes;
+    // pinned staging for ta_eval_plan_host results
+    void* h_stage;
+    size_t h_stage_bytes;
+};
+
+char* ta_err_buf();
+int ta_set_err(int code, const char* fmt, const char* a = "", long long b = 0);
+
+#define TA_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return ta_set_err(TA_ERR_CUDA, "CUDA error %s at " __FILE__ ":%lld",              \
+                              cudaGetErrorString(e_), (long long)__LINE__);                  \
+    } while (0)
+
+// cudaGetLastError() after a launch; counts the launch on success.
+int ta_check_launch(ta_ctx* ctx, const char* what);
+// Returns a device scratch buffer of at least `bytes` (stream-ordered; contents undefined).
+int ta_workspace(ta_ctx* ctx, cudaStream_t st, size_t bytes, void** out);
+
+#endif  // TA_INTERNAL_H

@@ -1,0 +1,392 @@
+// ta_match.cu — greedy assignment kernels (sm_100a).
+//
+//   k_match_greedy   generic: one CTA per group, IoU matrix read from global memory, any
+//                    group size (taken-bitmaps in shared memory)
+//   k_frame_eval     fused frame path: one WARP per (image, category) group; GT boxes staged
+//                    in shared memory, IoU tile computed into shared memory and consumed by
+//                    the (range cfg x threshold) matcher lanes without touching HBM
+//
+// Both implement the reference loop of tao_amodal/evaluation/tao_amodal/eval.py:396-443 /
+// lvis_amodal/eval.py:244-290 (see ta_match_one in ta_device_fns.cuh for the equivalence of
+// the "ignored GTs last + break" walk with a two-class search in original GT order).
+#include <limits.h>
+#include "ta_internal.h"
+#include "ta_device_fns.cuh"
+
+// ------------------------------------------------------------------------------------------
+// generic matcher
+// ------------------------------------------------------------------------------------------
+struct MatchArgs {
+    const int32_t* grp_list;
+    const int64_t* grp_dt_off;
+    const int64_t* grp_gt_off;
+    const int32_t* grp_cat;
+    const int64_t* iou_off;
+    const double* iou;
+    int n_thr;
+    const double* thrs;
+    int n_cfg;
+    const ta_range_cfg* cfgs;
+    int64_t n_dt, n_gt;
+    const double* dt_a;
+    const double* dt_b;
+    const uint8_t* dt_flag;
+    const double* gt_a;
+    const double* gt_b;
+    const int32_t* gt_hp;
+    const uint8_t* gt_flag;
+    uint32_t* dt_tpfp;
+    int32_t* num_gt;
+    int32_t* dt_match_gt;
+    uint8_t* gt_ignore_out;
+    int cfgs_per_warp;
+};
+
+// OR of `bits` over the n_thr consecutive lanes of a cfg segment; valid in the lane t == 0.
+__device__ __forceinline__ uint32_t seg_or(uint32_t bits, int lane, int n_thr, int cw) {
+    uint32_t word = bits;
+    for (int o = 1; o < n_thr; o <<= 1) {
+        const uint32_t other = __shfl_down_sync(0xffffffffu, word, o);
+        if (lane + o < 32 && ((lane + o) / n_thr) == cw) word |= other;
+    }
+    return word;
+}
+
+__global__ void k_match_greedy(MatchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int grp = a.grp_list ? a.grp_list[blockIdx.x] : (int)blockIdx.x;
+    const int64_t d0 = a.grp_dt_off[grp], g0 = a.grp_gt_off[grp];
+    const int D = (int)(a.grp_dt_off[grp + 1] - d0), G = (int)(a.grp_gt_off[grp + 1] - g0);
+    if (D == 0 && G == 0) return;
+    const int nthreads = blockDim.x;
+    const int words = (G + 31) >> 5;
+    // shared layout: taken[words][nthreads] u32, then gt_ig[n_cfg][G] u8
+    uint32_t* taken = reinterpret_cast<uint32_t*>(smem_raw);
+    uint8_t* gt_ig = smem_raw + (size_t)words * nthreads * sizeof(uint32_t);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cpw = a.cfgs_per_warp;
+    const int cw = lane / a.n_thr;
+    const int t = lane - cw * a.n_thr;
+    const int cfg = warp * cpw + cw;
+    const bool active = (cw < cpw) && (cfg < a.n_cfg);
+
+    // ---- GT ignore flags for every cfg (eval.py:348-368 / lvis eval.py:201-217)
+    for (int idx = threadIdx.x; idx < a.n_cfg * G; idx += nthreads) {
+        const int c = idx / G, g = idx - c * G;
+        const uint8_t ig = ta_gt_ignored(a.cfgs[c], a.gt_a[g0 + g], a.gt_b ? a.gt_b[g0 + g] : 0.0,
+                                         a.gt_hp ? a.gt_hp[g0 + g] : 0, a.gt_flag[g0 + g]);
+        gt_ig[idx] = ig;
+        if (a.gt_ignore_out) a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + g] = ig;
+    }
+    for (int w = 0; w < words; ++w) taken[w * nthreads + threadIdx.x] = 0u;
+    __syncthreads();
+    // ---- number of non-ignored GT per (category, cfg) (eval.py:520-522)
+    if (threadIdx.x < a.n_cfg && G > 0) {
+        int cnt = 0;
+        for (int g = 0; g < G; ++g) cnt += gt_ig[threadIdx.x * G + g] == 0;
+        if (cnt) atomicAdd(&a.num_gt[(int64_t)a.grp_cat[grp] * a.n_cfg + threadIdx.x], cnt);
+    }
+    if (D == 0) return;
+
+    const double thr = active ? a.thrs[t] : 2.0;
+    const double* iou = a.iou + a.iou_off[grp];
+    const uint8_t* my_ig = gt_ig + (active ? cfg : 0) * G;
+    ta_range_cfg rc;
+    if (active) rc = a.cfgs[cfg];
+    uint32_t* my_taken = taken + threadIdx.x;
+
+    for (int d = 0; d < D; ++d) {
+        uint32_t bits = 0;
+        if (active) {
+            int m = -1;
+            if (G > 0) m = ta_match_one(iou + (int64_t)d * G, G, my_ig, my_taken, nthreads, thr);
+            const uint8_t dflag = a.dt_flag[d0 + d];
+            bool unmatched = true, ig = false;
+            if (m >= 0) {
+                if (dflag & 2) my_taken[(m >> 5) * nthreads] |= 1u << (m & 31);   // eval.py:407,428
+                unmatched = (a.gt_flag[g0 + m] & 4) != 0;                         // eval.py:427,443
+                ig = my_ig[m] != 0;                                               // eval.py:425
+            }
+            if (unmatched && !ig)
+                ig = ta_dt_unmatched_ignored(rc, a.dt_a[d0 + d], a.dt_b ? a.dt_b[d0 + d] : 0.0, dflag);
+            if (!ig) bits = unmatched ? (1u << (16 + t)) : (1u << t);
+            if (a.dt_match_gt)
+                a.dt_match_gt[((int64_t)cfg * a.n_thr + t) * a.n_dt + d0 + d] = m;
+        }
+        const uint32_t word = seg_or(bits, lane, a.n_thr, cw);
+        if (active && t == 0) a.dt_tpfp[(d0 + d) * a.n_cfg + cfg] = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused frame path
+// ------------------------------------------------------------------------------------------
+#define FE_WARPS 4
+#define FE_MAX_GT 32          // GT boxes of a group handled on chip (taken / ignore masks = 1 word)
+#define FE_MAX_PAIRS 512      // IoU tile doubles per warp
+#define FE_MAX_CFG 32
+
+struct FrameArgs {
+    int64_t n_groups;
+    const int64_t* grp_dt_off;
+    const int64_t* grp_gt_off;
+    const int32_t* grp_cat;
+    const double* dt_box;
+    const double* gt_box;
+    int n_thr;
+    const double* thrs;
+    int n_cfg;
+    const ta_range_cfg* cfgs;
+    int64_t n_dt, n_gt;
+    const uint8_t* dt_flag;
+    const double* gt_vis;
+    const uint8_t* gt_flag;
+    const int64_t* iou_off;
+    double* iou;
+    int write_iou;
+    uint32_t* dt_tpfp;
+    int32_t* num_gt;
+    int32_t* dt_match_gt;
+    uint8_t* gt_ignore_out;
+};
+
+struct FrameSmem {
+    double iou[FE_WARPS][FE_MAX_PAIRS];
+    double gtb[FE_WARPS][FE_MAX_GT][4];
+    uint32_t dmask[FE_WARPS][FE_MAX_PAIRS];   // per detection: bit c = ignored when unmatched under
+                                              // cfg c; the detection's flag byte in bits 24..31
+    uint32_t gig[FE_WARPS][FE_MAX_CFG];       // per cfg: bit g = GT g ignored
+};
+
+__global__ void __launch_bounds__(FE_WARPS * 32)
+k_frame_eval(FrameArgs a) {
+    __shared__ FrameSmem sm;
+    __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < a.n_cfg; i += blockDim.x) cfg_s[i] = a.cfgs[i];
+    __syncthreads();
+    const int n_thr = a.n_thr, n_cfg = a.n_cfg;
+    const int cpw = 32 / n_thr;
+    const int cw = lane / n_thr;
+    const int t = lane - cw * n_thr;
+    const double my_thr = (cw < cpw) ? a.thrs[t] : 2.0;
+    const double thr_c = (my_thr < 1.0 - 1e-10) ? my_thr : 1.0 - 1e-10;   // min([iou_thr, 1 - 1e-10])
+    double* iou_s = sm.iou[warp];
+    uint32_t* dmask_s = sm.dmask[warp];
+    uint32_t* gig_s = sm.gig[warp];
+    const uint32_t fp_all = ((1u << n_thr) - 1u) << 16;
+
+    const int64_t w0 = (int64_t)blockIdx.x * FE_WARPS + warp;
+    const int64_t wstride = (int64_t)gridDim.x * FE_WARPS;
+    for (int64_t grp = w0; grp < a.n_groups; grp += wstride) {
+        const int64_t d0 = a.grp_dt_off[grp], g0 = a.grp_gt_off[grp];
+        const int D = (int)(a.grp_dt_off[grp + 1] - d0), G = (int)(a.grp_gt_off[grp + 1] - g0);
+        if (D == 0 && G == 0) continue;
+        if (G > FE_MAX_GT || (int64_t)D * G > FE_MAX_PAIRS) continue;   // big_list path
+        __syncwarp();
+        if (G == 0) {
+            // every detection is unmatched at every threshold (lvis eval.py:233-235 with no GT):
+            // FP unless the unmatched-ignore rule fires
+            for (int d = lane; d < D; d += 32) {
+                const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
+                const double area = q.x * q.y;
+                const uint8_t fl = a.dt_flag[d0 + d];
+                uint32_t* o = a.dt_tpfp + (d0 + d) * n_cfg;
+                for (int c = 0; c < n_cfg; ++c)
+                    o[c] = ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, fl) ? 0u : fp_all;
+            }
+            if (a.dt_match_gt)
+                for (int e = lane; e < n_cfg * n_thr * D; e += 32) {
+                    const int ct = e / D, d = e - ct * D;
+                    a.dt_match_gt[(int64_t)ct * a.n_dt + d0 + d] = -1;
+                }
+            continue;
+        }
+        // ---- stage GT boxes, GT ignore masks per cfg, non-ignored GT counts
+        double vis = 0.0;
+        uint8_t gfl = 0;
+        if (lane < G) {
+            const double2 p = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane));
+            const double2 q = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane) + 2);
+            sm.gtb[warp][lane][0] = p.x; sm.gtb[warp][lane][1] = p.y;
+            sm.gtb[warp][lane][2] = q.x; sm.gtb[warp][lane][3] = q.y;
+            vis = a.gt_vis[g0 + lane];
+            gfl = a.gt_flag[g0 + lane];
+        }
+        const uint32_t gsent = __ballot_sync(0xffffffffu, (gfl & 4) != 0);   // id == "unmatched" value
+        const uint32_t gall = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+        uint32_t my_gig = 0;
+        for (int c = 0; c < n_cfg; ++c) {
+            const bool ig = (lane < G) && ta_gt_ignored(cfg_s[c], vis, 0.0, 0, gfl);
+            const uint32_t m = __ballot_sync(0xffffffffu, ig);
+            if (lane == c) my_gig = m;
+            if (a.gt_ignore_out && lane < G) a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + lane] = ig;
+        }
+        if (lane < n_cfg) {
+            gig_s[lane] = my_gig;
+            const int cnt = G - __popc(my_gig);
+            if (cnt) atomicAdd(&a.num_gt[(int64_t)a.grp_cat[grp] * n_cfg + lane], cnt);
+        }
+        // ---- per-detection unmatched-ignore masks
+        for (int d = lane; d < D; d += 32) {
+            const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
+            const double area = q.x * q.y;
+            const uint8_t fl = a.dt_flag[d0 + d];
+            uint32_t m = (uint32_t)fl << 24;
+            for (int c = 0; c < n_cfg; ++c)
+                if (ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, fl)) m |= 1u << c;
+            dmask_s[d] = m;
+        }
+        __syncwarp();
+        // ---- IoU tile (maskApi.c:109-120), lanes over the D*G pairs
+        const int n_pair = D * G;
+        double* iou_g = a.write_iou ? a.iou + a.iou_off[grp] : nullptr;
+        for (int e = lane; e < n_pair; e += 32) {
+            const int d = e / G, g = e - d * G;
+            const double2 dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d));
+            const double2 dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
+            const double* gb = sm.gtb[warp][g];
+            const double v = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, gb[0], gb[1], gb[2], gb[3]);
+            iou_s[e] = v;
+            if (iou_g) iou_g[e] = v;
+        }
+        __syncwarp();
+        // ---- matchers: lane = (cfg within round, threshold)
+        for (int c0 = 0; c0 < n_cfg; c0 += cpw) {
+            const int cfg = c0 + cw;
+            const bool active = (cw < cpw) && (cfg < n_cfg);
+            const uint32_t gig = active ? gig_s[cfg] : 0u;
+            uint32_t taken = 0u;
+            for (int d = 0; d < D; ++d) {
+                const uint32_t free0 = ~taken & ~gig & gall;   // regular GTs still free
+                const uint32_t free1 = ~taken & gig & gall;    // ignored GTs still free
+                double best0 = thr_c, best1 = thr_c;
+                int m0 = -1, m1 = -1;
+                const double* row = iou_s + d * G;
+                for (int g = 0; g < G; ++g) {
+                    const double v = row[g];
+                    if (((free0 >> g) & 1u) && !(v < best0)) { best0 = v; m0 = g; }
+                    if (((free1 >> g) & 1u) && !(v < best1)) { best1 = v; m1 = g; }
+                }
+                const int m = (m0 >= 0) ? m0 : m1;
+                const uint32_t dm = dmask_s[d];
+                bool unmatched = true, ig = false;
+                if (m >= 0) {
+                    if (dm & (2u << 24)) taken |= 1u << m;
+                    unmatched = (gsent >> m) & 1u;
+                    ig = (gig >> m) & 1u;
+                }
+                if (unmatched && !ig) ig = (dm >> cfg) & 1u;
+                uint32_t bits = 0;
+                if (active && !ig) bits = unmatched ? (1u << (16 + t)) : (1u << t);
+                const uint32_t word = seg_or(bits, lane, n_thr, cw);
+                if (active && t == 0) a.dt_tpfp[(d0 + d) * n_cfg + cfg] = word;
+                if (a.dt_match_gt && active)
+                    a.dt_match_gt[((int64_t)cfg * n_thr + t) * a.n_dt + d0 + d] = m;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int ta_frame_eval_max_gt(void) { return FE_MAX_GT; }
+extern "C" int ta_frame_eval_max_pairs(void) { return FE_MAX_PAIRS; }
+
+extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
+                               const int32_t* grp_list, int64_t n_list,
+                               const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+                               const int32_t* grp_cat, const int64_t* iou_off, const double* iou,
+                               int32_t n_thr, const double* iou_thrs,
+                               int32_t n_cfg, const ta_range_cfg* cfgs,
+                               int64_t n_dt, const double* dt_attr_a, const double* dt_attr_b,
+                               const uint8_t* dt_flag,
+                               int64_t n_gt, const double* gt_attr_a, const double* gt_attr_b,
+                               const int32_t* gt_hp, const uint8_t* gt_flag, int32_t g_max,
+                               uint32_t* dt_tpfp, int32_t* num_gt,
+                               int32_t* dt_match_gt, uint8_t* gt_ignore_out) {
+    if (!ctx) return ta_set_err(TA_ERR_INVALID, "ta_match_greedy: ctx is NULL");
+    if (n_thr < 1 || n_thr > TA_MAX_THRS)
+        return ta_set_err(TA_ERR_INVALID, "ta_match_greedy: n_thr must be in [1,16], got %s%lld", "", n_thr);
+    if (n_cfg < 1 || n_groups < 0 || g_max < 0)
+        return ta_set_err(TA_ERR_INVALID, "ta_match_greedy: bad sizes");
+    if (grp_list) n_groups = n_list;
+    if (n_groups <= 0) return TA_OK;
+    if (n_groups > INT_MAX) return ta_set_err(TA_ERR_TOO_LARGE, "ta_match_greedy: too many groups");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    const int cpw = 32 / n_thr;
+    const int warps = (n_cfg + cpw - 1) / cpw;
+    if (warps * 32 > 1024) return ta_set_err(TA_ERR_TOO_LARGE, "ta_match_greedy: too many range cfgs");
+    const int threads = warps * 32;
+    const int words = (g_max + 31) / 32;
+    const size_t smem = (size_t)words * threads * sizeof(uint32_t) + (size_t)n_cfg * g_max;
+    if (smem > (size_t)ctx->smem_optin)
+        return ta_set_err(TA_ERR_TOO_LARGE,
+                          "ta_match_greedy: a group with %s%lld ground-truth entities does not fit in shared memory",
+                          "", (long long)g_max);
+    MatchArgs a{grp_list, grp_dt_off, grp_gt_off, grp_cat, iou_off, iou, n_thr, iou_thrs, n_cfg, cfgs,
+                n_dt, n_gt, dt_attr_a, dt_attr_b, dt_flag, gt_attr_a, gt_attr_b, gt_hp,
+                gt_flag, dt_tpfp, num_gt, dt_match_gt, gt_ignore_out, cpw};
+    if (smem > 48 * 1024)
+        TA_CUDA(cudaFuncSetAttribute(k_match_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    k_match_greedy<<<(unsigned)n_groups, threads, smem, (cudaStream_t)stream>>>(a);
+    return ta_check_launch(ctx, "k_match_greedy");
+}
+
+// dt area for the big-group route of the frame path: w*h of the box (lvis results.py:56)
+__global__ void k_box_area_list(int64_t n_list, const int32_t* __restrict__ grp_list,
+                                const int64_t* __restrict__ grp_dt_off,
+                                const double* __restrict__ dt_box, double* __restrict__ area) {
+    const int64_t grp = grp_list[blockIdx.x];
+    const int64_t d0 = grp_dt_off[grp], d1 = grp_dt_off[grp + 1];
+    for (int64_t d = d0 + threadIdx.x; d < d1; d += blockDim.x)
+        area[d] = dt_box[4 * d + 2] * dt_box[4 * d + 3];
+}
+
+extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
+                             const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+                             const int32_t* grp_cat, const double* dt_box, const double* gt_box,
+                             int32_t n_thr, const double* iou_thrs, int32_t n_cfg,
+                             const ta_range_cfg* cfgs, int64_t n_dt, const uint8_t* dt_flag,
+                             int64_t n_gt, const double* gt_attr_a, const uint8_t* gt_flag,
+                             int64_t n_big, const int32_t* big_list, int32_t g_max_big,
+                             const int64_t* iou_off, double* iou, int32_t write_iou,
+                             uint32_t* dt_tpfp, int32_t* num_gt,
+                             int32_t* dt_match_gt, uint8_t* gt_ignore_out) {
+    if (!ctx) return ta_set_err(TA_ERR_INVALID, "ta_frame_eval: ctx is NULL");
+    if (n_thr < 1 || n_thr > TA_MAX_THRS)
+        return ta_set_err(TA_ERR_INVALID, "ta_frame_eval: n_thr must be in [1,16], got %s%lld", "", n_thr);
+    if (n_cfg < 1 || n_cfg > FE_MAX_CFG || n_groups < 0 || n_big < 0)
+        return ta_set_err(TA_ERR_INVALID, "ta_frame_eval: bad sizes");
+    if ((write_iou || n_big > 0) && (!iou || !iou_off))
+        return ta_set_err(TA_ERR_INVALID, "ta_frame_eval: iou storage required");
+    if (n_groups == 0) return TA_OK;
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    FrameArgs a{n_groups, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box, n_thr, iou_thrs, n_cfg,
+                cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, iou, write_iou,
+                dt_tpfp, num_gt, dt_match_gt, gt_ignore_out};
+    int64_t blocks = (n_groups + FE_WARPS - 1) / FE_WARPS;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs of 4 warps per SM
+    if (blocks > cap) blocks = cap;
+    k_frame_eval<<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
+    int rc = ta_check_launch(ctx, "k_frame_eval");
+    if (rc || n_big == 0) return rc;
+    // oversize groups: generic kernels, IoU through `iou`; their detection areas go to scratch
+    void* ws = nullptr;
+    rc = ta_workspace(ctx, st, (size_t)n_dt * sizeof(double), &ws);
+    if (rc) return rc;
+    k_box_area_list<<<(unsigned)n_big, 128, 0, st>>>(n_big, big_list, grp_dt_off, dt_box, (double*)ws);
+    rc = ta_check_launch(ctx, "k_box_area_list");
+    if (rc) return rc;
+    rc = ta_box_iou(ctx, stream, n_groups, big_list, n_big, grp_dt_off, grp_gt_off, dt_box, gt_box,
+                    iou_off, iou);
+    if (rc) return rc;
+    return ta_match_greedy(ctx, stream, n_groups, big_list, n_big, grp_dt_off, grp_gt_off, grp_cat,
+                           iou_off, iou, n_thr, iou_thrs, n_cfg, cfgs, n_dt, (const double*)ws,
+                           nullptr, dt_flag, n_gt, gt_attr_a, nullptr, nullptr, gt_flag, g_max_big,
+                           dt_tpfp, num_gt, dt_match_gt, gt_ignore_out);
+}

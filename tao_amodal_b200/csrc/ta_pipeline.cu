@@ -1,0 +1,132 @@
+// ta_pipeline.cu — ta_eval_plan_host: H2D -> IoU -> match -> accumulate -> D2H on the context's
+// stream.  Device memory comes from the stream-ordered pool (cudaMallocAsync; the context sets
+// the pool's release threshold so repeated calls reuse the same pages).
+#include "ta_internal.h"
+
+namespace {
+struct DevArena {
+    cudaStream_t st;
+    void* ptrs[64];
+    int n = 0;
+    int64_t h2d = 0;
+    explicit DevArena(cudaStream_t s) : st(s) {}
+    ~DevArena() { for (int i = 0; i < n; ++i) cudaFreeAsync(ptrs[i], st); }
+    cudaError_t alloc(void** p, size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(p, bytes, st);
+        if (e == cudaSuccess) ptrs[n++] = *p;
+        return e;
+    }
+    template <typename T>
+    cudaError_t upload(const T** dev, const T* host, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = alloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (count && host) {
+            e = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
+            h2d += (int64_t)(count * sizeof(T));
+        }
+        *dev = static_cast<const T*>(p);
+        return e;
+    }
+};
+}  // namespace
+
+extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
+                                 double* precision, double* recall,
+                                 int64_t* tp_cnt, int64_t* fp_cnt, int32_t* num_gt,
+                                 int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!ctx || !pl || !precision || !recall)
+        return ta_set_err(TA_ERR_INVALID, "ta_eval_plan_host: NULL argument");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->own_stream;
+    const bool track = pl->dt_trk_off != nullptr;
+    const int64_t G = pl->n_groups;
+    int rc = TA_OK;
+    {
+        DevArena ar(st);
+        const int64_t *grp_dt_off, *grp_gt_off, *iou_off, *cat_dt_off, *dt_trk_off = nullptr,
+                      *gt_trk_off = nullptr;
+        const int32_t *grp_cat, *acc_perm, *big_list = nullptr, *dt_slot = nullptr,
+                      *gt_slot = nullptr, *gt_hp = nullptr;
+        const double *dt_box, *gt_box, *dt_a = nullptr, *dt_b = nullptr, *gt_a, *gt_b = nullptr,
+                     *thrs, *recs;
+        const uint8_t *dt_flag, *gt_flag;
+        const ta_range_cfg* cfgs;
+        TA_CUDA(ar.upload(&grp_dt_off, pl->grp_dt_off, G + 1));
+        TA_CUDA(ar.upload(&grp_gt_off, pl->grp_gt_off, G + 1));
+        TA_CUDA(ar.upload(&iou_off, pl->iou_off, G + 1));
+        TA_CUDA(ar.upload(&cat_dt_off, pl->cat_dt_off, (size_t)pl->n_cat + 1));
+        TA_CUDA(ar.upload(&grp_cat, pl->grp_cat, G));
+        TA_CUDA(ar.upload(&acc_perm, pl->acc_perm, pl->n_dt));
+        TA_CUDA(ar.upload(&dt_box, pl->dt_box, (size_t)pl->n_dt_boxes * 4));
+        TA_CUDA(ar.upload(&gt_box, pl->gt_box, (size_t)pl->n_gt_boxes * 4));
+        TA_CUDA(ar.upload(&gt_a, pl->gt_attr_a, pl->n_gt));
+        TA_CUDA(ar.upload(&dt_flag, pl->dt_flag, pl->n_dt));
+        TA_CUDA(ar.upload(&gt_flag, pl->gt_flag, pl->n_gt));
+        if (track) {
+            TA_CUDA(ar.upload(&dt_trk_off, pl->dt_trk_off, pl->n_dt + 1));
+            TA_CUDA(ar.upload(&gt_trk_off, pl->gt_trk_off, pl->n_gt + 1));
+            TA_CUDA(ar.upload(&dt_slot, pl->dt_slot, pl->n_dt_boxes));
+            TA_CUDA(ar.upload(&gt_slot, pl->gt_slot, pl->n_gt_boxes));
+            TA_CUDA(ar.upload(&dt_a, pl->dt_attr_a, pl->n_dt));
+            TA_CUDA(ar.upload(&dt_b, pl->dt_attr_b, pl->n_dt));
+            TA_CUDA(ar.upload(&gt_b, pl->gt_attr_b, pl->n_gt));
+            TA_CUDA(ar.upload(&gt_hp, pl->gt_hp, pl->n_gt));
+        } else if (pl->n_big > 0) {
+            TA_CUDA(ar.upload(&big_list, pl->big_list, pl->n_big));
+        }
+        TA_CUDA(ar.upload(&thrs, pl->iou_thrs, pl->n_thr));
+        TA_CUDA(ar.upload(&recs, pl->rec_thrs, pl->n_rec));
+        TA_CUDA(ar.upload(&cfgs, pl->cfgs, pl->n_cfg));
+
+        const int64_t n_iou = pl->iou_off[G];
+        const size_t n_cell = (size_t)pl->n_thr * pl->n_cat * pl->n_cfg;
+        const size_t n_prec = n_cell * pl->n_rec;
+        void *d_iou, *d_tpfp, *d_numgt, *d_prec, *d_rec, *d_tp, *d_fp;
+        // the frame path keeps IoU tiles on chip; only oversize groups use the global buffer
+        TA_CUDA(ar.alloc(&d_iou, (track || pl->n_big > 0) ? (size_t)n_iou * 8 : 16));
+        TA_CUDA(ar.alloc(&d_tpfp, (size_t)pl->n_cfg * pl->n_dt * 4));
+        TA_CUDA(ar.alloc(&d_numgt, (size_t)pl->n_cat * pl->n_cfg * 4));
+        TA_CUDA(ar.alloc(&d_prec, n_prec * 8));
+        TA_CUDA(ar.alloc(&d_rec, n_cell * 8));
+        TA_CUDA(ar.alloc(&d_tp, n_cell * 8));
+        TA_CUDA(ar.alloc(&d_fp, n_cell * 8));
+        TA_CUDA(cudaMemsetAsync(d_numgt, 0, (size_t)pl->n_cat * pl->n_cfg * 4, st));
+
+        if (track) {
+            rc = ta_track_iou(ctx, st, pl->iou_mode, G, grp_dt_off, grp_gt_off, dt_trk_off, dt_box,
+                              dt_slot, gt_trk_off, gt_box, gt_slot, pl->n_slots_max, iou_off,
+                              (double*)d_iou);
+            if (rc == TA_OK)
+                rc = ta_match_greedy(ctx, st, G, nullptr, 0, grp_dt_off, grp_gt_off, grp_cat, iou_off,
+                                     (const double*)d_iou, pl->n_thr, thrs, pl->n_cfg, cfgs,
+                                     pl->n_dt, dt_a, dt_b, dt_flag, pl->n_gt, gt_a, gt_b, gt_hp,
+                                     gt_flag, pl->g_max, (uint32_t*)d_tpfp, (int32_t*)d_numgt,
+                                     nullptr, nullptr);
+        } else {
+            rc = ta_frame_eval(ctx, st, G, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box,
+                               pl->n_thr, thrs, pl->n_cfg, cfgs, pl->n_dt, dt_flag, pl->n_gt, gt_a,
+                               gt_flag, pl->n_big, big_list, pl->g_max, iou_off, (double*)d_iou, 0,
+                               (uint32_t*)d_tpfp, (int32_t*)d_numgt, nullptr, nullptr);
+        }
+        if (rc == TA_OK)
+            rc = ta_pr_accumulate(ctx, st, pl->n_cat, cat_dt_off, acc_perm, pl->n_dt,
+                                  (const uint32_t*)d_tpfp, (const int32_t*)d_numgt, pl->n_thr,
+                                  pl->n_cfg, pl->n_rec, recs, (double*)d_prec, (double*)d_rec,
+                                  (int64_t*)d_tp, (int64_t*)d_fp);
+        int64_t d2h = 0;
+        if (rc == TA_OK) {
+            TA_CUDA(cudaMemcpyAsync(precision, d_prec, n_prec * 8, cudaMemcpyDeviceToHost, st));
+            TA_CUDA(cudaMemcpyAsync(recall, d_rec, n_cell * 8, cudaMemcpyDeviceToHost, st));
+            d2h += (int64_t)((n_prec + n_cell) * 8);
+            if (tp_cnt) { TA_CUDA(cudaMemcpyAsync(tp_cnt, d_tp, n_cell * 8, cudaMemcpyDeviceToHost, st)); d2h += n_cell * 8; }
+            if (fp_cnt) { TA_CUDA(cudaMemcpyAsync(fp_cnt, d_fp, n_cell * 8, cudaMemcpyDeviceToHost, st)); d2h += n_cell * 8; }
+            if (num_gt) { TA_CUDA(cudaMemcpyAsync(num_gt, d_numgt, (size_t)pl->n_cat * pl->n_cfg * 4, cudaMemcpyDeviceToHost, st)); d2h += (int64_t)pl->n_cat * pl->n_cfg * 4; }
+        }
+        if (h2d_bytes) *h2d_bytes = ar.h2d;
+        if (d2h_bytes) *d2h_bytes = d2h;
+    }   // arena frees are stream-ordered after the kernels
+    TA_CUDA(cudaStreamSynchronize(st));
+    return rc;
+}

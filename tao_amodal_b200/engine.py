@@ -45,7 +45,7 @@ class EvalOutput:
     d2h_bytes: int = 0
     # detail (optional)
     iou: Optional[np.ndarray] = None          # f64 [sum D*G], group g at plan.iou_off[g]
-    dt_tpfp: Optional[np.ndarray] = None      # u32 [n_cfg, n_dt]
+    dt_tpfp: Optional[np.ndarray] = None      # u32 [n_dt, n_cfg]
     dt_match_gt: Optional[np.ndarray] = None  # i32 [n_cfg, n_thr, n_dt]
     gt_ignore: Optional[np.ndarray] = None    # u8  [n_cfg, n_gt]
 
@@ -63,6 +63,13 @@ def plan_limits(plan: EvalPlan):
     return g_max, n_slots
 
 
+def frame_big_groups(plan: EvalPlan, max_gt: int, max_pairs: int) -> np.ndarray:
+    """Groups of a frame-path plan that exceed the on-chip limits of ta_frame_eval."""
+    D = np.diff(plan.grp_dt_off)
+    G = np.diff(plan.grp_gt_off)
+    return np.nonzero((G > max_gt) | (D * G > max_pairs))[0].astype(np.int32)
+
+
 def _ptr(a: Optional[np.ndarray]):
     if a is None:
         return None
@@ -75,12 +82,21 @@ class Engine:
 
     def __init__(self, device: int = 0):
         self.lib = _lib.load()
-        if self.lib.ta_abi_version() != 1:
+        if self.lib.ta_abi_version() != 2:
             raise RuntimeError("libta_eval.so ABI version mismatch")
         self.device = int(device)
         h = C.c_void_p()
         _lib.check(self.lib.ta_ctx_create(self.device, C.byref(h)))
         self._ctx = h
+        self.fe_max_gt = int(self.lib.ta_frame_eval_max_gt())
+        self.fe_max_pairs = int(self.lib.ta_frame_eval_max_pairs())
+
+    def big_list(self, plan: EvalPlan) -> np.ndarray:
+        bl = getattr(plan, "_big_list", None)
+        if bl is None:
+            bl = frame_big_groups(plan, self.fe_max_gt, self.fe_max_pairs)
+            plan._big_list = bl
+        return bl
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -116,10 +132,12 @@ class Engine:
         ph.n_cat, ph.n_cfg, ph.n_thr, ph.n_rec = n_cat, n_cfg, n_thr, n_rec
         ph.n_slots_max, ph.g_max = n_slots, g_max
         ph.iou_mode = _lib.IOU_MODES[iou_mode]
-        ph.sentinel = plan.sentinel
+        big = None if track else self.big_list(plan)
+        ph.n_big = 0 if big is None else int(big.size)
         keep = dict(
             grp_dt_off=plan.grp_dt_off, grp_gt_off=plan.grp_gt_off, iou_off=plan.iou_off,
             cat_dt_off=plan.cat_dt_off, grp_cat=plan.grp_cat, acc_perm=plan.acc_perm,
+            big_list=big if (big is not None and big.size) else None,
             dt_box=plan.dt_box, gt_box=plan.gt_box,
             dt_trk_off=plan.dt_trk_box_off if track else None,
             gt_trk_off=plan.gt_trk_box_off if track else None,
@@ -128,8 +146,7 @@ class Engine:
             dt_attr_a=plan.dt_attr_a, dt_attr_b=plan.dt_attr_b,
             gt_attr_a=plan.gt_attr_a, gt_attr_b=plan.gt_attr_b,
             dt_flag=plan.dt_flag, gt_flag=plan.gt_flag, gt_hp=plan.gt_hp,
-            dt_id=plan.dt_id, gt_id=plan.gt_id, iou_thrs=iou_thrs, rec_thrs=rec_thrs,
-            cfgs=plan.range_cfgs)
+            iou_thrs=iou_thrs, rec_thrs=rec_thrs, cfgs=plan.range_cfgs)
         for k, v in keep.items():
             setattr(ph, k, _ptr(v))
         if out is None:
@@ -163,12 +180,12 @@ class Engine:
                 p["gt_box"], p["gt_slot"], dev.n_slots, p["iou_off"], p["iou"]))
         else:
             _lib.check(self.lib.ta_box_iou(
-                self._ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["dt_box"],
-                p["gt_box"], p["iou_off"], p["iou"]))
+                self._ctx, st, plan.n_groups, None, 0, p["grp_dt_off"], p["grp_gt_off"],
+                p["dt_box"], p["gt_box"], p["iou_off"], p["iou"]))
 
     def stage_match(self, dev: "DevicePlan", detail: bool = False):
         """evaluate_vid / evaluate_img of every group x range x threshold
-        (eval.py:337-457 / lvis eval.py:194-303)."""
+        (eval.py:337-457 / lvis eval.py:194-303) from the IoU matrices of stage_iou."""
         import torch
         plan = dev.plan
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -177,11 +194,30 @@ class Engine:
             dev.ensure_detail()
         p = dev.ptr
         _lib.check(self.lib.ta_match_greedy(
-            self._ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["grp_cat"],
+            self._ctx, st, plan.n_groups, None, 0, p["grp_dt_off"], p["grp_gt_off"], p["grp_cat"],
             p["iou_off"], p["iou"], dev.n_thr, p["iou_thrs"], plan.n_cfg, p["cfgs"],
-            plan.n_dt, p["dt_attr_a"], p["dt_attr_b"], p["dt_flag"], p["dt_id"],
-            plan.n_gt, p["gt_attr_a"], p["gt_attr_b"], p["gt_hp"], p["gt_flag"], p["gt_id"],
-            plan.sentinel, dev.g_max, p["dt_tpfp"], p["num_gt"],
+            plan.n_dt, p["dt_attr_a"], p["dt_attr_b"], p["dt_flag"],
+            plan.n_gt, p["gt_attr_a"], p["gt_attr_b"], p["gt_hp"], p["gt_flag"],
+            dev.g_max, p["dt_tpfp"], p["num_gt"],
+            p["dt_match_gt"] if detail else None, p["gt_ignore"] if detail else None))
+
+    def stage_frame_eval(self, dev: "DevicePlan", detail: bool = False):
+        """Fused frame path: LVISEval.compute_iou + evaluate_img in one kernel
+        (lvis_amodal/eval.py:168-303)."""
+        import torch
+        plan = dev.plan
+        assert plan.kind == "lvis"
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        dev.t["num_gt"].zero_()
+        if detail:
+            dev.ensure_detail()
+        p = dev.ptr
+        _lib.check(self.lib.ta_frame_eval(
+            self._ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["grp_cat"],
+            p["dt_box"], p["gt_box"], dev.n_thr, p["iou_thrs"], plan.n_cfg, p["cfgs"],
+            plan.n_dt, p["dt_flag"], plan.n_gt, p["gt_attr_a"], p["gt_flag"],
+            dev.n_big, p["big_list"] if dev.n_big else None, dev.g_max,
+            p["iou_off"], p["iou"], 1 if detail else 0, p["dt_tpfp"], p["num_gt"],
             p["dt_match_gt"] if detail else None, p["gt_ignore"] if detail else None))
 
     def stage_accumulate(self, dev: "DevicePlan"):
@@ -195,12 +231,16 @@ class Engine:
             p["precision"], p["recall"], p["tp_cnt"], p["fp_cnt"]))
 
     def evaluate_device(self, dev: "DevicePlan", detail: bool = False,
-                        iou_mode: str = "3d_iou", fetch: bool = True):
+                        iou_mode: str = "3d_iou", fetch: bool = True, fused: bool = True):
         """IoU -> match -> accumulate on dev's buffers (asynchronous on torch's current
-        stream until results are fetched).  Returns EvalOutput (fetch=True) or None."""
+        stream until results are fetched).  The frame path runs the fused kernel unless
+        fused=False (then ta_box_iou + ta_match_greedy).  Returns EvalOutput or None."""
         plan = dev.plan
-        self.stage_iou(dev, iou_mode)
-        self.stage_match(dev, detail)
+        if plan.kind == "lvis" and fused:
+            self.stage_frame_eval(dev, detail)
+        else:
+            self.stage_iou(dev, iou_mode)
+            self.stage_match(dev, detail)
         self.stage_accumulate(dev)
         if not fetch:
             return None
@@ -213,7 +253,7 @@ class Engine:
             n_iou = int(plan.iou_off[-1]) if plan.iou_off.size else 0
             out.iou = t["iou"].cpu().numpy()[:n_iou]
             out.dt_tpfp = (t["dt_tpfp"].cpu().numpy().view(np.uint32)[:plan.n_cfg * plan.n_dt]
-                           .reshape(plan.n_cfg, plan.n_dt))
+                           .reshape(plan.n_dt, plan.n_cfg))
             out.dt_match_gt = t["dt_match_gt"].cpu().numpy()[:, :, :plan.n_dt]
             out.gt_ignore = t["gt_ignore"].cpu().numpy()[:, :plan.n_gt]
         return out
@@ -239,10 +279,14 @@ class DevicePlan:
             dt_attr_a=plan.dt_attr_a, dt_attr_b=plan.dt_attr_b,
             gt_attr_a=plan.gt_attr_a, gt_attr_b=plan.gt_attr_b,
             dt_flag=plan.dt_flag, gt_flag=plan.gt_flag, gt_hp=plan.gt_hp,
-            dt_id=plan.dt_id, gt_id=plan.gt_id,
             iou_thrs=np.ascontiguousarray(iou_thrs, dtype=np.float64),
             rec_thrs=np.ascontiguousarray(rec_thrs, dtype=np.float64),
             cfgs=plan.range_cfgs.view(np.uint8))
+        self.n_big = 0
+        if not track:
+            big = eng.big_list(plan)
+            self.n_big = int(big.size)
+            host["big_list"] = big
         if track:
             host.update(dt_trk_off=plan.dt_trk_box_off, gt_trk_off=plan.gt_trk_box_off,
                         dt_slot=plan.dt_box_slot, gt_slot=plan.gt_box_slot)

@@ -58,7 +58,7 @@ def cell_record(plan: EvalPlan, g: int, cfg: int, n_thr: int, dt_tpfp: np.ndarra
             h = hit[t]
             if h.any():
                 gt_m[t, pos[m[t, h]]] = dt_ids[h].astype(np.float64)   # later dt overwrites
-    w = dt_tpfp[cfg, d0:d1].astype(np.uint32)
+    w = dt_tpfp[d0:d1, cfg].astype(np.uint32)
     t_idx = np.arange(n_thr, dtype=np.uint32)[:, None]
     counted = ((w[None, :] >> t_idx) | (w[None, :] >> (t_idx + np.uint32(16)))) & np.uint32(1)
     unit_key = "video_id" if plan.kind == "tao" else "image_id"
@@ -103,7 +103,7 @@ def dt_pointers(plan: EvalPlan, n_thr: int, dt_tpfp: np.ndarray, num_gt: np.ndar
             if num_gt[c, cfg] == 0 or int(plan.cat_grp_off[c + 1] - plan.cat_grp_off[c]) == 0:
                 per_cfg.append({})
                 continue
-            w = dt_tpfp[cfg, order].astype(np.uint32)[None, :]
+            w = dt_tpfp[order, cfg].astype(np.uint32)[None, :]
             per_cfg.append({"dt_ids": plan.dt_id[order],
                             "tps": ((w >> t_idx) & 1).astype(bool),
                             "fps": ((w >> (t_idx + np.uint32(16))) & 1).astype(bool)})

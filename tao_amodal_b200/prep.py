@@ -108,13 +108,14 @@ class EvalPlan:
     dt_score: np.ndarray         # f64
     dt_attr_a: np.ndarray        # f64 area (tao: mean track area)
     dt_attr_b: np.ndarray        # f64 number of annotations (tao) / zeros (lvis)
-    dt_flag: np.ndarray          # u8 bit0: category not exhaustively annotated in this unit
+    dt_flag: np.ndarray          # u8 bit0: category not exhaustively annotated in this unit,
+                                 #    bit1: id > 0, i.e. the detection locks the GT it matches
     dt_id: np.ndarray            # int64 track id (tao) / annotation id (lvis)
     # gt entities
     gt_attr_a: np.ndarray        # f64 mean area (tao) / visibility (lvis)
     gt_attr_b: np.ndarray        # f64 number of annotations (tao) / zeros (lvis)
     gt_hp: np.ndarray            # int32 frames with visibility < 0.8 (tao) / zeros
-    gt_flag: np.ndarray          # u8 bit0: ignore, bit1: out_of_frame
+    gt_flag: np.ndarray          # u8 bit0: ignore, bit1: out_of_frame, bit2: id == sentinel
     gt_id: np.ndarray            # int64
     # boxes
     dt_box: np.ndarray           # f64 [N,4]; lvis: one per entity
@@ -444,12 +445,14 @@ def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
         dt_score=dt_score,
         dt_attr_a=np.ascontiguousarray(dt_ent["area_mean"][d_sel]),
         dt_attr_b=np.ascontiguousarray(dt_ent["n_anns"][d_sel].astype(np.float64)),
-        dt_flag=np.ascontiguousarray(in_nel[d_sel].astype(np.uint8)),
+        dt_flag=np.ascontiguousarray(in_nel[d_sel].astype(np.uint8)
+                                     | ((tu[d_t][d_sel] > 0).astype(np.uint8) << 1)),
         dt_id=np.ascontiguousarray(tu[d_t][d_sel]),
         gt_attr_a=np.ascontiguousarray(gt_ent["area_mean"][g_perm]),
         gt_attr_b=np.ascontiguousarray(gt_ent["n_anns"][g_perm].astype(np.float64)),
         gt_hp=np.ascontiguousarray(gt_ent["n_hp"][g_perm].astype(np.int32)),
-        gt_flag=np.ascontiguousarray(gt.trk_ignore[g_trow][g_perm].astype(np.uint8) & 1),
+        gt_flag=np.ascontiguousarray((gt.trk_ignore[g_trow][g_perm].astype(np.uint8) & 1)
+                                     | ((gt.trk_id[g_trow][g_perm] == -1).astype(np.uint8) << 2)),
         gt_id=np.ascontiguousarray(gt.trk_id[g_trow][g_perm]),
         dt_box=db, gt_box=gb, dt_trk_box_off=db_off, gt_trk_box_off=gb_off,
         dt_box_slot=dslot, gt_box_slot=gslot,
@@ -606,13 +609,14 @@ def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
         dt_score=dt_score,
         dt_attr_a=np.ascontiguousarray(d_area[d_sel]),
         dt_attr_b=np.zeros(d_sel.size),
-        dt_flag=np.ascontiguousarray(in_nel[kept][d_perm].astype(np.uint8)),
+        dt_flag=np.ascontiguousarray(in_nel[kept][d_perm].astype(np.uint8) | np.uint8(2)),
         dt_id=np.ascontiguousarray((d_sel + 1).astype(np.int64)),
         gt_attr_a=np.ascontiguousarray(gt.ann_visibility[g_sel]),
         gt_attr_b=np.zeros(g_sel.size),
         gt_hp=np.zeros(g_sel.size, dtype=np.int32),
         gt_flag=np.ascontiguousarray(((gt.ann_ignore[g_sel] & 1)
-                                      | ((gt.ann_oof[g_sel] == 1).astype(np.uint8) << 1))
+                                      | ((gt.ann_oof[g_sel] == 1).astype(np.uint8) << 1)
+                                      | ((gt.ann_id[g_sel] == 0).astype(np.uint8) << 2))
                                      .astype(np.uint8)),
         gt_id=np.ascontiguousarray(gt.ann_id[g_sel]),
         dt_box=np.ascontiguousarray(d_box[d_sel].astype(np.float64)),

@@ -72,9 +72,9 @@ int hs_match_greedy(int64_t n_groups, const int64_t* grp_dt_off, const int64_t* 
                     const int32_t* grp_cat, const int64_t* iou_off, const double* iou,
                     int32_t n_thr, const double* thrs, int32_t n_cfg, const ta_range_cfg* cfgs,
                     int64_t n_dt, const double* dt_a, const double* dt_b, const uint8_t* dt_flag,
-                    const int64_t* dt_id, int64_t n_gt, const double* gt_a, const double* gt_b,
-                    const int32_t* gt_hp, const uint8_t* gt_flag, const int64_t* gt_id,
-                    int64_t sentinel, int32_t g_max, uint32_t* dt_tpfp, int32_t* num_gt,
+                    int64_t n_gt, const double* gt_a, const double* gt_b,
+                    const int32_t* gt_hp, const uint8_t* gt_flag,
+                    int32_t g_max, uint32_t* dt_tpfp, int32_t* num_gt,
                     int32_t* dt_match_gt, uint8_t* gt_ignore_out) {
     (void)g_max;
     for (int64_t grp = 0; grp < n_groups; ++grp) {
@@ -91,23 +91,23 @@ int hs_match_greedy(int64_t n_groups, const int64_t* grp_dt_off, const int64_t* 
                 if (gt_ignore_out) gt_ignore_out[(int64_t)c * n_gt + g0 + g] = ig[g];
             }
             num_gt[(int64_t)grp_cat[grp] * n_cfg + c] += cnt;
-            for (int d = 0; d < D; ++d) dt_tpfp[(int64_t)c * n_dt + d0 + d] = 0;
+            for (int d = 0; d < D; ++d) dt_tpfp[(d0 + d) * n_cfg + c] = 0;
             for (int t = 0; t < n_thr; ++t) {
                 std::vector<uint32_t> taken(words ? words : 1, 0u);
                 for (int d = 0; d < D; ++d) {
                     int m = -1;
                     if (G > 0) m = ta_match_one(iou + iou_off[grp] + (int64_t)d * G, G, ig.data(),
                                                 taken.data(), 1, thrs[t]);
-                    const int64_t did = dt_id[d0 + d];
+                    const uint8_t dfl = dt_flag[d0 + d];
                     bool unmatched = true, ign = false;
                     if (m >= 0) {
-                        if (did > 0) taken[m >> 5] |= 1u << (m & 31);
-                        unmatched = gt_id[g0 + m] == sentinel;
+                        if (dfl & 2) taken[m >> 5] |= 1u << (m & 31);
+                        unmatched = (gt_flag[g0 + m] & 4) != 0;
                         ign = ig[m] != 0;
                     }
                     if (unmatched && !ign)
                         ign = ta_dt_unmatched_ignored(cfgs[c], dt_a[d0 + d], dt_b[d0 + d], dt_flag[d0 + d]);
-                    if (!ign) dt_tpfp[(int64_t)c * n_dt + d0 + d] |= unmatched ? (1u << (16 + t)) : (1u << t);
+                    if (!ign) dt_tpfp[(d0 + d) * n_cfg + c] |= unmatched ? (1u << (16 + t)) : (1u << t);
                     if (dt_match_gt) dt_match_gt[((int64_t)c * n_thr + t) * n_dt + d0 + d] = m;
                 }
             }
@@ -138,7 +138,7 @@ int hs_pr_accumulate(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* ac
                 for (int k = 0; k < n_rec; ++k) { tk[k] = ta_min_tp_for_recall(rec_thrs[k], ngt); bucket[k] = 0.0; }
                 int64_t tp = 0, fp = 0;
                 for (int64_t p = cat_dt_off[c]; p < cat_dt_off[c + 1]; ++p) {
-                    const uint32_t w = dt_tpfp[(int64_t)cfg * n_dt + acc_perm[p]];
+                    const uint32_t w = dt_tpfp[(int64_t)acc_perm[p] * n_cfg + cfg];
                     if ((w >> t) & 1u) {
                         ++tp;
                         const double pr = ta_precision_at(tp, fp);

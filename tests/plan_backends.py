@@ -49,21 +49,21 @@ def run_hostsim(plan, iou_mode="3d_iou", iou_thrs=engine.IOU_THRS, rec_thrs=engi
         hs.hs_box_iou.argtypes = [I64] + [C.c_void_p] * 6
         hs.hs_box_iou(plan.n_groups, _p(plan.grp_dt_off), _p(plan.grp_gt_off), _p(plan.dt_box),
                       _p(plan.gt_box), _p(plan.iou_off), _p(iou))
-    tpfp = np.zeros((n_cfg, plan.n_dt), dtype=np.uint32)
+    tpfp = np.zeros((plan.n_dt, n_cfg), dtype=np.uint32)
     num_gt = np.zeros((n_cat, n_cfg), dtype=np.int32)
     match_gt = np.full((n_cfg, n_thr, plan.n_dt), -1, dtype=np.int32)
     gt_ig = np.zeros((n_cfg, plan.n_gt), dtype=np.uint8)
     thr = np.ascontiguousarray(iou_thrs, dtype=np.float64)
     rec = np.ascontiguousarray(rec_thrs, dtype=np.float64)
     P = C.c_void_p
-    hs.hs_match_greedy.argtypes = ([I64, P, P, P, P, P, I32, P, I32, P, I64, P, P, P, P, I64,
-                                    P, P, P, P, P, I64, I32, P, P, P, P])
+    hs.hs_match_greedy.argtypes = ([I64, P, P, P, P, P, I32, P, I32, P, I64, P, P, P, I64,
+                                    P, P, P, P, I32, P, P, P, P])
     g_max, _ = engine.plan_limits(plan)
     hs.hs_match_greedy(plan.n_groups, _p(plan.grp_dt_off), _p(plan.grp_gt_off), _p(plan.grp_cat),
                        _p(plan.iou_off), _p(iou), n_thr, _p(thr), n_cfg, _p(plan.range_cfgs),
                        plan.n_dt, _p(plan.dt_attr_a), _p(plan.dt_attr_b), _p(plan.dt_flag),
-                       _p(plan.dt_id), plan.n_gt, _p(plan.gt_attr_a), _p(plan.gt_attr_b),
-                       _p(plan.gt_hp), _p(plan.gt_flag), _p(plan.gt_id), plan.sentinel, g_max,
+                       plan.n_gt, _p(plan.gt_attr_a), _p(plan.gt_attr_b),
+                       _p(plan.gt_hp), _p(plan.gt_flag), g_max,
                        _p(tpfp), _p(num_gt), _p(match_gt), _p(gt_ig))
     out = engine.EvalOutput(
         precision=np.empty((n_thr, n_rec, n_cat, n_cfg)), recall=np.empty((n_thr, n_cat, n_cfg)),

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_null_ctx_errors():
     lib = _lib.load()
-    assert lib.ta_abi_version() == 1
+    assert lib.ta_abi_version() == 2
     rc = lib.ta_track_iou(None, None, 0, 0, None, None, None, None, None, None, None, None, 0,
                           None, None)
     assert rc == _lib.TA_ERR_INVALID
@@ -37,4 +37,4 @@ def test_abi_version_and_null_ctx_errors():
 def test_struct_layouts_match_header():
     from tao_amodal_b200 import prep
     assert C.sizeof(_lib.RangeCfg) == prep.RANGE_CFG_DTYPE.itemsize == 72
-    assert C.sizeof(_lib.PlanHost) == 5 * 8 + 7 * 4 + 4 + 8 + 24 * 8
+    assert C.sizeof(_lib.PlanHost) == 6 * 8 + 8 * 4 + 23 * 8
