@@ -131,8 +131,9 @@ int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
  * kernel — LVISEval.compute_iou + evaluate_img (lvis_amodal/eval.py:168-303) — with the
  * group's GT boxes staged in shared memory and its IoU tile kept on chip.  Detection area
  * (the unmatched-ignore test of :281-283) is w*h of the box, as lvis_amodal/results.py:56
- * defines it.  Groups with more than ta_frame_eval_max_gt() GT boxes or more than
- * ta_frame_eval_max_pairs() box pairs must be listed in big_list: they are routed through
+ * defines it.  Groups with GT and more than ta_frame_eval_max_gt() GT boxes, more than
+ * ta_frame_eval_max_dt() detections or more than ta_frame_eval_max_pairs() box pairs must
+ * be listed in big_list: they are routed through
  * ta_box_iou + ta_match_greedy using `iou` (sized by iou_off) as their IoU storage.  With
  * write_iou != 0 every group's IoU matrix is also written to `iou`.
  * gt_attr_a is the GT visibility.  Outputs as in ta_match_greedy.                       */
@@ -147,6 +148,7 @@ int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
                   uint32_t* dt_tpfp, int32_t* num_gt,
                   int32_t* dt_match_gt, uint8_t* gt_ignore_out);
 int ta_frame_eval_max_gt(void);
+int ta_frame_eval_max_dt(void);
 int ta_frame_eval_max_pairs(void);
 
 /* Precision / recall accumulation.  Replaces TaoEval.accumulate (eval.py:459-584) and

@@ -26,7 +26,7 @@ IOU_MODES = {"3d_iou": 0, "avg_iou": 1, "imagenetvid": 2, "3d_iou_seq": 3}
 EXPORTS = [
     "ta_abi_version", "ta_last_error", "ta_ctx_create", "ta_ctx_destroy", "ta_ctx_sm_count",
     "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
-    "ta_frame_eval_max_gt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
+    "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
 ]
 
 

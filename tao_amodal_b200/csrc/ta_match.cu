@@ -42,16 +42,6 @@ struct MatchArgs {
     int cfgs_per_warp;
 };
 
-// OR of `bits` over the n_thr consecutive lanes of a cfg segment; valid in the lane t == 0.
-__device__ __forceinline__ uint32_t seg_or(uint32_t bits, int lane, int n_thr, int cw) {
-    uint32_t word = bits;
-    for (int o = 1; o < n_thr; o <<= 1) {
-        const uint32_t other = __shfl_down_sync(0xffffffffu, word, o);
-        if (lane + o < 32 && ((lane + o) / n_thr) == cw) word |= other;
-    }
-    return word;
-}
-
 __global__ void k_match_greedy(MatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = a.grp_list ? a.grp_list[blockIdx.x] : (int)blockIdx.x;
@@ -96,8 +86,10 @@ __global__ void k_match_greedy(MatchArgs a) {
     if (active) rc = a.cfgs[cfg];
     uint32_t* my_taken = taken + threadIdx.x;
 
+    const int sh = cw * a.n_thr;
+    const uint32_t thr_all = (1u << a.n_thr) - 1u;
     for (int d = 0; d < D; ++d) {
-        uint32_t bits = 0;
+        bool tp = false, fp = false;
         if (active) {
             int m = -1;
             if (G > 0) m = ta_match_one(iou + (int64_t)d * G, G, my_ig, my_taken, nthreads, thr);
@@ -110,22 +102,41 @@ __global__ void k_match_greedy(MatchArgs a) {
             }
             if (unmatched && !ig)
                 ig = ta_dt_unmatched_ignored(rc, a.dt_a[d0 + d], a.dt_b ? a.dt_b[d0 + d] : 0.0, dflag);
-            if (!ig) bits = unmatched ? (1u << (16 + t)) : (1u << t);
+            tp = !ig && !unmatched;
+            fp = !ig && unmatched;
             if (a.dt_match_gt)
                 a.dt_match_gt[((int64_t)cfg * a.n_thr + t) * a.n_dt + d0 + d] = m;
         }
-        const uint32_t word = seg_or(bits, lane, a.n_thr, cw);
-        if (active && t == 0) a.dt_tpfp[(d0 + d) * a.n_cfg + cfg] = word;
+        // the n_thr lanes of a cfg are consecutive: its TP / FP words are slices of two ballots
+        const uint32_t bt = __ballot_sync(0xffffffffu, tp);
+        const uint32_t bf = __ballot_sync(0xffffffffu, fp);
+        if (active && t == 0)
+            a.dt_tpfp[(d0 + d) * a.n_cfg + cfg] = ((bt >> sh) & thr_all) | (((bf >> sh) & thr_all) << 16);
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // fused frame path
+//
+// One warp per (image, category) group; a warp owns FE_RUN consecutive groups at a time so the
+// non-ignored-GT counts of a category are accumulated in registers and flushed with one atomic
+// per (run, cfg).  Three routes per group, all bit-equivalent to lvis_amodal/eval.py:244-290:
+//   A  no GT:   every detection is unmatched at every threshold.
+//   B  "simple" group — no detection reaches the lowest IoU threshold with more than one GT.
+//      Then a detection's only possible match g* does not depend on the range cfg (the
+//      regular-before-ignored preference only arbitrates between several candidates), so one
+//      lane per GT walks the detections in score order with the thresholds packed in a bit
+//      mask: matched = ge(d) & ~taken(g*), taken |= ge(d) if d locks.  All cfg x threshold
+//      cells of the group come out of one pass.
+//   C  general: lane = (cfg, threshold) sequential matcher over the shared-memory IoU tile,
+//      with a per-detection shortcut when that detection has at most one candidate.
 // ------------------------------------------------------------------------------------------
 #define FE_WARPS 4
+#define FE_RUN 16             // consecutive groups per warp task
 #define FE_MAX_GT 32          // GT boxes of a group handled on chip (taken / ignore masks = 1 word)
+#define FE_MAX_DT 256         // detections of a group handled on chip (when it has GT)
 #define FE_MAX_PAIRS 512      // IoU tile doubles per warp
-#define FE_MAX_CFG 32
+#define FE_MAX_CFG 16
 
 struct FrameArgs {
     int64_t n_groups;
@@ -151,11 +162,14 @@ struct FrameArgs {
     uint8_t* gt_ignore_out;
 };
 
+// per-detection word: bits 0..15 "ignored when unmatched" per cfg, bit 16 locks its GT
+// candidate word:     bits 0..15 thresholds reached by the best GT (route B: later the matched
+//                     thresholds), bits 16..20 that GT, bits 21..22 min(#candidates, 2)
 struct FrameSmem {
     double iou[FE_WARPS][FE_MAX_PAIRS];
     double gtb[FE_WARPS][FE_MAX_GT][4];
-    uint32_t dmask[FE_WARPS][FE_MAX_PAIRS];   // per detection: bit c = ignored when unmatched under
-                                              // cfg c; the detection's flag byte in bits 24..31
+    uint32_t dmask[FE_WARPS][FE_MAX_DT];
+    uint32_t cand[FE_WARPS][FE_MAX_DT];
     uint32_t gig[FE_WARPS][FE_MAX_CFG];       // per cfg: bit g = GT g ignored
 };
 
@@ -163,129 +177,212 @@ __global__ void __launch_bounds__(FE_WARPS * 32)
 k_frame_eval(FrameArgs a) {
     __shared__ FrameSmem sm;
     __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
+    __shared__ double thr_s[TA_MAX_THRS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < a.n_cfg; i += blockDim.x) cfg_s[i] = a.cfgs[i];
-    __syncthreads();
     const int n_thr = a.n_thr, n_cfg = a.n_cfg;
+    for (int i = threadIdx.x; i < n_cfg; i += blockDim.x) cfg_s[i] = a.cfgs[i];
+    if (threadIdx.x < n_thr) {
+        const double th = a.thrs[threadIdx.x];
+        thr_s[threadIdx.x] = (th < 1.0 - 1e-10) ? th : 1.0 - 1e-10;   // min([iou_thr, 1 - 1e-10])
+    }
+    __syncthreads();
+    double thr_min = thr_s[0];
+    for (int i = 1; i < n_thr; ++i) thr_min = (thr_s[i] < thr_min) ? thr_s[i] : thr_min;
     const int cpw = 32 / n_thr;
     const int cw = lane / n_thr;
     const int t = lane - cw * n_thr;
-    const double my_thr = (cw < cpw) ? a.thrs[t] : 2.0;
-    const double thr_c = (my_thr < 1.0 - 1e-10) ? my_thr : 1.0 - 1e-10;   // min([iou_thr, 1 - 1e-10])
+    const double thr_c = (cw < cpw) ? thr_s[t] : 2.0;
+    const uint32_t thr_all = (1u << n_thr) - 1u;
     double* iou_s = sm.iou[warp];
     uint32_t* dmask_s = sm.dmask[warp];
+    uint32_t* cand_s = sm.cand[warp];
     uint32_t* gig_s = sm.gig[warp];
-    const uint32_t fp_all = ((1u << n_thr) - 1u) << 16;
 
+    const int64_t n_tasks = (a.n_groups + FE_RUN - 1) / FE_RUN;
     const int64_t w0 = (int64_t)blockIdx.x * FE_WARPS + warp;
     const int64_t wstride = (int64_t)gridDim.x * FE_WARPS;
-    for (int64_t grp = w0; grp < a.n_groups; grp += wstride) {
-        const int64_t d0 = a.grp_dt_off[grp], g0 = a.grp_gt_off[grp];
-        const int D = (int)(a.grp_dt_off[grp + 1] - d0), G = (int)(a.grp_gt_off[grp + 1] - g0);
-        if (D == 0 && G == 0) continue;
-        if (G > FE_MAX_GT || (int64_t)D * G > FE_MAX_PAIRS) continue;   // big_list path
-        __syncwarp();
-        if (G == 0) {
-            // every detection is unmatched at every threshold (lvis eval.py:233-235 with no GT):
-            // FP unless the unmatched-ignore rule fires
+    for (int64_t task = w0; task < n_tasks; task += wstride) {
+        const int64_t grp0 = task * FE_RUN;
+        const int64_t grp1 = (grp0 + FE_RUN < a.n_groups) ? grp0 + FE_RUN : a.n_groups;
+        int acc = 0, acc_cat = -1;          // lane c < n_cfg: non-ignored GT of (acc_cat, cfg c)
+        for (int64_t grp = grp0; grp < grp1; ++grp) {
+            const int64_t d0 = a.grp_dt_off[grp], g0 = a.grp_gt_off[grp];
+            const int D = (int)(a.grp_dt_off[grp + 1] - d0), G = (int)(a.grp_gt_off[grp + 1] - g0);
+            if (D == 0 && G == 0) continue;
+            __syncwarp();
+            if (G == 0) {
+                // ---- route A
+                for (int d = lane; d < D; d += 32) {
+                    const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
+                    const double area = q.x * q.y;
+                    const uint8_t fl = a.dt_flag[d0 + d];
+                    uint32_t* o = a.dt_tpfp + (d0 + d) * n_cfg;
+                    for (int c = 0; c < n_cfg; ++c)
+                        o[c] = ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, fl) ? 0u : (thr_all << 16);
+                }
+                if (a.dt_match_gt)
+                    for (int e = lane; e < n_cfg * n_thr * D; e += 32) {
+                        const int ct = e / D, d = e - ct * D;
+                        a.dt_match_gt[(int64_t)ct * a.n_dt + d0 + d] = -1;
+                    }
+                continue;
+            }
+            if (G > FE_MAX_GT || D > FE_MAX_DT || D * G > FE_MAX_PAIRS) continue;   // big_list route
+            // ---- stage GT boxes, GT ignore masks per cfg, non-ignored GT counts
+            double vis = 0.0;
+            uint8_t gfl = 0;
+            if (lane < G) {
+                const double2 p = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane));
+                const double2 q = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane) + 2);
+                sm.gtb[warp][lane][0] = p.x; sm.gtb[warp][lane][1] = p.y;
+                sm.gtb[warp][lane][2] = q.x; sm.gtb[warp][lane][3] = q.y;
+                vis = a.gt_vis[g0 + lane];
+                gfl = a.gt_flag[g0 + lane];
+            }
+            const uint32_t gsent = __ballot_sync(0xffffffffu, (gfl & 4) != 0);   // id == "unmatched" value
+            uint32_t my_gig = 0;
+            for (int c = 0; c < n_cfg; ++c) {
+                const bool ig = (lane < G) && ta_gt_ignored(cfg_s[c], vis, 0.0, 0, gfl);
+                const uint32_t m = __ballot_sync(0xffffffffu, ig);
+                if (lane == c) my_gig = m;
+                if (a.gt_ignore_out && lane < G) a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + lane] = ig;
+            }
+            {
+                const int cat = a.grp_cat[grp];
+                if (cat != acc_cat) {
+                    if (acc > 0) atomicAdd(&a.num_gt[(int64_t)acc_cat * n_cfg + lane], acc);
+                    acc = 0;
+                    acc_cat = cat;
+                }
+                if (lane < n_cfg) {
+                    gig_s[lane] = my_gig;
+                    acc += G - __popc(my_gig);
+                }
+            }
+            __syncwarp();
+            // ---- IoU tile (maskApi.c:109-120): lane = (detection within pass, GT)
+            const int dpp = 32 / G;                      // detections per pass
+            const int dsub = lane / G, gl = lane - dsub * G;
+            double* iou_g = a.write_iou ? a.iou + a.iou_off[grp] : nullptr;
+            if (dsub < dpp) {
+                const double* gb = sm.gtb[warp][gl];
+                const double gx = gb[0], gy = gb[1], gw = gb[2], gh = gb[3];
+                for (int d = dsub; d < D; d += dpp) {
+                    const double2 dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d));
+                    const double2 dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
+                    const double v = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, gx, gy, gw, gh);
+                    iou_s[d * G + gl] = v;
+                    if (iou_g) iou_g[d * G + gl] = v;
+                }
+            }
+            __syncwarp();
+            // ---- per detection: unmatched-ignore mask, lock bit, candidate summary
+            bool multi = false;
             for (int d = lane; d < D; d += 32) {
                 const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
                 const double area = q.x * q.y;
                 const uint8_t fl = a.dt_flag[d0 + d];
-                uint32_t* o = a.dt_tpfp + (d0 + d) * n_cfg;
+                uint32_t m = (fl & 2) ? (1u << 16) : 0u;
                 for (int c = 0; c < n_cfg; ++c)
-                    o[c] = ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, fl) ? 0u : fp_all;
-            }
-            if (a.dt_match_gt)
-                for (int e = lane; e < n_cfg * n_thr * D; e += 32) {
-                    const int ct = e / D, d = e - ct * D;
-                    a.dt_match_gt[(int64_t)ct * a.n_dt + d0 + d] = -1;
-                }
-            continue;
-        }
-        // ---- stage GT boxes, GT ignore masks per cfg, non-ignored GT counts
-        double vis = 0.0;
-        uint8_t gfl = 0;
-        if (lane < G) {
-            const double2 p = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane));
-            const double2 q = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane) + 2);
-            sm.gtb[warp][lane][0] = p.x; sm.gtb[warp][lane][1] = p.y;
-            sm.gtb[warp][lane][2] = q.x; sm.gtb[warp][lane][3] = q.y;
-            vis = a.gt_vis[g0 + lane];
-            gfl = a.gt_flag[g0 + lane];
-        }
-        const uint32_t gsent = __ballot_sync(0xffffffffu, (gfl & 4) != 0);   // id == "unmatched" value
-        const uint32_t gall = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-        uint32_t my_gig = 0;
-        for (int c = 0; c < n_cfg; ++c) {
-            const bool ig = (lane < G) && ta_gt_ignored(cfg_s[c], vis, 0.0, 0, gfl);
-            const uint32_t m = __ballot_sync(0xffffffffu, ig);
-            if (lane == c) my_gig = m;
-            if (a.gt_ignore_out && lane < G) a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + lane] = ig;
-        }
-        if (lane < n_cfg) {
-            gig_s[lane] = my_gig;
-            const int cnt = G - __popc(my_gig);
-            if (cnt) atomicAdd(&a.num_gt[(int64_t)a.grp_cat[grp] * n_cfg + lane], cnt);
-        }
-        // ---- per-detection unmatched-ignore masks
-        for (int d = lane; d < D; d += 32) {
-            const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
-            const double area = q.x * q.y;
-            const uint8_t fl = a.dt_flag[d0 + d];
-            uint32_t m = (uint32_t)fl << 24;
-            for (int c = 0; c < n_cfg; ++c)
-                if (ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, fl)) m |= 1u << c;
-            dmask_s[d] = m;
-        }
-        __syncwarp();
-        // ---- IoU tile (maskApi.c:109-120), lanes over the D*G pairs
-        const int n_pair = D * G;
-        double* iou_g = a.write_iou ? a.iou + a.iou_off[grp] : nullptr;
-        for (int e = lane; e < n_pair; e += 32) {
-            const int d = e / G, g = e - d * G;
-            const double2 dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d));
-            const double2 dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
-            const double* gb = sm.gtb[warp][g];
-            const double v = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, gb[0], gb[1], gb[2], gb[3]);
-            iou_s[e] = v;
-            if (iou_g) iou_g[e] = v;
-        }
-        __syncwarp();
-        // ---- matchers: lane = (cfg within round, threshold)
-        for (int c0 = 0; c0 < n_cfg; c0 += cpw) {
-            const int cfg = c0 + cw;
-            const bool active = (cw < cpw) && (cfg < n_cfg);
-            const uint32_t gig = active ? gig_s[cfg] : 0u;
-            uint32_t taken = 0u;
-            for (int d = 0; d < D; ++d) {
-                const uint32_t free0 = ~taken & ~gig & gall;   // regular GTs still free
-                const uint32_t free1 = ~taken & gig & gall;    // ignored GTs still free
-                double best0 = thr_c, best1 = thr_c;
-                int m0 = -1, m1 = -1;
+                    if (ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, fl)) m |= 1u << c;
+                dmask_s[d] = m;
+                int cnt = 0, gs = 0;
+                double vs = 0.0;
                 const double* row = iou_s + d * G;
                 for (int g = 0; g < G; ++g) {
                     const double v = row[g];
-                    if (((free0 >> g) & 1u) && !(v < best0)) { best0 = v; m0 = g; }
-                    if (((free1 >> g) & 1u) && !(v < best1)) { best1 = v; m1 = g; }
+                    if (!(v < thr_min)) { ++cnt; gs = g; vs = v; }
                 }
-                const int m = (m0 >= 0) ? m0 : m1;
-                const uint32_t dm = dmask_s[d];
-                bool unmatched = true, ig = false;
-                if (m >= 0) {
-                    if (dm & (2u << 24)) taken |= 1u << m;
-                    unmatched = (gsent >> m) & 1u;
-                    ig = (gig >> m) & 1u;
+                uint32_t ge = 0;
+                if (cnt == 1)
+                    for (int k = 0; k < n_thr; ++k) ge |= (!(vs < thr_s[k])) ? (1u << k) : 0u;
+                cand_s[d] = ge | ((uint32_t)gs << 16) | ((uint32_t)(cnt > 2 ? 2 : cnt) << 21);
+                multi |= cnt > 1;
+            }
+            const bool general = __any_sync(0xffffffffu, multi);
+            __syncwarp();
+            if (!general) {
+                // ---- route B: lane g walks the detections whose only candidate is g
+                if (lane < G) {
+                    uint32_t taken = 0;
+                    for (int d = 0; d < D; ++d) {
+                        const uint32_t cd = cand_s[d];
+                        if (((cd >> 21) & 3u) == 1u && ((cd >> 16) & 31u) == (uint32_t)lane) {
+                            const uint32_t ge = cd & 0xffffu;
+                            cand_s[d] = (cd & ~0xffffu) | (ge & ~taken);
+                            if (dmask_s[d] & (1u << 16)) taken |= ge;     // eval.py:248, :270
+                        }
+                    }
                 }
-                if (unmatched && !ig) ig = (dm >> cfg) & 1u;
-                uint32_t bits = 0;
-                if (active && !ig) bits = unmatched ? (1u << (16 + t)) : (1u << t);
-                const uint32_t word = seg_or(bits, lane, n_thr, cw);
-                if (active && t == 0) a.dt_tpfp[(d0 + d) * n_cfg + cfg] = word;
-                if (a.dt_match_gt && active)
-                    a.dt_match_gt[((int64_t)cfg * n_thr + t) * a.n_dt + d0 + d] = m;
+                __syncwarp();
+                for (int d = lane; d < D; d += 32) {
+                    const uint32_t cd = cand_s[d], dm = dmask_s[d];
+                    const uint32_t M = (((cd >> 21) & 3u) == 1u) ? (cd & 0xffffu) : 0u;
+                    const int gs = (cd >> 16) & 31;
+                    const bool sent = (gsent >> gs) & 1u;
+                    uint32_t* o = a.dt_tpfp + (d0 + d) * n_cfg;
+                    for (int c = 0; c < n_cfg; ++c) {
+                        const bool gi = (gig_s[c] >> gs) & 1u;
+                        const bool dc = (dm >> c) & 1u;
+                        const uint32_t tp = (!sent && !gi) ? M : 0u;
+                        const uint32_t fp = ((sent && !gi && !dc) ? M : 0u) | (dc ? 0u : (thr_all & ~M));
+                        o[c] = tp | (fp << 16);
+                    }
+                    if (a.dt_match_gt)
+                        for (int c = 0; c < n_cfg; ++c)
+                            for (int k = 0; k < n_thr; ++k)
+                                a.dt_match_gt[((int64_t)c * n_thr + k) * a.n_dt + d0 + d] =
+                                    ((M >> k) & 1u) ? gs : -1;
+                }
+                continue;
+            }
+            // ---- route C: lane = (cfg within round, threshold)
+            const uint32_t gall = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+            for (int c0 = 0; c0 < n_cfg; c0 += cpw) {
+                const int cfg = c0 + cw;
+                const bool active = (cw < cpw) && (cfg < n_cfg);
+                const uint32_t gig = active ? gig_s[cfg] : 0u;
+                const int sh = cw * n_thr;
+                uint32_t taken = 0u;
+                for (int d = 0; d < D; ++d) {
+                    const uint32_t cd = cand_s[d], dm = dmask_s[d];
+                    const uint32_t cnt = (cd >> 21) & 3u;
+                    const double* row = iou_s + d * G;
+                    int m = -1;
+                    if (cnt == 1u) {
+                        const int gs = (cd >> 16) & 31;
+                        if (!(row[gs] < thr_c) && !((taken >> gs) & 1u)) m = gs;
+                    } else if (cnt > 1u) {
+                        const uint32_t free0 = ~taken & ~gig & gall;   // regular GTs still free
+                        const uint32_t free1 = ~taken & gig & gall;    // ignored GTs still free
+                        double best0 = thr_c, best1 = thr_c;
+                        int m0 = -1, m1 = -1;
+                        for (int g = 0; g < G; ++g) {
+                            const double v = row[g];
+                            if (((free0 >> g) & 1u) && !(v < best0)) { best0 = v; m0 = g; }
+                            if (((free1 >> g) & 1u) && !(v < best1)) { best1 = v; m1 = g; }
+                        }
+                        m = (m0 >= 0) ? m0 : m1;
+                    }
+                    bool unmatched = true, ig = false;
+                    if (m >= 0) {
+                        if (dm & (1u << 16)) taken |= 1u << m;
+                        unmatched = (gsent >> m) & 1u;
+                        ig = (gig >> m) & 1u;
+                    }
+                    if (unmatched && !ig) ig = (dm >> cfg) & 1u;
+                    const bool cnts = active && !ig;
+                    const uint32_t bt = __ballot_sync(0xffffffffu, cnts && !unmatched);
+                    const uint32_t bf = __ballot_sync(0xffffffffu, cnts && unmatched);
+                    if (active && t == 0)
+                        a.dt_tpfp[(d0 + d) * n_cfg + cfg] =
+                            ((bt >> sh) & thr_all) | (((bf >> sh) & thr_all) << 16);
+                    if (a.dt_match_gt && active)
+                        a.dt_match_gt[((int64_t)cfg * n_thr + t) * a.n_dt + d0 + d] = m;
+                }
             }
         }
+        if (acc > 0) atomicAdd(&a.num_gt[(int64_t)acc_cat * n_cfg + lane], acc);
     }
 }
 
@@ -293,6 +390,7 @@ k_frame_eval(FrameArgs a) {
 // C ABI
 // ------------------------------------------------------------------------------------------
 extern "C" int ta_frame_eval_max_gt(void) { return FE_MAX_GT; }
+extern "C" int ta_frame_eval_max_dt(void) { return FE_MAX_DT; }
 extern "C" int ta_frame_eval_max_pairs(void) { return FE_MAX_PAIRS; }
 
 extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
@@ -369,7 +467,8 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     FrameArgs a{n_groups, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box, n_thr, iou_thrs, n_cfg,
                 cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, iou, write_iou,
                 dt_tpfp, num_gt, dt_match_gt, gt_ignore_out};
-    int64_t blocks = (n_groups + FE_WARPS - 1) / FE_WARPS;
+    const int64_t n_tasks = (n_groups + FE_RUN - 1) / FE_RUN;
+    int64_t blocks = (n_tasks + FE_WARPS - 1) / FE_WARPS;
     const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs of 4 warps per SM
     if (blocks > cap) blocks = cap;
     k_frame_eval<<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);

@@ -7,24 +7,28 @@
 // samples it at the first position whose recall reaches each of the 101 recall thresholds
 // (:561-571).  Equivalent formulation used here: the value at recall threshold k is the maximum
 // precision over all TRUE POSITIVES whose running TP count is >= tk[k], where tk[k] is the
-// smallest count with count / num_gt >= rec_thrs[k].  So every TP raises exactly one bucket
-// (the last k with tk[k] <= its count) and a suffix maximum over k finishes the row.
+// smallest count with count / num_gt >= rec_thrs[k] (a false positive never exceeds the
+// precision of the true positive before it).
 //
 // The category lists are cut into chunks of PR_CHUNK detections so that long categories do not
-// serialise:
+// serialise.  Precisions are compared as exact rationals (tp, tp + fp) — rounding is monotone, so
+// the maximum of the rounded quotients is the rounded quotient of the rational maximum — and
+// only the <= 101 winners per cell are divided (ta_precision_at):
 //   k_pr_plan      chunk table: first chunk of every category
 //   k_pr_count     per chunk: TP / FP totals of every (cfg, threshold)  (ballot + popc)
 //   k_pr_scan      per category: exclusive scan of the chunk totals, tk tables, recall, counts
-//   k_pr_bucket    per chunk: running counts -> precision of every TP -> bucket max
-//                  (shared-memory atomicMax, then one global atomicMax per touched bucket)
-//   k_pr_finalize  per (threshold, category, cfg): suffix max over the recall axis, -1 fill
+//   k_pr_envelope  per chunk, one THREAD per (cfg, threshold) cell walking the chunk's
+//                  detections backwards from shared memory: running counts, suffix-maximum
+//                  precision, and the answer of every recall threshold whose tk-th true
+//                  positive lies inside the chunk
+//   k_pr_finalize  per cell: suffix maximum across the chunks (backwards), merge with the
+//                  in-chunk answers, divide, write precision (-1 fill without GT)
 #include <limits.h>
 #include "ta_internal.h"
 #include "ta_device_fns.cuh"
 
 #define PR_CHUNK 256          // detections per chunk == threads per block
 #define PR_WARPS (PR_CHUNK / 32)
-#define PR_CPB 6              // range cfgs handled by one k_pr_bucket block
 
 struct PrArgs {
     int n_cat, n_thr, n_cfg, n_rec;
@@ -38,21 +42,28 @@ struct PrArgs {
     // scratch
     int32_t* chunk_start;        // [n_cat + 1]
     uint32_t* chunk_cnt;         // [n_chunks_ub][n_cfg][32]: bit t -> TP count, bit 16+t -> FP count
+    uint32_t* cat_tot;           // [n_cat][n_cfg][32] category totals (same bit layout)
     int32_t* tk;                 // [n_cat][n_cfg][n_rec]
+    unsigned long long* chunk_best;  // [n_chunks_ub][n_cfg][n_thr] packed (t << 32 | n)
     // outputs
-    unsigned long long* prec_bits;   // precision buffer viewed as u64 (max of fp64 bit patterns)
+    unsigned long long* prec_bits;   // precision buffer viewed as u64: packed (t << 32 | n) until
+                                     // k_pr_finalize turns it into doubles
     double* precision;
     double* recall;
     int64_t* tp_cnt;
     int64_t* fp_cnt;
 };
 
-__global__ void k_pr_plan(PrArgs a) {
-    // single warp: exclusive scan of ceil(len / PR_CHUNK) over the categories
-    const int lane = threadIdx.x;
-    int carry = 0;
-    for (int base = 0; base < a.n_cat; base += 32) {
-        const int c = base + lane;
+__global__ void __launch_bounds__(1024)
+k_pr_plan(PrArgs a) {
+    // one block: exclusive scan of ceil(len / PR_CHUNK) over the categories
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < a.n_cat; base += 1024) {
+        const int c = base + threadIdx.x;
         int n = 0;
         if (c < a.n_cat) n = (int)((a.cat_dt_off[c + 1] - a.cat_dt_off[c] + PR_CHUNK - 1) / PR_CHUNK);
         int incl = n;
@@ -60,10 +71,24 @@ __global__ void k_pr_plan(PrArgs a) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        if (c < a.n_cat) a.chunk_start[c] = carry + incl - n;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = wsum[lane], w = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            wsum[lane] = w - v;          // exclusive prefix of the warp sums
+        }
+        __syncthreads();
+        const int excl = carry_s + wsum[warp] + incl - n;
+        if (c < a.n_cat) a.chunk_start[c] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + n;
+        __syncthreads();
     }
-    if (lane == 0) a.chunk_start[a.n_cat] = carry;
+    if (threadIdx.x == 0) a.chunk_start[a.n_cat] = carry_s;
 }
 
 // category of a chunk: last c with chunk_start[c] <= chunk
@@ -119,12 +144,24 @@ __global__ void k_pr_scan(PrArgs a) {
     for (int j = threadIdx.x; j < n_ctr; j += blockDim.x) {
         const int cfg = j >> 5, bit = j & 31;
         uint32_t run = 0;
-        for (int ch = ch0; ch < ch1; ++ch) {
+        int ch = ch0;
+        for (; ch + 8 <= ch1; ch += 8) {          // 8 independent loads in flight
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = a.chunk_cnt[((int64_t)(ch + u) * a.n_cfg) * 32 + j];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                a.chunk_cnt[((int64_t)(ch + u) * a.n_cfg) * 32 + j] = run;
+                run += v[u];
+            }
+        }
+        for (; ch < ch1; ++ch) {
             uint32_t* q = a.chunk_cnt + ((int64_t)ch * a.n_cfg) * 32 + j;
             const uint32_t v = *q;
             *q = run;
             run += v;
         }
+        a.cat_tot[((int64_t)cat * a.n_cfg) * 32 + j] = run;
         const int ngt = a.num_gt[(int64_t)cat * a.n_cfg + cfg];
         const int t = bit & 15;
         if (t < a.n_thr) {
@@ -146,123 +183,115 @@ __global__ void k_pr_scan(PrArgs a) {
     }
 }
 
-__global__ void __launch_bounds__(PR_CHUNK)
-k_pr_bucket(PrArgs a) {
+// exact comparison of precisions tp/(fp + tp + eps) given as (t, n = tp + fp): cross products in
+// 64 bits; equal ratios prefer the larger n, which only matters for (1, 1): its rounded value
+// 1/(1 + 2^-52) is below k/k = 1.0 (for n >= 2 the eps term vanishes in fp64, eval.py:550)
+__device__ __forceinline__ bool pr_better(uint32_t t1, uint32_t n1, uint32_t t2, uint32_t n2) {
+    const unsigned long long x = (unsigned long long)t1 * n2, y = (unsigned long long)t2 * n1;
+    return x > y || (x == y && n1 > n2);
+}
+__device__ __forceinline__ unsigned long long pr_pack(uint32_t t, uint32_t n) {
+    return ((unsigned long long)t << 32) | n;
+}
+
+#define PR_ENV_MAX_CELLS 64   // (cfg, threshold) cells per k_pr_envelope block
+
+__global__ void __launch_bounds__(PR_ENV_MAX_CELLS)
+k_pr_envelope(PrArgs a, int cfgs_per_block) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: bucket u64 [PR_CPB][n_thr][n_rec] | tk i32 [PR_CPB][n_rec] | wpre u32 [PR_WARPS][PR_CPB][32]
-    unsigned long long* bucket = reinterpret_cast<unsigned long long*>(smem_raw);
-    int32_t* tk_s = reinterpret_cast<int32_t*>(bucket + (size_t)PR_CPB * a.n_thr * a.n_rec);
-    uint32_t* wpre = reinterpret_cast<uint32_t*>(tk_s + PR_CPB * a.n_rec);
-    __shared__ int s_cat;
+    // layout: words u32 [PR_CHUNK][ncf] | tk i32 [ncf][n_rec]
+    uint32_t* words = reinterpret_cast<uint32_t*>(smem_raw);
+    int32_t* tk_s = reinterpret_cast<int32_t*>(words + (size_t)PR_CHUNK * cfgs_per_block);
     const int chunk = blockIdx.x;
     if (chunk >= a.chunk_start[a.n_cat]) return;
-    if (threadIdx.x == 0) s_cat = pr_find_cat(a.chunk_start, a.n_cat, chunk);
-    __syncthreads();
-    const int cat = s_cat;
-    const int cfg0 = blockIdx.y * PR_CPB;
-    const int ncf = min(PR_CPB, a.n_cfg - cfg0);
-    // any cfg of this block with GT?  (cells without GT keep -1, nothing to accumulate)
-    bool any = false;
-    for (int c = 0; c < ncf; ++c) any |= a.num_gt[(int64_t)cat * a.n_cfg + cfg0 + c] != 0;
-    if (!any) return;
-    const int n_b = ncf * a.n_thr * a.n_rec;
-    for (int i = threadIdx.x; i < n_b; i += PR_CHUNK) bucket[i] = 0ull;
-    for (int i = threadIdx.x; i < ncf * a.n_rec; i += PR_CHUNK)
+    const int cat = pr_find_cat(a.chunk_start, a.n_cat, chunk);
+    const int cfg0 = blockIdx.y * cfgs_per_block;
+    const int ncf = min(cfgs_per_block, a.n_cfg - cfg0);
+    const int ch1 = a.chunk_start[cat + 1];
+    const int64_t p0 = a.cat_dt_off[cat] + (int64_t)(chunk - a.chunk_start[cat]) * PR_CHUNK;
+    const int n_pos = (int)min((int64_t)PR_CHUNK, a.cat_dt_off[cat + 1] - p0);
+    // ---- stage the chunk's TP/FP words (rows gathered through the score permutation) and tk
+    for (int i = threadIdx.x; i < n_pos * ncf; i += blockDim.x) {
+        const int p = i / ncf, c = i - p * ncf;
+        words[p * ncf + c] = a.dt_tpfp[(int64_t)a.acc_perm[p0 + p] * a.n_cfg + cfg0 + c];
+    }
+    for (int i = threadIdx.x; i < ncf * a.n_rec; i += blockDim.x)
         tk_s[i] = a.tk[((int64_t)cat * a.n_cfg + cfg0) * a.n_rec + i];
-    const int64_t p = a.cat_dt_off[cat] + (int64_t)(chunk - a.chunk_start[cat]) * PR_CHUNK + threadIdx.x;
-    const bool live = p < a.cat_dt_off[cat + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t* row = live ? a.dt_tpfp + (int64_t)a.acc_perm[p] * a.n_cfg + cfg0 : nullptr;
-    uint32_t w[PR_CPB];
-#pragma unroll
-    for (int c = 0; c < PR_CPB; ++c) w[c] = (live && c < ncf) ? row[c] : 0u;
-    // ---- per-warp totals of every (cfg, bit)
-#pragma unroll
-    for (int c = 0; c < PR_CPB; ++c) {
-        if (c < ncf) {
-            uint32_t mine = 0;
-            for (int b = 0; b < a.n_thr; ++b) {
-                const uint32_t mt = __ballot_sync(0xffffffffu, (w[c] >> b) & 1u);
-                const uint32_t mf = __ballot_sync(0xffffffffu, (w[c] >> (16 + b)) & 1u);
-                if (lane == b) mine = __popc(mt);
-                if (lane == 16 + b) mine = __popc(mf);
+    __syncthreads();
+    const int cell = threadIdx.x;
+    if (cell >= ncf * a.n_thr) return;
+    const int c = cell / a.n_thr, b = cell - c * a.n_thr;
+    const int cfg = cfg0 + c;
+    if (a.num_gt[(int64_t)cat * a.n_cfg + cfg] == 0) return;
+    // counts at the END of this chunk = exclusive prefix of the next chunk (category totals
+    // for the last chunk)
+    const uint32_t* nxt = (chunk + 1 < ch1) ? a.chunk_cnt + ((int64_t)(chunk + 1) * a.n_cfg + cfg) * 32
+                                            : a.cat_tot + ((int64_t)cat * a.n_cfg + cfg) * 32;
+    uint32_t tc = nxt[b], fc = nxt[16 + b];
+    const uint32_t t_begin = a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg) * 32 + b];
+    unsigned long long* best_out = a.chunk_best + ((int64_t)chunk * a.n_cfg + cfg) * a.n_thr + b;
+    if (tc == t_begin) { *best_out = 0ull; return; }          // no TP of this cell in the chunk
+    const int32_t* tkc = tk_s + c * a.n_rec;
+    // last recall threshold whose (clamped) tk is <= tc
+    int kq = a.n_rec - 1;
+    while (kq >= 0 && (uint32_t)max(tkc[kq], 1) > tc) --kq;
+    uint32_t bt = 0, bn = 0;
+    const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
+    const int64_t cc = (int64_t)cat * a.n_cfg + cfg;
+    for (int p = n_pos - 1; p >= 0; --p) {
+        const uint32_t w = words[p * ncf + c];
+        if ((w >> b) & 1u) {
+            const uint32_t n = tc + fc;
+            if (pr_better(tc, n, bt, bn)) { bt = tc; bn = n; }
+            while (kq >= 0 && (uint32_t)max(tkc[kq], 1) == tc) {
+                a.prec_bits[((int64_t)b * a.n_rec + kq) * per_t + cc] = pr_pack(bt, bn);
+                --kq;
             }
-            wpre[(warp * PR_CPB + c) * 32 + lane] = mine;
+            --tc;
+        } else if ((w >> (16 + b)) & 1u) {
+            --fc;
         }
     }
-    __syncthreads();
-    // ---- exclusive prefix over the warps + chunk offset (thread j <-> counter (cfg, bit))
-    if (threadIdx.x < ncf * 32) {
-        const int c = threadIdx.x >> 5, bit = threadIdx.x & 31;
-        uint32_t run = a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg0 + c) * 32 + bit];
-#pragma unroll
-        for (int w2 = 0; w2 < PR_WARPS; ++w2) {
-            uint32_t* q = &wpre[(w2 * PR_CPB + c) * 32 + bit];
-            const uint32_t v = *q;
-            *q = run;
-            run += v;
-        }
-    }
-    __syncthreads();
-    // ---- every TP raises its bucket
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int c = 0; c < PR_CPB; ++c) {
-        if (c < ncf && a.num_gt[(int64_t)cat * a.n_cfg + cfg0 + c] != 0) {
-            const int32_t* tkc = tk_s + c * a.n_rec;
-            for (int b = 0; b < a.n_thr; ++b) {
-                const bool tp = (w[c] >> b) & 1u;
-                const uint32_t mt = __ballot_sync(0xffffffffu, tp);
-                const uint32_t mf = __ballot_sync(0xffffffffu, (w[c] >> (16 + b)) & 1u);
-                if (tp) {
-                    const int64_t tc = (int64_t)wpre[(warp * PR_CPB + c) * 32 + b] + __popc(mt & lt) + 1;
-                    const int64_t fc = (int64_t)wpre[(warp * PR_CPB + c) * 32 + 16 + b] + __popc(mf & lt);
-                    int lo = 0, hi = a.n_rec;   // first k with tk[k] > tc
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if ((int64_t)tkc[mid] <= tc) lo = mid + 1; else hi = mid;
-                    }
-                    if (lo > 0) {
-                        const double pr = ta_precision_at(tc, fc);
-                        atomicMax(&bucket[((size_t)c * a.n_thr + b) * a.n_rec + lo - 1],
-                                  (unsigned long long)__double_as_longlong(pr));
-                    }
-                }
-            }
-        }
-    }
-    __syncthreads();
-    // ---- flush touched buckets: precision is [n_thr][n_rec][n_cat][n_cfg]
-    for (int i = threadIdx.x; i < n_b; i += PR_CHUNK) {
-        const unsigned long long v = bucket[i];
-        if (v) {
-            const int c = i / (a.n_thr * a.n_rec);
-            const int r = i - c * (a.n_thr * a.n_rec);
-            const int b = r / a.n_rec, k = r - b * a.n_rec;
-            atomicMax(&a.prec_bits[(((int64_t)b * a.n_rec + k) * a.n_cat + cat) * a.n_cfg + cfg0 + c], v);
-        }
-    }
+    *best_out = pr_pack(bt, bn);
 }
 
 __global__ void k_pr_finalize(PrArgs a) {
-    // thread <-> (threshold, category, cfg), cfg fastest: coalesced along the innermost axes
+    // thread <-> (threshold, category, cfg), cfg fastest
     const int64_t n_cell = (int64_t)a.n_thr * a.n_cat * a.n_cfg;
     const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (cell >= n_cell) return;
     const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
     const int t = (int)(cell / per_t);
     const int64_t cc = cell - (int64_t)t * per_t;          // cat * n_cfg + cfg
+    const int cat = (int)(cc / a.n_cfg), cfg = (int)(cc - (int64_t)cat * a.n_cfg);
     const int ngt = a.num_gt[cc];
-    if (ngt == 0) {
+    if (ngt == 0) {   // eval.py:522-525: the cell keeps its -1 initialisation
         for (int k = 0; k < a.n_rec; ++k) a.precision[((int64_t)t * a.n_rec + k) * per_t + cc] = -1.0;
         return;
     }
-    unsigned long long best = 0ull;   // bit pattern of +0.0; precisions are positive
-    for (int k = a.n_rec - 1; k >= 0; --k) {
-        const int64_t idx = ((int64_t)t * a.n_rec + k) * per_t + cc;
-        const unsigned long long v = a.prec_bits[idx];
-        best = v > best ? v : best;
-        a.prec_bits[idx] = best;
+    const int32_t* tkc = a.tk + cc * a.n_rec;
+    const int ch0 = a.chunk_start[cat], ch1 = a.chunk_start[cat + 1];
+    const uint32_t t_total = a.cat_tot[cc * 32 + t];
+    int kq = a.n_rec - 1;
+    // thresholds no detection reaches: the reference leaves 0.0 (eval.py:565-573)
+    while (kq >= 0 && (uint32_t)max(tkc[kq], 1) > t_total) {
+        a.precision[((int64_t)t * a.n_rec + kq) * per_t + cc] = 0.0;
+        --kq;
+    }
+    uint32_t bt = 0, bn = 0;   // best precision of all LATER chunks
+    for (int ch = ch1 - 1; ch >= ch0 && kq >= 0; --ch) {
+        const uint32_t t_begin = a.chunk_cnt[((int64_t)ch * a.n_cfg + cfg) * 32 + t];
+        while (kq >= 0 && (uint32_t)max(tkc[kq], 1) > t_begin) {
+            const int64_t idx = ((int64_t)t * a.n_rec + kq) * per_t + cc;
+            const unsigned long long q = a.prec_bits[idx];
+            uint32_t qt = (uint32_t)(q >> 32), qn = (uint32_t)q;
+            if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
+            a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
+            --kq;
+        }
+        const unsigned long long cb = a.chunk_best[((int64_t)ch * a.n_cfg + cfg) * a.n_thr + t];
+        const uint32_t ct = (uint32_t)(cb >> 32), cn = (uint32_t)cb;
+        if (pr_better(ct, cn, bt, bn)) { bt = ct; bn = cn; }
     }
 }
 
@@ -285,7 +314,9 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_start = take(((size_t)n_cat + 1) * 4);
     const size_t o_cnt = take((size_t)n_chunks_ub * n_cfg * 32 * 4);
+    const size_t o_tot = take((size_t)n_cat * n_cfg * 32 * 4);
     const size_t o_tk = take((size_t)n_cat * n_cfg * n_rec * 4);
+    const size_t o_best = take((size_t)n_chunks_ub * n_cfg * n_thr * 8);
     void* ws = nullptr;
     int rc = ta_workspace(ctx, st, off, &ws);
     if (rc) return rc;
@@ -297,13 +328,13 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     a.rec_thrs = rec_thrs;
     a.chunk_start = reinterpret_cast<int32_t*>(base + o_start);
     a.chunk_cnt = reinterpret_cast<uint32_t*>(base + o_cnt);
+    a.cat_tot = reinterpret_cast<uint32_t*>(base + o_tot);
     a.tk = reinterpret_cast<int32_t*>(base + o_tk);
+    a.chunk_best = reinterpret_cast<unsigned long long*>(base + o_best);
     a.prec_bits = reinterpret_cast<unsigned long long*>(precision);
     a.precision = precision; a.recall = recall; a.tp_cnt = tp_cnt; a.fp_cnt = fp_cnt;
 
-    const size_t n_cell = (size_t)n_thr * n_cat * n_cfg;
-    TA_CUDA(cudaMemsetAsync(precision, 0, n_cell * n_rec * sizeof(double), st));
-    k_pr_plan<<<1, 32, 0, st>>>(a);
+    k_pr_plan<<<1, 1024, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_plan"))) return rc;
     if (n_chunks_ub > 0) {
         k_pr_count<<<n_chunks_ub, PR_CHUNK, 0, st>>>(a);
@@ -312,16 +343,19 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     k_pr_scan<<<n_cat, 128, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_scan"))) return rc;
     if (n_chunks_ub > 0) {
-        const size_t smem = (size_t)PR_CPB * n_thr * n_rec * 8 + (size_t)PR_CPB * n_rec * 4 +
-                            (size_t)PR_WARPS * PR_CPB * 32 * 4;
+        int cpb = PR_ENV_MAX_CELLS / n_thr;
+        if (cpb > n_cfg) cpb = n_cfg;
+        const size_t smem = (size_t)PR_CHUNK * cpb * 4 + (size_t)cpb * n_rec * 4;
         if (smem > (size_t)ctx->smem_optin)
             return ta_set_err(TA_ERR_TOO_LARGE, "ta_pr_accumulate: too many recall thresholds");
-        TA_CUDA(cudaFuncSetAttribute(k_pr_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid(n_chunks_ub, (n_cfg + PR_CPB - 1) / PR_CPB);
-        k_pr_bucket<<<grid, PR_CHUNK, smem, st>>>(a);
-        if ((rc = ta_check_launch(ctx, "k_pr_bucket"))) return rc;
+        if (smem > 48 * 1024)
+            TA_CUDA(cudaFuncSetAttribute(k_pr_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(n_chunks_ub, (n_cfg + cpb - 1) / cpb);
+        k_pr_envelope<<<grid, PR_ENV_MAX_CELLS, smem, st>>>(a, cpb);
+        if ((rc = ta_check_launch(ctx, "k_pr_envelope"))) return rc;
     }
-    const int fin_blocks = (int)((n_cell + 255) / 256);
-    k_pr_finalize<<<fin_blocks, 256, 0, st>>>(a);
+    const size_t n_cell = (size_t)n_thr * n_cat * n_cfg;
+    const int fin_blocks = (int)((n_cell + 127) / 128);
+    k_pr_finalize<<<fin_blocks, 128, 0, st>>>(a);
     return ta_check_launch(ctx, "k_pr_finalize");
 }

@@ -63,11 +63,11 @@ def plan_limits(plan: EvalPlan):
     return g_max, n_slots
 
 
-def frame_big_groups(plan: EvalPlan, max_gt: int, max_pairs: int) -> np.ndarray:
+def frame_big_groups(plan: EvalPlan, max_gt: int, max_dt: int, max_pairs: int) -> np.ndarray:
     """Groups of a frame-path plan that exceed the on-chip limits of ta_frame_eval."""
     D = np.diff(plan.grp_dt_off)
     G = np.diff(plan.grp_gt_off)
-    return np.nonzero((G > max_gt) | (D * G > max_pairs))[0].astype(np.int32)
+    return np.nonzero((G > 0) & ((G > max_gt) | (D > max_dt) | (D * G > max_pairs)))[0].astype(np.int32)
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -89,12 +89,13 @@ class Engine:
         _lib.check(self.lib.ta_ctx_create(self.device, C.byref(h)))
         self._ctx = h
         self.fe_max_gt = int(self.lib.ta_frame_eval_max_gt())
+        self.fe_max_dt = int(self.lib.ta_frame_eval_max_dt())
         self.fe_max_pairs = int(self.lib.ta_frame_eval_max_pairs())
 
     def big_list(self, plan: EvalPlan) -> np.ndarray:
         bl = getattr(plan, "_big_list", None)
         if bl is None:
-            bl = frame_big_groups(plan, self.fe_max_gt, self.fe_max_pairs)
+            bl = frame_big_groups(plan, self.fe_max_gt, self.fe_max_dt, self.fe_max_pairs)
             plan._big_list = bl
         return bl
 
