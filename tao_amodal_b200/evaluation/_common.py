@@ -1,0 +1,80 @@
+"""Shared plumbing of the two drop-in evaluators."""
+from __future__ import annotations
+
+import json
+import os
+from typing import Dict, Tuple
+
+from ..columnar import DtColumns, GtColumns
+
+_ENGINES: Dict[int, object] = {}
+_JSON_CACHE: Dict[Tuple[str, float, int], object] = {}
+
+
+def get_engine(device: int = 0):
+    """One Engine (ta_ctx) per device per process."""
+    from ..engine import Engine
+    if device not in _ENGINES:
+        _ENGINES[device] = Engine(device)
+    return _ENGINES[device]
+
+
+def load_json(path: str):
+    """json.load with a per-process cache keyed by (path, mtime, size): the reference's CLI
+    parses the annotation file twice and the result file twice
+    (tools/eval_on_tao_amodal.py:100,122,127; lvis.py:27, results.py:29-30)."""
+    st = os.stat(path)
+    key = (os.path.abspath(path), st.st_mtime, st.st_size)
+    if key not in _JSON_CACHE:
+        with open(path, "r") as f:
+            _JSON_CACHE[key] = json.load(f)
+    return _JSON_CACHE[key]
+
+
+class LazyDict(dict):
+    """A dict whose content is produced on first access (the reference-shaped ``ious`` /
+    ``eval_vids`` views of device results are only materialised when somebody reads them)."""
+
+    def __init__(self, loader):
+        super().__init__()
+        self._loader = loader
+
+    def _fill(self):
+        if self._loader is not None:
+            loader, self._loader = self._loader, None
+            super().update(loader())
+
+    def __getitem__(self, k):
+        self._fill()
+        return super().__getitem__(k)
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __len__(self):
+        self._fill()
+        return super().__len__()
+
+    def __contains__(self, k):
+        self._fill()
+        return super().__contains__(k)
+
+    def __bool__(self):
+        return True
+
+    def keys(self):
+        self._fill()
+        return super().keys()
+
+    def values(self):
+        self._fill()
+        return super().values()
+
+    def items(self):
+        self._fill()
+        return super().items()
+
+    def get(self, k, default=None):
+        self._fill()
+        return super().get(k, default)

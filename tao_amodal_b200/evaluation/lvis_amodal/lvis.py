@@ -1,0 +1,80 @@
+"""``LVIS`` — annotation index of the frame evaluator (mirror of
+tao_amodal/evaluation/lvis_amodal/lvis.py:18-153; mask helpers :155-205 are out of scope:
+only ``iou_type='bbox'`` runs on the CUDA path)."""
+from __future__ import annotations
+
+import logging
+from collections import defaultdict
+
+from ...columnar import GtColumns
+from .._common import load_json
+
+_INDEX_ATTRS = ("img_ann_map", "cat_img_map", "anns", "cats", "imgs")
+
+
+class LVIS:
+    def __init__(self, annotation_path):
+        self.logger = logging.getLogger(__name__)
+        self.logger.info("Loading annotations.")
+        self.dataset = annotation_path if isinstance(annotation_path, dict) \
+            else load_json(annotation_path)
+        assert type(self.dataset) == dict, (
+            "Annotation file format {} not supported.".format(type(self.dataset)))
+        self.columns = GtColumns.from_dict(self.dataset)
+        self._indexed = False
+
+    def __getattr__(self, name):
+        if name in _INDEX_ATTRS and not self.__dict__.get("_indexed", True):
+            self._create_index()
+            return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _create_index(self):
+        """lvis.py:38-61, on first use."""
+        self.logger.info("Creating index.")
+        self._indexed = True
+        self.img_ann_map, self.cat_img_map = defaultdict(list), defaultdict(list)
+        self.anns, self.cats, self.imgs = {}, {}, {}
+        for ann in self.dataset["annotations"]:
+            self.img_ann_map[ann["image_id"]].append(ann)
+            self.anns[ann["id"]] = ann
+            self.cat_img_map[ann["category_id"]].append(ann["image_id"])
+        for img in self.dataset["images"]:
+            self.imgs[img["id"]] = img
+        for cat in self.dataset["categories"]:
+            self.cats[cat["id"]] = cat
+        self.logger.info("Index created.")
+
+    def get_ann_ids(self, img_ids=None, cat_ids=None, area_rng=None):
+        """lvis.py:63-97."""
+        if img_ids is None:
+            pool = self.dataset["annotations"]
+        else:
+            pool = [a for i in img_ids for a in self.img_ann_map[i]]
+        if cat_ids is None and area_rng is None:
+            return [a["id"] for a in pool]
+        cats = set(cat_ids)
+        lo, hi = (0, float("inf")) if area_rng is None else area_rng
+        return [a["id"] for a in pool
+                if a["category_id"] in cats and a["area"] > lo and a["area"] < hi]
+
+    def get_cat_ids(self):
+        return self.columns.cat_id.tolist() if not self._indexed else list(self.cats.keys())
+
+    def get_img_ids(self):
+        return self.columns.img_id.tolist() if not self._indexed else list(self.imgs.keys())
+
+    @staticmethod
+    def _load_helper(_dict, ids):
+        if ids is None:
+            return list(_dict.values())
+        return [_dict[i] for i in ids]
+
+    def load_anns(self, ids=None):
+        return self._load_helper(self.anns, ids)
+
+    def load_cats(self, ids):
+        return self._load_helper(self.cats, ids)
+
+    def load_imgs(self, ids):
+        return self._load_helper(self.imgs, ids)

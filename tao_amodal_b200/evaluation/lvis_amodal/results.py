@@ -1,0 +1,80 @@
+"""``LVISResults`` — prediction index of the frame evaluator (mirror of
+tao_amodal/evaluation/lvis_amodal/results.py:9-89, bbox results only).  Predictions are kept
+as columns; the reference-shaped ``dataset`` is materialised on demand."""
+from __future__ import annotations
+
+import copy
+import logging
+from collections import defaultdict
+
+import numpy as np
+
+from ...columnar import DtColumns
+from .._common import load_json
+from .lvis import LVIS
+
+
+class LVISResults(LVIS):
+    def __init__(self, lvis_gt, results, max_dets=300):
+        if isinstance(lvis_gt, LVIS):
+            self._gt = lvis_gt
+        elif isinstance(lvis_gt, str):
+            self._gt = LVIS(lvis_gt)
+        else:
+            raise TypeError("Unsupported type {} of lvis_gt.".format(lvis_gt))
+        self.logger = logging.getLogger(__name__)
+        self.logger.info("Loading and preparing results.")
+        self.max_dets = max_dets
+        if isinstance(results, DtColumns):
+            self._result_anns, dt = None, results
+        else:
+            if isinstance(results, str):
+                result_anns = load_json(results)
+            else:
+                self.logger.warn("Assuming user provided the results in correct format.")
+                result_anns = results
+            assert isinstance(result_anns, list), "results is not a list."
+            if len(result_anns) and "bbox" not in result_anns[0]:
+                raise NotImplementedError("only bbox results run on the CUDA path")
+            self._result_anns = result_anns
+            dt = DtColumns.from_list(result_anns)
+        if dt.n() == 0:
+            raise IndexError("list index out of range")                # results.py:42
+        self.columns = self._gt.columns
+        self.dt_columns = dt
+        if not np.isin(dt.image_id, np.unique(self.columns.img_id)).all():   # results.py:67-71
+            raise AssertionError("Results do not correspond to current LVIS set.")
+        self._indexed = False
+
+    @property
+    def dataset(self):
+        if "_dataset" not in self.__dict__:
+            ds = copy.deepcopy(self._gt.dataset)
+            anns = self._result_anns if self._result_anns is not None \
+                else self.dt_columns.to_list()
+            if self.max_dets >= 0:
+                anns = self.limit_dets_per_image(anns, self.max_dets)
+            for n, r in enumerate(anns):
+                x1, y1, w, h = r["bbox"]
+                if "segmentation" not in r:
+                    r["segmentation"] = [[x1, y1, x1, y1 + h, x1 + w, y1 + h, x1 + w, y1]]
+                r["area"] = w * h
+                r["id"] = n + 1
+            ds["annotations"] = anns
+            self.__dict__["_dataset"] = ds
+        return self.__dict__["_dataset"]
+
+    def limit_dets_per_image(self, anns, max_dets):
+        """results.py:73-84."""
+        per_img = defaultdict(list)
+        for r in anns:
+            per_img[r["image_id"]].append(r)
+        for k, lst in per_img.items():
+            if len(lst) > max_dets:
+                per_img[k] = sorted(lst, key=lambda r: r["score"], reverse=True)[:max_dets]
+        return [r for lst in per_img.values() for r in lst]
+
+    def get_top_results(self, img_id, score_thrs):
+        """results.py:86-89."""
+        anns = self.load_anns(self.get_ann_ids(img_ids=[img_id]))
+        return [a for a in anns if a["score"] > score_thrs]

@@ -309,9 +309,13 @@ def _acc_perm(n_cat, cat_dt_off, dt_score):
 
 # ---- TAO track path ----------------------------------------------------------------------
 def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
-                area_rng=TAO_AREA_RNG, time_rng=TAO_TIME_RNG) -> EvalPlan:
-    cat_ids = np.unique(gt.cat_id)
-    vid_ids = np.unique(gt.vid_id)
+                area_rng=TAO_AREA_RNG, time_rng=TAO_TIME_RNG,
+                vid_ids=None, cat_ids=None) -> EvalPlan:
+    """Plan of the track path.  vid_ids / cat_ids default to everything in the annotation
+    file (TaoEval.__init__, eval.py:169-170); subsets mirror assigning Params.vid_ids /
+    Params.cat_ids before evaluate()."""
+    cat_ids = np.unique(gt.cat_id if cat_ids is None else np.asarray(cat_ids, dtype=np.int64))
+    vid_ids = np.unique(gt.vid_id if vid_ids is None else np.asarray(vid_ids, dtype=np.int64))
     n_cat, n_vid = cat_ids.size, vid_ids.size
     mm = gt.merge_map
     g_cat_raw = _apply_merge(gt.ann_category_id, mm)
@@ -541,9 +545,11 @@ def _gather_track_boxes(ent, perm):
 
 # ---- LVIS frame path ---------------------------------------------------------------------
 def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
-                 vis_rng=LVIS_VIS_RNG) -> EvalPlan:
-    cat_ids = np.unique(gt.cat_id)
-    img_ids = np.unique(gt.img_id)
+                 vis_rng=LVIS_VIS_RNG, img_ids=None, cat_ids=None) -> EvalPlan:
+    """Plan of the frame path; img_ids / cat_ids as in prepare_tao (lvis eval.py:51-52)."""
+    cat_ids = np.unique(gt.cat_id if cat_ids is None else np.asarray(cat_ids, dtype=np.int64))
+    all_img_ids = np.unique(gt.img_id)
+    img_ids = all_img_ids if img_ids is None else np.unique(np.asarray(img_ids, dtype=np.int64))
     n_cat, n_img = cat_ids.size, img_ids.size
     img_keys, img_row = _last_row_of(gt.img_id)
 
@@ -568,10 +574,11 @@ def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
     d_box = dt.bbox[sel]
     d_score = dt.score[sel].astype(np.float64)
     d_area = d_box[:, 2] * d_box[:, 3]
-    d_unit_all = _index_of(img_ids, d_img)
-    if (d_unit_all < 0).any():
+    if (_index_of(all_img_ids, d_img) < 0).any():
         raise AssertionError("Results do not correspond to current LVIS set.")
-    d_valid = (_index_of(cat_ids, d_cat) >= 0) & (d_area > 0) & (d_area < INF)
+    d_unit_all = _index_of(img_ids, d_img)
+    d_valid = ((d_unit_all >= 0) & (_index_of(cat_ids, d_cat) >= 0)
+               & (d_area > 0) & (d_area < INF))
     d_rows = np.nonzero(d_valid)[0]
     d_unit = d_unit_all[d_rows]
     d_cidx = _index_of(cat_ids, d_cat[d_rows])
