@@ -43,6 +43,17 @@ def make_workload(name: str, rank: int, videos: int = 0):
     if videos:
         over["videos"] = videos
     gt, dt = synth.generate_named(name, **over)
+    if rank:
+        # every rank holds different videos of one N x 500-video dataset: make the video and
+        # image ids globally unique (they define the cross-rank tie order, parallel.py)
+        v_off, i_off = rank * 1_000_000, rank * 100_000_000
+        gt.vid_id = gt.vid_id + v_off
+        gt.img_video_id = gt.img_video_id + v_off
+        gt.trk_video_id = gt.trk_video_id + v_off
+        dt.video_id = dt.video_id + v_off
+        gt.img_id = gt.img_id + i_off
+        gt.ann_image_id = gt.ann_image_id + i_off
+        dt.image_id = dt.image_id + i_off
     lvis_plan = prep.prepare_lvis(gt, dt)
     dt2 = dt.copy()
     prep.make_track_ids_unique(dt2)
@@ -260,7 +271,7 @@ def main():
     exch = None
     if world > 1:
         from tao_amodal_b200 import parallel
-        exch = parallel.Exchange(eng, [d_tao, d_lvis], rank, world)
+        exch = {id(d): parallel.DeviceDistAccumulator(eng, d, rank, world) for d in (d_tao, d_lvis)}
 
     stage_names = ["tao_iou", "tao_match", "tao_acc", "lvis_eval", "lvis_acc"]
     ev = None
@@ -269,7 +280,7 @@ def main():
         if exch is None:
             eng.stage_accumulate(dev)
         else:
-            exch.accumulate(dev)
+            exch[id(dev)].accumulate()
 
     stages = [lambda: eng.stage_iou(d_tao), lambda: eng.stage_match(d_tao), lambda: acc(d_tao),
               lambda: eng.stage_frame_eval(d_lvis), lambda: acc(d_lvis)]
@@ -324,18 +335,47 @@ def main():
 
     e2e_steps = max(3, min(args.steps, 10))
     p_tao, p_lvis = pin(tao_plan), pin(lvis_plan)
-    outs = [None, None]
+    if world == 1:
+        def pinned_out(plan):
+            T, R, Cn, K = 10, 101, len(plan.cat_ids), plan.n_cfg
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+            from tao_amodal_b200.engine import EvalOutput
+            return EvalOutput(precision=mk((T, R, Cn, K), torch.float64),
+                              recall=mk((T, Cn, K), torch.float64),
+                              tp_cnt=mk((T, Cn, K), torch.int64), fp_cnt=mk((T, Cn, K), torch.int64),
+                              num_gt=mk((Cn, K), torch.int32))
+        outs = [pinned_out(tao_plan), pinned_out(lvis_plan)]
+
+        def e2e_step():
+            eng.evaluate_host(p_tao, out=outs[0])
+            eng.evaluate_host(p_lvis, out=outs[1])
+            return (outs[0].h2d_bytes + outs[1].h2d_bytes, outs[0].d2h_bytes + outs[1].d2h_bytes)
+    else:
+        def e2e_step():
+            # pinned host plan -> HBM, local IoU + matching, cross-rank exchange (setup included),
+            # owner-side PR, merged tensors back on rank 0's host
+            h2d = d2h = 0
+            for plan in (p_tao, p_lvis):
+                dev = eng.upload(plan)
+                h2d += dev.input_bytes
+                if plan.kind == "tao":
+                    eng.stage_iou(dev)
+                    eng.stage_match(dev)
+                else:
+                    eng.stage_frame_eval(dev)
+                parallel.DeviceDistAccumulator(eng, dev, rank, world).accumulate()
+                if rank == 0:
+                    for k in ("precision", "recall", "tp_cnt", "fp_cnt", "num_gt"):
+                        d2h += dev.t[k].cpu().numpy().nbytes
+            torch.cuda.synchronize()
+            return h2d, d2h
     for _ in range(2):
-        outs[0] = eng.evaluate_host(p_tao, out=outs[0])
-        outs[1] = eng.evaluate_host(p_lvis, out=outs[1])
+        e2e_step()
     sync()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        outs[0] = eng.evaluate_host(p_tao, out=outs[0])
-        outs[1] = eng.evaluate_host(p_lvis, out=outs[1])
+        h2d, d2h = e2e_step()
     e2e_s = time.perf_counter() - t0
-    h2d = outs[0].h2d_bytes + outs[1].h2d_bytes
-    d2h = outs[0].d2h_bytes + outs[1].d2h_bytes
 
     # ---- reduce over ranks: max time, sum units
     if world > 1:
@@ -393,7 +433,8 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "api": "ta_eval_plan_host (pinned host plan -> precision/recall on host)"},
+                "api": ("ta_eval_plan_host (pinned host plan -> precision/recall on host)" if world == 1
+                        else "upload + stages + cross-rank exchange + merged tensors on rank 0's host")},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "host_prep_s": t_prep,

@@ -65,13 +65,29 @@ def run_hostsim(plan, iou_mode="3d_iou", iou_thrs=engine.IOU_THRS, rec_thrs=engi
                        plan.n_gt, _p(plan.gt_attr_a), _p(plan.gt_attr_b),
                        _p(plan.gt_hp), _p(plan.gt_flag), g_max,
                        _p(tpfp), _p(num_gt), _p(match_gt), _p(gt_ig))
+    out = hostsim_pr(n_cat, plan.cat_dt_off, plan.acc_perm, tpfp, num_gt, n_cfg, iou_thrs, rec_thrs)
+    out.iou, out.dt_match_gt, out.gt_ignore = iou[:n_iou], match_gt, gt_ig
+    return out
+
+
+def hostsim_pr(n_cat, cat_dt_off, acc_perm, tpfp, num_gt, n_cfg, iou_thrs=engine.IOU_THRS,
+               rec_thrs=engine.REC_THRS):
+    """PR accumulation of the host simulation on explicit arrays (also used by the
+    multi-process exchange test)."""
+    hs = build_hostsim()
+    I64, I32, P = C.c_int64, C.c_int32, C.c_void_p
+    n_thr, n_rec = len(iou_thrs), len(rec_thrs)
+    n_dt = int(tpfp.shape[0])
+    rec = np.ascontiguousarray(rec_thrs, dtype=np.float64)
+    tpfp = np.ascontiguousarray(tpfp, dtype=np.uint32)
+    num_gt = np.ascontiguousarray(num_gt, dtype=np.int32)
     out = engine.EvalOutput(
         precision=np.empty((n_thr, n_rec, n_cat, n_cfg)), recall=np.empty((n_thr, n_cat, n_cfg)),
         tp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64),
-        fp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64), num_gt=num_gt,
-        iou=iou[:n_iou], dt_tpfp=tpfp, dt_match_gt=match_gt, gt_ignore=gt_ig)
+        fp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64), num_gt=num_gt, dt_tpfp=tpfp)
     hs.hs_pr_accumulate.argtypes = [I32, P, P, I64, P, P, I32, I32, I32, P, P, P, P, P]
-    hs.hs_pr_accumulate(n_cat, _p(plan.cat_dt_off), _p(plan.acc_perm), plan.n_dt, _p(tpfp),
+    hs.hs_pr_accumulate(n_cat, _p(np.asarray(cat_dt_off, dtype=np.int64)),
+                        _p(np.asarray(acc_perm, dtype=np.int32)), n_dt, _p(tpfp),
                         _p(num_gt), n_thr, n_cfg, n_rec, _p(rec), _p(out.precision),
                         _p(out.recall), _p(out.tp_cnt), _p(out.fp_cnt))
     return out
