@@ -173,7 +173,7 @@ struct FrameSmem {
     uint32_t gig[FE_WARPS][FE_MAX_CFG];       // per cfg: bit g = GT g ignored
 };
 
-__global__ void __launch_bounds__(FE_WARPS * 32)
+__global__ void __launch_bounds__(FE_WARPS * 32, 7)
 k_frame_eval(FrameArgs a) {
     __shared__ FrameSmem sm;
     __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
@@ -203,13 +203,24 @@ k_frame_eval(FrameArgs a) {
     const int64_t wstride = (int64_t)gridDim.x * FE_WARPS;
     for (int64_t task = w0; task < n_tasks; task += wstride) {
         const int64_t grp0 = task * FE_RUN;
-        const int64_t grp1 = (grp0 + FE_RUN < a.n_groups) ? grp0 + FE_RUN : a.n_groups;
+        const int n_in_task = (int)((grp0 + FE_RUN < a.n_groups) ? FE_RUN : a.n_groups - grp0);
+        // group table of the whole task in one coalesced load: lane i holds entry grp0 + i
+        int64_t dt_off_r = 0, gt_off_r = 0;
+        int cat_r = 0;
+        if (lane <= n_in_task) {
+            dt_off_r = a.grp_dt_off[grp0 + lane];
+            gt_off_r = a.grp_gt_off[grp0 + lane];
+        }
+        if (lane < n_in_task) cat_r = a.grp_cat[grp0 + lane];
         int acc = 0, acc_cat = -1;          // lane c < n_cfg: non-ignored GT of (acc_cat, cfg c)
-        for (int64_t grp = grp0; grp < grp1; ++grp) {
-            const int64_t d0 = a.grp_dt_off[grp], g0 = a.grp_gt_off[grp];
-            const int D = (int)(a.grp_dt_off[grp + 1] - d0), G = (int)(a.grp_gt_off[grp + 1] - g0);
+        for (int gi = 0; gi < n_in_task; ++gi) {
+            const int64_t grp = grp0 + gi;
+            const int64_t d0 = __shfl_sync(0xffffffffu, dt_off_r, gi);
+            const int64_t g0 = __shfl_sync(0xffffffffu, gt_off_r, gi);
+            const int D = (int)(__shfl_sync(0xffffffffu, dt_off_r, gi + 1) - d0);
+            const int G = (int)(__shfl_sync(0xffffffffu, gt_off_r, gi + 1) - g0);
+            const int cat = __shfl_sync(0xffffffffu, cat_r, gi);
             if (D == 0 && G == 0) continue;
-            __syncwarp();
             if (G == 0) {
                 // ---- route A
                 for (int d = lane; d < D; d += 32) {
@@ -228,16 +239,29 @@ k_frame_eval(FrameArgs a) {
                 continue;
             }
             if (G > FE_MAX_GT || D > FE_MAX_DT || D * G > FE_MAX_PAIRS) continue;   // big_list route
-            // ---- stage GT boxes, GT ignore masks per cfg, non-ignored GT counts
+            __syncwarp();
+            // ---- GT side: boxes to shared memory, ignore masks per cfg, non-ignored counts.
+            // All global loads of the group (GT lane data, first detection per lane) are issued
+            // before anything consumes them.
             double vis = 0.0;
             uint8_t gfl = 0;
+            double2 gp = make_double2(0, 0), gq = make_double2(0, 0);
             if (lane < G) {
-                const double2 p = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane));
-                const double2 q = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane) + 2);
-                sm.gtb[warp][lane][0] = p.x; sm.gtb[warp][lane][1] = p.y;
-                sm.gtb[warp][lane][2] = q.x; sm.gtb[warp][lane][3] = q.y;
+                gp = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane));
+                gq = *reinterpret_cast<const double2*>(a.gt_box + 4 * (g0 + lane) + 2);
                 vis = a.gt_vis[g0 + lane];
                 gfl = a.gt_flag[g0 + lane];
+            }
+            double2 dp = make_double2(0, 0), dq = make_double2(0, 0);
+            uint8_t dfl = 0;
+            if (lane < D) {
+                dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + lane));
+                dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + lane) + 2);
+                dfl = a.dt_flag[d0 + lane];
+            }
+            if (lane < G) {
+                sm.gtb[warp][lane][0] = gp.x; sm.gtb[warp][lane][1] = gp.y;
+                sm.gtb[warp][lane][2] = gq.x; sm.gtb[warp][lane][3] = gq.y;
             }
             const uint32_t gsent = __ballot_sync(0xffffffffu, (gfl & 4) != 0);   // id == "unmatched" value
             uint32_t my_gig = 0;
@@ -247,50 +271,39 @@ k_frame_eval(FrameArgs a) {
                 if (lane == c) my_gig = m;
                 if (a.gt_ignore_out && lane < G) a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + lane] = ig;
             }
-            {
-                const int cat = a.grp_cat[grp];
-                if (cat != acc_cat) {
-                    if (acc > 0) atomicAdd(&a.num_gt[(int64_t)acc_cat * n_cfg + lane], acc);
-                    acc = 0;
-                    acc_cat = cat;
-                }
-                if (lane < n_cfg) {
-                    gig_s[lane] = my_gig;
-                    acc += G - __popc(my_gig);
-                }
+            if (cat != acc_cat) {
+                if (acc > 0) atomicAdd(&a.num_gt[(int64_t)acc_cat * n_cfg + lane], acc);
+                acc = 0;
+                acc_cat = cat;
+            }
+            if (lane < n_cfg) {
+                gig_s[lane] = my_gig;
+                acc += G - __popc(my_gig);
             }
             __syncwarp();
-            // ---- IoU tile (maskApi.c:109-120): lane = (detection within pass, GT)
-            const int dpp = 32 / G;                      // detections per pass
-            const int dsub = lane / G, gl = lane - dsub * G;
+            // ---- detection side, lane = detection: IoU row (maskApi.c:109-120) into the tile
+            // (layout [g][d]: conflict-free stores, broadcast reads), unmatched-ignore mask, lock
+            // bit and candidate summary straight from registers
             double* iou_g = a.write_iou ? a.iou + a.iou_off[grp] : nullptr;
-            if (dsub < dpp) {
-                const double* gb = sm.gtb[warp][gl];
-                const double gx = gb[0], gy = gb[1], gw = gb[2], gh = gb[3];
-                for (int d = dsub; d < D; d += dpp) {
-                    const double2 dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d));
-                    const double2 dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
-                    const double v = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, gx, gy, gw, gh);
-                    iou_s[d * G + gl] = v;
-                    if (iou_g) iou_g[d * G + gl] = v;
-                }
-            }
-            __syncwarp();
-            // ---- per detection: unmatched-ignore mask, lock bit, candidate summary
             bool multi = false;
             for (int d = lane; d < D; d += 32) {
-                const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
-                const double area = q.x * q.y;
-                const uint8_t fl = a.dt_flag[d0 + d];
-                uint32_t m = (fl & 2) ? (1u << 16) : 0u;
+                if (d >= 32) {
+                    dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d));
+                    dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
+                    dfl = a.dt_flag[d0 + d];
+                }
+                const double area = dq.x * dq.y;
+                uint32_t m = (dfl & 2) ? (1u << 16) : 0u;
                 for (int c = 0; c < n_cfg; ++c)
-                    if (ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, fl)) m |= 1u << c;
+                    if (ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, dfl)) m |= 1u << c;
                 dmask_s[d] = m;
                 int cnt = 0, gs = 0;
                 double vs = 0.0;
-                const double* row = iou_s + d * G;
                 for (int g = 0; g < G; ++g) {
-                    const double v = row[g];
+                    const double* gb = sm.gtb[warp][g];
+                    const double v = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, gb[0], gb[1], gb[2], gb[3]);
+                    iou_s[g * D + d] = v;
+                    if (iou_g) iou_g[d * G + g] = v;
                     if (!(v < thr_min)) { ++cnt; gs = g; vs = v; }
                 }
                 uint32_t ge = 0;
@@ -322,10 +335,10 @@ k_frame_eval(FrameArgs a) {
                     const bool sent = (gsent >> gs) & 1u;
                     uint32_t* o = a.dt_tpfp + (d0 + d) * n_cfg;
                     for (int c = 0; c < n_cfg; ++c) {
-                        const bool gi = (gig_s[c] >> gs) & 1u;
+                        const bool gi2 = (gig_s[c] >> gs) & 1u;
                         const bool dc = (dm >> c) & 1u;
-                        const uint32_t tp = (!sent && !gi) ? M : 0u;
-                        const uint32_t fp = ((sent && !gi && !dc) ? M : 0u) | (dc ? 0u : (thr_all & ~M));
+                        const uint32_t tp = (!sent && !gi2) ? M : 0u;
+                        const uint32_t fp = ((sent && !gi2 && !dc) ? M : 0u) | (dc ? 0u : (thr_all & ~M));
                         o[c] = tp | (fp << 16);
                     }
                     if (a.dt_match_gt)
@@ -347,18 +360,17 @@ k_frame_eval(FrameArgs a) {
                 for (int d = 0; d < D; ++d) {
                     const uint32_t cd = cand_s[d], dm = dmask_s[d];
                     const uint32_t cnt = (cd >> 21) & 3u;
-                    const double* row = iou_s + d * G;
                     int m = -1;
                     if (cnt == 1u) {
                         const int gs = (cd >> 16) & 31;
-                        if (!(row[gs] < thr_c) && !((taken >> gs) & 1u)) m = gs;
+                        if (!(iou_s[gs * D + d] < thr_c) && !((taken >> gs) & 1u)) m = gs;
                     } else if (cnt > 1u) {
                         const uint32_t free0 = ~taken & ~gig & gall;   // regular GTs still free
                         const uint32_t free1 = ~taken & gig & gall;    // ignored GTs still free
                         double best0 = thr_c, best1 = thr_c;
                         int m0 = -1, m1 = -1;
                         for (int g = 0; g < G; ++g) {
-                            const double v = row[g];
+                            const double v = iou_s[g * D + d];
                             if (((free0 >> g) & 1u) && !(v < best0)) { best0 = v; m0 = g; }
                             if (((free1 >> g) & 1u) && !(v < best1)) { best1 = v; m1 = g; }
                         }

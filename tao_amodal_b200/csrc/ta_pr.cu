@@ -15,20 +15,21 @@
 // the maximum of the rounded quotients is the rounded quotient of the rational maximum — and
 // only the <= 101 winners per cell are divided (ta_precision_at):
 //   k_pr_plan      chunk table: first chunk of every category
-//   k_pr_count     per chunk: TP / FP totals of every (cfg, threshold)  (ballot + popc)
+//   k_pr_count     per chunk: TP / FP totals of every (cfg, threshold)  (bit-sliced carry-save
+//                  counters per lane + REDUX across the warp)
 //   k_pr_scan      per category: exclusive scan of the chunk totals, tk tables, recall, counts
 //   k_pr_envelope  per chunk, one THREAD per (cfg, threshold) cell walking the chunk's
 //                  detections backwards from shared memory: running counts, suffix-maximum
 //                  precision, and the answer of every recall threshold whose tk-th true
 //                  positive lies inside the chunk
-//   k_pr_finalize  per cell: suffix maximum across the chunks (backwards), merge with the
-//                  in-chunk answers, divide, write precision (-1 fill without GT)
+//   k_pr_suffix    per cell: best precision of all later chunks, for every chunk
+//   k_pr_finalize  per precision entry: merge the in-chunk answer with the later chunks' best,
+//                  divide, write (-1 without GT, 0 for recall levels nobody reaches)
 #include <limits.h>
 #include "ta_internal.h"
 #include "ta_device_fns.cuh"
 
 #define PR_CHUNK 256          // detections per chunk == threads per block
-#define PR_WARPS (PR_CHUNK / 32)
 
 struct PrArgs {
     int n_cat, n_thr, n_cfg, n_rec;
@@ -52,7 +53,10 @@ struct PrArgs {
     double* recall;
     int64_t* tp_cnt;
     int64_t* fp_cnt;
+    int* flags;                  // [1]: a category exceeds PR_MAX_CAT_DT
 };
+
+#define PR_MAX_CAT_DT (1 << 24)  // detections per category (packed candidates: 24-bit counts)
 
 __global__ void __launch_bounds__(1024)
 k_pr_plan(PrArgs a) {
@@ -65,7 +69,11 @@ k_pr_plan(PrArgs a) {
     for (int base = 0; base < a.n_cat; base += 1024) {
         const int c = base + threadIdx.x;
         int n = 0;
-        if (c < a.n_cat) n = (int)((a.cat_dt_off[c + 1] - a.cat_dt_off[c] + PR_CHUNK - 1) / PR_CHUNK);
+        if (c < a.n_cat) {
+            const int64_t len = a.cat_dt_off[c + 1] - a.cat_dt_off[c];
+            if (len >= PR_MAX_CAT_DT) atomicExch(&a.flags[1], 1);
+            n = (int)((len + PR_CHUNK - 1) / PR_CHUNK);
+        }
         int incl = n;
         for (int o = 1; o < 32; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -101,37 +109,41 @@ __device__ __forceinline__ int pr_find_cat(const int32_t* chunk_start, int n_cat
     return lo;
 }
 
-__global__ void __launch_bounds__(PR_CHUNK)
+// One warp per range cfg, lane = 8 consecutive positions of the chunk.  Each lane adds its 8
+// TP/FP words into bit-sliced counters (carry-save: all 32 bit positions at once), expands
+// them to one count per bit, and the warp sums the lanes with REDUX.
+#define PR_COUNT_MAX_CFG 8    // cfgs (warps) per k_pr_count block
+
+__global__ void __launch_bounds__(PR_COUNT_MAX_CFG * 32)
 k_pr_count(PrArgs a) {
-    __shared__ uint32_t wcnt[PR_WARPS][32];
-    __shared__ int s_cat;
     const int chunk = blockIdx.x;
     if (chunk >= a.chunk_start[a.n_cat]) return;
-    if (threadIdx.x == 0) s_cat = pr_find_cat(a.chunk_start, a.n_cat, chunk);
-    __syncthreads();
-    const int cat = s_cat;
-    const int64_t p = a.cat_dt_off[cat] + (int64_t)(chunk - a.chunk_start[cat]) * PR_CHUNK + threadIdx.x;
-    const bool live = p < a.cat_dt_off[cat + 1];
+    const int cat = pr_find_cat(a.chunk_start, a.n_cat, chunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t* row = live ? a.dt_tpfp + (int64_t)a.acc_perm[p] * a.n_cfg : nullptr;
-    for (int c = 0; c < a.n_cfg; ++c) {
-        const uint32_t w = live ? row[c] : 0u;
-        uint32_t mine = 0;
-        for (int b = 0; b < a.n_thr; ++b) {
-            const uint32_t mt = __ballot_sync(0xffffffffu, (w >> b) & 1u);
-            const uint32_t mf = __ballot_sync(0xffffffffu, (w >> (16 + b)) & 1u);
-            if (lane == b) mine = __popc(mt);
-            if (lane == 16 + b) mine = __popc(mf);
-        }
-        wcnt[warp][lane] = mine;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            uint32_t s = 0;
+    const int64_t p0 = a.cat_dt_off[cat] + (int64_t)(chunk - a.chunk_start[cat]) * PR_CHUNK;
+    const int n_pos = (int)min((int64_t)PR_CHUNK, a.cat_dt_off[cat + 1] - p0);
+    for (int cfg = blockIdx.y * PR_COUNT_MAX_CFG + warp; cfg < a.n_cfg;
+         cfg += gridDim.y * PR_COUNT_MAX_CFG) {
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #pragma unroll
-            for (int w2 = 0; w2 < PR_WARPS; ++w2) s += wcnt[w2][threadIdx.x];
-            a.chunk_cnt[((int64_t)chunk * a.n_cfg + c) * 32 + threadIdx.x] = s;
+        for (int u = 0; u < PR_CHUNK / 32; ++u) {
+            const int p = u * 32 + lane;               // coalesced permutation reads
+            uint32_t w = 0;
+            if (p < n_pos) w = a.dt_tpfp[(int64_t)a.acc_perm[p0 + p] * a.n_cfg + cfg];
+            const uint32_t k0 = c0 & w;  c0 ^= w;
+            const uint32_t k1 = c1 & k0; c1 ^= k0;
+            const uint32_t k2 = c2 & k1; c2 ^= k1;
+            c3 ^= k2;
         }
-        __syncthreads();
+        uint32_t mine = 0;
+        for (int b = 0; b < 32; ++b) {
+            if ((b & 15) >= a.n_thr) continue;
+            const uint32_t v = ((c0 >> b) & 1u) + (((c1 >> b) & 1u) << 1) + (((c2 >> b) & 1u) << 2) +
+                               (((c3 >> b) & 1u) << 3);
+            const uint32_t tot = __reduce_add_sync(0xffffffffu, v);
+            if (lane == b) mine = tot;
+        }
+        a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg) * 32 + lane] = mine;
     }
 }
 
@@ -190,8 +202,13 @@ __device__ __forceinline__ bool pr_better(uint32_t t1, uint32_t n1, uint32_t t2,
     const unsigned long long x = (unsigned long long)t1 * n2, y = (unsigned long long)t2 * n1;
     return x > y || (x == y && n1 > n2);
 }
-__device__ __forceinline__ unsigned long long pr_pack(uint32_t t, uint32_t n) {
-    return ((unsigned long long)t << 32) | n;
+// packed candidate: t (24 bits) | n (24 bits) | chunk index inside the category (16 bits);
+// ta_pr_accumulate rejects categories with 2^24 or more detections
+__device__ __forceinline__ unsigned long long pr_pack(uint32_t t, uint32_t n, uint32_t ch) {
+    return ((unsigned long long)t << 40) | ((unsigned long long)n << 16) | ch;
+}
+__device__ __forceinline__ void pr_unpack(unsigned long long q, uint32_t& t, uint32_t& n, uint32_t& ch) {
+    t = (uint32_t)(q >> 40); n = (uint32_t)(q >> 16) & 0xffffffu; ch = (uint32_t)q & 0xffffu;
 }
 
 #define PR_ENV_MAX_CELLS 64   // (cfg, threshold) cells per k_pr_envelope block
@@ -207,8 +224,8 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
     const int cat = pr_find_cat(a.chunk_start, a.n_cat, chunk);
     const int cfg0 = blockIdx.y * cfgs_per_block;
     const int ncf = min(cfgs_per_block, a.n_cfg - cfg0);
-    const int ch1 = a.chunk_start[cat + 1];
-    const int64_t p0 = a.cat_dt_off[cat] + (int64_t)(chunk - a.chunk_start[cat]) * PR_CHUNK;
+    const int ch0 = a.chunk_start[cat], ch1 = a.chunk_start[cat + 1];
+    const int64_t p0 = a.cat_dt_off[cat] + (int64_t)(chunk - ch0) * PR_CHUNK;
     const int n_pos = (int)min((int64_t)PR_CHUNK, a.cat_dt_off[cat + 1] - p0);
     // ---- stage the chunk's TP/FP words (rows gathered through the score permutation) and tk
     for (int i = threadIdx.x; i < n_pos * ncf; i += blockDim.x) {
@@ -235,7 +252,9 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
     // last recall threshold whose (clamped) tk is <= tc
     int kq = a.n_rec - 1;
     while (kq >= 0 && (uint32_t)max(tkc[kq], 1) > tc) --kq;
+    uint32_t next_tk = kq >= 0 ? (uint32_t)max(tkc[kq], 1) : 0u;
     uint32_t bt = 0, bn = 0;
+    const uint32_t ch_rel = (uint32_t)(chunk - ch0);
     const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
     const int64_t cc = (int64_t)cat * a.n_cfg + cfg;
     for (int p = n_pos - 1; p >= 0; --p) {
@@ -243,56 +262,57 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
         if ((w >> b) & 1u) {
             const uint32_t n = tc + fc;
             if (pr_better(tc, n, bt, bn)) { bt = tc; bn = n; }
-            while (kq >= 0 && (uint32_t)max(tkc[kq], 1) == tc) {
-                a.prec_bits[((int64_t)b * a.n_rec + kq) * per_t + cc] = pr_pack(bt, bn);
+            while (next_tk == tc) {
+                a.prec_bits[((int64_t)b * a.n_rec + kq) * per_t + cc] = pr_pack(bt, bn, ch_rel);
                 --kq;
+                next_tk = kq >= 0 ? (uint32_t)max(tkc[kq], 1) : 0u;
             }
             --tc;
         } else if ((w >> (16 + b)) & 1u) {
             --fc;
         }
     }
-    *best_out = pr_pack(bt, bn);
+    *best_out = pr_pack(bt, bn, 0);
+}
+
+// per (category, cfg, threshold): chunk_best[ch] <- best precision of all LATER chunks
+__global__ void k_pr_suffix(PrArgs a) {
+    const int cat = blockIdx.x;
+    const int ch0 = a.chunk_start[cat], ch1 = a.chunk_start[cat + 1];
+    const int n_cell = a.n_cfg * a.n_thr;
+    for (int j = threadIdx.x; j < n_cell; j += blockDim.x) {
+        if (a.num_gt[(int64_t)cat * a.n_cfg + j / a.n_thr] == 0) continue;
+        uint32_t bt = 0, bn = 0, dummy;
+        for (int ch = ch1 - 1; ch >= ch0; --ch) {
+            unsigned long long* q = a.chunk_best + (int64_t)ch * n_cell + j;
+            uint32_t ct, cn;
+            pr_unpack(*q, ct, cn, dummy);
+            *q = pr_pack(bt, bn, 0);
+            if (pr_better(ct, cn, bt, bn)) { bt = ct; bn = cn; }
+        }
+    }
 }
 
 __global__ void k_pr_finalize(PrArgs a) {
-    // thread <-> (threshold, category, cfg), cfg fastest
-    const int64_t n_cell = (int64_t)a.n_thr * a.n_cat * a.n_cfg;
-    const int64_t cell = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= n_cell) return;
+    // thread <-> one precision entry (threshold, recall k, category, cfg), cfg fastest
     const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
-    const int t = (int)(cell / per_t);
-    const int64_t cc = cell - (int64_t)t * per_t;          // cat * n_cfg + cfg
-    const int cat = (int)(cc / a.n_cfg), cfg = (int)(cc - (int64_t)cat * a.n_cfg);
+    const int64_t n = (int64_t)a.n_thr * a.n_rec * per_t;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int64_t cc = idx % per_t;                           // cat * n_cfg + cfg
+    const int64_t tk_idx = idx / per_t;                       // t * n_rec + k
+    const int k = (int)(tk_idx % a.n_rec), t = (int)(tk_idx / a.n_rec);
     const int ngt = a.num_gt[cc];
-    if (ngt == 0) {   // eval.py:522-525: the cell keeps its -1 initialisation
-        for (int k = 0; k < a.n_rec; ++k) a.precision[((int64_t)t * a.n_rec + k) * per_t + cc] = -1.0;
-        return;
-    }
-    const int32_t* tkc = a.tk + cc * a.n_rec;
-    const int ch0 = a.chunk_start[cat], ch1 = a.chunk_start[cat + 1];
-    const uint32_t t_total = a.cat_tot[cc * 32 + t];
-    int kq = a.n_rec - 1;
-    // thresholds no detection reaches: the reference leaves 0.0 (eval.py:565-573)
-    while (kq >= 0 && (uint32_t)max(tkc[kq], 1) > t_total) {
-        a.precision[((int64_t)t * a.n_rec + kq) * per_t + cc] = 0.0;
-        --kq;
-    }
-    uint32_t bt = 0, bn = 0;   // best precision of all LATER chunks
-    for (int ch = ch1 - 1; ch >= ch0 && kq >= 0; --ch) {
-        const uint32_t t_begin = a.chunk_cnt[((int64_t)ch * a.n_cfg + cfg) * 32 + t];
-        while (kq >= 0 && (uint32_t)max(tkc[kq], 1) > t_begin) {
-            const int64_t idx = ((int64_t)t * a.n_rec + kq) * per_t + cc;
-            const unsigned long long q = a.prec_bits[idx];
-            uint32_t qt = (uint32_t)(q >> 32), qn = (uint32_t)q;
-            if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
-            a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
-            --kq;
-        }
-        const unsigned long long cb = a.chunk_best[((int64_t)ch * a.n_cfg + cfg) * a.n_thr + t];
-        const uint32_t ct = (uint32_t)(cb >> 32), cn = (uint32_t)cb;
-        if (pr_better(ct, cn, bt, bn)) { bt = ct; bn = cn; }
-    }
+    if (ngt == 0) { a.precision[idx] = -1.0; return; }        // eval.py:522-525
+    const int cat = (int)(cc / a.n_cfg), cfg = (int)(cc - (int64_t)cat * a.n_cfg);
+    const uint32_t need = (uint32_t)max(a.tk[cc * a.n_rec + k], 1);
+    if (need > a.cat_tot[cc * 32 + t]) { a.precision[idx] = 0.0; return; }   // eval.py:565-573
+    uint32_t qt, qn, ch, bt, bn, dummy;
+    pr_unpack(a.prec_bits[idx], qt, qn, ch);
+    pr_unpack(a.chunk_best[((int64_t)(a.chunk_start[cat] + ch) * a.n_cfg + cfg) * a.n_thr + t],
+              bt, bn, dummy);
+    if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
+    a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
 }
 
 extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
@@ -306,6 +326,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     if (n_cat == 0) return TA_OK;
     if (n_dt / PR_CHUNK + n_cat + 1 > INT_MAX)
         return ta_set_err(TA_ERR_TOO_LARGE, "ta_pr_accumulate: too many detections");
+
     TA_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int n_chunks_ub = (int)(n_dt / PR_CHUNK) + n_cat;
@@ -334,10 +355,24 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     a.prec_bits = reinterpret_cast<unsigned long long*>(precision);
     a.precision = precision; a.recall = recall; a.tp_cnt = tp_cnt; a.fp_cnt = fp_cnt;
 
+    a.flags = ctx->d_flags;
     k_pr_plan<<<1, 1024, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_plan"))) return rc;
+    if (n_dt >= PR_MAX_CAT_DT) {
+        // only then can a single category be too long for the packed (24-bit) counts
+        int big = 0;
+        TA_CUDA(cudaMemcpyAsync(&big, ctx->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(cudaStreamSynchronize(st));
+        if (big) {
+            TA_CUDA(cudaMemsetAsync(ctx->d_flags + 1, 0, sizeof(int), st));
+            return ta_set_err(TA_ERR_TOO_LARGE,
+                              "ta_pr_accumulate: a category has 2^24 or more detections");
+        }
+    }
     if (n_chunks_ub > 0) {
-        k_pr_count<<<n_chunks_ub, PR_CHUNK, 0, st>>>(a);
+        const int warps = n_cfg < PR_COUNT_MAX_CFG ? n_cfg : PR_COUNT_MAX_CFG;
+        dim3 grid(n_chunks_ub, (n_cfg + PR_COUNT_MAX_CFG - 1) / PR_COUNT_MAX_CFG);
+        k_pr_count<<<grid, warps * 32, 0, st>>>(a);
         if ((rc = ta_check_launch(ctx, "k_pr_count"))) return rc;
     }
     k_pr_scan<<<n_cat, 128, 0, st>>>(a);
@@ -354,8 +389,9 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
         k_pr_envelope<<<grid, PR_ENV_MAX_CELLS, smem, st>>>(a, cpb);
         if ((rc = ta_check_launch(ctx, "k_pr_envelope"))) return rc;
     }
-    const size_t n_cell = (size_t)n_thr * n_cat * n_cfg;
-    const int fin_blocks = (int)((n_cell + 127) / 128);
-    k_pr_finalize<<<fin_blocks, 128, 0, st>>>(a);
+    k_pr_suffix<<<n_cat, 128, 0, st>>>(a);
+    if ((rc = ta_check_launch(ctx, "k_pr_suffix"))) return rc;
+    const size_t n_prec = (size_t)n_thr * n_rec * n_cat * n_cfg;
+    k_pr_finalize<<<(unsigned)((n_prec + 255) / 256), 256, 0, st>>>(a);
     return ta_check_launch(ctx, "k_pr_finalize");
 }
