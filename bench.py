@@ -68,6 +68,13 @@ def algorithmic_bytes(plan) -> dict:
     n_cfg, n_dt, n_gt = plan.n_cfg, plan.n_dt, plan.n_gt
     per_box = 36 if plan.kind == "tao" else 32
     n_cat = len(plan.cat_ids)
+    if plan.kind == "tao":
+        # the IoU kernel only touches groups that have both detections and GT
+        D, G = np.diff(plan.grp_dt_off), np.diff(plan.grp_gt_off)
+        act = (D > 0) & (G > 0)
+        db, gb = plan.dt_trk_box_off[plan.grp_dt_off], plan.gt_trk_box_off[plan.grp_gt_off]
+        nd_box = int((db[1:] - db[:-1])[act].sum())
+        ng_box = int((gb[1:] - gb[:-1])[act].sum())
     return {
         "iou": per_box * (nd_box + ng_box) + 8 * n_iou,
         # IoU matrix + dt (area, n_anns, flag) + gt (attr a, b, hp, flag) read, TP/FP words written

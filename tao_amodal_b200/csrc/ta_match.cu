@@ -173,6 +173,31 @@ struct FrameSmem {
     uint32_t gig[FE_WARPS][FE_MAX_CFG];       // per cfg: bit g = GT g ignored
 };
 
+struct FrameRules {
+    int n_da, n_ga;
+    uint32_t d_const, g_const, g_oof;         // cfg masks: constant-true tests, cfgs needing out_of_frame
+    double da_lo[FE_MAX_CFG], da_hi[FE_MAX_CFG], ga_lo[FE_MAX_CFG], ga_hi[FE_MAX_CFG];
+    uint32_t da_mask[FE_MAX_CFG], ga_mask[FE_MAX_CFG];
+};
+
+// cfg mask "this detection is ignored when unmatched" (lvis eval.py:281-286) for b = 0
+__device__ __forceinline__ uint32_t fe_dt_unmatched_mask(const FrameRules& r, double area, uint8_t fl,
+                                                         uint32_t cfg_all) {
+    uint32_t m = (fl & 1) ? cfg_all : r.d_const;
+    for (int k = 0; k < r.n_da; ++k)
+        if (area < r.da_lo[k] || area > r.da_hi[k]) m |= r.da_mask[k];
+    return m;
+}
+// cfg mask "this GT is ignored" (lvis eval.py:202-217) for b = 0, hp = 0
+__device__ __forceinline__ uint32_t fe_gt_ignore_mask(const FrameRules& r, double vis, uint8_t fl,
+                                                      uint32_t cfg_all) {
+    uint32_t m = (fl & 1) ? cfg_all : r.g_const;
+    if (!(fl & 2)) m |= r.g_oof;
+    for (int k = 0; k < r.n_ga; ++k)
+        if (vis < r.ga_lo[k] || vis > r.ga_hi[k]) m |= r.ga_mask[k];
+    return m;
+}
+
 __global__ void __launch_bounds__(FE_WARPS * 32, 7)
 k_frame_eval(FrameArgs a) {
     __shared__ FrameSmem sm;
@@ -186,6 +211,32 @@ k_frame_eval(FrameArgs a) {
         thr_s[threadIdx.x] = (th < 1.0 - 1e-10) ? th : 1.0 - 1e-10;   // min([iou_thr, 1 - 1e-10])
     }
     __syncthreads();
+    // The range tests are evaluated once per DISTINCT interval, not once per cfg: rules[] holds
+    // the distinct [lo, hi] intervals of the detection-area test and of the GT attribute test
+    // with the bit mask of the cfgs using each (LVISEval: one detection interval, six GT ones).
+    // The frame path has b = 0 and hp = 0 for every entity, so those tests are per-cfg constants.
+    __shared__ FrameRules rules;
+    if (threadIdx.x == 0) {
+        rules.n_da = rules.n_ga = 0;
+        rules.d_const = rules.g_const = rules.g_oof = 0;
+        for (int c = 0; c < n_cfg; ++c) {
+            const ta_range_cfg& r = cfg_s[c];
+            if (0.0 < r.dt_b_lo || 0.0 > r.dt_b_hi) rules.d_const |= 1u << c;
+            if (0.0 < r.gt_b_lo || 0.0 > r.gt_b_hi || 0 < r.gt_hp_min) rules.g_const |= 1u << c;
+            if (r.gt_need_oof) rules.g_oof |= 1u << c;
+            int k = 0;
+            for (; k < rules.n_da; ++k)
+                if (rules.da_lo[k] == r.dt_a_lo && rules.da_hi[k] == r.dt_a_hi) break;
+            if (k == rules.n_da) { rules.da_lo[k] = r.dt_a_lo; rules.da_hi[k] = r.dt_a_hi; rules.da_mask[k] = 0; ++rules.n_da; }
+            rules.da_mask[k] |= 1u << c;
+            for (k = 0; k < rules.n_ga; ++k)
+                if (rules.ga_lo[k] == r.gt_a_lo && rules.ga_hi[k] == r.gt_a_hi) break;
+            if (k == rules.n_ga) { rules.ga_lo[k] = r.gt_a_lo; rules.ga_hi[k] = r.gt_a_hi; rules.ga_mask[k] = 0; ++rules.n_ga; }
+            rules.ga_mask[k] |= 1u << c;
+        }
+    }
+    __syncthreads();
+    const uint32_t cfg_all = (n_cfg == 32) ? 0xffffffffu : ((1u << n_cfg) - 1u);
     double thr_min = thr_s[0];
     for (int i = 1; i < n_thr; ++i) thr_min = (thr_s[i] < thr_min) ? thr_s[i] : thr_min;
     const int cpw = 32 / n_thr;
@@ -212,32 +263,42 @@ k_frame_eval(FrameArgs a) {
             gt_off_r = a.grp_gt_off[grp0 + lane];
         }
         if (lane < n_in_task) cat_r = a.grp_cat[grp0 + lane];
+        // ---- route A for the whole task in one flat pass over its contiguous detections:
+        // every detection of a group without GT is unmatched at every threshold
+        {
+            const int64_t d_begin = __shfl_sync(0xffffffffu, dt_off_r, 0);
+            const int64_t d_end = __shfl_sync(0xffffffffu, dt_off_r, n_in_task);
+            for (int64_t base = d_begin; base < d_end; base += 32) {
+                const int64_t dd = base + lane;
+                int gi = 0;                   // last group of the task starting at or before dd
+#pragma unroll
+                for (int step = FE_RUN / 2; step >= 1; step >>= 1) {
+                    const int cnd = gi + step;
+                    const int64_t v = __shfl_sync(0xffffffffu, dt_off_r, cnd & 31);
+                    if (cnd < n_in_task && v <= dd) gi = cnd;
+                }
+                const int64_t ga = __shfl_sync(0xffffffffu, gt_off_r, gi);
+                const int64_t gb = __shfl_sync(0xffffffffu, gt_off_r, gi + 1);
+                if (dd < d_end && ga == gb) {
+                    const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * dd + 2);
+                    const uint32_t m = fe_dt_unmatched_mask(rules, q.x * q.y, a.dt_flag[dd], cfg_all);
+                    uint32_t* o = a.dt_tpfp + dd * n_cfg;
+                    for (int c = 0; c < n_cfg; ++c) o[c] = ((m >> c) & 1u) ? 0u : (thr_all << 16);
+                    if (a.dt_match_gt)
+                        for (int ct = 0; ct < n_cfg * n_thr; ++ct)
+                            a.dt_match_gt[(int64_t)ct * a.n_dt + dd] = -1;
+                }
+            }
+        }
         int acc = 0, acc_cat = -1;          // lane c < n_cfg: non-ignored GT of (acc_cat, cfg c)
         for (int gi = 0; gi < n_in_task; ++gi) {
             const int64_t grp = grp0 + gi;
-            const int64_t d0 = __shfl_sync(0xffffffffu, dt_off_r, gi);
             const int64_t g0 = __shfl_sync(0xffffffffu, gt_off_r, gi);
-            const int D = (int)(__shfl_sync(0xffffffffu, dt_off_r, gi + 1) - d0);
             const int G = (int)(__shfl_sync(0xffffffffu, gt_off_r, gi + 1) - g0);
+            if (G == 0) continue;           // route A (or an empty group)
+            const int64_t d0 = __shfl_sync(0xffffffffu, dt_off_r, gi);
+            const int D = (int)(__shfl_sync(0xffffffffu, dt_off_r, gi + 1) - d0);
             const int cat = __shfl_sync(0xffffffffu, cat_r, gi);
-            if (D == 0 && G == 0) continue;
-            if (G == 0) {
-                // ---- route A
-                for (int d = lane; d < D; d += 32) {
-                    const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
-                    const double area = q.x * q.y;
-                    const uint8_t fl = a.dt_flag[d0 + d];
-                    uint32_t* o = a.dt_tpfp + (d0 + d) * n_cfg;
-                    for (int c = 0; c < n_cfg; ++c)
-                        o[c] = ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, fl) ? 0u : (thr_all << 16);
-                }
-                if (a.dt_match_gt)
-                    for (int e = lane; e < n_cfg * n_thr * D; e += 32) {
-                        const int ct = e / D, d = e - ct * D;
-                        a.dt_match_gt[(int64_t)ct * a.n_dt + d0 + d] = -1;
-                    }
-                continue;
-            }
             if (G > FE_MAX_GT || D > FE_MAX_DT || D * G > FE_MAX_PAIRS) continue;   // big_list route
             __syncwarp();
             // ---- GT side: boxes to shared memory, ignore masks per cfg, non-ignored counts.
@@ -264,12 +325,13 @@ k_frame_eval(FrameArgs a) {
                 sm.gtb[warp][lane][2] = gq.x; sm.gtb[warp][lane][3] = gq.y;
             }
             const uint32_t gsent = __ballot_sync(0xffffffffu, (gfl & 4) != 0);   // id == "unmatched" value
+            const uint32_t gmask = (lane < G) ? fe_gt_ignore_mask(rules, vis, gfl, cfg_all) : 0u;
             uint32_t my_gig = 0;
             for (int c = 0; c < n_cfg; ++c) {
-                const bool ig = (lane < G) && ta_gt_ignored(cfg_s[c], vis, 0.0, 0, gfl);
-                const uint32_t m = __ballot_sync(0xffffffffu, ig);
+                const uint32_t m = __ballot_sync(0xffffffffu, (gmask >> c) & 1u);
                 if (lane == c) my_gig = m;
-                if (a.gt_ignore_out && lane < G) a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + lane] = ig;
+                if (a.gt_ignore_out && lane < G)
+                    a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + lane] = (gmask >> c) & 1u;
             }
             if (cat != acc_cat) {
                 if (acc > 0) atomicAdd(&a.num_gt[(int64_t)acc_cat * n_cfg + lane], acc);
@@ -292,11 +354,8 @@ k_frame_eval(FrameArgs a) {
                     dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
                     dfl = a.dt_flag[d0 + d];
                 }
-                const double area = dq.x * dq.y;
-                uint32_t m = (dfl & 2) ? (1u << 16) : 0u;
-                for (int c = 0; c < n_cfg; ++c)
-                    if (ta_dt_unmatched_ignored(cfg_s[c], area, 0.0, dfl)) m |= 1u << c;
-                dmask_s[d] = m;
+                dmask_s[d] = fe_dt_unmatched_mask(rules, dq.x * dq.y, dfl, cfg_all) |
+                             ((dfl & 2) ? (1u << 16) : 0u);
                 int cnt = 0, gs = 0;
                 double vs = 0.0;
                 for (int g = 0; g < G; ++g) {
