@@ -338,7 +338,12 @@ def main():
                     rep[f.name] = raw.numpy().view(v.dtype)
                 else:
                     rep[f.name] = torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
-        return dataclasses.replace(plan, **rep)
+        out = dataclasses.replace(plan, **rep)
+        from tao_amodal_b200.engine import lossless_f32_boxes
+        f32 = lossless_f32_boxes(out)
+        if f32 is not None:      # the transport copies must be pinned too
+            out._f32_boxes = tuple(torch.from_numpy(x).pin_memory().numpy() for x in f32)
+        return out
 
     e2e_steps = max(3, min(args.steps, 10))
     p_tao, p_lvis = pin(tao_plan), pin(lvis_plan)

@@ -170,12 +170,18 @@ int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* ca
  * back, and returns when they are valid.  This is the call the reference-side
  * TaoEval.run()/LVISEval.run() replacement makes (evaluate + accumulate, eval.py:662-665).
  * Track path when the *_trk_off pointers are non-NULL, frame path (fused) otherwise.   */
+#define TA_PLAN_BOX_F32 1
 typedef struct ta_plan_host {
     int64_t n_groups, n_dt, n_gt, n_dt_boxes, n_gt_boxes, n_big;
-    int32_t n_cat, n_cfg, n_thr, n_rec, n_slots_max, g_max, iou_mode, reserved;
+    int32_t n_cat, n_cfg, n_thr, n_rec, n_slots_max, g_max, iou_mode;
+    int32_t flags;                            /* TA_PLAN_BOX_F32: dt_box / gt_box point to float
+                                                 [N,4] arrays that hold the fp64 coordinates
+                                                 exactly (lossless transport: half the PCIe
+                                                 bytes); they are widened to fp64 on the device
+                                                 before any arithmetic */
     const int64_t *grp_dt_off, *grp_gt_off, *iou_off, *cat_dt_off;
     const int32_t *grp_cat, *acc_perm, *big_list;
-    const double  *dt_box, *gt_box;
+    const void    *dt_box, *gt_box;           /* double[N,4], or float[N,4] with TA_PLAN_BOX_F32 */
     const int64_t *dt_trk_off, *gt_trk_off;   /* NULL on the frame path */
     const int32_t *dt_slot, *gt_slot;         /* NULL on the frame path */
     const double  *dt_attr_a, *dt_attr_b, *gt_attr_a, *gt_attr_b;

@@ -47,7 +47,7 @@ class PlanHost(C.Structure):
         [(n, C.c_int64) for n in ("n_groups", "n_dt", "n_gt", "n_dt_boxes", "n_gt_boxes",
                                   "n_big")]
         + [(n, C.c_int32) for n in ("n_cat", "n_cfg", "n_thr", "n_rec", "n_slots_max", "g_max",
-                                    "iou_mode", "reserved")]
+                                    "iou_mode", "flags")]
         + [(n, C.c_void_p) for n in (
             "grp_dt_off", "grp_gt_off", "iou_off", "cat_dt_off", "grp_cat", "acc_perm", "big_list",
             "dt_box", "gt_box", "dt_trk_off", "gt_trk_off", "dt_slot", "gt_slot",

@@ -3,6 +3,16 @@
 // the pool's release threshold so repeated calls reuse the same pages).
 #include "ta_internal.h"
 
+// lossless fp32 -> fp64 widening of box coordinates shipped as float (TA_PLAN_BOX_F32)
+__global__ void k_widen_boxes(const float4* __restrict__ src, double* __restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = src[i];
+    double2* o = reinterpret_cast<double2*>(dst + 4 * i);
+    o[0] = make_double2((double)v.x, (double)v.y);
+    o[1] = make_double2((double)v.z, (double)v.w);
+}
+
 namespace {
 struct DevArena {
     cudaStream_t st;
@@ -59,8 +69,29 @@ extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
         TA_CUDA(ar.upload(&cat_dt_off, pl->cat_dt_off, (size_t)pl->n_cat + 1));
         TA_CUDA(ar.upload(&grp_cat, pl->grp_cat, G));
         TA_CUDA(ar.upload(&acc_perm, pl->acc_perm, pl->n_dt));
-        TA_CUDA(ar.upload(&dt_box, pl->dt_box, (size_t)pl->n_dt_boxes * 4));
-        TA_CUDA(ar.upload(&gt_box, pl->gt_box, (size_t)pl->n_gt_boxes * 4));
+        if (pl->flags & TA_PLAN_BOX_F32) {
+            const float *s_dt, *s_gt;
+            void *w_dt, *w_gt;
+            TA_CUDA(ar.upload(&s_dt, (const float*)pl->dt_box, (size_t)pl->n_dt_boxes * 4));
+            TA_CUDA(ar.upload(&s_gt, (const float*)pl->gt_box, (size_t)pl->n_gt_boxes * 4));
+            TA_CUDA(ar.alloc(&w_dt, (size_t)pl->n_dt_boxes * 32));
+            TA_CUDA(ar.alloc(&w_gt, (size_t)pl->n_gt_boxes * 32));
+            if (pl->n_dt_boxes) {
+                k_widen_boxes<<<(unsigned)((pl->n_dt_boxes + 255) / 256), 256, 0, st>>>(
+                    (const float4*)s_dt, (double*)w_dt, pl->n_dt_boxes);
+                if ((rc = ta_check_launch(ctx, "k_widen_boxes"))) return rc;
+            }
+            if (pl->n_gt_boxes) {
+                k_widen_boxes<<<(unsigned)((pl->n_gt_boxes + 255) / 256), 256, 0, st>>>(
+                    (const float4*)s_gt, (double*)w_gt, pl->n_gt_boxes);
+                if ((rc = ta_check_launch(ctx, "k_widen_boxes"))) return rc;
+            }
+            dt_box = (const double*)w_dt;
+            gt_box = (const double*)w_gt;
+        } else {
+            TA_CUDA(ar.upload(&dt_box, (const double*)pl->dt_box, (size_t)pl->n_dt_boxes * 4));
+            TA_CUDA(ar.upload(&gt_box, (const double*)pl->gt_box, (size_t)pl->n_gt_boxes * 4));
+        }
         TA_CUDA(ar.upload(&gt_a, pl->gt_attr_a, pl->n_gt));
         TA_CUDA(ar.upload(&dt_flag, pl->dt_flag, pl->n_dt));
         TA_CUDA(ar.upload(&gt_flag, pl->gt_flag, pl->n_gt));

@@ -70,6 +70,21 @@ def frame_big_groups(plan: EvalPlan, max_gt: int, max_dt: int, max_pairs: int) -
     return np.nonzero((G > 0) & ((G > max_gt) | (D > max_dt) | (D * G > max_pairs)))[0].astype(np.int32)
 
 
+def lossless_f32_boxes(plan: EvalPlan):
+    """(dt_box, gt_box) as float32 when every coordinate survives the round trip through
+    float32 exactly (true for detector outputs that were float32 to begin with), else None.
+    Cached on the plan; ta_eval_plan_host then ships half the box bytes over PCIe and widens
+    them back to the identical fp64 values on the device."""
+    got = getattr(plan, "_f32_boxes", 0)
+    if got == 0:
+        d32, g32 = plan.dt_box.astype(np.float32), plan.gt_box.astype(np.float32)
+        ok = (np.array_equal(d32.astype(np.float64), plan.dt_box)
+              and np.array_equal(g32.astype(np.float64), plan.gt_box))
+        got = (np.ascontiguousarray(d32), np.ascontiguousarray(g32)) if ok else None
+        plan._f32_boxes = got
+    return got
+
+
 def _ptr(a: Optional[np.ndarray]):
     if a is None:
         return None
@@ -121,7 +136,7 @@ class Engine:
     # ------------------------------------------------------------------ host-buffer call
     def evaluate_host(self, plan: EvalPlan, iou_mode: str = "3d_iou",
                       iou_thrs: np.ndarray = IOU_THRS, rec_thrs: np.ndarray = REC_THRS,
-                      out: Optional[EvalOutput] = None) -> EvalOutput:
+                      out: Optional[EvalOutput] = None, compress_boxes: bool = True) -> EvalOutput:
         n_thr, n_rec, n_cfg, n_cat = len(iou_thrs), len(rec_thrs), plan.n_cfg, len(plan.cat_ids)
         g_max, n_slots = plan_limits(plan)
         iou_thrs = np.ascontiguousarray(iou_thrs, dtype=np.float64)
@@ -135,11 +150,14 @@ class Engine:
         ph.iou_mode = _lib.IOU_MODES[iou_mode]
         big = None if track else self.big_list(plan)
         ph.n_big = 0 if big is None else int(big.size)
+        f32 = lossless_f32_boxes(plan) if compress_boxes else None
+        ph.flags = 1 if f32 is not None else 0
+        dt_box, gt_box = f32 if f32 is not None else (plan.dt_box, plan.gt_box)
         keep = dict(
             grp_dt_off=plan.grp_dt_off, grp_gt_off=plan.grp_gt_off, iou_off=plan.iou_off,
             cat_dt_off=plan.cat_dt_off, grp_cat=plan.grp_cat, acc_perm=plan.acc_perm,
             big_list=big if (big is not None and big.size) else None,
-            dt_box=plan.dt_box, gt_box=plan.gt_box,
+            dt_box=dt_box, gt_box=gt_box,
             dt_trk_off=plan.dt_trk_box_off if track else None,
             gt_trk_off=plan.gt_trk_box_off if track else None,
             dt_slot=plan.dt_box_slot if track else None,

@@ -126,3 +126,23 @@ def test_cfg2_sized_synthetic_matches_oracle(eng):
     assert np.array_equal(ref_l["tp_cnt"], o_l.tp_cnt)
     assert np.array_equal(ref_l["fp_cnt"], o_l.fp_cnt)
     assert np.array_equal(ref_l["num_gt"], o_l.num_gt)
+
+
+def test_lossless_f32_box_transport(eng):
+    """Boxes that are exactly representable in float32 travel as float32 and are widened on the
+    device: results identical to the fp64 transport; off-grid boxes fall back to fp64."""
+    from conftest import load_golden
+    from tao_amodal_b200.engine import lossless_f32_boxes
+    g = load_golden("small")
+    tao_plan, lvis_plan = plans_from_json(*golden_inputs(g))
+    for plan in (tao_plan, lvis_plan):
+        assert lossless_f32_boxes(plan) is not None
+        a = eng.evaluate_host(plan, compress_boxes=True)
+        b = eng.evaluate_host(plan, compress_boxes=False)
+        assert a.h2d_bytes < b.h2d_bytes
+        assert np.array_equal(a.precision, b.precision) and np.array_equal(a.tp_cnt, b.tp_cnt)
+    g = load_golden("small_float")
+    tao_plan, _ = plans_from_json(*golden_inputs(g))
+    assert lossless_f32_boxes(tao_plan) is None
+    o = eng.evaluate_host(tao_plan)
+    assert np.array_equal(g["tao_precision"], o.precision.reshape(g["tao_precision"].shape))
