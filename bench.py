@@ -359,8 +359,7 @@ def main():
         outs = [pinned_out(tao_plan), pinned_out(lvis_plan)]
 
         def e2e_step():
-            eng.evaluate_host(p_tao, out=outs[0])
-            eng.evaluate_host(p_lvis, out=outs[1])
+            eng.evaluate_host_many([p_tao, p_lvis], outs=outs)
             return (outs[0].h2d_bytes + outs[1].h2d_bytes, outs[0].d2h_bytes + outs[1].d2h_bytes)
     else:
         def e2e_step():
@@ -445,7 +444,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "api": ("ta_eval_plan_host (pinned host plan -> precision/recall on host)" if world == 1
+                "api": ("Engine.evaluate_host_many -> ta_eval_plan_host per plan (pinned host plans -> precision/recall on host)" if world == 1
                         else "upload + stages + cross-rank exchange + merged tensors on rank 0's host")},
         "gpu_launches": int(launches),
         "roofline": roofline,

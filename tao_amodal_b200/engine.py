@@ -53,6 +53,9 @@ class EvalOutput:
 def plan_limits(plan: EvalPlan):
     """(g_max, n_slots_max) of a plan: the largest GT count of a group and 1 + the largest
     frame slot (0 on the frame path)."""
+    cached = getattr(plan, "_limits", None)
+    if cached is not None:
+        return cached
     g_cnt = np.diff(plan.grp_gt_off)
     g_max = int(g_cnt.max()) if g_cnt.size else 0
     n_slots = 0
@@ -60,6 +63,7 @@ def plan_limits(plan: EvalPlan):
         for s in (plan.dt_box_slot, plan.gt_box_slot):
             if s is not None and s.size:
                 n_slots = max(n_slots, int(s.max()) + 1)
+    plan._limits = (g_max, n_slots)
     return g_max, n_slots
 
 
@@ -103,6 +107,7 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self.lib.ta_ctx_create(self.device, C.byref(h)))
         self._ctx = h
+        self._extra = []
         self.fe_max_gt = int(self.lib.ta_frame_eval_max_gt())
         self.fe_max_dt = int(self.lib.ta_frame_eval_max_dt())
         self.fe_max_pairs = int(self.lib.ta_frame_eval_max_pairs())
@@ -116,6 +121,9 @@ class Engine:
 
     def close(self):
         if getattr(self, "_ctx", None):
+            for h in getattr(self, "_extra", []):
+                self.lib.ta_ctx_destroy(h)
+            self._extra = []
             self.lib.ta_ctx_destroy(self._ctx)
             self._ctx = None
 
@@ -127,16 +135,47 @@ class Engine:
 
     @property
     def launches(self) -> int:
-        return int(self.lib.ta_ctx_launch_count(self._ctx))
+        return sum(int(self.lib.ta_ctx_launch_count(h)) for h in [self._ctx] + self._extra)
 
     @property
     def sm_count(self) -> int:
         return int(self.lib.ta_ctx_sm_count(self._ctx))
 
     # ------------------------------------------------------------------ host-buffer call
+    def evaluate_host_many(self, plans, outs=None, **kw):
+        """Several plans at once (the CLI's frame + track evaluations): one host thread and one
+        ta_ctx / stream per plan, so the H2D copy of one plan overlaps the kernels and the D2H
+        copy of another.  ctypes releases the GIL during the C calls."""
+        import threading
+        while len(self._extra) < len(plans) - 1:
+            h = C.c_void_p()
+            _lib.check(self.lib.ta_ctx_create(self.device, C.byref(h)))
+            self._extra.append(h)
+        ctxs = [self._ctx] + self._extra
+        outs = list(outs) if outs is not None else [None] * len(plans)
+        errs = [None] * len(plans)
+
+        def work(i):
+            try:
+                outs[i] = self.evaluate_host(plans[i], out=outs[i], _ctx=ctxs[i], **kw)
+            except BaseException as e:      # re-raised on the calling thread
+                errs[i] = e
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(1, len(plans))]
+        for t in th:
+            t.start()
+        work(0)
+        for t in th:
+            t.join()
+        for e in errs:
+            if e is not None:
+                raise e
+        return outs
+
     def evaluate_host(self, plan: EvalPlan, iou_mode: str = "3d_iou",
                       iou_thrs: np.ndarray = IOU_THRS, rec_thrs: np.ndarray = REC_THRS,
-                      out: Optional[EvalOutput] = None, compress_boxes: bool = True) -> EvalOutput:
+                      out: Optional[EvalOutput] = None, compress_boxes: bool = True,
+                      _ctx=None) -> EvalOutput:
         n_thr, n_rec, n_cfg, n_cat = len(iou_thrs), len(rec_thrs), plan.n_cfg, len(plan.cat_ids)
         g_max, n_slots = plan_limits(plan)
         iou_thrs = np.ascontiguousarray(iou_thrs, dtype=np.float64)
@@ -177,7 +216,7 @@ class Engine:
                 num_gt=np.empty((n_cat, n_cfg), dtype=np.int32))
         h2d, d2h = C.c_int64(0), C.c_int64(0)
         _lib.check(self.lib.ta_eval_plan_host(
-            self._ctx, C.byref(ph), _ptr(out.precision), _ptr(out.recall), _ptr(out.tp_cnt),
+            _ctx or self._ctx, C.byref(ph), _ptr(out.precision), _ptr(out.recall), _ptr(out.tp_cnt),
             _ptr(out.fp_cnt), _ptr(out.num_gt), C.byref(h2d), C.byref(d2h)))
         out.h2d_bytes, out.d2h_bytes = int(h2d.value), int(d2h.value)
         return out

@@ -146,3 +146,15 @@ def test_lossless_f32_box_transport(eng):
     assert lossless_f32_boxes(tao_plan) is None
     o = eng.evaluate_host(tao_plan)
     assert np.array_equal(g["tao_precision"], o.precision.reshape(g["tao_precision"].shape))
+
+
+def test_concurrent_host_calls(eng):
+    """Two plans evaluated concurrently (one ta_ctx / stream / host thread each)."""
+    from conftest import load_golden
+    g = load_golden("edge_mix")
+    tao_plan, lvis_plan = plans_from_json(*golden_inputs(g))
+    for _ in range(3):
+        o_t, o_l = eng.evaluate_host_many([tao_plan, lvis_plan])
+        assert np.array_equal(g["tao_precision"], o_t.precision.reshape(g["tao_precision"].shape))
+        assert np.array_equal(g["lvis_precision"], o_l.precision)
+        assert np.array_equal(g["lvis_tp_cnt"], o_l.tp_cnt)
