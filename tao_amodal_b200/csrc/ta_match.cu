@@ -374,8 +374,29 @@ k_frame_eval(FrameArgs a) {
             const bool general = __any_sync(0xffffffffu, multi);
             __syncwarp();
             if (!general) {
-                // ---- route B: lane g walks the detections whose only candidate is g
-                if (lane < G) {
+                // ---- route B
+                if (D <= 32) {
+                    // lane = detection.  Threshold k of GT g is taken before detection d iff an
+                    // earlier locking detection with the same single candidate g reaches k:
+                    // one ballot per threshold, intersected with "same GT" and "earlier lane"
+                    const uint32_t cd = (lane < D) ? cand_s[lane] : 0u;
+                    const bool single = ((cd >> 21) & 3u) == 1u;
+                    const uint32_t gs = (cd >> 16) & 31u, ge = cd & 0xffffu;
+                    const bool locks = single && ((lane < D ? dmask_s[lane] : 0u) & (1u << 16));
+                    uint32_t same = 0;
+                    for (int g = 0; g < G; ++g) {
+                        const uint32_t bg = __ballot_sync(0xffffffffu, single && gs == (uint32_t)g);
+                        if (gs == (uint32_t)g) same = bg;
+                    }
+                    const uint32_t earlier = same & ((1u << lane) - 1u);
+                    uint32_t taken = 0;
+                    for (int k = 0; k < n_thr; ++k) {
+                        const uint32_t bk = __ballot_sync(0xffffffffu, locks && ((ge >> k) & 1u));
+                        if (bk & earlier) taken |= 1u << k;
+                    }
+                    if (lane < D && single) cand_s[lane] = (cd & ~0xffffu) | (ge & ~taken);
+                } else if (lane < G) {
+                    // lane g walks the detections whose only candidate is g
                     uint32_t taken = 0;
                     for (int d = 0; d < D; ++d) {
                         const uint32_t cd = cand_s[d];

@@ -253,7 +253,7 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
     int kq = a.n_rec - 1;
     while (kq >= 0 && (uint32_t)max(tkc[kq], 1) > tc) --kq;
     uint32_t next_tk = kq >= 0 ? (uint32_t)max(tkc[kq], 1) : 0u;
-    uint32_t bt = 0, bn = 0;
+    uint32_t bt = 0, bn = 1;       // precision 0: the first true positive always beats it
     const uint32_t ch_rel = (uint32_t)(chunk - ch0);
     const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
     const int64_t cc = (int64_t)cat * a.n_cfg + cfg;
@@ -261,7 +261,9 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
         const uint32_t w = words[p * ncf + c];
         if ((w >> b) & 1u) {
             const uint32_t n = tc + fc;
-            if (pr_better(tc, n, bt, bn)) { bt = tc; bn = n; }
+            // strict ">" is enough here: a tie keeps the later detection's pair, and the only
+            // value-changing tie, (1,1) vs (k,k), has (1,1) as the candidate (first TP overall)
+            if ((unsigned long long)tc * bn > (unsigned long long)bt * n) { bt = tc; bn = n; }
             while (next_tk == tc) {
                 a.prec_bits[((int64_t)b * a.n_rec + kq) * per_t + cc] = pr_pack(bt, bn, ch_rel);
                 --kq;

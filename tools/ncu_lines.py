@@ -22,7 +22,7 @@ def main():
             hdr = r
             ie, ws = hdr.index("Instructions Executed"), hdr.index("# Samples")
         elif hdr and len(r) > ie and r[0].isdigit() and r[ie].isdigit():
-            data.append((int(r[ie]), int(r[ws] or 0), cur_file, r[0], r[1]))
+            data.append((int(r[ie]), int(r[ws]) if r[ws].isdigit() else 0, cur_file, r[0], r[1]))
     tot_i = sum(d[0] for d in data) or 1
     tot_s = sum(d[1] for d in data) or 1
     print("total warp instructions %d, samples %d" % (tot_i, tot_s))
