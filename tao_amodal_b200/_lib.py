@@ -13,7 +13,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libta_eval.so")
+# TA_EVAL_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("TA_EVAL_LIB") or os.path.join(_HERE, "csrc", "libta_eval.so")
 
 TA_OK = 0
 TA_ERR_INVALID = -1

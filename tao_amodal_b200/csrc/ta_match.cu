@@ -134,7 +134,7 @@ __global__ void k_match_greedy(MatchArgs a) {
 #define FE_WARPS 4
 #define FE_RUN 16             // consecutive groups per warp task
 #define FE_MAX_GT 32          // GT boxes of a group handled on chip (taken / ignore masks = 1 word)
-#define FE_MAX_DT 256         // detections of a group handled on chip (when it has GT)
+#define FE_MAX_DT 128         // detections of a group handled on chip (when it has GT)
 #define FE_MAX_PAIRS 512      // IoU tile doubles per warp
 #define FE_MAX_CFG 16
 
@@ -198,13 +198,18 @@ __device__ __forceinline__ uint32_t fe_gt_ignore_mask(const FrameRules& r, doubl
     return m;
 }
 
-__global__ void __launch_bounds__(FE_WARPS * 32, 7)
+// DETAIL = the optional per-cell outputs (IoU matrices, matched GT, GT ignore flags); the
+// evaluation path instantiates the lean variant
+// NT / NC > 0 fix the number of thresholds / range cfgs at compile time (the evaluators'
+// defaults, 10 x 6) so the per-cfg and per-threshold loops unroll.
+template <bool DETAIL, int NT, int NC>
+__global__ void __launch_bounds__(FE_WARPS * 32, 8)
 k_frame_eval(FrameArgs a) {
     __shared__ FrameSmem sm;
     __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
     __shared__ double thr_s[TA_MAX_THRS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_thr = a.n_thr, n_cfg = a.n_cfg;
+    const int n_thr = NT ? NT : a.n_thr, n_cfg = NC ? NC : a.n_cfg;
     for (int i = threadIdx.x; i < n_cfg; i += blockDim.x) cfg_s[i] = a.cfgs[i];
     if (threadIdx.x < n_thr) {
         const double th = a.thrs[threadIdx.x];
@@ -284,7 +289,7 @@ k_frame_eval(FrameArgs a) {
                     const uint32_t m = fe_dt_unmatched_mask(rules, q.x * q.y, a.dt_flag[dd], cfg_all);
                     uint32_t* o = a.dt_tpfp + dd * n_cfg;
                     for (int c = 0; c < n_cfg; ++c) o[c] = ((m >> c) & 1u) ? 0u : (thr_all << 16);
-                    if (a.dt_match_gt)
+                    if (DETAIL && a.dt_match_gt)
                         for (int ct = 0; ct < n_cfg * n_thr; ++ct)
                             a.dt_match_gt[(int64_t)ct * a.n_dt + dd] = -1;
                 }
@@ -330,7 +335,7 @@ k_frame_eval(FrameArgs a) {
             for (int c = 0; c < n_cfg; ++c) {
                 const uint32_t m = __ballot_sync(0xffffffffu, (gmask >> c) & 1u);
                 if (lane == c) my_gig = m;
-                if (a.gt_ignore_out && lane < G)
+                if (DETAIL && a.gt_ignore_out && lane < G)
                     a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + lane] = (gmask >> c) & 1u;
             }
             if (cat != acc_cat) {
@@ -346,7 +351,7 @@ k_frame_eval(FrameArgs a) {
             // ---- detection side, lane = detection: IoU row (maskApi.c:109-120) into the tile
             // (layout [g][d]: conflict-free stores, broadcast reads), unmatched-ignore mask, lock
             // bit and candidate summary straight from registers
-            double* iou_g = a.write_iou ? a.iou + a.iou_off[grp] : nullptr;
+            double* iou_g = (DETAIL && a.write_iou) ? a.iou + a.iou_off[grp] : nullptr;
             bool multi = false;
             for (int d = lane; d < D; d += 32) {
                 if (d >= 32) {
@@ -362,7 +367,7 @@ k_frame_eval(FrameArgs a) {
                     const double* gb = sm.gtb[warp][g];
                     const double v = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, gb[0], gb[1], gb[2], gb[3]);
                     iou_s[g * D + d] = v;
-                    if (iou_g) iou_g[d * G + g] = v;
+                    if (DETAIL && iou_g) iou_g[d * G + g] = v;
                     if (!(v < thr_min)) { ++cnt; gs = g; vs = v; }
                 }
                 uint32_t ge = 0;
@@ -421,7 +426,7 @@ k_frame_eval(FrameArgs a) {
                         const uint32_t fp = ((sent && !gi2 && !dc) ? M : 0u) | (dc ? 0u : (thr_all & ~M));
                         o[c] = tp | (fp << 16);
                     }
-                    if (a.dt_match_gt)
+                    if (DETAIL && a.dt_match_gt)
                         for (int c = 0; c < n_cfg; ++c)
                             for (int k = 0; k < n_thr; ++k)
                                 a.dt_match_gt[((int64_t)c * n_thr + k) * a.n_dt + d0 + d] =
@@ -469,7 +474,7 @@ k_frame_eval(FrameArgs a) {
                     if (active && t == 0)
                         a.dt_tpfp[(d0 + d) * n_cfg + cfg] =
                             ((bt >> sh) & thr_all) | (((bf >> sh) & thr_all) << 16);
-                    if (a.dt_match_gt && active)
+                    if (DETAIL && a.dt_match_gt && active)
                         a.dt_match_gt[((int64_t)cfg * n_thr + t) * a.n_dt + d0 + d] = m;
                 }
             }
@@ -563,7 +568,12 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     int64_t blocks = (n_tasks + FE_WARPS - 1) / FE_WARPS;
     const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs of 4 warps per SM
     if (blocks > cap) blocks = cap;
-    k_frame_eval<<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
+    if (write_iou || dt_match_gt || gt_ignore_out)
+        k_frame_eval<true, 0, 0><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
+    else if (n_thr == 10 && n_cfg == 6)
+        k_frame_eval<false, 10, 6><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
+    else
+        k_frame_eval<false, 0, 0><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
     int rc = ta_check_launch(ctx, "k_frame_eval");
     if (rc || n_big == 0) return rc;
     // oversize groups: generic kernels, IoU through `iou`; their detection areas go to scratch

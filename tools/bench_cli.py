@@ -1,0 +1,87 @@
+#!/usr/bin/env python
+"""Wall-clock of the drop-in CLI on the headline set (BASELINE.json: 1 M predictions / 100 k GT
+boxes, 5 000 videos, 1203 categories), JSON in -> metrics out, next to the CPU oracle port of
+the reference on the same files (single core).  The real reference cannot travel to the GPU
+box; the port visits only non-empty cells, so it is FASTER than the reference (SURVEY.md §3.4
+estimates ~73 min for the reference on this shape) and the ratio printed here is conservative.
+
+    python tools/bench_cli.py [--config cfg5] [--videos N] [--skip-cpu] [--out gpurun_out/cli.json]
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="cfg5")
+    ap.add_argument("--videos", type=int, default=0)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-videos", type=int, default=100,
+                    help="videos of the set given to the CPU port (scaled linearly to the full set)")
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    from tao_amodal_b200 import synth
+    from tao_amodal_b200.columnar import subset_videos
+    over = {"videos": args.videos} if args.videos else {}
+    gt, dt = synth.generate_named(args.config, **over)
+    td = tempfile.mkdtemp(prefix="ta_cli_")
+    ap_, rp, lp = (os.path.join(td, f) for f in ("gt.json", "dt.json", "eval.log"))
+    json.dump(gt.to_dict(), open(ap_, "w"))
+    json.dump(dt.to_list(), open(rp, "w"))
+    res = {"config": args.config, "videos": int(len(gt.vid_id)), "pred_boxes": int(dt.n()),
+           "gt_boxes": int(gt.n_anns()), "annotation_mb": os.path.getsize(ap_) / 1e6,
+           "prediction_mb": os.path.getsize(rp) / 1e6}
+
+    import eval_on_tao_amodal as cli
+    import torch
+    torch.cuda.init()
+    from tao_amodal_b200.evaluation._common import _JSON_CACHE, get_engine
+    get_engine(0)                                     # CUDA context creation is not the CLI's work
+    runs = []
+    for _ in range(2):
+        _JSON_CACHE.clear()
+        out = io.StringIO()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(out):
+            cli.main(["--track_result", rp, "--output_log", lp, "--annotation", ap_])
+        runs.append(time.perf_counter() - t0)
+    res["cli_wall_s"] = min(runs)
+    res["cli_runs_s"] = runs
+    res["log_tail"] = open(lp).read().strip().splitlines()[-1]
+
+    if not args.skip_cpu:
+        import copy
+        from oracle import lvis_frame, tao_track
+        vids = gt.vid_id[:args.cpu_videos]
+        g, d = subset_videos(gt, dt, vids)
+        gd, dl = g.to_dict(), d.to_list()
+        t0 = time.perf_counter()
+        lvis_frame.evaluate_lvis(copy.deepcopy(gd), copy.deepcopy(dl), keep_cells=False)
+        dl2 = copy.deepcopy(dl)
+        tao_track.uniquify_track_ids(dl2)
+        tao_track.evaluate_tao(gd, dl2, keep_cells=False)
+        t_cpu = time.perf_counter() - t0
+        scale = len(gt.vid_id) / float(len(vids))
+        res["cpu_port_subset_s"] = t_cpu
+        res["cpu_port_subset_videos"] = int(len(vids))
+        res["cpu_port_full_estimate_s"] = t_cpu * scale
+        res["speedup_vs_cpu_port"] = t_cpu * scale / res["cli_wall_s"]
+        res["cpu_cores"] = 1
+    res["reference_estimate_s"] = 73 * 60 if args.config == "cfg5" and not args.videos else None
+    print(json.dumps(res))
+    if args.out:
+        json.dump(res, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
