@@ -465,4 +465,22 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    # stdout carries exactly one JSON line: anything libraries print there (e.g. NCCL's version
+    # banner) is diverted to stderr while the benchmark runs
+    _real = os.dup(1)
+    os.dup2(2, 1)
+    _buf = []
+    _print = print
+
+    def print(*a, **k):          # noqa: A001 - bench-local capture of the JSON line
+        _buf.append(" ".join(str(x) for x in a))
+
+    try:
+        rc = main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_real, 1)
+        os.close(_real)
+    for line in _buf:
+        _print(line, flush=True)
+    sys.exit(rc)
