@@ -21,19 +21,21 @@ int ta_check_launch(ta_ctx* ctx, const char* what) {
     return TA_OK;
 }
 
-int ta_workspace(ta_ctx* ctx, cudaStream_t st, size_t bytes, void** out) {
-    if (bytes > ctx->ws_bytes) {
+int ta_workspace(ta_ctx* ctx, cudaStream_t st, size_t bytes, void** out, int slot) {
+    void*& buf = slot ? ctx->ws2 : ctx->ws;
+    size_t& have = slot ? ctx->ws2_bytes : ctx->ws_bytes;
+    if (bytes > have) {
         // rare (first call / a larger problem): plain cudaFree + cudaMalloc, which also order
         // themselves after any kernel still using the old buffer
         (void)st;
-        if (ctx->ws) TA_CUDA(cudaFree(ctx->ws));
-        ctx->ws = nullptr;
-        ctx->ws_bytes = 0;
+        if (buf) TA_CUDA(cudaFree(buf));
+        buf = nullptr;
+        have = 0;
         size_t want = bytes + bytes / 4 + 4096;
-        TA_CUDA(cudaMalloc(&ctx->ws, want));
-        ctx->ws_bytes = want;
+        TA_CUDA(cudaMalloc(&buf, want));
+        have = want;
     }
-    *out = ctx->ws;
+    *out = buf;
     return TA_OK;
 }
 
@@ -70,6 +72,7 @@ extern "C" int ta_ctx_destroy(ta_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->own_stream);
     if (c->ws) cudaFree(c->ws);
+    if (c->ws2) cudaFree(c->ws2);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     cudaFree(c->d_flags);
     cudaStreamDestroy(c->own_stream);

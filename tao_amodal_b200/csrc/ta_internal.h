@@ -19,6 +19,8 @@ struct ta_ctx {
     // stream-ordered scratch of ta_pr_accumulate, grown on demand
     void* ws;
     size_t ws_bytes;
+    void* ws2;             // second scratch slot (frame path: detection -> group map, lists)
+    size_t ws2_bytes;
     // pinned staging for ta_eval_plan_host results
     void* h_stage;
     size_t h_stage_bytes;
@@ -38,6 +40,6 @@ int ta_set_err(int code, const char* fmt, const char* a = "", long long b = 0);
 // cudaGetLastError() after a launch; counts the launch on success.
 int ta_check_launch(ta_ctx* ctx, const char* what);
 // Returns a device scratch buffer of at least `bytes` (stream-ordered; contents undefined).
-int ta_workspace(ta_ctx* ctx, cudaStream_t st, size_t bytes, void** out);
+int ta_workspace(ta_ctx* ctx, cudaStream_t st, size_t bytes, void** out, int slot = 0);
 
 #endif  // TA_INTERNAL_H

@@ -160,6 +160,11 @@ struct FrameArgs {
     int32_t* num_gt;
     int32_t* dt_match_gt;
     uint8_t* gt_ignore_out;
+    // flat path
+    const int32_t* dt_grp;        // group of every detection
+    int32_t* grp_flag;            // per group: already on the complex list
+    int32_t* complex_list;        // groups that need the general matcher (route C)
+    int32_t* complex_count;
 };
 
 // per-detection word: bits 0..15 "ignored when unmatched" per cfg, bit 16 locks its GT
@@ -198,29 +203,14 @@ __device__ __forceinline__ uint32_t fe_gt_ignore_mask(const FrameRules& r, doubl
     return m;
 }
 
-// DETAIL = the optional per-cell outputs (IoU matrices, matched GT, GT ignore flags); the
-// evaluation path instantiates the lean variant
-// NT / NC > 0 fix the number of thresholds / range cfgs at compile time (the evaluators'
-// defaults, 10 x 6) so the per-cfg and per-threshold loops unroll.
-template <bool DETAIL, int NT, int NC>
-__global__ void __launch_bounds__(FE_WARPS * 32, 8)
-k_frame_eval(FrameArgs a) {
-    __shared__ FrameSmem sm;
-    __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
-    __shared__ double thr_s[TA_MAX_THRS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_thr = NT ? NT : a.n_thr, n_cfg = NC ? NC : a.n_cfg;
+__device__ __forceinline__ void fe_setup(const FrameArgs& a, int n_thr, int n_cfg,
+                                         ta_range_cfg* cfg_s, double* thr_s, FrameRules& rules) {
     for (int i = threadIdx.x; i < n_cfg; i += blockDim.x) cfg_s[i] = a.cfgs[i];
     if (threadIdx.x < n_thr) {
         const double th = a.thrs[threadIdx.x];
-        thr_s[threadIdx.x] = (th < 1.0 - 1e-10) ? th : 1.0 - 1e-10;   // min([iou_thr, 1 - 1e-10])
+        thr_s[threadIdx.x] = (th < 1.0 - 1e-10) ? th : 1.0 - 1e-10;
     }
     __syncthreads();
-    // The range tests are evaluated once per DISTINCT interval, not once per cfg: rules[] holds
-    // the distinct [lo, hi] intervals of the detection-area test and of the GT attribute test
-    // with the bit mask of the cfgs using each (LVISEval: one detection interval, six GT ones).
-    // The frame path has b = 0 and hp = 0 for every entity, so those tests are per-cfg constants.
-    __shared__ FrameRules rules;
     if (threadIdx.x == 0) {
         rules.n_da = rules.n_ga = 0;
         rules.d_const = rules.g_const = rules.g_oof = 0;
@@ -241,6 +231,24 @@ k_frame_eval(FrameArgs a) {
         }
     }
     __syncthreads();
+}
+
+// DETAIL = the optional per-cell outputs (IoU matrices, matched GT, GT ignore flags); the
+// evaluation path instantiates the lean variant
+// NT / NC > 0 fix the number of thresholds / range cfgs at compile time (the evaluators'
+// defaults, 10 x 6) so the per-cfg and per-threshold loops unroll.
+// LIST: process the groups of a.complex_list one per task (the flat kernel's leftovers) and
+// leave num_gt alone (k_frame_num_gt has counted them already).
+template <bool DETAIL, int NT, int NC, bool LIST>
+__global__ void __launch_bounds__(FE_WARPS * 32, 8)
+k_frame_eval(FrameArgs a) {
+    __shared__ FrameSmem sm;
+    __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
+    __shared__ double thr_s[TA_MAX_THRS];
+    __shared__ FrameRules rules;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_thr = NT ? NT : a.n_thr, n_cfg = NC ? NC : a.n_cfg;
+    fe_setup(a, n_thr, n_cfg, cfg_s, thr_s, rules);
     const uint32_t cfg_all = (n_cfg == 32) ? 0xffffffffu : ((1u << n_cfg) - 1u);
     double thr_min = thr_s[0];
     for (int i = 1; i < n_thr; ++i) thr_min = (thr_s[i] < thr_min) ? thr_s[i] : thr_min;
@@ -254,12 +262,12 @@ k_frame_eval(FrameArgs a) {
     uint32_t* cand_s = sm.cand[warp];
     uint32_t* gig_s = sm.gig[warp];
 
-    const int64_t n_tasks = (a.n_groups + FE_RUN - 1) / FE_RUN;
+    const int64_t n_tasks = LIST ? (int64_t)*a.complex_count : (a.n_groups + FE_RUN - 1) / FE_RUN;
     const int64_t w0 = (int64_t)blockIdx.x * FE_WARPS + warp;
     const int64_t wstride = (int64_t)gridDim.x * FE_WARPS;
     for (int64_t task = w0; task < n_tasks; task += wstride) {
-        const int64_t grp0 = task * FE_RUN;
-        const int n_in_task = (int)((grp0 + FE_RUN < a.n_groups) ? FE_RUN : a.n_groups - grp0);
+        const int64_t grp0 = LIST ? (int64_t)a.complex_list[task] : task * FE_RUN;
+        const int n_in_task = LIST ? 1 : (int)((grp0 + FE_RUN < a.n_groups) ? FE_RUN : a.n_groups - grp0);
         // group table of the whole task in one coalesced load: lane i holds entry grp0 + i
         int64_t dt_off_r = 0, gt_off_r = 0;
         int cat_r = 0;
@@ -338,14 +346,14 @@ k_frame_eval(FrameArgs a) {
                 if (DETAIL && a.gt_ignore_out && lane < G)
                     a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + lane] = (gmask >> c) & 1u;
             }
-            if (cat != acc_cat) {
+            if (!LIST && cat != acc_cat) {
                 if (acc > 0) atomicAdd(&a.num_gt[(int64_t)acc_cat * n_cfg + lane], acc);
                 acc = 0;
                 acc_cat = cat;
             }
             if (lane < n_cfg) {
                 gig_s[lane] = my_gig;
-                acc += G - __popc(my_gig);
+                if (!LIST) acc += G - __popc(my_gig);
             }
             __syncwarp();
             // ---- detection side, lane = detection: IoU row (maskApi.c:109-120) into the tile
@@ -479,7 +487,215 @@ k_frame_eval(FrameArgs a) {
                 }
             }
         }
-        if (acc > 0) atomicAdd(&a.num_gt[(int64_t)acc_cat * n_cfg + lane], acc);
+        if (!LIST && acc > 0) atomicAdd(&a.num_gt[(int64_t)acc_cat * n_cfg + lane], acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// flat frame path: one LANE per detection
+//
+// A warp owns 32 consecutive detections of the (category, image)-sorted array, whatever groups
+// they belong to, so lanes stay busy however small the groups are.  Each lane computes the IoUs
+// of its detection with the GTs of its group straight from global memory (neighbouring lanes
+// share the GT boxes through L1) and summarises them as in route B of k_frame_eval: number of
+// GTs reaching the lowest threshold, the last such GT g*, the mask ge of thresholds it reaches.
+// For a detection with a single candidate the greedy loop of lvis eval.py:244-290 reduces to
+//     matched(d) = ge(d) & ~OR{ ge(d') : d' earlier in the group, same g*, d' locks }
+// "same group and same g*" is a __match_any_sync on (group, g*), "reaches threshold k and locks"
+// one ballot per threshold.  The detections of the window's first group that lie before the
+// window are replayed (candidates only) to seed the taken masks, so windows are independent.
+// Groups in which some detection has several candidates are appended to complex_list and
+// redone by k_frame_eval<LIST> (general matcher), which overwrites their rows.
+// ------------------------------------------------------------------------------------------
+struct FlatCand {
+    int cnt, gs;
+    uint32_t ge;
+};
+
+__device__ __forceinline__ FlatCand fe_candidate(const double* __restrict__ gt_box, int64_t g0, int G,
+                                                 double2 dp, double2 dq, double thr_min,
+                                                 const double* thr_s, int n_thr) {
+    FlatCand c{0, 0, 0u};
+    double vs = 0.0;
+    for (int g = 0; g < G; ++g) {
+        const double2 gp = *reinterpret_cast<const double2*>(gt_box + 4 * (g0 + g));
+        const double2 gq = *reinterpret_cast<const double2*>(gt_box + 4 * (g0 + g) + 2);
+        const double v = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, gp.x, gp.y, gq.x, gq.y);
+        if (!(v < thr_min)) { ++c.cnt; c.gs = g; vs = v; }
+    }
+    if (c.cnt == 1)
+        for (int k = 0; k < n_thr; ++k) c.ge |= (!(vs < thr_s[k])) ? (1u << k) : 0u;
+    return c;
+}
+
+#define FF_WARPS 8
+
+template <int NT, int NC>
+__global__ void __launch_bounds__(FF_WARPS * 32)
+k_frame_flat(FrameArgs a) {
+    __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
+    __shared__ double thr_s[TA_MAX_THRS];
+    __shared__ FrameRules rules;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_thr = NT ? NT : a.n_thr, n_cfg = NC ? NC : a.n_cfg;
+    fe_setup(a, n_thr, n_cfg, cfg_s, thr_s, rules);
+    const uint32_t cfg_all = (n_cfg == 32) ? 0xffffffffu : ((1u << n_cfg) - 1u);
+    double thr_min = thr_s[0];
+    for (int i = 1; i < n_thr; ++i) thr_min = (thr_s[i] < thr_min) ? thr_s[i] : thr_min;
+    const uint32_t thr_all = (1u << n_thr) - 1u;
+    const uint32_t lanes_lt = (1u << lane) - 1u;
+
+    const int64_t n_win = (a.n_dt + 31) / 32;
+    const int64_t w0 = (int64_t)blockIdx.x * FF_WARPS + warp;
+    const int64_t wstride = (int64_t)gridDim.x * FF_WARPS;
+    for (int64_t win = w0; win < n_win; win += wstride) {
+        const int64_t base = win * 32;
+        const int64_t d = base + lane;
+        const bool valid = d < a.n_dt;
+        int grp = -1, G = 0;
+        int64_t d0 = 0, g0 = 0;
+        double2 dp = make_double2(0, 0), dq = make_double2(0, 0);
+        uint8_t dfl = 0;
+        if (valid) {
+            grp = a.dt_grp[d];
+            dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * d);
+            dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * d + 2);
+            dfl = a.dt_flag[d];
+            d0 = a.grp_dt_off[grp];
+            g0 = a.grp_gt_off[grp];
+            G = (int)(a.grp_gt_off[grp + 1] - g0);
+        }
+        const bool skip = G > FE_MAX_GT;          // needs the big_list route (g* has 5 bits)
+        // ---- replay: detections of lane 0's group that precede the window seed its taken masks
+        const int grp_f = __shfl_sync(0xffffffffu, grp, 0);
+        const int G_f = __shfl_sync(0xffffffffu, G, 0);
+        const int64_t d0_f = __shfl_sync(0xffffffffu, d0, 0);
+        const int64_t g0_f = __shfl_sync(0xffffffffu, g0, 0);
+        uint32_t carry = 0;                        // lane g: thresholds of GT g taken before the window
+        if (G_f > 0 && G_f <= FE_MAX_GT && d0_f < base) {
+            for (int64_t rb = d0_f; rb < base; rb += 32) {
+                const int64_t rd = rb + lane;
+                uint32_t x = 0;
+                int rgs = -1;
+                if (rd < base) {
+                    const double2 rp = *reinterpret_cast<const double2*>(a.dt_box + 4 * rd);
+                    const double2 rq = *reinterpret_cast<const double2*>(a.dt_box + 4 * rd + 2);
+                    const FlatCand rc = fe_candidate(a.gt_box, g0_f, G_f, rp, rq, thr_min, thr_s, n_thr);
+                    if (rc.cnt == 1 && (a.dt_flag[rd] & 2)) { x = rc.ge; rgs = rc.gs; }
+                }
+                for (int g = 0; g < G_f; ++g) {
+                    const uint32_t m = __reduce_or_sync(0xffffffffu, rgs == g ? x : 0u);
+                    if (lane == g) carry |= m;
+                }
+            }
+        }
+        // ---- own candidate
+        FlatCand c{0, 0, 0u};
+        const bool work = valid && G > 0 && !skip;
+        if (work) {
+            c = fe_candidate(a.gt_box, g0, G, dp, dq, thr_min, thr_s, n_thr);
+            if (c.cnt > 1 && atomicExch(&a.grp_flag[grp], 1) == 0)
+                a.complex_list[atomicAdd(a.complex_count, 1)] = grp;
+        }
+        const bool single = work && c.cnt == 1;
+        const bool locks = single && (dfl & 2);
+        const uint32_t key = single ? (((uint32_t)grp << 5) | (uint32_t)c.gs) : (0x80000000u | lane);
+        // (group << 5 | g*) is exact while the group index stays below 2^26; beyond that two
+        // different groups could alias, so compare the group separately
+        uint32_t same = __match_any_sync(0xffffffffu, key);
+        if (a.n_groups >= (1 << 26)) same &= __match_any_sync(0xffffffffu, grp);
+        const uint32_t earlier = same & lanes_lt;
+        uint32_t taken = 0;
+        for (int k = 0; k < n_thr; ++k) {
+            const uint32_t bk = __ballot_sync(0xffffffffu, locks && ((c.ge >> k) & 1u));
+            if (bk & earlier) taken |= 1u << k;
+        }
+        const uint32_t cr = __shfl_sync(0xffffffffu, carry, c.gs & 31);
+        if (single && grp == grp_f) taken |= cr;
+        const uint32_t M = single ? (c.ge & ~taken) : 0u;
+        // ---- TP / FP words of every cfg
+        if (valid && !skip) {
+            const uint32_t dm = fe_dt_unmatched_mask(rules, dq.x * dq.y, dfl, cfg_all);
+            uint32_t gmask = 0;
+            bool sent = false;
+            if (M) {
+                const uint8_t gfl = a.gt_flag[g0 + c.gs];
+                gmask = fe_gt_ignore_mask(rules, a.gt_vis[g0 + c.gs], gfl, cfg_all);
+                sent = (gfl & 4) != 0;
+            }
+            uint32_t* o = a.dt_tpfp + d * n_cfg;
+            for (int cf = 0; cf < n_cfg; ++cf) {
+                const bool gi = (gmask >> cf) & 1u, dc = (dm >> cf) & 1u;
+                const uint32_t tp = (!sent && !gi) ? M : 0u;
+                const uint32_t fp = ((sent && !gi && !dc) ? M : 0u) | (dc ? 0u : (thr_all & ~M));
+                o[cf] = tp | (fp << 16);
+            }
+        }
+    }
+}
+
+// detection -> group map: one warp per 32 consecutive groups, coalesced writes
+__global__ void k_fill_dt_grp(int64_t n_groups, const int64_t* __restrict__ grp_dt_off,
+                              int32_t* __restrict__ dt_grp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t grp0 = wid * 32;
+    if (grp0 >= n_groups) return;
+    const int n_in = (int)((grp0 + 32 < n_groups) ? 32 : n_groups - grp0);
+    const int64_t off = grp_dt_off[grp0 + (lane < n_in ? lane : n_in)];
+    const int64_t d_begin = __shfl_sync(0xffffffffu, off, 0);
+    const int64_t d_end = grp_dt_off[grp0 + n_in];
+    for (int64_t base = d_begin; base < d_end; base += 32) {
+        const int64_t dd = base + lane;
+        int gi = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int cnd = gi + step;
+            const int64_t v = __shfl_sync(0xffffffffu, off, cnd & 31);
+            if (cnd < n_in && v <= dd) gi = cnd;
+        }
+        if (dd < d_end) dt_grp[dd] = (int32_t)(grp0 + gi);
+    }
+}
+
+// non-ignored GT count per (category, cfg) (lvis eval.py:363-365), one lane per group; lanes of a
+// warp that share the category are summed with REDUX before the atomic
+template <int NC>
+__global__ void k_frame_num_gt(FrameArgs a) {
+    __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
+    __shared__ double thr_s[TA_MAX_THRS];
+    __shared__ FrameRules rules;
+    const int n_cfg = NC ? NC : a.n_cfg;
+    fe_setup(a, a.n_thr, n_cfg, cfg_s, thr_s, rules);
+    const uint32_t cfg_all = (n_cfg == 32) ? 0xffffffffu : ((1u << n_cfg) - 1u);
+    const int lane = threadIdx.x & 31;
+    const int64_t grp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int cnt[FE_MAX_CFG];
+#pragma unroll
+    for (int c = 0; c < FE_MAX_CFG; ++c) cnt[c] = 0;
+    int cat = -1 - lane;
+    if (grp < a.n_groups) {
+        const int64_t g0 = a.grp_gt_off[grp], g1 = a.grp_gt_off[grp + 1];
+        const int64_t D = a.grp_dt_off[grp + 1] - a.grp_dt_off[grp];
+        const int64_t G = g1 - g0;
+        // oversize groups are counted by the generic matcher that evaluates them
+        if (G > 0 && !(G > FE_MAX_GT || D > FE_MAX_DT || D * G > FE_MAX_PAIRS)) {
+            cat = a.grp_cat[grp];
+            for (int64_t g = g0; g < g1; ++g) {
+                const uint32_t m = fe_gt_ignore_mask(rules, a.gt_vis[g], a.gt_flag[g], cfg_all);
+#pragma unroll
+                for (int c = 0; c < FE_MAX_CFG; ++c) cnt[c] += (c < n_cfg) && !((m >> c) & 1u);
+            }
+        }
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, cat);
+    const bool leader = (__ffs(peers) - 1) == lane;
+#pragma unroll
+    for (int c = 0; c < FE_MAX_CFG; ++c) {
+        if (c < n_cfg) {
+            const int tot = __reduce_add_sync(peers, cnt[c]);
+            if (leader && cat >= 0 && tot) atomicAdd(&a.num_gt[(int64_t)cat * n_cfg + c], tot);
+        }
     }
 }
 
@@ -563,18 +779,54 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     cudaStream_t st = (cudaStream_t)stream;
     FrameArgs a{n_groups, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box, n_thr, iou_thrs, n_cfg,
                 cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, iou, write_iou,
-                dt_tpfp, num_gt, dt_match_gt, gt_ignore_out};
-    const int64_t n_tasks = (n_groups + FE_RUN - 1) / FE_RUN;
-    int64_t blocks = (n_tasks + FE_WARPS - 1) / FE_WARPS;
-    const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs of 4 warps per SM
-    if (blocks > cap) blocks = cap;
-    if (write_iou || dt_match_gt || gt_ignore_out)
-        k_frame_eval<true, 0, 0><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
-    else if (n_thr == 10 && n_cfg == 6)
-        k_frame_eval<false, 10, 6><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
-    else
-        k_frame_eval<false, 0, 0><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
-    int rc = ta_check_launch(ctx, "k_frame_eval");
+                dt_tpfp, num_gt, dt_match_gt, gt_ignore_out, nullptr, nullptr, nullptr, nullptr};
+    const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs per SM
+    int rc;
+    if (write_iou || dt_match_gt || gt_ignore_out) {
+        // detail outputs: the warp-per-group kernel does everything
+        const int64_t n_tasks = (n_groups + FE_RUN - 1) / FE_RUN;
+        int64_t blocks = (n_tasks + FE_WARPS - 1) / FE_WARPS;
+        if (blocks > cap) blocks = cap;
+        k_frame_eval<true, 0, 0, false><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
+        rc = ta_check_launch(ctx, "k_frame_eval");
+    } else {
+        // evaluation path: lane-per-detection kernel, GT counts, then the general matcher on the
+        // (few) groups whose detections have several candidate GTs
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_grp = take((size_t)(n_dt > 0 ? n_dt : 1) * 4);
+        const size_t o_flag = take((size_t)n_groups * 4 + 4);      // flags + the list counter
+        const size_t o_list = take((size_t)n_groups * 4);
+        void* ws2 = nullptr;
+        if ((rc = ta_workspace(ctx, st, off, &ws2, 1))) return rc;
+        char* base = static_cast<char*>(ws2);
+        int32_t* dt_grp = reinterpret_cast<int32_t*>(base + o_grp);
+        a.dt_grp = dt_grp;
+        a.grp_flag = reinterpret_cast<int32_t*>(base + o_flag);
+        a.complex_count = a.grp_flag + n_groups;
+        a.complex_list = reinterpret_cast<int32_t*>(base + o_list);
+        TA_CUDA(cudaMemsetAsync(a.grp_flag, 0, (size_t)n_groups * 4 + 4, st));
+        const bool spec = (n_thr == 10 && n_cfg == 6);
+        if (n_dt > 0) {
+            const int64_t fill_warps = (n_groups + 31) / 32;
+            k_fill_dt_grp<<<(unsigned)((fill_warps + 7) / 8), 256, 0, st>>>(n_groups, grp_dt_off, dt_grp);
+            if ((rc = ta_check_launch(ctx, "k_fill_dt_grp"))) return rc;
+            int64_t blocks = ((n_dt + 31) / 32 + FF_WARPS - 1) / FF_WARPS;
+            if (blocks > cap) blocks = cap;
+            if (spec) k_frame_flat<10, 6><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
+            else k_frame_flat<0, 0><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
+            if ((rc = ta_check_launch(ctx, "k_frame_flat"))) return rc;
+        }
+        if (spec) k_frame_num_gt<6><<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a);
+        else k_frame_num_gt<0><<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a);
+        if ((rc = ta_check_launch(ctx, "k_frame_num_gt"))) return rc;
+        if (n_dt > 0) {
+            const int64_t blocks = ctx->sm_count * 2;       // list length is only known on the device
+            if (spec) k_frame_eval<false, 10, 6, true><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
+            else k_frame_eval<false, 0, 0, true><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
+        }
+        rc = ta_check_launch(ctx, "k_frame_eval");
+    }
     if (rc || n_big == 0) return rc;
     // oversize groups: generic kernels, IoU through `iou`; their detection areas go to scratch
     void* ws = nullptr;
