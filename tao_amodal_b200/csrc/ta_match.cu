@@ -528,10 +528,10 @@ __device__ __forceinline__ FlatCand fe_candidate(const double* __restrict__ gt_b
     return c;
 }
 
-#define FF_WARPS 8
+#define FF_WARPS 4
 
 template <int NT, int NC>
-__global__ void __launch_bounds__(FF_WARPS * 32)
+__global__ void __launch_bounds__(FF_WARPS * 32, 8)
 k_frame_flat(FrameArgs a) {
     __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
     __shared__ double thr_s[TA_MAX_THRS];
@@ -634,34 +634,14 @@ k_frame_flat(FrameArgs a) {
     }
 }
 
-// detection -> group map: one warp per 32 consecutive groups, coalesced writes
-__global__ void k_fill_dt_grp(int64_t n_groups, const int64_t* __restrict__ grp_dt_off,
-                              int32_t* __restrict__ dt_grp) {
-    const int lane = threadIdx.x & 31;
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t grp0 = wid * 32;
-    if (grp0 >= n_groups) return;
-    const int n_in = (int)((grp0 + 32 < n_groups) ? 32 : n_groups - grp0);
-    const int64_t off = grp_dt_off[grp0 + (lane < n_in ? lane : n_in)];
-    const int64_t d_begin = __shfl_sync(0xffffffffu, off, 0);
-    const int64_t d_end = grp_dt_off[grp0 + n_in];
-    for (int64_t base = d_begin; base < d_end; base += 32) {
-        const int64_t dd = base + lane;
-        int gi = 0;
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-            const int cnd = gi + step;
-            const int64_t v = __shfl_sync(0xffffffffu, off, cnd & 31);
-            if (cnd < n_in && v <= dd) gi = cnd;
-        }
-        if (dd < d_end) dt_grp[dd] = (int32_t)(grp0 + gi);
-    }
-}
-
-// non-ignored GT count per (category, cfg) (lvis eval.py:363-365), one lane per group; lanes of a
-// warp that share the category are summed with REDUX before the atomic
+// Per 32 consecutive groups (one warp): (1) detection -> group map, coalesced writes over the
+// groups' contiguous detections; (2) non-ignored GT count per (category, cfg)
+// (lvis eval.py:363-365) over the groups' contiguous GT boxes — lanes that share the category
+// are summed with REDUX before the atomic.  The group of a detection / GT index is found by a
+// 5-step search over the 33 offsets held one per lane.
 template <int NC>
-__global__ void k_frame_num_gt(FrameArgs a) {
+__global__ void __launch_bounds__(256)
+k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp) {
     __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
     __shared__ double thr_s[TA_MAX_THRS];
     __shared__ FrameRules rules;
@@ -669,31 +649,55 @@ __global__ void k_frame_num_gt(FrameArgs a) {
     fe_setup(a, a.n_thr, n_cfg, cfg_s, thr_s, rules);
     const uint32_t cfg_all = (n_cfg == 32) ? 0xffffffffu : ((1u << n_cfg) - 1u);
     const int lane = threadIdx.x & 31;
-    const int64_t grp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int cnt[FE_MAX_CFG];
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t grp0 = wid * 32;
+    if (grp0 >= a.n_groups) return;
+    const int n_in = (int)((grp0 + 32 < a.n_groups) ? 32 : a.n_groups - grp0);
+    const int li = lane < n_in ? lane : n_in;
+    const int64_t doff = a.grp_dt_off[grp0 + li], goff = a.grp_gt_off[grp0 + li];
+    const int64_t d_end = a.grp_dt_off[grp0 + n_in], g_end = a.grp_gt_off[grp0 + n_in];
+    const int cat_l = a.grp_cat[grp0 + (lane < n_in ? lane : n_in - 1)];
+    // oversize groups are evaluated AND counted by the generic matcher (big_list route)
+    const int64_t dn = __shfl_down_sync(0xffffffffu, doff, 1), gn = __shfl_down_sync(0xffffffffu, goff, 1);
+    const int64_t D_l = (lane + 1 < n_in ? dn : d_end) - doff, G_l = (lane + 1 < n_in ? gn : g_end) - goff;
+    const bool big_l = lane < n_in && (G_l > FE_MAX_GT || D_l > FE_MAX_DT || D_l * G_l > FE_MAX_PAIRS);
+    const uint32_t big_mask = __ballot_sync(0xffffffffu, big_l);
+    // ---- (1)
+    if (dt_grp) {
+        const int64_t d_begin = __shfl_sync(0xffffffffu, doff, 0);
+        for (int64_t base = d_begin; base < d_end; base += 32) {
+            const int64_t dd = base + lane;
+            int gi = 0;
 #pragma unroll
-    for (int c = 0; c < FE_MAX_CFG; ++c) cnt[c] = 0;
-    int cat = -1 - lane;
-    if (grp < a.n_groups) {
-        const int64_t g0 = a.grp_gt_off[grp], g1 = a.grp_gt_off[grp + 1];
-        const int64_t D = a.grp_dt_off[grp + 1] - a.grp_dt_off[grp];
-        const int64_t G = g1 - g0;
-        // oversize groups are counted by the generic matcher that evaluates them
-        if (G > 0 && !(G > FE_MAX_GT || D > FE_MAX_DT || D * G > FE_MAX_PAIRS)) {
-            cat = a.grp_cat[grp];
-            for (int64_t g = g0; g < g1; ++g) {
-                const uint32_t m = fe_gt_ignore_mask(rules, a.gt_vis[g], a.gt_flag[g], cfg_all);
-#pragma unroll
-                for (int c = 0; c < FE_MAX_CFG; ++c) cnt[c] += (c < n_cfg) && !((m >> c) & 1u);
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int cnd = gi + step;
+                const int64_t v = __shfl_sync(0xffffffffu, doff, cnd & 31);
+                if (cnd < n_in && v <= dd) gi = cnd;
             }
+            if (dd < d_end) dt_grp[dd] = (int32_t)(grp0 + gi);
         }
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, cat);
-    const bool leader = (__ffs(peers) - 1) == lane;
+    // ---- (2)
+    const int64_t g_begin = __shfl_sync(0xffffffffu, goff, 0);
+    for (int64_t base = g_begin; base < g_end; base += 32) {
+        const int64_t gg = base + lane;
+        int gi = 0;
 #pragma unroll
-    for (int c = 0; c < FE_MAX_CFG; ++c) {
-        if (c < n_cfg) {
-            const int tot = __reduce_add_sync(peers, cnt[c]);
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int cnd = gi + step;
+            const int64_t v = __shfl_sync(0xffffffffu, goff, cnd & 31);
+            if (cnd < n_in && v <= gg) gi = cnd;
+        }
+        int cat = __shfl_sync(0xffffffffu, cat_l, gi);
+        uint32_t m = cfg_all;                                  // "ignored everywhere" = counts nothing
+        if (gg < g_end && !((big_mask >> gi) & 1u))
+            m = fe_gt_ignore_mask(rules, a.gt_vis[gg], a.gt_flag[gg], cfg_all);
+        else
+            cat = -1 - lane;
+        const uint32_t peers = __match_any_sync(0xffffffffu, cat);
+        const bool leader = (__ffs(peers) - 1) == lane;
+        for (int c = 0; c < n_cfg; ++c) {
+            const int tot = __reduce_add_sync(peers, (int)(!((m >> c) & 1u)));
             if (leader && cat >= 0 && tot) atomicAdd(&a.num_gt[(int64_t)cat * n_cfg + c], tot);
         }
     }
@@ -807,19 +811,21 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
         a.complex_list = reinterpret_cast<int32_t*>(base + o_list);
         TA_CUDA(cudaMemsetAsync(a.grp_flag, 0, (size_t)n_groups * 4 + 4, st));
         const bool spec = (n_thr == 10 && n_cfg == 6);
+        {
+            const int64_t prep_warps = (n_groups + 31) / 32;
+            const unsigned pb = (unsigned)((prep_warps + 7) / 8);
+            if (spec) k_frame_prep<6><<<pb, 256, 0, st>>>(a, n_dt > 0 ? dt_grp : nullptr);
+            else k_frame_prep<0><<<pb, 256, 0, st>>>(a, n_dt > 0 ? dt_grp : nullptr);
+            if ((rc = ta_check_launch(ctx, "k_frame_prep"))) return rc;
+        }
         if (n_dt > 0) {
-            const int64_t fill_warps = (n_groups + 31) / 32;
-            k_fill_dt_grp<<<(unsigned)((fill_warps + 7) / 8), 256, 0, st>>>(n_groups, grp_dt_off, dt_grp);
-            if ((rc = ta_check_launch(ctx, "k_fill_dt_grp"))) return rc;
             int64_t blocks = ((n_dt + 31) / 32 + FF_WARPS - 1) / FF_WARPS;
-            if (blocks > cap) blocks = cap;
+            const int64_t fcap = (int64_t)ctx->sm_count * 16;
+            if (blocks > fcap) blocks = fcap;
             if (spec) k_frame_flat<10, 6><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
             else k_frame_flat<0, 0><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
             if ((rc = ta_check_launch(ctx, "k_frame_flat"))) return rc;
         }
-        if (spec) k_frame_num_gt<6><<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a);
-        else k_frame_num_gt<0><<<(unsigned)((n_groups + 255) / 256), 256, 0, st>>>(a);
-        if ((rc = ta_check_launch(ctx, "k_frame_num_gt"))) return rc;
         if (n_dt > 0) {
             const int64_t blocks = ctx->sm_count * 2;       // list length is only known on the device
             if (spec) k_frame_eval<false, 10, 6, true><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);

@@ -256,21 +256,25 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
     uint32_t bt = 0, bn = 1;       // precision 0: the first true positive always beats it
     const uint32_t ch_rel = (uint32_t)(chunk - ch0);
     const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
-    const int64_t cc = (int64_t)cat * a.n_cfg + cfg;
-    for (int p = n_pos - 1; p >= 0; --p) {
-        const uint32_t w = words[p * ncf + c];
-        if ((w >> b) & 1u) {
+    // answers of this cell: prec_bits[(b * n_rec + k) * per_t + cat * n_cfg + cfg]
+    unsigned long long* qp = a.prec_bits + ((int64_t)b * a.n_rec + kq) * per_t + (int64_t)cat * a.n_cfg + cfg;
+    const uint32_t tp_bit = 1u << b, fp_bit = 1u << (16 + b);
+    const uint32_t* wp = words + (n_pos - 1) * ncf + c;
+    for (int p = n_pos; p > 0; --p, wp -= ncf) {
+        const uint32_t w = *wp;
+        if (w & tp_bit) {
             const uint32_t n = tc + fc;
             // strict ">" is enough here: a tie keeps the later detection's pair, and the only
             // value-changing tie, (1,1) vs (k,k), has (1,1) as the candidate (first TP overall)
             if ((unsigned long long)tc * bn > (unsigned long long)bt * n) { bt = tc; bn = n; }
             while (next_tk == tc) {
-                a.prec_bits[((int64_t)b * a.n_rec + kq) * per_t + cc] = pr_pack(bt, bn, ch_rel);
+                *qp = pr_pack(bt, bn, ch_rel);
+                qp -= per_t;
                 --kq;
                 next_tk = kq >= 0 ? (uint32_t)max(tkc[kq], 1) : 0u;
             }
             --tc;
-        } else if ((w >> (16 + b)) & 1u) {
+        } else if (w & fp_bit) {
             --fc;
         }
     }
@@ -285,7 +289,20 @@ __global__ void k_pr_suffix(PrArgs a) {
     for (int j = threadIdx.x; j < n_cell; j += blockDim.x) {
         if (a.num_gt[(int64_t)cat * a.n_cfg + j / a.n_thr] == 0) continue;
         uint32_t bt = 0, bn = 0, dummy;
-        for (int ch = ch1 - 1; ch >= ch0; --ch) {
+        int ch = ch1 - 1;
+        for (; ch - 7 >= ch0; ch -= 8) {              // 8 independent loads in flight
+            unsigned long long v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = a.chunk_best[(int64_t)(ch - u) * n_cell + j];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                uint32_t ct, cn;
+                pr_unpack(v[u], ct, cn, dummy);
+                a.chunk_best[(int64_t)(ch - u) * n_cell + j] = pr_pack(bt, bn, 0);
+                if (pr_better(ct, cn, bt, bn)) { bt = ct; bn = cn; }
+            }
+        }
+        for (; ch >= ch0; --ch) {
             unsigned long long* q = a.chunk_best + (int64_t)ch * n_cell + j;
             uint32_t ct, cn;
             pr_unpack(*q, ct, cn, dummy);
