@@ -61,13 +61,16 @@ def make_workload(name: str, rank: int, videos: int = 0):
     return gt, dt, tao_plan, lvis_plan
 
 
-def algorithmic_bytes(plan) -> dict:
-    """Per-launch algorithmic HBM bytes of each kernel."""
+def algorithmic_bytes(plan, cells_with_gt: int = 0) -> dict:
+    """Algorithmic HBM bytes of each kernel for one launch on this plan (DESIGN.md §4,
+    SURVEY §8d).  cells_with_gt = number of (category, cfg) cells with non-ignored GT (only
+    those produce precision values other than the -1 fill)."""
     nd_box, ng_box = plan.dt_box.shape[0], plan.gt_box.shape[0]
     n_iou = int(plan.iou_off[-1])
     n_cfg, n_dt, n_gt = plan.n_cfg, plan.n_dt, plan.n_gt
     per_box = 36 if plan.kind == "tao" else 32
     n_cat = len(plan.cat_ids)
+    T, R = 10, 101
     if plan.kind == "tao":
         # the IoU kernel only touches groups that have both detections and GT
         D, G = np.diff(plan.grp_dt_off), np.diff(plan.grp_gt_off)
@@ -75,15 +78,25 @@ def algorithmic_bytes(plan) -> dict:
         db, gb = plan.dt_trk_box_off[plan.grp_dt_off], plan.gt_trk_box_off[plan.grp_gt_off]
         nd_box = int((db[1:] - db[:-1])[act].sum())
         ng_box = int((gb[1:] - gb[:-1])[act].sum())
+    n_chunks = int(np.ceil(np.diff(plan.cat_dt_off) / 256.0).sum())
     return {
         "iou": per_box * (nd_box + ng_box) + 8 * n_iou,
         # IoU matrix + dt (area, n_anns, flag) + gt (attr a, b, hp, flag) read, TP/FP words written
         "match": 8 * n_iou + 17 * n_dt + 21 * n_gt + 4 * n_cfg * n_dt,
-        # fused frame kernel: boxes + flags + visibility + group table read, TP/FP words written
-        "frame_eval": 32 * (nd_box + ng_box) + n_dt + 9 * n_gt + 20 * plan.n_groups
+        # lane-per-detection frame kernel: boxes, flags, detection->group map, group offsets of
+        # the groups with detections, GT visibility; TP/FP words written
+        "frame_flat": 32 * (nd_box + ng_box) + 5 * n_dt + 9 * n_gt + 16 * plan.n_groups
                       + 4 * n_cfg * n_dt,
-        # permutation + TP/FP words read twice (count, bucket), precision tensor written
-        "accumulate": 2 * n_dt * (4 + 4 * n_cfg) + 8 * 10 * 101 * n_cat * n_cfg,
+        # group table + GT visibility/flags read, detection->group map written
+        "frame_prep": 20 * plan.n_groups + 9 * n_gt + 4 * n_dt,
+        # permutation + TP/FP words read, chunk counters written
+        "pr_count": n_dt * (4 + 4 * n_cfg) + 128 * n_cfg * n_chunks,
+        # permutation + TP/FP words + chunk counters read; chunk bests and the answered recall
+        # levels of the cells that have GT written
+        "pr_envelope": n_dt * (4 + 4 * n_cfg) + (128 + 8 * T) * n_cfg * n_chunks
+                       + 8 * T * R * cells_with_gt,
+        # precision tensor written once, answered entries read once
+        "pr_finalize": 8 * T * R * n_cat * n_cfg + 8 * T * R * cells_with_gt,
     }
 
 
@@ -280,6 +293,7 @@ def main():
         from tao_amodal_b200 import parallel
         exch = {id(d): parallel.DeviceDistAccumulator(eng, d, rank, world) for d in (d_tao, d_lvis)}
 
+    cells_with_gt = [int((eng.evaluate_device(dv).num_gt > 0).sum()) for dv in (d_tao, d_lvis)]
     stage_names = ["tao_iou", "tao_match", "tao_acc", "lvis_eval", "lvis_acc"]
     ev = None
 
@@ -315,11 +329,14 @@ def main():
            for _ in stage_names] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = eng.launches
+    eng.timing(True)           # per-kernel CUDA events inside the library (ta_ctx_timing)
     e0.record()
     for s in range(args.steps):
         step(ev[s])
     e1.record()
     sync()
+    kernel_ms = eng.timing_read()
+    eng.timing(False)
     clocks = sampler.stop()
     launches = eng.launches - l0
     dev_ms = e0.elapsed_time(e1)
@@ -407,32 +424,44 @@ def main():
     value = pairs_total / (ms_per_step * 1e-3)
     e2e_value = pairs_total / (e2e_s / e2e_steps)
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel (largest share of the step by summed launch time)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    bytes_by_stage = {}
-    ab_t, ab_l = algorithmic_bytes(tao_plan), algorithmic_bytes(lvis_plan)
-    bytes_by_stage = {"tao_iou": ab_t["iou"], "tao_match": ab_t["match"],
-                      "tao_acc": ab_t["accumulate"], "lvis_eval": ab_l["frame_eval"],
-                      "lvis_acc": ab_l["accumulate"]}
-    dom = max(stage_ms, key=stage_ms.get)
-    kernel_names = {"tao_iou": "k_track_iou_tiled", "tao_match": "k_match_greedy",
-                    "lvis_eval": "k_frame_eval", "tao_acc": "k_pr_bucket",
-                    "lvis_acc": "k_pr_bucket"}
-    per_stage = {n: {"ms": stage_ms[n], "alg_bytes": bytes_by_stage[n],
-                     "gbs": bytes_by_stage[n] / (stage_ms[n] * 1e-3) / 1e9 if stage_ms[n] > 0 else None}
-                 for n in stage_names}
-    achieved = per_stage[dom]["gbs"]
+    ab_t, ab_l = algorithmic_bytes(tao_plan, cells_with_gt[0]), algorithmic_bytes(lvis_plan, cells_with_gt[1])
+    # algorithmic bytes of each kernel per STEP (summed over its launches in one step)
+    kernel_bytes = {
+        "k_track_iou_tiled": ab_t["iou"], "k_match_greedy": ab_t["match"],
+        "k_frame_flat": ab_l["frame_flat"], "k_frame_prep": ab_l["frame_prep"],
+        "k_pr_count": ab_t["pr_count"] + ab_l["pr_count"],
+        "k_pr_envelope": ab_t["pr_envelope"] + ab_l["pr_envelope"],
+        "k_pr_finalize": ab_t["pr_finalize"] + ab_l["pr_finalize"],
+    }
+    per_kernel = {}
+    for name, (ms_tot, n_launch) in kernel_ms.items():
+        ms_step = ms_tot / args.steps
+        b = kernel_bytes.get(name)
+        per_kernel[name] = {"ms_per_step": ms_step, "launches_per_step": n_launch / args.steps,
+                            "alg_bytes_per_step": b,
+                            "gbs": (b / (ms_step * 1e-3) / 1e9) if (b and ms_step > 0) else None}
+    ranked = [k for k in sorted(per_kernel, key=lambda k: -per_kernel[k]["ms_per_step"])
+              if per_kernel[k]["gbs"] is not None]
+    dom = ranked[0]
+    achieved = per_kernel[dom]["gbs"]
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get(kernel_names[dom])
-    roofline = {"bound": "hbm", "kernel": kernel_names[dom], "stage": dom, "achieved": achieved,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "stages": per_stage}
+        tr = json.load(open(tr_path)).get(dom)
+        traffic = float(sum(tr)) if isinstance(tr, list) else tr
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic,
+                "note": "achieved = algorithmic bytes of the kernel's launches in one step / their "
+                        "summed CUDA-event time (events recorded by the library after every launch)",
+                "kernels": per_kernel,
+                "stages_ms": stage_ms}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -196,6 +196,15 @@ int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* plan,
                       int64_t* tp_cnt, int64_t* fp_cnt, int32_t* num_gt,
                       int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* Optional per-kernel timing for benchmarks.  While enabled the context records a CUDA event
+ * after every kernel launch (and a marker at every API entry); ta_ctx_timing_read waits for
+ * them, aggregates the intervals by kernel name and resets the log.  names receives the
+ * distinct kernel names separated by '\n'; total_ms[i] / launches[i] belong to the i-th name.
+ * Returns the number of distinct names (<= cap) or a negative ta_status.                */
+int ta_ctx_timing(ta_ctx* ctx, int enable);
+int ta_ctx_timing_read(ta_ctx* ctx, char* names, int names_cap, double* total_ms, int* launches,
+                       int cap);
+
 /* Number of kernel launches issued through this context since creation. */
 int64_t ta_ctx_launch_count(const ta_ctx* ctx);
 

@@ -27,7 +27,7 @@ IOU_MODES = {"3d_iou": 0, "avg_iou": 1, "imagenetvid": 2, "3d_iou_seq": 3}
 EXPORTS = [
     "ta_abi_version", "ta_last_error", "ta_ctx_create", "ta_ctx_destroy", "ta_ctx_sm_count",
     "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
-    "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
+    "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
 ]
 
 
@@ -87,6 +87,8 @@ def load() -> C.CDLL:
     lib.ta_ctx_destroy.argtypes = [P]
     lib.ta_ctx_sm_count.argtypes = [P]
     lib.ta_ctx_launch_count.argtypes = [P]
+    lib.ta_ctx_timing.argtypes = [P, C.c_int]
+    lib.ta_ctx_timing_read.argtypes = [P, C.c_char_p, C.c_int, P, P, C.c_int]
     lib.ta_ctx_launch_count.restype = I64
     lib.ta_track_iou.argtypes = [P, P, C.c_int, I64, P, P, P, P, P, P, P, P, I32, P, P]
     lib.ta_box_iou.argtypes = [P, P, I64, P, I64, P, P, P, P, P, P]

@@ -18,7 +18,67 @@ int ta_check_launch(ta_ctx* ctx, const char* what) {
         return TA_ERR_CUDA;
     }
     ctx->launches++;
+    if (ctx->timing && ctx->n_ev < TA_MAX_EVENTS) {
+        cudaEventRecord(ctx->ev[ctx->n_ev], ctx->cur_stream);
+        ctx->ev_name[ctx->n_ev++] = what;
+    }
     return TA_OK;
+}
+
+void ta_begin(ta_ctx* ctx, cudaStream_t st) {
+    ctx->cur_stream = st;
+    if (ctx->timing && ctx->n_ev < TA_MAX_EVENTS) {
+        cudaEventRecord(ctx->ev[ctx->n_ev], st);
+        ctx->ev_name[ctx->n_ev++] = nullptr;
+    }
+}
+
+extern "C" int ta_ctx_timing(ta_ctx* c, int enable) {
+    if (!c) return ta_set_err(TA_ERR_INVALID, "ta_ctx_timing: ctx is NULL");
+    TA_CUDA(cudaSetDevice(c->device));
+    if (enable && !c->ev) {
+        c->ev = new cudaEvent_t[TA_MAX_EVENTS];
+        c->ev_name = new const char*[TA_MAX_EVENTS];
+        for (int i = 0; i < TA_MAX_EVENTS; ++i) TA_CUDA(cudaEventCreate(&c->ev[i]));
+    }
+    c->timing = enable ? 1 : 0;
+    c->n_ev = 0;
+    return TA_OK;
+}
+
+extern "C" int ta_ctx_timing_read(ta_ctx* c, char* names, int names_cap, double* total_ms,
+                                  int* launches, int cap) {
+    if (!c || !names || !total_ms || !launches)
+        return ta_set_err(TA_ERR_INVALID, "ta_ctx_timing_read: NULL argument");
+    TA_CUDA(cudaSetDevice(c->device));
+    int n = 0, used = 0;
+    const char* seen[256];
+    if (names_cap > 0) names[0] = 0;
+    for (int i = 1; i < c->n_ev; ++i) {
+        if (!c->ev_name[i]) continue;
+        TA_CUDA(cudaEventSynchronize(c->ev[i]));
+        float ms = 0.f;
+        TA_CUDA(cudaEventElapsedTime(&ms, c->ev[i - 1], c->ev[i]));
+        int k = 0;
+        for (; k < n; ++k) if (seen[k] == c->ev_name[i] || !strcmp(seen[k], c->ev_name[i])) break;
+        if (k == n) {
+            if (n >= cap || n >= 256) continue;
+            const int len = (int)strlen(c->ev_name[i]);
+            if (used + len + 2 > names_cap) continue;
+            memcpy(names + used, c->ev_name[i], len);
+            names[used + len] = '\n';
+            names[used + len + 1] = 0;
+            used += len + 1;
+            seen[n] = c->ev_name[i];
+            total_ms[n] = 0.0;
+            launches[n] = 0;
+            ++n;
+        }
+        total_ms[k] += ms;
+        launches[k] += 1;
+    }
+    c->n_ev = 0;
+    return n;
 }
 
 int ta_workspace(ta_ctx* ctx, cudaStream_t st, size_t bytes, void** out, int slot) {
@@ -73,6 +133,11 @@ extern "C" int ta_ctx_destroy(ta_ctx* c) {
     cudaStreamSynchronize(c->own_stream);
     if (c->ws) cudaFree(c->ws);
     if (c->ws2) cudaFree(c->ws2);
+    if (c->ev) {
+        for (int i = 0; i < TA_MAX_EVENTS; ++i) cudaEventDestroy(c->ev[i]);
+        delete[] c->ev;
+        delete[] c->ev_name;
+    }
     if (c->h_stage) cudaFreeHost(c->h_stage);
     cudaFree(c->d_flags);
     cudaStreamDestroy(c->own_stream);

@@ -24,7 +24,18 @@ struct ta_ctx {
     // pinned staging for ta_eval_plan_host results
     void* h_stage;
     size_t h_stage_bytes;
+    // optional per-kernel timing (ta_ctx_timing): one event after every launch, one marker at
+    // every API entry; a kernel's time is the interval since the previous event on the stream
+    cudaStream_t cur_stream;
+    int timing;
+    int n_ev;
+    cudaEvent_t* ev;
+    const char** ev_name;      // NULL = entry marker
 };
+
+#define TA_MAX_EVENTS 16384
+// Call at every API entry that launches kernels: remembers the stream for ta_check_launch.
+void ta_begin(ta_ctx* ctx, cudaStream_t st);
 
 char* ta_err_buf();
 int ta_set_err(int code, const char* fmt, const char* a = "", long long b = 0);

@@ -246,6 +246,7 @@ extern "C" int ta_track_iou(ta_ctx* ctx, void* stream, int mode, int64_t n_group
     if (n_groups == 0) return TA_OK;
     if (n_groups > INT_MAX) return ta_set_err(TA_ERR_TOO_LARGE, "ta_track_iou: too many groups");
     TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     TrackIouArgs a{grp_dt_off, grp_gt_off, dt_trk_off, dt_box, dt_slot,
                    gt_trk_off, gt_box, gt_slot, iou_off, iou_out, 0};
@@ -283,6 +284,7 @@ extern "C" int ta_box_iou(ta_ctx* ctx, void* stream, int64_t n_groups,
     if (grp_list) n_groups = n_list;
     if (n_groups <= 0) return TA_OK;
     TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
     const int64_t warps_needed = n_groups;
     int64_t blocks = (warps_needed + 7) / 8;
     const int64_t cap = (int64_t)ctx->sm_count * 32;   // persistent-ish: 8 CTAs of 8 warps per SM

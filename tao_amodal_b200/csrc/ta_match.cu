@@ -731,6 +731,7 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
     if (n_groups <= 0) return TA_OK;
     if (n_groups > INT_MAX) return ta_set_err(TA_ERR_TOO_LARGE, "ta_match_greedy: too many groups");
     TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
     const int cpw = 32 / n_thr;
     const int warps = (n_cfg + cpw - 1) / cpw;
     if (warps * 32 > 1024) return ta_set_err(TA_ERR_TOO_LARGE, "ta_match_greedy: too many range cfgs");
@@ -780,6 +781,7 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
         return ta_set_err(TA_ERR_INVALID, "ta_frame_eval: iou storage required");
     if (n_groups == 0) return TA_OK;
     TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     FrameArgs a{n_groups, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box, n_thr, iou_thrs, n_cfg,
                 cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, iou, write_iou,
@@ -830,8 +832,8 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
             const int64_t blocks = ctx->sm_count * 2;       // list length is only known on the device
             if (spec) k_frame_eval<false, 10, 6, true><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
             else k_frame_eval<false, 0, 0, true><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
+            rc = ta_check_launch(ctx, "k_frame_eval_list");
         }
-        rc = ta_check_launch(ctx, "k_frame_eval");
     }
     if (rc || n_big == 0) return rc;
     // oversize groups: generic kernels, IoU through `iou`; their detection areas go to scratch

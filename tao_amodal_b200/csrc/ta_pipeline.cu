@@ -50,6 +50,7 @@ extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
         return ta_set_err(TA_ERR_INVALID, "ta_eval_plan_host: NULL argument");
     TA_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->own_stream;
+    ta_begin(ctx, st);
     const bool track = pl->dt_trk_off != nullptr;
     const int64_t G = pl->n_groups;
     int rc = TA_OK;

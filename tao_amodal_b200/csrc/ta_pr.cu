@@ -347,6 +347,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
         return ta_set_err(TA_ERR_TOO_LARGE, "ta_pr_accumulate: too many detections");
 
     TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     const int n_chunks_ub = (int)(n_dt / PR_CHUNK) + n_cat;
     // scratch layout

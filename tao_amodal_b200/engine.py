@@ -137,6 +137,21 @@ class Engine:
     def launches(self) -> int:
         return sum(int(self.lib.ta_ctx_launch_count(h)) for h in [self._ctx] + self._extra)
 
+    def timing(self, enable: bool):
+        """Switch the per-kernel event log of the main context on / off (bench.py)."""
+        _lib.check(self.lib.ta_ctx_timing(self._ctx, 1 if enable else 0))
+
+    def timing_read(self):
+        """{kernel name: (total ms, launches)} since the last read."""
+        names = C.create_string_buffer(8192)
+        ms = (C.c_double * 128)()
+        cnt = (C.c_int * 128)()
+        n = self.lib.ta_ctx_timing_read(self._ctx, names, 8192, ms, cnt, 128)
+        if n < 0:
+            _lib.check(n)
+        keys = names.value.decode().split("\n")[:n]
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(keys)}
+
     @property
     def sm_count(self) -> int:
         return int(self.lib.ta_ctx_sm_count(self._ctx))

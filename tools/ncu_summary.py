@@ -56,7 +56,7 @@ def full(src, dst, traffic_json=None):
     with open(dst, "w") as f:
         f.write("# ncu --set full summary (one launch per row; per-launch values)\n\nsource: `%s`\n\n" % src)
         for r in data:
-            name = r[ki].split("(")[0]
+            name = r[ki].split("(")[0].replace("void ", "").split("<")[0]
             f.write("## %s\n\n| metric | value | unit |\n|---|---|---|\n" % name)
             vals = {}
             for m in FULL_METRICS:
@@ -70,17 +70,11 @@ def full(src, dst, traffic_json=None):
                     v, u = vals[m]
                     return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
                 tb = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-                traffic[name] = max(traffic.get(name, 0), tb)     # largest launch of that kernel
+                traffic.setdefault(name, []).append(tb)           # one entry per launch of the step
             except Exception:
                 pass
     if traffic_json:
-        old = {}
-        try:
-            old = json.load(open(traffic_json))
-        except Exception:
-            pass
-        old.update(traffic)
-        json.dump(old, open(traffic_json, "w"), indent=1)
+        json.dump(traffic, open(traffic_json, "w"), indent=1)
     print(open(dst).read()[:3000])
 
 
