@@ -115,10 +115,51 @@ def run_case(name: str, ref) -> dict:
     return out
 
 
+def run_nocats(name: str, ref) -> dict:
+    """Params.use_cats = 0 (eval.py:257-260, :293-303): all categories of a video / image are
+    evaluated as one.  LVISEval.summarize indexes the single pseudo category with the
+    per-category frequency groups and raises IndexError in the reference, so only its
+    accumulate() outputs are stored."""
+    gt, res = cases.build(name)
+    out = {"in_gt_json": np.asarray(json.dumps(gt)), "in_dt_json": np.asarray(json.dumps(res))}
+    with tempfile.TemporaryDirectory() as td:
+        ap, rp = (os.path.join(td, f) for f in ("gt.json", "dt.json"))
+        json.dump(gt, open(ap, "w"))
+        json.dump(res, open(rp, "w"))
+        le = ref.LVISEval(ap, rp, "bbox")
+        le.params.use_cats = 0
+        le.evaluate()
+        le.accumulate()
+        out["lvis_precision"], out["lvis_recall"] = le.eval["precision"], le.eval["recall"]
+        try:
+            le.summarize()
+            out["lvis_summarize_error"] = np.asarray("")
+        except Exception as e:          # noqa: BLE001 - recording the reference's behaviour
+            out["lvis_summarize_error"] = np.asarray(type(e).__name__)
+        res2 = json.load(open(rp))
+        reference_make_track_ids_unique()(res2)
+        te = ref.TaoEval(ref.Tao(ap), res2)
+        te.params.use_cats = 0
+        te.run()
+        out["tao_precision"], out["tao_recall"] = te.eval["precision"], te.eval["recall"]
+        out["tao_results"] = golden_io.results_vector(te.results)
+        for k, v in golden_io.flatten_cells(dict(te.eval_vids)).items():
+            out["tao_" + k] = v
+    return out
+
+
 def main(argv):
     names = argv or list(cases.CASES)
     ref = ref_shims.load_reference()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if names == ["nocats"]:
+        for n in ("small", "edge_mix"):
+            out = run_nocats(n, ref)
+            path = os.path.join(GOLDEN_DIR, n + "_nocats.npz")
+            np.savez_compressed(path, **out)
+            print("%-18s -> %s  TAO AP=%.6f  lvis summarize: %r" % (
+                n, path, out["tao_results"][0], str(out["lvis_summarize_error"])))
+        return
     for n in names:
         out = run_case(n, ref)
         path = os.path.join(GOLDEN_DIR, n + ".npz")

@@ -108,14 +108,12 @@ class LVISEval:
         p = self.params
         if p.iou_type != "bbox":
             raise NotImplementedError("only iou_type='bbox' runs on the CUDA path")
-        if not p.use_cats:
-            raise NotImplementedError("use_cats=0 is not supported by the CUDA path yet")
         if len(p.iou_thrs) > 16:
             raise ValueError("at most 16 IoU thresholds are supported")
         self._plan = prep.prepare_lvis(
             self.lvis_gt.columns, self.lvis_dt.dt_columns, max_dets=self.lvis_dt.max_dets,
             vis_rng=p.visibility_rng, img_ids=p.img_ids,
-            cat_ids=p.cat_ids if p.cat_ids else None)
+            cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats))
         self.freq_groups = self._plan.freq_groups
 
     def evaluate(self):

@@ -84,14 +84,12 @@ class TaoEval:
         p = self.params
         if p.iou_type != "bbox":
             raise NotImplementedError("only iou_type='bbox' runs on the CUDA path")
-        if not p.use_cats:
-            raise NotImplementedError("use_cats=0 is not supported by the CUDA path yet")
         if len(p.iou_thrs) > 16:
             raise ValueError("at most 16 IoU thresholds are supported")
         self._plan = prep.prepare_tao(
             self.tao_gt.columns, self.tao_dt.dt_columns, max_dets=self.tao_dt.max_dets,
             area_rng=p.area_rng, time_rng=p.time_rng, vid_ids=p.vid_ids,
-            cat_ids=p.cat_ids if p.cat_ids else None)
+            cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats))
 
     def evaluate(self, show_progress=False):
         """Per-video evaluation: IoU matrices + greedy matching of every (video, category,

@@ -275,13 +275,22 @@ def cpython_set_order(ids: list) -> list:
     return list(set(ids) & set(list(ids)))
 
 
-def _layout(n_units, g_unit, g_cat, g_key, d_unit, d_cat, d_key, d_score):
-    """Sort entities into (category, unit) groups.  Returns group table + permutations."""
-    gk = g_cat.astype(np.int64) * n_units + g_unit
-    dk = d_cat.astype(np.int64) * n_units + d_unit
+def _layout(n_units, g_unit, g_cat, g_key, d_unit, d_cat, d_key, d_score, use_cats=True):
+    """Sort entities into (category, unit) groups.  Returns group table + permutations.
+
+    use_cats=False (Params.use_cats = 0, eval.py:293-303): one group per unit holding the
+    entities of all categories, concatenated in category order then in-cell order."""
+    if use_cats:
+        gk = g_cat.astype(np.int64) * n_units + g_unit
+        dk = d_cat.astype(np.int64) * n_units + d_unit
+        g_perm = np.lexsort((g_key, gk))
+        d_perm = np.lexsort((d_key, -d_score, dk))
+    else:
+        gk = g_unit.astype(np.int64)
+        dk = d_unit.astype(np.int64)
+        g_perm = np.lexsort((g_key, g_cat, gk))
+        d_perm = np.lexsort((d_key, d_cat, -d_score, dk))
     keys = np.unique(np.concatenate([gk, dk]))
-    g_perm = np.lexsort((g_key, gk))
-    d_perm = np.lexsort((d_key, -d_score, dk))
     g_cnt = np.bincount(_index_of(keys, gk), minlength=keys.size)
     d_cnt = np.bincount(_index_of(keys, dk), minlength=keys.size)
     grp_gt_off = np.zeros(keys.size + 1, dtype=np.int64)
@@ -310,7 +319,7 @@ def _acc_perm(n_cat, cat_dt_off, dt_score):
 # ---- TAO track path ----------------------------------------------------------------------
 def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
                 area_rng=TAO_AREA_RNG, time_rng=TAO_TIME_RNG,
-                vid_ids=None, cat_ids=None) -> EvalPlan:
+                vid_ids=None, cat_ids=None, use_cats: bool = True) -> EvalPlan:
     """Plan of the track path.  vid_ids / cat_ids default to everything in the annotation
     file (TaoEval.__init__, eval.py:169-170); subsets mirror assigning Params.vid_ids /
     Params.cat_ids before evaluate()."""
@@ -428,13 +437,17 @@ def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
     in_present = _index_of(present, d_unit.astype(np.int64) * n_cat + d_cidx) >= 0
     in_neg = _ragged_contains(gt.vid_neg, v_row_of_unit[d_unit], t_cat[d_t])
     keep = in_present | in_neg
+    if not use_cats:
+        keep = np.ones_like(keep)          # eval.py:230: the federated filter needs use_cats
     in_nel = _ragged_contains(gt.vid_nel, v_row_of_unit[d_unit], t_cat[d_t])
 
     kept = np.nonzero(keep)[0]
     (keys, grp_cat, grp_unit, grp_gt_off, grp_dt_off, iou_off, g_perm, d_perm) = _layout(
         n_vid, g_unit, g_cidx, gt_ent["first_key"],
-        d_unit[kept], d_cidx[kept], dt_ent["first_key"][kept], t_score[d_t][kept])
+        d_unit[kept], d_cidx[kept], dt_ent["first_key"][kept], t_score[d_t][kept], use_cats)
     d_sel = kept[d_perm]
+    if not use_cats:
+        cat_ids, n_cat = np.asarray([-1], dtype=np.int64), 1      # eval.py:259-260
 
     gb_off, gb, gslot = _gather_track_boxes(gt_ent, g_perm)
     db_off, db, dslot = _gather_track_boxes(dt_ent, d_sel)
@@ -545,7 +558,8 @@ def _gather_track_boxes(ent, perm):
 
 # ---- LVIS frame path ---------------------------------------------------------------------
 def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
-                 vis_rng=LVIS_VIS_RNG, img_ids=None, cat_ids=None) -> EvalPlan:
+                 vis_rng=LVIS_VIS_RNG, img_ids=None, cat_ids=None,
+                 use_cats: bool = True) -> EvalPlan:
     """Plan of the frame path; img_ids / cat_ids as in prepare_tao (lvis eval.py:51-52)."""
     cat_ids = np.unique(gt.cat_id if cat_ids is None else np.asarray(cat_ids, dtype=np.int64))
     all_img_ids = np.unique(gt.img_id)
@@ -595,18 +609,20 @@ def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
 
     (keys, grp_cat, grp_unit, grp_gt_off, grp_dt_off, iou_off, g_perm, d_perm) = _layout(
         n_img, g_unit, g_cidx, g_rows, d_unit[kept], d_cidx[kept], d_rows[kept],
-        d_score[d_rows][kept])
+        d_score[d_rows][kept], use_cats)
     d_sel = d_rows[kept][d_perm]
     g_sel = g_rows[g_perm]
-    cat_grp_off, cat_dt_off = _cat_offsets(n_cat, grp_cat, grp_dt_off)
-    dt_score = np.ascontiguousarray(d_score[d_sel])
 
-    # frequency groups (eval.py:107-113)
+    # frequency groups (eval.py:107-113): indices into the category list
     cat_keys, cat_row = _last_row_of(gt.cat_id)
     freq = gt.cat_freq[cat_row[_index_of(cat_keys, cat_ids)]]
     if (freq > 2).any():
         raise KeyError("frequency")
     freq_groups = [np.nonzero(freq == k)[0].tolist() for k in range(3)]
+    if not use_cats:
+        cat_ids, n_cat = np.asarray([-1], dtype=np.int64), 1      # lvis eval.py:127-128
+    cat_grp_off, cat_dt_off = _cat_offsets(n_cat, grp_cat, grp_dt_off)
+    dt_score = np.ascontiguousarray(d_score[d_sel])
 
     plan = EvalPlan(
         kind="lvis", cat_ids=cat_ids, unit_ids=img_ids, n_groups=int(keys.size),

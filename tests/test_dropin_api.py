@@ -110,3 +110,27 @@ def test_constructor_errors_match_reference(tmp_path):
     bad[0]["image_id"] = 10 ** 9
     with pytest.raises(AssertionError, match="Results do not correspond"):
         TaoResults(tao, bad)
+
+
+def test_use_cats_zero_through_the_classes(tmp_path):
+    from conftest import load_golden
+    from tao_amodal_b200.evaluation.lvis_amodal import LVISEval
+    from tao_amodal_b200.evaluation.tao_amodal import Tao, TaoEval
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import eval_on_tao_amodal as cli
+    g = load_golden("small_nocats")
+    ap, rp = _write(tmp_path, g)
+    res = json.load(open(rp))
+    cli.make_track_ids_unique(res)
+    te = TaoEval(Tao(ap), res)
+    te.params.use_cats = 0
+    te.run()
+    assert np.array_equal(g["tao_precision"], te.eval["precision"])
+    assert np.array_equal(g["tao_results"], golden_io.results_vector(te.results))
+    le = LVISEval(ap, rp, "bbox")
+    le.params.use_cats = 0
+    le.evaluate()
+    le.accumulate()
+    assert np.array_equal(g["lvis_precision"], le.eval["precision"])
+    with pytest.raises(IndexError):        # the reference fails the same way (frequency groups)
+        le.summarize()

@@ -22,3 +22,27 @@ def test_lvis_plan_hostsim_matches_reference(golden):
     _, lvis_plan = plans_from_json(gt, res)
     out = run_hostsim(lvis_plan)
     compare_with_golden(golden, "lvis_", lvis_plan, out, exact_iou=True)
+
+
+@pytest.mark.parametrize("case", ["small_nocats", "edge_mix_nocats"])
+def test_use_cats_zero_matches_reference(case):
+    """Params.use_cats = 0: one pseudo category per video / image (eval.py:257-260, :293-303)."""
+    from conftest import load_golden
+    from oracle import golden_io
+    from tao_amodal_b200 import materialize, prep
+    from tao_amodal_b200.columnar import DtColumns, GtColumns
+    g = load_golden(case)
+    gt_d, res = golden_inputs(g)
+    gt, dt = GtColumns.from_dict(gt_d), DtColumns.from_list(res)
+    lvis_plan = prep.prepare_lvis(gt, dt, use_cats=False)
+    out = run_hostsim(lvis_plan)
+    assert np.array_equal(g["lvis_precision"], out.precision)
+    assert np.array_equal(g["lvis_recall"], out.recall)
+    prep.make_track_ids_unique(dt)
+    tao_plan = prep.prepare_tao(gt, dt, use_cats=False)
+    out = run_hostsim(tao_plan)
+    assert np.array_equal(g["tao_precision"], out.precision.reshape(g["tao_precision"].shape))
+    assert np.array_equal(g["tao_recall"], out.recall.reshape(g["tao_recall"].shape))
+    cells = materialize.cells_dict(tao_plan, 10, out)
+    for k, v in golden_io.flatten_cells(cells).items():
+        assert np.array_equal(g["tao_" + k], v), k
