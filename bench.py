@@ -454,7 +454,10 @@ def main():
     tr_path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr_path):
         tr = json.load(open(tr_path)).get(dom)
-        traffic = float(sum(tr)) if isinstance(tr, list) else tr
+        if isinstance(tr, list):     # ncu dram bytes of the kernel's launches of one step
+            traffic = float(sum(tr[:max(1, int(round(per_kernel[dom]["launches_per_step"])))]))
+        else:
+            traffic = tr
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                 "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
