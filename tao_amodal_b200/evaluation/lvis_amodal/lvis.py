@@ -6,6 +6,7 @@ from __future__ import annotations
 import logging
 from collections import defaultdict
 
+from ... import ingest
 from ...columnar import GtColumns
 from .._common import load_json
 
@@ -16,14 +17,21 @@ class LVIS:
     def __init__(self, annotation_path):
         self.logger = logging.getLogger(__name__)
         self.logger.info("Loading annotations.")
-        self.dataset = annotation_path if isinstance(annotation_path, dict) \
-            else load_json(annotation_path)
-        assert type(self.dataset) == dict, (
-            "Annotation file format {} not supported.".format(type(self.dataset)))
-        self.columns = GtColumns.from_dict(self.dataset)
+        if isinstance(annotation_path, dict):
+            self.dataset = annotation_path
+            self.columns = GtColumns.from_dict(self.dataset)
+        else:
+            # native single-pass reader; ``self.dataset`` is parsed only when read
+            self._path = annotation_path
+            self.columns = ingest.load_gt(annotation_path)
         self._indexed = False
 
     def __getattr__(self, name):
+        if name == "dataset" and "_path" in self.__dict__:
+            ds = load_json(self.__dict__["_path"])
+            assert type(ds) == dict, "Annotation file format {} not supported.".format(type(ds))
+            self.__dict__["dataset"] = ds
+            return ds
         if name in _INDEX_ATTRS and not self.__dict__.get("_indexed", True):
             self._create_index()
             return self.__dict__[name]

@@ -9,6 +9,7 @@ from collections import defaultdict
 
 import numpy as np
 
+from ... import ingest
 from ...columnar import DtColumns
 from .._common import load_json
 from .lvis import LVIS
@@ -25,19 +26,19 @@ class LVISResults(LVIS):
         self.logger = logging.getLogger(__name__)
         self.logger.info("Loading and preparing results.")
         self.max_dets = max_dets
+        self._results_path = None
         if isinstance(results, DtColumns):
             self._result_anns, dt = None, results
+        elif isinstance(results, str):
+            self._results_path, self._result_anns = results, None
+            dt = ingest.load_dt(results)       # native single-pass reader (bbox results)
         else:
-            if isinstance(results, str):
-                result_anns = load_json(results)
-            else:
-                self.logger.warn("Assuming user provided the results in correct format.")
-                result_anns = results
-            assert isinstance(result_anns, list), "results is not a list."
-            if len(result_anns) and "bbox" not in result_anns[0]:
+            self.logger.warn("Assuming user provided the results in correct format.")
+            assert isinstance(results, list), "results is not a list."
+            if len(results) and "bbox" not in results[0]:
                 raise NotImplementedError("only bbox results run on the CUDA path")
-            self._result_anns = result_anns
-            dt = DtColumns.from_list(result_anns)
+            self._result_anns = results
+            dt = DtColumns.from_list(results)
         if dt.n() == 0:
             raise IndexError("list index out of range")                # results.py:42
         self.columns = self._gt.columns
@@ -50,8 +51,12 @@ class LVISResults(LVIS):
     def dataset(self):
         if "_dataset" not in self.__dict__:
             ds = copy.deepcopy(self._gt.dataset)
-            anns = self._result_anns if self._result_anns is not None \
-                else self.dt_columns.to_list()
+            if self._result_anns is not None:
+                anns = self._result_anns
+            elif self._results_path is not None:
+                anns = load_json(self._results_path)
+            else:
+                anns = self.dt_columns.to_list()
             if self.max_dets >= 0:
                 anns = self.limit_dets_per_image(anns, self.max_dets)
             for n, r in enumerate(anns):

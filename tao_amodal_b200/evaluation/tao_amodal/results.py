@@ -15,6 +15,7 @@ from collections import defaultdict
 
 import numpy as np
 
+from ... import ingest
 from ...columnar import DtColumns
 from ... import prep
 from .._common import load_json
@@ -31,18 +32,19 @@ class TaoResults(Tao):
             raise TypeError("Unsupported type {} of tao_gt.".format(tao_gt))
         self.logger = logging.getLogger('tao.results')
         self.max_dets = max_dets
+        self._results_path = None
         if isinstance(results, DtColumns):
-            self._result_anns = None
-            dt = results
+            self._result_anns, dt = None, results
+        elif isinstance(results, str):
+            # native single-pass reader; the list-of-dicts form is parsed only if
+            # ``dataset`` is read
+            self._results_path, self._result_anns = results, None
+            dt = ingest.load_dt(results)
         else:
-            if isinstance(results, str):
-                result_anns = load_json(results)
-            else:
-                self.logger.warn("Assuming results file is a list of dicts.")   # results.py:40
-                result_anns = results
-            assert isinstance(result_anns, list), "results is not a list."
-            self._result_anns = result_anns
-            dt = DtColumns.from_list(result_anns)
+            self.logger.warn("Assuming results file is a list of dicts.")   # results.py:40
+            assert isinstance(results, list), "results is not a list."
+            self._result_anns = results
+            dt = DtColumns.from_list(results)
         self.merge_map = dict(self._gt.merge_map)
         self.columns = self._gt.columns
         self.dt_columns = dt
@@ -74,7 +76,12 @@ class TaoResults(Tao):
 
     def _materialise(self):
         ds = copy.deepcopy(self._gt.dataset)
-        anns = self._result_anns if self._result_anns is not None else self.dt_columns.to_list()
+        if self._result_anns is not None:
+            anns = self._result_anns
+        elif self._results_path is not None:
+            anns = load_json(self._results_path)
+        else:
+            anns = self.dt_columns.to_list()
         mm = self.merge_map
         for r in anns:
             if r["category_id"] in mm:

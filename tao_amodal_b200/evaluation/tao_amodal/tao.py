@@ -10,6 +10,7 @@ from __future__ import annotations
 import logging
 from collections import defaultdict
 
+from ... import ingest
 from ...columnar import GtColumns
 from .._common import load_json
 
@@ -31,21 +32,29 @@ class Tao:
                 assert key in annotation_path, (
                     f'Provided dictionary does not contain key {key}')
             self.dataset = annotation_path
+            assert type(self.dataset) == dict, (
+                "Annotation file format {} not supported.".format(type(self.dataset)))
+            self.columns = GtColumns.from_dict(self.dataset)
         else:
-            self.dataset = load_json(annotation_path)
-        assert type(self.dataset) == dict, (
-            "Annotation file format {} not supported.".format(type(self.dataset)))
+            # native single-pass reader (csrc/ta_json.cpp); the dict form of the file
+            # (``self.dataset``) is only parsed if somebody reads it
+            self._path = annotation_path
+            self.columns = ingest.load_gt(annotation_path, need_videos_tracks=True)
         self._init_columns()
 
     # -------------------------------------------------------------------------------- columns
     def _init_columns(self):
-        self.columns = GtColumns.from_dict(self.dataset)
         self.merge_map = dict(self.columns.merge_map)
         if not self.merge_map:
             logging.error('Did not merge any categories.')      # tao.py:104-105
         self._indexed = False
 
     def __getattr__(self, name):
+        if name == "dataset" and "_path" in self.__dict__:
+            ds = load_json(self.__dict__["_path"])
+            assert type(ds) == dict, "Annotation file format {} not supported.".format(type(ds))
+            self.__dict__["dataset"] = ds
+            return ds
         # dict indices of tao.py:108-160, built lazily
         if name in _INDEX_ATTRS and not self.__dict__.get("_indexed", True):
             self._create_index()

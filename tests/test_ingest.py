@@ -1,0 +1,82 @@
+"""Native JSON ingest (libta_ingest.so) against the dict-based column builders: identical
+columns on every golden input, same exceptions on malformed / incomplete files.  CPU only."""
+import json
+from dataclasses import fields
+
+import numpy as np
+import pytest
+
+from conftest import golden_inputs
+from tao_amodal_b200 import ingest
+from tao_amodal_b200.columnar import DtColumns, GtColumns
+
+
+def _same(a, b):
+    if isinstance(a, tuple):
+        return all(_same(x, y) for x, y in zip(a, b))
+    if isinstance(a, np.ndarray):
+        return (a.dtype == b.dtype and a.shape == b.shape
+                and np.array_equal(a, b, equal_nan=a.dtype.kind == "f"))
+    return a == b
+
+
+def test_columns_identical_on_golden_inputs(golden, tmp_path):
+    gt, res = golden_inputs(golden)
+    ap, rp = str(tmp_path / "gt.json"), str(tmp_path / "dt.json")
+    json.dump(gt, open(ap, "w"))
+    json.dump(res, open(rp, "w"), indent=1)          # whitespace variations
+    g_n, d_n = ingest.load_gt(ap, need_videos_tracks=True), ingest.load_dt(rp)
+    g_p, d_p = GtColumns.from_dict(gt), DtColumns.from_list(res)
+    for f in fields(GtColumns):
+        assert _same(getattr(g_n, f.name), getattr(g_p, f.name)), f.name
+    for f in fields(DtColumns):
+        assert _same(getattr(d_n, f.name), getattr(d_p, f.name)), f.name
+
+
+def test_odd_but_valid_json(tmp_path):
+    gt = {"info": {"nested": {"a": [1, {"b": 'x"y'}]}}, "licenses": [],
+          "images": [{"id": 7, "file_name": 'a\\b".jpg', "video_id": 3, "frame_index": 2,
+                      "neg_category_ids": [], "not_exhaustive_category_ids": [5, 6]}],
+          "videos": [{"id": 3, "neg_category_ids": [9], "not_exhaustive_category_ids": []}],
+          "tracks": [{"id": 1, "category_id": 5, "video_id": 3, "ignore": True}],
+          "categories": [{"id": 5, "frequency": "r", "merged": [{"id": 50, "name": "q"}, {"id": 51}]},
+                         {"id": 6, "name": "no frequency"}],
+          "annotations": [{"id": 1, "image_id": 7, "track_id": 1, "category_id": 5,
+                           "bbox": [1, 2.5, 3e1, 4], "area": 120, "visibility": 0.25,
+                           "out_of_frame": False, "ignore": 0, "extra": None},
+                          {"id": 2, "image_id": 7, "category_id": 5, "bbox": [0, 0, 1, 1],
+                           "area": 1.0, "out_of_frame": 1}]}
+    p = str(tmp_path / "gt.json")
+    json.dump(gt, open(p, "w"))
+    a, b = ingest.load_gt(p, need_videos_tracks=True), GtColumns.from_dict(gt)
+    for f in fields(GtColumns):
+        assert _same(getattr(a, f.name), getattr(b, f.name)), f.name
+    assert a.merge_map == {50: 5, 51: 5} and a.ann_track_id.tolist() == [1, -1]
+    assert np.isnan(a.ann_visibility[1]) and a.ann_oof.tolist() == [0, 1]
+    res = [{"image_id": 7, "category_id": 5, "bbox": [1, 2, 3, 4], "score": 1, "track_id": 4,
+            "video_id": 3, "segmentation": {"counts": "abc", "size": [1, 2]}},
+           {"score": 2.5e-1, "bbox": [0.1, 0.2, 0.3, 0.4], "category_id": 6, "image_id": 7}]
+    p = str(tmp_path / "dt.json")
+    json.dump(res, open(p, "w"))
+    a, b = ingest.load_dt(p), DtColumns.from_list(res)
+    for f in fields(DtColumns):
+        assert _same(getattr(a, f.name), getattr(b, f.name)), f.name
+
+
+def test_errors_mirror_the_dict_path(tmp_path):
+    p = str(tmp_path / "x.json")
+    open(p, "w").write('[{"image_id": 1, "category_id": 2, "bbox": [1,2,3,4]}]')
+    with pytest.raises(KeyError, match="score"):
+        ingest.load_dt(p)
+    open(p, "w").write('{"a": 1}')
+    with pytest.raises(AssertionError, match="not a list"):
+        ingest.load_dt(p)
+    open(p, "w").write('[{"image_id": 1, "category_id": 2, "bbox": [1,2,3,4], "score": 0.5}')
+    with pytest.raises(json.JSONDecodeError):
+        ingest.load_dt(p)
+    open(p, "w").write('{"images": [], "annotations": [], "categories": []}')
+    ingest.load_gt(p)                                   # enough for the frame evaluator
+    with pytest.raises(KeyError, match="videos"):
+        ingest.load_gt(p, need_videos_tracks=True)      # Tao needs videos and tracks
+    with pytest.raises(FileNotFoundError):
+        ingest.load_gt(str(tmp_path / "missing.json"))

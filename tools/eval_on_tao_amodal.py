@@ -22,7 +22,7 @@ from tao_amodal_b200.columnar import DtColumns                      # noqa: E402
 from tao_amodal_b200.evaluation._common import load_json           # noqa: E402
 from tao_amodal_b200.evaluation.lvis_amodal import LVISEval        # noqa: E402
 from tao_amodal_b200.evaluation.tao_amodal import Tao, TaoEval     # noqa: E402
-from tao_amodal_b200 import prep                                   # noqa: E402
+from tao_amodal_b200 import ingest, prep                           # noqa: E402
 
 BBOX_METRICS = ["AP", "AP50", "AP75", "AP-HO", "AP50-HO", "AP75-HO", "AP-PO", "AP50-PO",
                 "AP75-PO", "AP-HV", "AP50-HV", "AP75-HV", "AP-OOF", "AP50-OOF", "AP75-OOF",
@@ -90,7 +90,7 @@ def eval_tao_track(ann_path, results_path, logger, device=0):
     tao_gt = Tao(ann_path)
     logger.info('Done')
     logger.info('Loading results...')
-    dt = DtColumns.from_list(load_json(results_path))
+    dt = ingest.load_dt(results_path).copy()      # native reader; the cached columns stay intact
     prep.make_track_ids_unique(dt)
     logger.info('Done')
     logger.info('Building')
