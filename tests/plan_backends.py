@@ -137,3 +137,38 @@ def compare_with_golden(g, prefix, plan, out, exact_iou=True, iou_atol=0.0):
     assert np.array_equal(g[prefix + "fp_cnt"], fp)
     assert golden_io.results_keys(res) == [str(k) for k in g[prefix + "results_keys"]]
     assert np.array_equal(g[prefix + "results"], golden_io.results_vector(res))
+
+
+def random_small_set(seed: int):
+    """A small random dataset (reference JSON structures): shape, tie density, id sparsity and
+    GT overlap vary with the seed; every 4th seed duplicates GT boxes across tracks so that
+    detections have several candidate GTs (the general matcher route)."""
+    from tao_amodal_b200 import synth
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    gtc, dtc = synth.generate_named(
+        "tiny", seed=500 + seed, videos=int(rng.integers(2, 5)), frames=int(rng.integers(6, 30)),
+        pred_tracks=int(rng.integers(4, 16)), gt_tracks=int(rng.integers(2, 7)),
+        categories=int(rng.integers(4, 14)), max_present=int(rng.integers(1, 4)),
+        score_quantum=[0.0, 0.1, 0.25][seed % 3], sparse_image_ids=bool(seed % 2),
+        keep_prob=float(rng.uniform(0.5, 1.0)))
+    gt, res = gtc.to_dict(), dtc.to_list()
+    if seed % 4 == 3:
+        by_trk = {}
+        for a in gt["annotations"]:
+            by_trk.setdefault(a["track_id"], []).append(a)
+        tids = sorted(by_trk)
+        for t_src, t_dst in zip(tids[::2], tids[1::2]):
+            src = {a["image_id"]: a for a in by_trk[t_src]}
+            for a in by_trk[t_dst]:
+                if a["image_id"] in src:
+                    a["bbox"] = list(src[a["image_id"]]["bbox"])
+                    a["area"] = a["bbox"][2] * a["bbox"][3]
+        cat_of = {t["id"]: t["category_id"] for t in gt["tracks"]}
+        for t_src, t_dst in zip(tids[::2], tids[1::2]):     # same category, or they never meet
+            for t in gt["tracks"]:
+                if t["id"] == t_dst and t["video_id"] == next(
+                        x["video_id"] for x in gt["tracks"] if x["id"] == t_src):
+                    t["category_id"] = cat_of[t_src]
+                    for a in by_trk[t_dst]:
+                        a["category_id"] = cat_of[t_src]
+    return gt, res

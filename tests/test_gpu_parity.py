@@ -158,3 +158,27 @@ def test_concurrent_host_calls(eng):
         assert np.array_equal(g["tao_precision"], o_t.precision.reshape(g["tao_precision"].shape))
         assert np.array_equal(g["lvis_precision"], o_l.precision)
         assert np.array_equal(g["lvis_tp_cnt"], o_l.tp_cnt)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_sets_gpu_vs_host_arithmetic(seed, eng):
+    """Random small datasets (incl. overlapping GT -> several candidates per detection, the
+    general matcher behind the flat frame kernel) through every CUDA route: host-buffer call,
+    device stages with and without the per-cell outputs."""
+    import copy
+    from plan_backends import random_small_set
+    gt, res = random_small_set(seed)
+    tao_plan, lvis_plan = plans_from_json(copy.deepcopy(gt), copy.deepcopy(res))
+    for plan in (tao_plan, lvis_plan):
+        ref = run_hostsim(plan)
+        h = eng.evaluate_host(plan)
+        d = eng.evaluate_device(eng.upload(plan), detail=True)
+        q = eng.evaluate_device(eng.upload(plan), detail=False)
+        for o in (h, d, q):
+            assert np.array_equal(o.precision, ref.precision)
+            assert np.array_equal(o.recall, ref.recall)
+            assert np.array_equal(o.tp_cnt, ref.tp_cnt)
+            assert np.array_equal(o.fp_cnt, ref.fp_cnt)
+            assert np.array_equal(o.num_gt, ref.num_gt)
+        assert np.array_equal(d.dt_tpfp, ref.dt_tpfp)
+        assert np.array_equal(d.dt_match_gt, ref.dt_match_gt)

@@ -48,8 +48,10 @@ def main():
     from tao_amodal_b200.evaluation._common import _JSON_CACHE, get_engine
     get_engine(0)                                     # CUDA context creation is not the CLI's work
     runs = []
+    from tao_amodal_b200 import ingest
     for _ in range(2):
         _JSON_CACHE.clear()
+        ingest._CACHE.clear()            # every run parses both files from disk
         out = io.StringIO()
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(out):
