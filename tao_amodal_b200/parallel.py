@@ -15,9 +15,9 @@ moves one compact record per detection to the rank that owns its category:
   every evaluation:
       all_to_all of the TP/FP words  u32 [n_dt][n_cfg]   (the only per-step payload)
       all_reduce(SUM) of num_gt      i32 [C][n_cfg]
-      ta_pr_accumulate on the owner's categories
-      reduce(SUM) of precision / recall / TP / FP to rank 0 (non-owned categories are zeroed,
-      so the sum is an exact selection).
+      ta_pr_accumulate on the owner's categories, renumbered densely (local index =
+      category index // world), so each rank produces a [T, R, ceil(C / world), n_cfg] slice
+      gather of the slices to rank 0, which interleaves them back into [T, R, C, n_cfg].
 
 Categories are dealt round-robin (owner = category index mod world) to spread the skew of
 category sizes.  Works with the NCCL backend on CUDA tensors and with gloo on CPU tensors (the
@@ -81,15 +81,17 @@ class DistAccumulator:
             return out
 
         r_cat, r_score, r_key = xchg(cat), xchg(score), xchg(key)
+        r_loc = r_cat // world              # dense local category index on the owner
         # (category, -score, key) order through three stable sorts, least significant first
         p = torch.sort(r_key, stable=True).indices
         p = p[torch.sort(-r_score[p], stable=True).indices]
-        p = p[torch.sort(r_cat[p], stable=True).indices]
+        p = p[torch.sort(r_loc[p], stable=True).indices]
         self.acc_perm = p.to(torch.int32).contiguous()
-        cnt = torch.bincount(r_cat, minlength=self.n_cat)
-        self.cat_dt_off = torch.zeros(self.n_cat + 1, dtype=torch.int64, device=device)
+        self.n_loc = -(-self.n_cat // world)                        # ceil(C / world), padded
+        self.n_own = len(range(rank, self.n_cat, world))
+        cnt = torch.bincount(r_loc, minlength=self.n_loc)
+        self.cat_dt_off = torch.zeros(self.n_loc + 1, dtype=torch.int64, device=device)
         self.cat_dt_off[1:] = torch.cumsum(cnt, 0)
-        self.owned = (torch.arange(self.n_cat, device=device) % world) == rank
         self.recv_rows = torch.empty((max(self.n_recv, 1), self.n_cfg), dtype=torch.int32,
                                      device=device)
 
@@ -103,30 +105,44 @@ class DistAccumulator:
         return out
 
     def global_num_gt(self, num_gt_local):
-        """Sum over ranks; returns (global counts, counts with non-owned categories zeroed)."""
+        """Sum over ranks; returns (global counts [C, n_cfg], this rank's categories
+        [ceil(C / world), n_cfg], zero-padded)."""
+        import torch
         import torch.distributed as dist
         g = num_gt_local.clone()
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
-        return g, g * self.owned.to(g.dtype)[:, None]
+        own = torch.zeros((self.n_loc, g.shape[1]), dtype=g.dtype, device=g.device)
+        own[:self.n_own] = g[self.rank::self.world]
+        return g, own
 
-    def merge_to_root(self, precision, recall, tp_cnt, fp_cnt):
-        """Zero the categories this rank does not own and sum everything onto rank 0."""
+    def merge_to_root(self, parts, full=None):
+        """parts: this rank's [.., n_loc, n_cfg] tensors (category axis = -2).  Rank 0 receives
+        every rank's slice and interleaves them into the matching `full` tensors."""
+        import torch
         import torch.distributed as dist
-        own = self.owned
-        precision.mul_(own.to(precision.dtype)[None, None, :, None])
-        recall.mul_(own.to(recall.dtype)[None, :, None])
-        for x in (tp_cnt, fp_cnt):
-            x.mul_(own.to(x.dtype)[None, :, None])
-        for x in (precision, recall, tp_cnt, fp_cnt):
-            dist.reduce(x, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+        for i, x in enumerate(parts):
+            x = x.contiguous()
+            recv = [torch.empty_like(x) for _ in range(self.world)] if self.rank == 0 else None
+            dist.gather(x, recv, dst=0, group=self.group)
+            if self.rank == 0:
+                for r in range(self.world):
+                    n_r = len(range(r, self.n_cat, self.world))
+                    full[i][..., r::self.world, :] = recv[r][..., :n_r, :]
 
 
 class DeviceDistAccumulator(DistAccumulator):
     """DistAccumulator driving ta_pr_accumulate on the owner's slice (CUDA / NCCL)."""
 
     def __init__(self, eng, dev, rank: int, world: int, group=None):
+        import torch
         super().__init__(dev.plan, rank, world, dev.dev, group)
         self.eng, self.dev = eng, dev
+        T, R, L, K = dev.n_thr, dev.n_rec, self.n_loc, self.n_cfg
+        d = dev.dev
+        self.part = {"precision": torch.empty((T, R, L, K), dtype=torch.float64, device=d),
+                     "recall": torch.empty((T, L, K), dtype=torch.float64, device=d),
+                     "tp_cnt": torch.empty((T, L, K), dtype=torch.int64, device=d),
+                     "fp_cnt": torch.empty((T, L, K), dtype=torch.int64, device=d)}
 
     def accumulate(self):
         import ctypes as C
@@ -136,14 +152,16 @@ class DeviceDistAccumulator(DistAccumulator):
         t = dev.t
         n_dt, n_cfg = dev.plan.n_dt, self.n_cfg
         rows = self.exchange_tpfp(t["dt_tpfp"][:n_dt * n_cfg].view(n_dt, n_cfg))
-        num_gt, num_gt_owned = self.global_num_gt(t["num_gt"])
+        num_gt, num_gt_own = self.global_num_gt(t["num_gt"])
         st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
         P = lambda x: C.c_void_p(x.data_ptr())
+        q = self.part
         _lib.check(eng.lib.ta_pr_accumulate(
-            eng._ctx, st, self.n_cat, P(self.cat_dt_off), P(self.acc_perm), self.n_recv, P(rows),
-            P(num_gt_owned), dev.n_thr, n_cfg, dev.n_rec, dev.ptr["rec_thrs"],
-            P(t["precision"]), P(t["recall"]), P(t["tp_cnt"]), P(t["fp_cnt"])))
-        self.merge_to_root(t["precision"], t["recall"], t["tp_cnt"], t["fp_cnt"])
+            eng._ctx, st, self.n_loc, P(self.cat_dt_off), P(self.acc_perm), self.n_recv, P(rows),
+            P(num_gt_own), dev.n_thr, n_cfg, dev.n_rec, dev.ptr["rec_thrs"],
+            P(q["precision"]), P(q["recall"]), P(q["tp_cnt"]), P(q["fp_cnt"])))
+        names = ("precision", "recall", "tp_cnt", "fp_cnt")
+        self.merge_to_root([q[k] for k in names], [t[k] for k in names])
         t["num_gt"].copy_(num_gt)
 
 

@@ -43,12 +43,14 @@ def _worker(rank, world, port, case, kind, q):
         local = run_hostsim(plan)                       # per-rank IoU + matching
         acc = parallel.DistAccumulator(plan, rank, world, torch.device("cpu"))
         rows = acc.exchange_tpfp(torch.from_numpy(local.dt_tpfp.view(np.int32)))
-        num_gt, num_gt_owned = acc.global_num_gt(torch.from_numpy(local.num_gt))
-        out = hostsim_pr(len(plan.cat_ids), acc.cat_dt_off.numpy(), acc.acc_perm.numpy(),
-                         rows.numpy().view(np.uint32), num_gt_owned.numpy(), plan.n_cfg)
-        pr, rc = torch.from_numpy(out.precision), torch.from_numpy(out.recall)
-        tp, fp = torch.from_numpy(out.tp_cnt), torch.from_numpy(out.fp_cnt)
-        acc.merge_to_root(pr, rc, tp, fp)
+        num_gt, num_gt_own = acc.global_num_gt(torch.from_numpy(local.num_gt))
+        out = hostsim_pr(acc.n_loc, acc.cat_dt_off.numpy(), acc.acc_perm.numpy(),
+                         rows.numpy().view(np.uint32), num_gt_own.numpy(), plan.n_cfg)
+        parts = [torch.from_numpy(x) for x in (out.precision, out.recall, out.tp_cnt, out.fp_cnt)]
+        C_, K = len(plan.cat_ids), plan.n_cfg
+        pr, rc = torch.empty((10, 101, C_, K), dtype=torch.float64), torch.empty((10, C_, K), dtype=torch.float64)
+        tp, fp = torch.empty((10, C_, K), dtype=torch.int64), torch.empty((10, C_, K), dtype=torch.int64)
+        acc.merge_to_root(parts, [pr, rc, tp, fp])
         if rank == 0:
             shape = g[kind + "_precision"].shape
             ok = (np.array_equal(g[kind + "_precision"], pr.numpy().reshape(shape))
