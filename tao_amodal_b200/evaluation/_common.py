@@ -78,3 +78,25 @@ class LazyDict(dict):
     def get(self, k, default=None):
         self._fill()
         return super().get(k, default)
+
+
+def dist_info():
+    """(rank, world) of the default torch.distributed group, (0, 1) when not initialised.
+    With world > 1 the evaluators shard videos across ranks (parallel.py)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return 0, 1
+
+
+def dist_accumulate(eng, dev, rank, world):
+    """Cross-rank PR accumulation; every rank ends up with the merged tensors."""
+    import torch.distributed as dist
+    from .. import parallel
+    acc = parallel.DeviceDistAccumulator(eng, dev, rank, world)
+    acc.accumulate()
+    for k in ("precision", "recall", "tp_cnt", "fp_cnt"):
+        dist.broadcast(dev.t[k], src=0)

@@ -16,7 +16,7 @@ import numpy as np
 
 from ... import materialize, prep
 from ...columnar import DtColumns
-from .._common import LazyDict, get_engine
+from .._common import LazyDict, dist_accumulate, dist_info, get_engine
 from .lvis import LVIS
 from .results import LVISResults
 
@@ -102,6 +102,7 @@ class LVISEval:
         self.params.cat_ids = sorted(self.lvis_gt.get_cat_ids())
         self.device = device
         self._plan = self._dev = self._detail = None
+        self._rank, self._world = 0, 1
 
     def _prepare(self):
         """Columnar equivalent of lvis eval.py:59-113 (prep.prepare_lvis)."""
@@ -110,9 +111,23 @@ class LVISEval:
             raise NotImplementedError("only iou_type='bbox' runs on the CUDA path")
         if len(p.iou_thrs) > 16:
             raise ValueError("at most 16 IoU thresholds are supported")
+        img_ids = p.img_ids
+        self._rank, self._world = dist_info()
+        if self._world > 1:
+            # images travel with their video (same partition as the track evaluator); files
+            # without video ids are split by image id
+            from ... import parallel
+            cols = self.lvis_gt.columns
+            sel = np.isin(cols.img_id, np.asarray(img_ids, dtype=np.int64))
+            vid = cols.img_video_id[sel]
+            if (vid >= 0).all() and vid.size:
+                mine = parallel.shard_videos(np.unique(vid), self._world)[self._rank]
+                img_ids = cols.img_id[sel][np.isin(vid, mine)]
+            else:
+                img_ids = np.array_split(np.unique(cols.img_id[sel]), self._world)[self._rank]
         self._plan = prep.prepare_lvis(
             self.lvis_gt.columns, self.lvis_dt.dt_columns, max_dets=self.lvis_dt.max_dets,
-            vis_rng=p.visibility_rng, img_ids=p.img_ids,
+            vis_rng=p.visibility_rng, img_ids=img_ids,
             cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats))
         self.freq_groups = self._plan.freq_groups
 
@@ -147,7 +162,10 @@ class LVISEval:
             self.logger.warn("Please run evaluate first.")
             return
         eng = get_engine(self.device)
-        eng.stage_accumulate(self._dev)
+        if self._world > 1:
+            dist_accumulate(eng, self._dev, self._rank, self._world)
+        else:
+            eng.stage_accumulate(self._dev)
         p = self.params
         T, R, C, NR = len(p.iou_thrs), len(p.rec_thrs), len(self._plan.cat_ids), \
             len(p.visibility_rng)

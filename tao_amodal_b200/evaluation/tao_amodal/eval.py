@@ -17,7 +17,7 @@ import numpy as np
 
 from ... import materialize, prep
 from ...columnar import DtColumns
-from .._common import LazyDict, get_engine
+from .._common import LazyDict, dist_accumulate, dist_info, get_engine
 from .results import TaoResults
 from .tao import Tao
 
@@ -77,6 +77,7 @@ class TaoEval:
         self._plan = None
         self._dev = None
         self._detail = None
+        self._rank, self._world = 0, 1
 
     # ------------------------------------------------------------------------ device stages
     def _prepare(self):
@@ -86,9 +87,16 @@ class TaoEval:
             raise NotImplementedError("only iou_type='bbox' runs on the CUDA path")
         if len(p.iou_thrs) > 16:
             raise ValueError("at most 16 IoU thresholds are supported")
+        vid_ids = p.vid_ids
+        self._rank, self._world = dist_info()
+        if self._world > 1:
+            # one shard of videos per GPU (torchrun): IoU + matching are local, accumulate()
+            # exchanges the per-track records (parallel.py)
+            from ... import parallel
+            vid_ids = parallel.shard_videos(np.unique(vid_ids), self._world)[self._rank]
         self._plan = prep.prepare_tao(
             self.tao_gt.columns, self.tao_dt.dt_columns, max_dets=self.tao_dt.max_dets,
-            area_rng=p.area_rng, time_rng=p.time_rng, vid_ids=p.vid_ids,
+            area_rng=p.area_rng, time_rng=p.time_rng, vid_ids=vid_ids,
             cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats))
 
     def evaluate(self, show_progress=False):
@@ -126,9 +134,11 @@ class TaoEval:
         if self._dev is None:
             self.logger.warn("Please run evaluate first.")
             return
-        import torch
         eng = get_engine(self.device)
-        eng.stage_accumulate(self._dev)
+        if self._world > 1:
+            dist_accumulate(eng, self._dev, self._rank, self._world)
+        else:
+            eng.stage_accumulate(self._dev)
         p = self.params
         T, R, C = len(p.iou_thrs), len(p.rec_thrs), len(self._plan.cat_ids)
         A, Tm = len(p.area_rng), len(p.time_rng)

@@ -7,6 +7,11 @@ log-file / console / stdout lines, evaluated on the GPU.
 Differences that do not change any output: runs from any working directory, parses each JSON
 file once (the reference parses both twice), ``--annotation`` has no machine-specific default,
 ``--device`` (additive) selects the GPU.
+
+Multi-GPU: launch with torchrun, e.g.
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 \
+        tools/eval_on_tao_amodal.py --track_result P --output_log L --annotation A
+Every rank evaluates its shard of the videos on its own GPU; rank 0 writes the log and stdout.
 """
 import argparse
 import logging
@@ -123,19 +128,38 @@ def main(argv=None):
     if not args.annotation:
         parser.error("--annotation is required (the reference's default is a path on its "
                      "authors' machine, tools/eval_on_tao_amodal.py:39)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    device = args.device
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(device)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", device))
     output_log = Path(args.output_log)
     logger = logging.getLogger("__main__")
-    logger.setLevel(logging.INFO)
-    output_log.parent.mkdir(parents=True, exist_ok=True)
-    handler = logging.FileHandler(output_log, mode='w')
-    logger.addHandler(handler)
+    handler = None
+    if rank == 0:
+        logger.setLevel(logging.INFO)
+        output_log.parent.mkdir(parents=True, exist_ok=True)
+        handler = logging.FileHandler(output_log, mode='w')
+        logger.addHandler(handler)
+    else:           # other ranks compute their shard silently
+        logging.disable(logging.CRITICAL)
+        sys.stdout = open(os.devnull, "w")
     try:
         evaluate_predictions_on_lvis(args.annotation, args.track_result, "bbox", logger,
-                                     device=args.device)
-        eval_tao_track(args.annotation, args.track_result, logger, device=args.device)
+                                     device=device)
+        eval_tao_track(args.annotation, args.track_result, logger, device=device)
     finally:
-        handler.close()
-        logger.removeHandler(handler)
+        if handler is not None:
+            handler.close()
+            logger.removeHandler(handler)
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
     return 0
 
 
