@@ -47,7 +47,9 @@ def main():
         if r.returncode != 0:
             print(r.stderr[-3000:])
             raise SystemExit("%s run failed" % name)
-        outs[name] = (open(log).read(), r.stdout)
+        # NCCL prints its version banner on stdout at communicator creation
+        so = "\n".join(l for l in r.stdout.splitlines() if not l.startswith("NCCL version"))
+        outs[name] = (open(log).read(), so)
     same_log = outs["single"][0] == outs["dist"][0]
     same_out = outs["single"][1] == outs["dist"][1]
     res.update(gpus=args.gpus, config=args.config, log_identical=same_log, stdout_identical=same_out,
@@ -57,8 +59,9 @@ def main():
         json.dump(res, open(args.out, "w"), indent=1)
     if not (same_log and same_out):
         import difflib
-        print("\n".join(list(difflib.unified_diff(outs["single"][0].splitlines(),
-                                                   outs["dist"][0].splitlines(), lineterm=""))[:40]))
+        for k in (0, 1):
+            print("\n".join(list(difflib.unified_diff(outs["single"][k].splitlines(),
+                                                       outs["dist"][k].splitlines(), lineterm=""))[:40]))
         raise SystemExit(1)
 
 
