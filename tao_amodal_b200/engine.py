@@ -365,6 +365,7 @@ class DevicePlan:
                         dt_slot=plan.dt_box_slot, gt_slot=plan.gt_box_slot)
         self.t = {}
         self.input_bytes = 0
+        self._input_keys = []
         for k, v in host.items():
             v = np.ascontiguousarray(v)
             self.input_bytes += v.nbytes
@@ -372,6 +373,14 @@ class DevicePlan:
                 self.t[k] = torch.zeros(16, dtype=torch.uint8, device=dev)
             else:
                 self.t[k] = torch.from_numpy(v).to(dev)
+                self._input_keys.append(k)
+        self._host_of = lambda pl: dict(
+            grp_dt_off=pl.grp_dt_off, grp_gt_off=pl.grp_gt_off, iou_off=pl.iou_off,
+            cat_dt_off=pl.cat_dt_off, grp_cat=pl.grp_cat, acc_perm=pl.acc_perm,
+            dt_box=pl.dt_box, gt_box=pl.gt_box, dt_attr_a=pl.dt_attr_a, dt_attr_b=pl.dt_attr_b,
+            gt_attr_a=pl.gt_attr_a, gt_attr_b=pl.gt_attr_b, dt_flag=pl.dt_flag,
+            gt_flag=pl.gt_flag, gt_hp=pl.gt_hp, dt_trk_off=pl.dt_trk_box_off,
+            gt_trk_off=pl.gt_trk_box_off, dt_slot=pl.dt_box_slot, gt_slot=pl.gt_box_slot)
         n_iou = int(plan.iou_off[-1]) if plan.iou_off.size else 0
         C_, T, R = self.n_cat, self.n_thr, self.n_rec
         self.t["iou"] = torch.empty(max(n_iou, 1), dtype=torch.float64, device=dev)
@@ -382,6 +391,20 @@ class DevicePlan:
         self.t["tp_cnt"] = torch.empty((T, C_, n_cfg), dtype=torch.int64, device=dev)
         self.t["fp_cnt"] = torch.empty((T, C_, n_cfg), dtype=torch.int64, device=dev)
         self._refresh()
+
+    def reload(self, plan: EvalPlan) -> int:
+        """Copy the arrays of `plan` (same shapes as the uploaded one, e.g. its pinned twin) into
+        the existing device buffers, asynchronously on the current stream.  Returns the bytes."""
+        import torch
+        src = self._host_of(plan)
+        n = 0
+        for k in self._input_keys:
+            v = src.get(k)
+            if v is None:
+                continue
+            self.t[k].copy_(torch.from_numpy(v), non_blocking=True)
+            n += v.nbytes
+        return n
 
     def ensure_detail(self):
         import torch
