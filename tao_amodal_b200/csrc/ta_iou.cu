@@ -36,7 +36,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // CPython set iteration order, eval.py:83).
 // ------------------------------------------------------------------------------------------
 #define GT_TILE 8
-#define TI_WARPS 8
+#define TI_WARPS 16
 
 struct TrackIouArgs {
     const int64_t* grp_dt_off;
@@ -52,7 +52,7 @@ struct TrackIouArgs {
     int S;  // slots per window
 };
 
-__global__ void __launch_bounds__(TI_WARPS * 32)
+__global__ void __launch_bounds__(TI_WARPS * 32, 2)
 k_track_iou_tiled(TrackIouArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = a.S;
@@ -251,8 +251,10 @@ extern "C" int ta_track_iou(ta_ctx* ctx, void* stream, int mode, int64_t n_group
     TrackIouArgs a{grp_dt_off, grp_gt_off, dt_trk_off, dt_box, dt_slot,
                    gt_trk_off, gt_box, gt_slot, iou_off, iou_out, 0};
     if (mode == TA_IOU_3D) {
-        int S = 64;
-        while (S < n_slots_max && S < 384) S += (S < 128 ? 64 : 128);
+        // slots per shared-memory window: the whole video when it fits (2 CTAs of 16 warps per SM
+        // need <= ~110 KB each), else 384-slot windows
+        int S = ((n_slots_max + 15) / 16) * 16;
+        if (S < 16) S = 16;
         if (S > 384) S = 384;
         a.S = S;
         const size_t smem = (size_t)2 * GT_TILE * (S + 1) * sizeof(double2);

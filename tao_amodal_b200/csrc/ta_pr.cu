@@ -313,16 +313,24 @@ __global__ void k_pr_suffix(PrArgs a) {
 }
 
 __global__ void k_pr_finalize(PrArgs a) {
-    // blockIdx.y <-> (threshold, recall level); threads along (category, cfg): the precision
-    // tensor [T][R][C][cfg] is written once, fully coalesced, without integer divisions
+    // thread <-> one precision entry (threshold, recall k, category, cfg), cfg fastest: the
+    // tensor [T][R][C][cfg] is written once, fully coalesced
     const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
-    const int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // cat * n_cfg + cfg
-    if (cc >= per_t) return;
-    const int tk_idx = blockIdx.y;                                          // t * n_rec + k
-    const int t = tk_idx / a.n_rec, k = tk_idx - t * a.n_rec;
-    const int64_t idx = (int64_t)tk_idx * per_t + cc;
+    const int64_t n = (int64_t)a.n_thr * a.n_rec * per_t;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    int64_t cc, tk_idx;
+    if (n < (1ll << 31)) {                       // 32-bit division is several times cheaper
+        const uint32_t q = (uint32_t)idx / (uint32_t)per_t;
+        tk_idx = q;
+        cc = (uint32_t)idx - q * (uint32_t)per_t;
+    } else {
+        tk_idx = idx / per_t;
+        cc = idx - tk_idx * per_t;
+    }
     const int ngt = a.num_gt[cc];
     if (ngt == 0) { a.precision[idx] = -1.0; return; }        // eval.py:522-525
+    const int t = (int)tk_idx / a.n_rec, k = (int)tk_idx - t * a.n_rec;
     const int cat = (int)(cc / a.n_cfg), cfg = (int)(cc - (int64_t)cat * a.n_cfg);
     const uint32_t need = (uint32_t)max(a.tk[cc * a.n_rec + k], 1);
     if (need > a.cat_tot[cc * 32 + t]) { a.precision[idx] = 0.0; return; }   // eval.py:565-573
@@ -411,8 +419,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     }
     k_pr_suffix<<<n_cat, 128, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_suffix"))) return rc;
-    const size_t per_t = (size_t)n_cat * n_cfg;
-    dim3 fgrid((unsigned)((per_t + 255) / 256), (unsigned)(n_thr * n_rec));
-    k_pr_finalize<<<fgrid, 256, 0, st>>>(a);
+    const size_t n_prec = (size_t)n_thr * n_rec * n_cat * n_cfg;
+    k_pr_finalize<<<(unsigned)((n_prec + 255) / 256), 256, 0, st>>>(a);
     return ta_check_launch(ctx, "k_pr_finalize");
 }
