@@ -40,78 +40,85 @@ struct MatchArgs {
     int32_t* dt_match_gt;
     uint8_t* gt_ignore_out;
     int cfgs_per_warp;
+    // device-side group list (the flat kernels' leftovers): CTAs loop over dev_list[0 .. *dev_count)
+    const int32_t* dev_list;
+    const int32_t* dev_count;
+    int skip_num_gt;              // the GT counts of these groups were taken by k_frame_prep
 };
 
 __global__ void k_match_greedy(MatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int grp = a.grp_list ? a.grp_list[blockIdx.x] : (int)blockIdx.x;
-    const int64_t d0 = a.grp_dt_off[grp], g0 = a.grp_gt_off[grp];
-    const int D = (int)(a.grp_dt_off[grp + 1] - d0), G = (int)(a.grp_gt_off[grp + 1] - g0);
-    if (D == 0 && G == 0) return;
     const int nthreads = blockDim.x;
-    const int words = (G + 31) >> 5;
-    // shared layout: taken[words][nthreads] u32, then gt_ig[n_cfg][G] u8
-    uint32_t* taken = reinterpret_cast<uint32_t*>(smem_raw);
-    uint8_t* gt_ig = smem_raw + (size_t)words * nthreads * sizeof(uint32_t);
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cpw = a.cfgs_per_warp;
     const int cw = lane / a.n_thr;
     const int t = lane - cw * a.n_thr;
     const int cfg = warp * cpw + cw;
     const bool active = (cw < cpw) && (cfg < a.n_cfg);
+    const int n_items = a.dev_list ? *a.dev_count : (int)gridDim.x;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int grp = a.dev_list ? a.dev_list[item] : (a.grp_list ? a.grp_list[item] : item);
+        const int64_t d0 = a.grp_dt_off[grp], g0 = a.grp_gt_off[grp];
+        const int D = (int)(a.grp_dt_off[grp + 1] - d0), G = (int)(a.grp_gt_off[grp + 1] - g0);
+        if (D == 0 && G == 0) continue;
+        __syncthreads();          // shared state of the previous group fully consumed
+        const int words = (G + 31) >> 5;
+        // shared layout: taken[words][nthreads] u32, then gt_ig[n_cfg][G] u8
+        uint32_t* taken = reinterpret_cast<uint32_t*>(smem_raw);
+        uint8_t* gt_ig = smem_raw + (size_t)words * nthreads * sizeof(uint32_t);
 
-    // ---- GT ignore flags for every cfg (eval.py:348-368 / lvis eval.py:201-217)
-    for (int idx = threadIdx.x; idx < a.n_cfg * G; idx += nthreads) {
-        const int c = idx / G, g = idx - c * G;
-        const uint8_t ig = ta_gt_ignored(a.cfgs[c], a.gt_a[g0 + g], a.gt_b ? a.gt_b[g0 + g] : 0.0,
-                                         a.gt_hp ? a.gt_hp[g0 + g] : 0, a.gt_flag[g0 + g]);
-        gt_ig[idx] = ig;
-        if (a.gt_ignore_out) a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + g] = ig;
-    }
-    for (int w = 0; w < words; ++w) taken[w * nthreads + threadIdx.x] = 0u;
-    __syncthreads();
-    // ---- number of non-ignored GT per (category, cfg) (eval.py:520-522)
-    if (threadIdx.x < a.n_cfg && G > 0) {
-        int cnt = 0;
-        for (int g = 0; g < G; ++g) cnt += gt_ig[threadIdx.x * G + g] == 0;
-        if (cnt) atomicAdd(&a.num_gt[(int64_t)a.grp_cat[grp] * a.n_cfg + threadIdx.x], cnt);
-    }
-    if (D == 0) return;
-
-    const double thr = active ? a.thrs[t] : 2.0;
-    const double* iou = a.iou + a.iou_off[grp];
-    const uint8_t* my_ig = gt_ig + (active ? cfg : 0) * G;
-    ta_range_cfg rc;
-    if (active) rc = a.cfgs[cfg];
-    uint32_t* my_taken = taken + threadIdx.x;
-
-    const int sh = cw * a.n_thr;
-    const uint32_t thr_all = (1u << a.n_thr) - 1u;
-    for (int d = 0; d < D; ++d) {
-        bool tp = false, fp = false;
-        if (active) {
-            int m = -1;
-            if (G > 0) m = ta_match_one(iou + (int64_t)d * G, G, my_ig, my_taken, nthreads, thr);
-            const uint8_t dflag = a.dt_flag[d0 + d];
-            bool unmatched = true, ig = false;
-            if (m >= 0) {
-                if (dflag & 2) my_taken[(m >> 5) * nthreads] |= 1u << (m & 31);   // eval.py:407,428
-                unmatched = (a.gt_flag[g0 + m] & 4) != 0;                         // eval.py:427,443
-                ig = my_ig[m] != 0;                                               // eval.py:425
-            }
-            if (unmatched && !ig)
-                ig = ta_dt_unmatched_ignored(rc, a.dt_a[d0 + d], a.dt_b ? a.dt_b[d0 + d] : 0.0, dflag);
-            tp = !ig && !unmatched;
-            fp = !ig && unmatched;
-            if (a.dt_match_gt)
-                a.dt_match_gt[((int64_t)cfg * a.n_thr + t) * a.n_dt + d0 + d] = m;
+        // ---- GT ignore flags for every cfg (eval.py:348-368 / lvis eval.py:201-217)
+        for (int idx = threadIdx.x; idx < a.n_cfg * G; idx += nthreads) {
+            const int c = idx / G, g = idx - c * G;
+            const uint8_t ig = ta_gt_ignored(a.cfgs[c], a.gt_a[g0 + g], a.gt_b ? a.gt_b[g0 + g] : 0.0,
+                                             a.gt_hp ? a.gt_hp[g0 + g] : 0, a.gt_flag[g0 + g]);
+            gt_ig[idx] = ig;
+            if (a.gt_ignore_out) a.gt_ignore_out[(int64_t)c * a.n_gt + g0 + g] = ig;
         }
-        // the n_thr lanes of a cfg are consecutive: its TP / FP words are slices of two ballots
-        const uint32_t bt = __ballot_sync(0xffffffffu, tp);
-        const uint32_t bf = __ballot_sync(0xffffffffu, fp);
-        if (active && t == 0)
-            a.dt_tpfp[(d0 + d) * a.n_cfg + cfg] = ((bt >> sh) & thr_all) | (((bf >> sh) & thr_all) << 16);
+        for (int w = 0; w < words; ++w) taken[w * nthreads + threadIdx.x] = 0u;
+        __syncthreads();
+        // ---- number of non-ignored GT per (category, cfg) (eval.py:520-522)
+        if (!a.skip_num_gt && threadIdx.x < a.n_cfg && G > 0) {
+            int cnt = 0;
+            for (int g = 0; g < G; ++g) cnt += gt_ig[threadIdx.x * G + g] == 0;
+            if (cnt) atomicAdd(&a.num_gt[(int64_t)a.grp_cat[grp] * a.n_cfg + threadIdx.x], cnt);
+        }
+        if (D == 0) continue;
+
+        const double thr = active ? a.thrs[t] : 2.0;
+        const double* iou = a.iou + a.iou_off[grp];
+        const uint8_t* my_ig = gt_ig + (active ? cfg : 0) * G;
+        ta_range_cfg rc;
+        if (active) rc = a.cfgs[cfg];
+        uint32_t* my_taken = taken + threadIdx.x;
+
+        const int sh = cw * a.n_thr;
+        const uint32_t thr_all = (1u << a.n_thr) - 1u;
+        for (int d = 0; d < D; ++d) {
+            bool tp = false, fp = false;
+            if (active) {
+                int m = -1;
+                if (G > 0) m = ta_match_one(iou + (int64_t)d * G, G, my_ig, my_taken, nthreads, thr);
+                const uint8_t dflag = a.dt_flag[d0 + d];
+                bool unmatched = true, ig = false;
+                if (m >= 0) {
+                    if (dflag & 2) my_taken[(m >> 5) * nthreads] |= 1u << (m & 31);   // eval.py:407,428
+                    unmatched = (a.gt_flag[g0 + m] & 4) != 0;                         // eval.py:427,443
+                    ig = my_ig[m] != 0;                                               // eval.py:425
+                }
+                if (unmatched && !ig)
+                    ig = ta_dt_unmatched_ignored(rc, a.dt_a[d0 + d], a.dt_b ? a.dt_b[d0 + d] : 0.0, dflag);
+                tp = !ig && !unmatched;
+                fp = !ig && unmatched;
+                if (a.dt_match_gt)
+                    a.dt_match_gt[((int64_t)cfg * a.n_thr + t) * a.n_dt + d0 + d] = m;
+            }
+            // the n_thr lanes of a cfg are consecutive: its TP / FP words are slices of two ballots
+            const uint32_t bt = __ballot_sync(0xffffffffu, tp);
+            const uint32_t bf = __ballot_sync(0xffffffffu, fp);
+            if (active && t == 0)
+                a.dt_tpfp[(d0 + d) * a.n_cfg + cfg] = ((bt >> sh) & thr_all) | (((bf >> sh) & thr_all) << 16);
+        }
     }
 }
 
@@ -160,6 +167,12 @@ struct FrameArgs {
     int32_t* num_gt;
     int32_t* dt_match_gt;
     uint8_t* gt_ignore_out;
+    // track path (NULL on the frame path: area = w*h of the box, b = 0, hp = 0)
+    const double* dt_a;           // detection attribute a (mean track area)
+    const double* dt_b;           // detection attribute b (number of annotations)
+    const double* gt_b;
+    const int32_t* gt_hp;
+    int exclude_big;              // k_frame_prep: leave oversize frame groups to the big_list route
     // flat path
     const int32_t* dt_grp;        // group of every detection
     int32_t* grp_flag;            // per group: already on the complex list
@@ -178,29 +191,55 @@ struct FrameSmem {
     uint32_t gig[FE_WARPS][FE_MAX_CFG];       // per cfg: bit g = GT g ignored
 };
 
+// Range tests evaluated once per DISTINCT interval instead of once per cfg: the distinct
+// [lo, hi] intervals of the four interval tests of ta_range_cfg (detection a / b, GT a / b), the
+// distinct gt_hp_min values and the cfgs that need out_of_frame, each with the bit mask of the
+// cfgs using it.  Intervals (-inf, +inf) and disabled hp rules are dropped.  LVISEval: one
+// detection interval, five GT visibility intervals; TaoEval: 4 area x 4 duration intervals
+// for 20 cfgs.
+#define RR_MAX 32
 struct FrameRules {
-    int n_da, n_ga;
-    uint32_t d_const, g_const, g_oof;         // cfg masks: constant-true tests, cfgs needing out_of_frame
-    double da_lo[FE_MAX_CFG], da_hi[FE_MAX_CFG], ga_lo[FE_MAX_CFG], ga_hi[FE_MAX_CFG];
-    uint32_t da_mask[FE_MAX_CFG], ga_mask[FE_MAX_CFG];
+    int n_da, n_db, n_ga, n_gb, n_hp;
+    uint32_t g_oof;
+    double da_lo[RR_MAX], da_hi[RR_MAX], db_lo[RR_MAX], db_hi[RR_MAX];
+    double ga_lo[RR_MAX], ga_hi[RR_MAX], gb_lo[RR_MAX], gb_hi[RR_MAX];
+    uint32_t da_mask[RR_MAX], db_mask[RR_MAX], ga_mask[RR_MAX], gb_mask[RR_MAX], hp_mask[RR_MAX];
+    int32_t hp_min[RR_MAX];
 };
 
-// cfg mask "this detection is ignored when unmatched" (lvis eval.py:281-286) for b = 0
-__device__ __forceinline__ uint32_t fe_dt_unmatched_mask(const FrameRules& r, double area, uint8_t fl,
-                                                         uint32_t cfg_all) {
-    uint32_t m = (fl & 1) ? cfg_all : r.d_const;
+// cfg mask "this detection is ignored when unmatched" (eval.py:432-439, lvis eval.py:281-286)
+__device__ __forceinline__ uint32_t fe_dt_unmatched_mask(const FrameRules& r, double a, double b,
+                                                         uint8_t fl, uint32_t cfg_all) {
+    uint32_t m = (fl & 1) ? cfg_all : 0u;
     for (int k = 0; k < r.n_da; ++k)
-        if (area < r.da_lo[k] || area > r.da_hi[k]) m |= r.da_mask[k];
+        if (a < r.da_lo[k] || a > r.da_hi[k]) m |= r.da_mask[k];
+    for (int k = 0; k < r.n_db; ++k)
+        if (b < r.db_lo[k] || b > r.db_hi[k]) m |= r.db_mask[k];
     return m;
 }
-// cfg mask "this GT is ignored" (lvis eval.py:202-217) for b = 0, hp = 0
-__device__ __forceinline__ uint32_t fe_gt_ignore_mask(const FrameRules& r, double vis, uint8_t fl,
-                                                      uint32_t cfg_all) {
-    uint32_t m = (fl & 1) ? cfg_all : r.g_const;
+// cfg mask "this GT is ignored" (eval.py:349-368, lvis eval.py:202-217)
+__device__ __forceinline__ uint32_t fe_gt_ignore_mask(const FrameRules& r, double a, double b,
+                                                      int32_t hp, uint8_t fl, uint32_t cfg_all) {
+    uint32_t m = (fl & 1) ? cfg_all : 0u;
     if (!(fl & 2)) m |= r.g_oof;
     for (int k = 0; k < r.n_ga; ++k)
-        if (vis < r.ga_lo[k] || vis > r.ga_hi[k]) m |= r.ga_mask[k];
+        if (a < r.ga_lo[k] || a > r.ga_hi[k]) m |= r.ga_mask[k];
+    for (int k = 0; k < r.n_gb; ++k)
+        if (b < r.gb_lo[k] || b > r.gb_hi[k]) m |= r.gb_mask[k];
+    for (int k = 0; k < r.n_hp; ++k)
+        if (hp < r.hp_min[k]) m |= r.hp_mask[k];
     return m;
+}
+
+__device__ __forceinline__ void fe_add_interval(double lo, double hi, int c, int& n, double* los,
+                                                double* his, uint32_t* masks) {
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    if (lo == -INF && hi == INF) return;            // never excludes anything
+    int k = 0;
+    for (; k < n; ++k)
+        if (los[k] == lo && his[k] == hi) break;
+    if (k == n) { los[k] = lo; his[k] = hi; masks[k] = 0; ++n; }
+    masks[k] |= 1u << c;
 }
 
 __device__ __forceinline__ void fe_setup(const FrameArgs& a, int n_thr, int n_cfg,
@@ -212,22 +251,21 @@ __device__ __forceinline__ void fe_setup(const FrameArgs& a, int n_thr, int n_cf
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        rules.n_da = rules.n_ga = 0;
-        rules.d_const = rules.g_const = rules.g_oof = 0;
+        rules.n_da = rules.n_db = rules.n_ga = rules.n_gb = rules.n_hp = 0;
+        rules.g_oof = 0;
         for (int c = 0; c < n_cfg; ++c) {
             const ta_range_cfg& r = cfg_s[c];
-            if (0.0 < r.dt_b_lo || 0.0 > r.dt_b_hi) rules.d_const |= 1u << c;
-            if (0.0 < r.gt_b_lo || 0.0 > r.gt_b_hi || 0 < r.gt_hp_min) rules.g_const |= 1u << c;
+            fe_add_interval(r.dt_a_lo, r.dt_a_hi, c, rules.n_da, rules.da_lo, rules.da_hi, rules.da_mask);
+            fe_add_interval(r.dt_b_lo, r.dt_b_hi, c, rules.n_db, rules.db_lo, rules.db_hi, rules.db_mask);
+            fe_add_interval(r.gt_a_lo, r.gt_a_hi, c, rules.n_ga, rules.ga_lo, rules.ga_hi, rules.ga_mask);
+            fe_add_interval(r.gt_b_lo, r.gt_b_hi, c, rules.n_gb, rules.gb_lo, rules.gb_hi, rules.gb_mask);
             if (r.gt_need_oof) rules.g_oof |= 1u << c;
-            int k = 0;
-            for (; k < rules.n_da; ++k)
-                if (rules.da_lo[k] == r.dt_a_lo && rules.da_hi[k] == r.dt_a_hi) break;
-            if (k == rules.n_da) { rules.da_lo[k] = r.dt_a_lo; rules.da_hi[k] = r.dt_a_hi; rules.da_mask[k] = 0; ++rules.n_da; }
-            rules.da_mask[k] |= 1u << c;
-            for (k = 0; k < rules.n_ga; ++k)
-                if (rules.ga_lo[k] == r.gt_a_lo && rules.ga_hi[k] == r.gt_a_hi) break;
-            if (k == rules.n_ga) { rules.ga_lo[k] = r.gt_a_lo; rules.ga_hi[k] = r.gt_a_hi; rules.ga_mask[k] = 0; ++rules.n_ga; }
-            rules.ga_mask[k] |= 1u << c;
+            if (r.gt_hp_min != INT_MIN) {
+                int k = 0;
+                for (; k < rules.n_hp; ++k) if (rules.hp_min[k] == r.gt_hp_min) break;
+                if (k == rules.n_hp) { rules.hp_min[k] = r.gt_hp_min; rules.hp_mask[k] = 0; ++rules.n_hp; }
+                rules.hp_mask[k] |= 1u << c;
+            }
         }
     }
     __syncthreads();
@@ -294,7 +332,7 @@ k_frame_eval(FrameArgs a) {
                 const int64_t gb = __shfl_sync(0xffffffffu, gt_off_r, gi + 1);
                 if (dd < d_end && ga == gb) {
                     const double2 q = *reinterpret_cast<const double2*>(a.dt_box + 4 * dd + 2);
-                    const uint32_t m = fe_dt_unmatched_mask(rules, q.x * q.y, a.dt_flag[dd], cfg_all);
+                    const uint32_t m = fe_dt_unmatched_mask(rules, q.x * q.y, 0.0, a.dt_flag[dd], cfg_all);
                     uint32_t* o = a.dt_tpfp + dd * n_cfg;
                     for (int c = 0; c < n_cfg; ++c) o[c] = ((m >> c) & 1u) ? 0u : (thr_all << 16);
                     if (DETAIL && a.dt_match_gt)
@@ -338,7 +376,7 @@ k_frame_eval(FrameArgs a) {
                 sm.gtb[warp][lane][2] = gq.x; sm.gtb[warp][lane][3] = gq.y;
             }
             const uint32_t gsent = __ballot_sync(0xffffffffu, (gfl & 4) != 0);   // id == "unmatched" value
-            const uint32_t gmask = (lane < G) ? fe_gt_ignore_mask(rules, vis, gfl, cfg_all) : 0u;
+            const uint32_t gmask = (lane < G) ? fe_gt_ignore_mask(rules, vis, 0.0, 0, gfl, cfg_all) : 0u;
             uint32_t my_gig = 0;
             for (int c = 0; c < n_cfg; ++c) {
                 const uint32_t m = __ballot_sync(0xffffffffu, (gmask >> c) & 1u);
@@ -367,7 +405,7 @@ k_frame_eval(FrameArgs a) {
                     dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d0 + d) + 2);
                     dfl = a.dt_flag[d0 + d];
                 }
-                dmask_s[d] = fe_dt_unmatched_mask(rules, dq.x * dq.y, dfl, cfg_all) |
+                dmask_s[d] = fe_dt_unmatched_mask(rules, dq.x * dq.y, 0.0, dfl, cfg_all) |
                              ((dfl & 2) ? (1u << 16) : 0u);
                 int cnt = 0, gs = 0;
                 double vs = 0.0;
@@ -530,10 +568,26 @@ __device__ __forceinline__ FlatCand fe_candidate(const double* __restrict__ gt_b
 
 #define FF_WARPS 4
 
-template <int NT, int NC>
+// candidate summary from a row of a precomputed IoU matrix (track path)
+__device__ __forceinline__ FlatCand fe_candidate_row(const double* __restrict__ row, int G,
+                                                     double thr_min, const double* thr_s, int n_thr) {
+    FlatCand c{0, 0, 0u};
+    double vs = 0.0;
+    for (int g = 0; g < G; ++g) {
+        const double v = row[g];
+        if (!(v < thr_min)) { ++c.cnt; c.gs = g; vs = v; }
+    }
+    if (c.cnt == 1)
+        for (int k = 0; k < n_thr; ++k) c.ge |= (!(vs < thr_s[k])) ? (1u << k) : 0u;
+    return c;
+}
+
+// TRACK: detections are tracks; IoUs come from the matrix ta_track_iou wrote (a.iou / a.iou_off),
+// attributes from dt_a / dt_b / gt_b / gt_hp, and groups with more than 32 GT go to the list.
+template <int NT, int NC, bool TRACK>
 __global__ void __launch_bounds__(FF_WARPS * 32, 8)
 k_frame_flat(FrameArgs a) {
-    __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
+    __shared__ ta_range_cfg cfg_s[RR_MAX];
     __shared__ double thr_s[TA_MAX_THRS];
     __shared__ FrameRules rules;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -558,14 +612,20 @@ k_frame_flat(FrameArgs a) {
         uint8_t dfl = 0;
         if (valid) {
             grp = a.dt_grp[d];
-            dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * d);
-            dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * d + 2);
+            if (!TRACK) {
+                dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * d);
+                dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * d + 2);
+            }
             dfl = a.dt_flag[d];
             d0 = a.grp_dt_off[grp];
             g0 = a.grp_gt_off[grp];
             G = (int)(a.grp_gt_off[grp + 1] - g0);
         }
-        const bool skip = G > FE_MAX_GT;          // needs the big_list route (g* has 5 bits)
+        // g* has 5 bits: larger groups need the general matcher (frame path: big_list route;
+        // track path: appended to the complex list here)
+        const bool skip = G > FE_MAX_GT;
+        if (TRACK && skip && atomicExch(&a.grp_flag[grp], 1) == 0)
+            a.complex_list[atomicAdd(a.complex_count, 1)] = grp;
         // ---- replay: detections of lane 0's group that precede the window seed its taken masks
         const int grp_f = __shfl_sync(0xffffffffu, grp, 0);
         const int G_f = __shfl_sync(0xffffffffu, G, 0);
@@ -578,9 +638,15 @@ k_frame_flat(FrameArgs a) {
                 uint32_t x = 0;
                 int rgs = -1;
                 if (rd < base) {
-                    const double2 rp = *reinterpret_cast<const double2*>(a.dt_box + 4 * rd);
-                    const double2 rq = *reinterpret_cast<const double2*>(a.dt_box + 4 * rd + 2);
-                    const FlatCand rc = fe_candidate(a.gt_box, g0_f, G_f, rp, rq, thr_min, thr_s, n_thr);
+                    FlatCand rc;
+                    if (TRACK) {
+                        rc = fe_candidate_row(a.iou + a.iou_off[grp_f] + (rd - d0_f) * G_f, G_f,
+                                              thr_min, thr_s, n_thr);
+                    } else {
+                        const double2 rp = *reinterpret_cast<const double2*>(a.dt_box + 4 * rd);
+                        const double2 rq = *reinterpret_cast<const double2*>(a.dt_box + 4 * rd + 2);
+                        rc = fe_candidate(a.gt_box, g0_f, G_f, rp, rq, thr_min, thr_s, n_thr);
+                    }
                     if (rc.cnt == 1 && (a.dt_flag[rd] & 2)) { x = rc.ge; rgs = rc.gs; }
                 }
                 for (int g = 0; g < G_f; ++g) {
@@ -593,7 +659,10 @@ k_frame_flat(FrameArgs a) {
         FlatCand c{0, 0, 0u};
         const bool work = valid && G > 0 && !skip;
         if (work) {
-            c = fe_candidate(a.gt_box, g0, G, dp, dq, thr_min, thr_s, n_thr);
+            if (TRACK)
+                c = fe_candidate_row(a.iou + a.iou_off[grp] + (d - d0) * G, G, thr_min, thr_s, n_thr);
+            else
+                c = fe_candidate(a.gt_box, g0, G, dp, dq, thr_min, thr_s, n_thr);
             if (c.cnt > 1 && atomicExch(&a.grp_flag[grp], 1) == 0)
                 a.complex_list[atomicAdd(a.complex_count, 1)] = grp;
         }
@@ -615,12 +684,18 @@ k_frame_flat(FrameArgs a) {
         const uint32_t M = single ? (c.ge & ~taken) : 0u;
         // ---- TP / FP words of every cfg
         if (valid && !skip) {
-            const uint32_t dm = fe_dt_unmatched_mask(rules, dq.x * dq.y, dfl, cfg_all);
+            const uint32_t dm = TRACK
+                ? fe_dt_unmatched_mask(rules, a.dt_a[d], a.dt_b ? a.dt_b[d] : 0.0, dfl, cfg_all)
+                : fe_dt_unmatched_mask(rules, dq.x * dq.y, 0.0, dfl, cfg_all);
             uint32_t gmask = 0;
             bool sent = false;
             if (M) {
-                const uint8_t gfl = a.gt_flag[g0 + c.gs];
-                gmask = fe_gt_ignore_mask(rules, a.gt_vis[g0 + c.gs], gfl, cfg_all);
+                const int64_t gg = g0 + c.gs;
+                const uint8_t gfl = a.gt_flag[gg];
+                gmask = TRACK
+                    ? fe_gt_ignore_mask(rules, a.gt_vis[gg], a.gt_b ? a.gt_b[gg] : 0.0,
+                                        a.gt_hp ? a.gt_hp[gg] : 0, gfl, cfg_all)
+                    : fe_gt_ignore_mask(rules, a.gt_vis[gg], 0.0, 0, gfl, cfg_all);
                 sent = (gfl & 4) != 0;
             }
             uint32_t* o = a.dt_tpfp + d * n_cfg;
@@ -642,7 +717,7 @@ k_frame_flat(FrameArgs a) {
 template <int NC>
 __global__ void __launch_bounds__(256)
 k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp) {
-    __shared__ ta_range_cfg cfg_s[FE_MAX_CFG];
+    __shared__ ta_range_cfg cfg_s[RR_MAX];
     __shared__ double thr_s[TA_MAX_THRS];
     __shared__ FrameRules rules;
     const int n_cfg = NC ? NC : a.n_cfg;
@@ -660,7 +735,8 @@ k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp) {
     // oversize groups are evaluated AND counted by the generic matcher (big_list route)
     const int64_t dn = __shfl_down_sync(0xffffffffu, doff, 1), gn = __shfl_down_sync(0xffffffffu, goff, 1);
     const int64_t D_l = (lane + 1 < n_in ? dn : d_end) - doff, G_l = (lane + 1 < n_in ? gn : g_end) - goff;
-    const bool big_l = lane < n_in && (G_l > FE_MAX_GT || D_l > FE_MAX_DT || D_l * G_l > FE_MAX_PAIRS);
+    const bool big_l = a.exclude_big && lane < n_in &&
+                       (G_l > FE_MAX_GT || D_l > FE_MAX_DT || D_l * G_l > FE_MAX_PAIRS);
     const uint32_t big_mask = __ballot_sync(0xffffffffu, big_l);
     // ---- (1)
     if (dt_grp) {
@@ -691,7 +767,8 @@ k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp) {
         int cat = __shfl_sync(0xffffffffu, cat_l, gi);
         uint32_t m = cfg_all;                                  // "ignored everywhere" = counts nothing
         if (gg < g_end && !((big_mask >> gi) & 1u))
-            m = fe_gt_ignore_mask(rules, a.gt_vis[gg], a.gt_flag[gg], cfg_all);
+            m = fe_gt_ignore_mask(rules, a.gt_vis[gg], a.gt_b ? a.gt_b[gg] : 0.0,
+                                  a.gt_hp ? a.gt_hp[gg] : 0, a.gt_flag[gg], cfg_all);
         else
             cat = -1 - lane;
         const uint32_t peers = __match_any_sync(0xffffffffu, cat);
@@ -744,11 +821,48 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
                           "", (long long)g_max);
     MatchArgs a{grp_list, grp_dt_off, grp_gt_off, grp_cat, iou_off, iou, n_thr, iou_thrs, n_cfg, cfgs,
                 n_dt, n_gt, dt_attr_a, dt_attr_b, dt_flag, gt_attr_a, gt_attr_b, gt_hp,
-                gt_flag, dt_tpfp, num_gt, dt_match_gt, gt_ignore_out, cpw};
+                gt_flag, dt_tpfp, num_gt, dt_match_gt, gt_ignore_out, cpw, nullptr, nullptr, 0};
     if (smem > 48 * 1024)
         TA_CUDA(cudaFuncSetAttribute(k_match_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-    k_match_greedy<<<(unsigned)n_groups, threads, smem, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!grp_list && !dt_match_gt && !gt_ignore_out && n_cfg <= 32 && n_dt > 0) {
+        // evaluation route: GT counts + lane-per-detection matcher on the IoU matrix; the general
+        // matcher below only sees the groups whose detections have several candidate GTs
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_grp = take((size_t)n_dt * 4);
+        const size_t o_flag = take((size_t)n_groups * 4 + 4);
+        const size_t o_list = take((size_t)n_groups * 4);
+        void* ws2 = nullptr;
+        int rc = ta_workspace(ctx, st, off, &ws2, 1);
+        if (rc) return rc;
+        char* base = static_cast<char*>(ws2);
+        FrameArgs f{n_groups, grp_dt_off, grp_gt_off, grp_cat, nullptr, nullptr, n_thr, iou_thrs, n_cfg,
+                    cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, const_cast<double*>(iou), 0,
+                    dt_tpfp, num_gt, nullptr, nullptr,
+                    dt_attr_a, dt_attr_b, gt_attr_b, gt_hp, 0,
+                    reinterpret_cast<int32_t*>(base + o_grp),
+                    reinterpret_cast<int32_t*>(base + o_flag), reinterpret_cast<int32_t*>(base + o_list),
+                    reinterpret_cast<int32_t*>(base + o_flag) + n_groups};
+        TA_CUDA(cudaMemsetAsync(f.grp_flag, 0, (size_t)n_groups * 4 + 4, st));
+        const int64_t prep_warps = (n_groups + 31) / 32;
+        k_frame_prep<0><<<(unsigned)((prep_warps + 7) / 8), 256, 0, st>>>(f, const_cast<int32_t*>(f.dt_grp));
+        if ((rc = ta_check_launch(ctx, "k_frame_prep"))) return rc;
+        int64_t blocks = ((n_dt + 31) / 32 + FF_WARPS - 1) / FF_WARPS;
+        const int64_t fcap = (int64_t)ctx->sm_count * 16;
+        if (blocks > fcap) blocks = fcap;
+        k_frame_flat<0, 0, true><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(f);
+        if ((rc = ta_check_launch(ctx, "k_track_flat"))) return rc;
+        a.dev_list = f.complex_list;
+        a.dev_count = f.complex_count;
+        a.skip_num_gt = 1;
+        int64_t lblocks = (int64_t)ctx->sm_count * 2;
+        if (lblocks > n_groups) lblocks = n_groups;
+        k_match_greedy<<<(unsigned)lblocks, threads, smem, st>>>(a);
+        return ta_check_launch(ctx, "k_match_greedy_list");
+    }
+    k_match_greedy<<<(unsigned)n_groups, threads, smem, st>>>(a);
     return ta_check_launch(ctx, "k_match_greedy");
 }
 
@@ -785,7 +899,8 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     cudaStream_t st = (cudaStream_t)stream;
     FrameArgs a{n_groups, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box, n_thr, iou_thrs, n_cfg,
                 cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, iou, write_iou,
-                dt_tpfp, num_gt, dt_match_gt, gt_ignore_out, nullptr, nullptr, nullptr, nullptr};
+                dt_tpfp, num_gt, dt_match_gt, gt_ignore_out,
+                nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr};
     const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs per SM
     int rc;
     if (write_iou || dt_match_gt || gt_ignore_out) {
@@ -824,8 +939,8 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
             int64_t blocks = ((n_dt + 31) / 32 + FF_WARPS - 1) / FF_WARPS;
             const int64_t fcap = (int64_t)ctx->sm_count * 16;
             if (blocks > fcap) blocks = fcap;
-            if (spec) k_frame_flat<10, 6><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
-            else k_frame_flat<0, 0><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
+            if (spec) k_frame_flat<10, 6, false><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
+            else k_frame_flat<0, 0, false><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
             if ((rc = ta_check_launch(ctx, "k_frame_flat"))) return rc;
         }
         if (n_dt > 0) {
