@@ -145,6 +145,7 @@ __global__ void k_match_greedy(MatchArgs a) {
 #define FE_MAX_PAIRS 512      // IoU tile doubles per warp
 #define FE_MAX_CFG 16
 
+struct FrameRules;
 struct FrameArgs {
     int64_t n_groups;
     const int64_t* grp_dt_off;
@@ -178,6 +179,7 @@ struct FrameArgs {
     int32_t* grp_flag;            // per group: already on the complex list
     int32_t* complex_list;        // groups that need the general matcher (route C)
     int32_t* complex_count;
+    const FrameRules* rules_g;    // range-test tables built once per call by k_frame_rules
 };
 
 // per-detection word: bits 0..15 "ignored when unmatched" per cfg, bit 16 locks its GT
@@ -242,6 +244,31 @@ __device__ __forceinline__ void fe_add_interval(double lo, double hi, int c, int
     masks[k] |= 1u << c;
 }
 
+__device__ __forceinline__ void fe_build_rules(const ta_range_cfg* cfg_s, int n_cfg, FrameRules& rules) {
+    rules.n_da = rules.n_db = rules.n_ga = rules.n_gb = rules.n_hp = 0;
+    rules.g_oof = 0;
+    for (int c = 0; c < n_cfg; ++c) {
+        const ta_range_cfg& r = cfg_s[c];
+        fe_add_interval(r.dt_a_lo, r.dt_a_hi, c, rules.n_da, rules.da_lo, rules.da_hi, rules.da_mask);
+        fe_add_interval(r.dt_b_lo, r.dt_b_hi, c, rules.n_db, rules.db_lo, rules.db_hi, rules.db_mask);
+        fe_add_interval(r.gt_a_lo, r.gt_a_hi, c, rules.n_ga, rules.ga_lo, rules.ga_hi, rules.ga_mask);
+        fe_add_interval(r.gt_b_lo, r.gt_b_hi, c, rules.n_gb, rules.gb_lo, rules.gb_hi, rules.gb_mask);
+        if (r.gt_need_oof) rules.g_oof |= 1u << c;
+        if (r.gt_hp_min != INT_MIN) {
+            int k = 0;
+            for (; k < rules.n_hp; ++k) if (rules.hp_min[k] == r.gt_hp_min) break;
+            if (k == rules.n_hp) { rules.hp_min[k] = r.gt_hp_min; rules.hp_mask[k] = 0; ++rules.n_hp; }
+            rules.hp_mask[k] |= 1u << c;
+        }
+    }
+}
+
+// one thread, once per API call: the tables every other kernel of the call copies into shared
+// memory (building them per CTA costs tens of microseconds of serial work with 20 cfgs)
+__global__ void k_frame_rules(const ta_range_cfg* cfgs, int n_cfg, FrameRules* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) fe_build_rules(cfgs, n_cfg, *out);
+}
+
 __device__ __forceinline__ void fe_setup(const FrameArgs& a, int n_thr, int n_cfg,
                                          ta_range_cfg* cfg_s, double* thr_s, FrameRules& rules) {
     for (int i = threadIdx.x; i < n_cfg; i += blockDim.x) cfg_s[i] = a.cfgs[i];
@@ -249,25 +276,9 @@ __device__ __forceinline__ void fe_setup(const FrameArgs& a, int n_thr, int n_cf
         const double th = a.thrs[threadIdx.x];
         thr_s[threadIdx.x] = (th < 1.0 - 1e-10) ? th : 1.0 - 1e-10;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        rules.n_da = rules.n_db = rules.n_ga = rules.n_gb = rules.n_hp = 0;
-        rules.g_oof = 0;
-        for (int c = 0; c < n_cfg; ++c) {
-            const ta_range_cfg& r = cfg_s[c];
-            fe_add_interval(r.dt_a_lo, r.dt_a_hi, c, rules.n_da, rules.da_lo, rules.da_hi, rules.da_mask);
-            fe_add_interval(r.dt_b_lo, r.dt_b_hi, c, rules.n_db, rules.db_lo, rules.db_hi, rules.db_mask);
-            fe_add_interval(r.gt_a_lo, r.gt_a_hi, c, rules.n_ga, rules.ga_lo, rules.ga_hi, rules.ga_mask);
-            fe_add_interval(r.gt_b_lo, r.gt_b_hi, c, rules.n_gb, rules.gb_lo, rules.gb_hi, rules.gb_mask);
-            if (r.gt_need_oof) rules.g_oof |= 1u << c;
-            if (r.gt_hp_min != INT_MIN) {
-                int k = 0;
-                for (; k < rules.n_hp; ++k) if (rules.hp_min[k] == r.gt_hp_min) break;
-                if (k == rules.n_hp) { rules.hp_min[k] = r.gt_hp_min; rules.hp_mask[k] = 0; ++rules.n_hp; }
-                rules.hp_mask[k] |= 1u << c;
-            }
-        }
-    }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.rules_g);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&rules);
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameRules) / 4); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
 }
 
@@ -831,6 +842,7 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
         // matcher below only sees the groups whose detections have several candidate GTs
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_rules = take(sizeof(FrameRules));
         const size_t o_grp = take((size_t)n_dt * 4);
         const size_t o_flag = take((size_t)n_groups * 4 + 4);
         const size_t o_list = take((size_t)n_groups * 4);
@@ -838,13 +850,16 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
         int rc = ta_workspace(ctx, st, off, &ws2, 1);
         if (rc) return rc;
         char* base = static_cast<char*>(ws2);
+        FrameRules* rules_g = reinterpret_cast<FrameRules*>(base + o_rules);
+        k_frame_rules<<<1, 32, 0, st>>>(cfgs, n_cfg, rules_g);
+        if ((rc = ta_check_launch(ctx, "k_frame_rules"))) return rc;
         FrameArgs f{n_groups, grp_dt_off, grp_gt_off, grp_cat, nullptr, nullptr, n_thr, iou_thrs, n_cfg,
                     cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, const_cast<double*>(iou), 0,
                     dt_tpfp, num_gt, nullptr, nullptr,
                     dt_attr_a, dt_attr_b, gt_attr_b, gt_hp, 0,
                     reinterpret_cast<int32_t*>(base + o_grp),
                     reinterpret_cast<int32_t*>(base + o_flag), reinterpret_cast<int32_t*>(base + o_list),
-                    reinterpret_cast<int32_t*>(base + o_flag) + n_groups};
+                    reinterpret_cast<int32_t*>(base + o_flag) + n_groups, rules_g};
         TA_CUDA(cudaMemsetAsync(f.grp_flag, 0, (size_t)n_groups * 4 + 4, st));
         const int64_t prep_warps = (n_groups + 31) / 32;
         k_frame_prep<0><<<(unsigned)((prep_warps + 7) / 8), 256, 0, st>>>(f, const_cast<int32_t*>(f.dt_grp));
@@ -900,9 +915,23 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     FrameArgs a{n_groups, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box, n_thr, iou_thrs, n_cfg,
                 cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, iou, write_iou,
                 dt_tpfp, num_gt, dt_match_gt, gt_ignore_out,
-                nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr};
+                nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs per SM
     int rc;
+    // scratch (slot 1): rule tables, detection -> group map, complex-group flags / list
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_rules = take(sizeof(FrameRules));
+    const size_t o_grp = take((size_t)(n_dt > 0 ? n_dt : 1) * 4);
+    const size_t o_flag = take((size_t)n_groups * 4 + 4);      // flags + the list counter
+    const size_t o_list = take((size_t)n_groups * 4);
+    void* ws2 = nullptr;
+    if ((rc = ta_workspace(ctx, st, off, &ws2, 1))) return rc;
+    char* base = static_cast<char*>(ws2);
+    FrameRules* rules_g = reinterpret_cast<FrameRules*>(base + o_rules);
+    k_frame_rules<<<1, 32, 0, st>>>(cfgs, n_cfg, rules_g);
+    if ((rc = ta_check_launch(ctx, "k_frame_rules"))) return rc;
+    a.rules_g = rules_g;
     if (write_iou || dt_match_gt || gt_ignore_out) {
         // detail outputs: the warp-per-group kernel does everything
         const int64_t n_tasks = (n_groups + FE_RUN - 1) / FE_RUN;
@@ -913,14 +942,6 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     } else {
         // evaluation path: lane-per-detection kernel, GT counts, then the general matcher on the
         // (few) groups whose detections have several candidate GTs
-        size_t off = 0;
-        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-        const size_t o_grp = take((size_t)(n_dt > 0 ? n_dt : 1) * 4);
-        const size_t o_flag = take((size_t)n_groups * 4 + 4);      // flags + the list counter
-        const size_t o_list = take((size_t)n_groups * 4);
-        void* ws2 = nullptr;
-        if ((rc = ta_workspace(ctx, st, off, &ws2, 1))) return rc;
-        char* base = static_cast<char*>(ws2);
         int32_t* dt_grp = reinterpret_cast<int32_t*>(base + o_grp);
         a.dt_grp = dt_grp;
         a.grp_flag = reinterpret_cast<int32_t*>(base + o_flag);
