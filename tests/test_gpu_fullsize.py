@@ -37,6 +37,14 @@ def test_counts_identity_and_kernel_variants_agree(big):
     for k in ("iou", "dt_tpfp", "dt_match_gt", "gt_ignore", "num_gt", "precision", "recall",
               "tp_cnt", "fp_cnt"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    # the evaluation route (lane-per-detection kernels, no per-cell outputs) against the
+    # warp-per-group kernels that produce the per-cell outputs
+    for plan, ref in ((lvis, a),):
+        q = eng.evaluate_device(eng.upload(plan), detail=False)
+        h = eng.evaluate_host(plan)
+        for o in (q, h):
+            for k in ("num_gt", "precision", "recall", "tp_cnt", "fp_cnt"):
+                assert np.array_equal(getattr(o, k), getattr(ref, k)), k
     n_cat_dt = np.diff(lvis.cat_dt_off)
     assert ((a.tp_cnt + a.fp_cnt) <= n_cat_dt[None, :, None]).all()
     # per-detection words agree with the accumulated totals
@@ -51,6 +59,9 @@ def test_counts_identity_and_kernel_variants_agree(big):
     y = eng.evaluate_device(eng.upload(tao), detail=True, iou_mode="3d_iou_seq")
     assert np.array_equal(x.iou, y.iou)
     assert np.array_equal(x.precision, y.precision)
+    z = eng.evaluate_device(eng.upload(tao), detail=False)      # lane-per-track matcher
+    for k in ("num_gt", "precision", "recall", "tp_cnt", "fp_cnt"):
+        assert np.array_equal(getattr(z, k), getattr(x, k)), k
 
 
 def test_input_order_invariance(big):
