@@ -566,7 +566,19 @@ __device__ __forceinline__ FlatCand fe_candidate(const double* __restrict__ gt_b
                                                  const double* thr_s, int n_thr) {
     FlatCand c{0, 0, 0u};
     double vs = 0.0;
-    for (int g = 0; g < G; ++g) {
+    // two GT boxes per iteration: both loads are in flight before either IoU is computed
+    int g = 0;
+    for (; g + 1 < G; g += 2) {
+        const double2 p0 = *reinterpret_cast<const double2*>(gt_box + 4 * (g0 + g));
+        const double2 q0 = *reinterpret_cast<const double2*>(gt_box + 4 * (g0 + g) + 2);
+        const double2 p1 = *reinterpret_cast<const double2*>(gt_box + 4 * (g0 + g) + 4);
+        const double2 q1 = *reinterpret_cast<const double2*>(gt_box + 4 * (g0 + g) + 6);
+        const double v0 = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, p0.x, p0.y, q0.x, q0.y);
+        const double v1 = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, p1.x, p1.y, q1.x, q1.y);
+        if (!(v0 < thr_min)) { ++c.cnt; c.gs = g; vs = v0; }
+        if (!(v1 < thr_min)) { ++c.cnt; c.gs = g + 1; vs = v1; }
+    }
+    if (g < G) {
         const double2 gp = *reinterpret_cast<const double2*>(gt_box + 4 * (g0 + g));
         const double2 gq = *reinterpret_cast<const double2*>(gt_box + 4 * (g0 + g) + 2);
         const double v = ta_bb_iou(dp.x, dp.y, dq.x, dq.y, gp.x, gp.y, gq.x, gq.y);
