@@ -46,3 +46,27 @@ def test_use_cats_zero_matches_reference(case):
     cells = materialize.cells_dict(tao_plan, 10, out)
     for k, v in golden_io.flatten_cells(cells).items():
         assert np.array_equal(g["tao_" + k], v), k
+
+
+@pytest.mark.parametrize("mode", ["avg_iou", "imagenetvid"])
+def test_alternative_iou_modes_match_reference(mode):
+    """Params.iou_3d_type = avg_iou / imagenetvid (eval.py:51-70, :99-117).  imagenetvid is a
+    ratio of counts (exact); avg_iou is numpy's mean over CPython-set-ordered frames in the
+    reference, a sequential ascending-frame sum here: equal to 1e-12, same decisions."""
+    from conftest import load_golden
+    from oracle import golden_io
+    from tao_amodal_b200 import materialize
+    g = load_golden("small_" + mode)
+    gt, res = golden_inputs(g)
+    tao_plan, _ = plans_from_json(gt, res)
+    out = run_hostsim(tao_plan, mode)
+    flat = golden_io.flatten_ious(materialize.iou_dict(tao_plan, out.iou))
+    assert np.array_equal(g["tao_iou_keys"], flat["iou_keys"])
+    if mode == "imagenetvid":
+        assert np.array_equal(g["tao_iou_vals"], flat["iou_vals"])
+    else:
+        np.testing.assert_allclose(flat["iou_vals"], g["tao_iou_vals"], rtol=0, atol=1e-12)
+    cells = materialize.cells_dict(tao_plan, 10, out)
+    for k, v in golden_io.flatten_cells(cells).items():
+        assert np.array_equal(g["tao_" + k], v), k
+    assert np.array_equal(g["tao_precision"], out.precision.reshape(g["tao_precision"].shape))
