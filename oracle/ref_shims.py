@@ -9,11 +9,14 @@ touches the reference's files:
    tao_amodal/evaluation/tao_amodal/eval.py:530-531 and
    lvis_amodal/eval.py:373-374)  -> alias of ``float``.
 2. ``pycocotools.mask``  (third-party, not vendored under tao_amodal/, not
-   installed here).  Only ``iou`` is called in bbox mode
-   (lvis_amodal/eval.py:191).  The stand-in restates ``bbIou`` from the
-   in-tree copy visualization/tao/third_party/pysot/training_dataset/coco/
-   pycocotools/common/maskApi.c:109-120 and the wrapper semantics of
-   _mask.pyx:218-239 (returns [] when either side is empty, shape [D,G]).
+   installed here).  Served by the reference tree's OWN C source of it —
+   visualization/tao/third_party/pysot/training_dataset/coco/pycocotools/
+   common/maskApi.c compiled where it lies into oracle/_ref/ (oracle/Makefile,
+   bound by oracle/maskapi_ref.py with the wrapper semantics of _mask.pyx) —
+   so ``iou`` (bbox: bbIou :109-120, segm: rleIou :75-96), ``frPyObjects``,
+   ``merge``, ``area``, ``toBbox`` run the real code.  Without that library
+   only ``iou`` on boxes is available, as a numpy restatement of bbIou
+   (_mask.pyx:218-239: [] when either side is empty, shape [D,G]).
 3. ``matplotlib``  (imported by lvis_amodal/vis.py:6,8 through
    lvis_amodal/__init__.py:5; never called)  -> empty stub modules.
 4. ``detectron2``  (tools/eval_on_tao_amodal.py:20-21; only
@@ -78,7 +81,14 @@ def install_shims() -> None:
     if "pycocotools" not in sys.modules:
         pk = types.ModuleType("pycocotools")
         mk = types.ModuleType("pycocotools.mask")
-        mk.iou = _bb_iou_stub
+        from . import maskapi_ref
+        if maskapi_ref.available() or maskapi_ref.build():
+            for fn in ("iou", "merge", "frPyObjects", "encode", "decode", "area", "toBbox"):
+                setattr(mk, fn, getattr(maskapi_ref, fn))
+            mk.BACKEND = "reference C (oracle/_ref/libmaskapi_ref.so)"
+        else:
+            mk.iou = _bb_iou_stub
+            mk.BACKEND = "numpy restatement of bbIou"
         pk.mask = mk
         sys.modules["pycocotools"] = pk
         sys.modules["pycocotools.mask"] = mk
