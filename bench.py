@@ -95,6 +95,11 @@ def algorithmic_bytes(plan, cells_with_gt: int = 0) -> dict:
         # levels of the cells that have GT written
         "pr_envelope": n_dt * (4 + 4 * n_cfg) + (128 + 8 * T) * n_cfg * n_chunks
                        + 8 * T * R * cells_with_gt,
+        # bit-plane variant (TA_PR_IMPL=1): k_pr_bits reads permutation + words, writes the TP / FP
+        # planes (64 B per cell and chunk) and the chunk counters; k_pr_envelope_bits reads the
+        # planes + counters and writes what k_pr_envelope writes
+        "pr_bits": n_dt * (4 + 4 * n_cfg) + (128 + 64 * T) * n_cfg * n_chunks,
+        "pr_envelope_bits": (128 + 64 * T + 8 * T) * n_cfg * n_chunks + 8 * T * R * cells_with_gt,
         # precision tensor written once, answered entries read once
         "pr_finalize": 8 * T * R * n_cat * n_cfg + 8 * T * R * cells_with_gt,
     }
@@ -437,6 +442,8 @@ def main():
         "k_frame_flat": ab_l["frame_flat"], "k_frame_prep": ab_l["frame_prep"],
         "k_pr_count": ab_t["pr_count"] + ab_l["pr_count"],
         "k_pr_envelope": ab_t["pr_envelope"] + ab_l["pr_envelope"],
+        "k_pr_bits": ab_t["pr_bits"] + ab_l["pr_bits"],
+        "k_pr_envelope_bits": ab_t["pr_envelope_bits"] + ab_l["pr_envelope_bits"],
         "k_pr_finalize": ab_t["pr_finalize"] + ab_l["pr_finalize"],
     }
     per_kernel = {}

@@ -139,4 +139,110 @@ TA_HD double ta_precision_at(int64_t tp, int64_t fp) {
     return t / ((f + t) + 2.220446049250313e-16);
 }
 
+// ---- precision / recall accumulation helpers (ta_pr.cu; host build: tests/hostsim) ----------
+
+#ifdef __CUDA_ARCH__
+#define TA_CLZ(x) __clz((int)(x))
+#define TA_POPC(x) __popc(x)
+#else
+#define TA_CLZ(x) ((x) ? __builtin_clz(x) : 32)
+#define TA_POPC(x) __builtin_popcount(x)
+#endif
+
+// exact comparison of precisions tp/(fp + tp + eps) given as (t, n = tp + fp): cross products in
+// 64 bits; equal ratios prefer the larger n, which only matters for (1, 1): its rounded value
+// 1/(1 + 2^-52) is below k/k = 1.0 (for n >= 2 the eps term vanishes in fp64, eval.py:550)
+TA_HD bool pr_better(uint32_t t1, uint32_t n1, uint32_t t2, uint32_t n2) {
+    const unsigned long long x = (unsigned long long)t1 * n2, y = (unsigned long long)t2 * n1;
+    return x > y || (x == y && n1 > n2);
+}
+// packed candidate: t (24 bits) | n (24 bits) | chunk index inside the category (16 bits);
+// ta_pr_accumulate rejects categories with 2^24 or more detections
+TA_HD unsigned long long pr_pack(uint32_t t, uint32_t n, uint32_t ch) {
+    return ((unsigned long long)t << 40) | ((unsigned long long)n << 16) | ch;
+}
+TA_HD void pr_unpack(unsigned long long q, uint32_t& t, uint32_t& n, uint32_t& ch) {
+    t = (uint32_t)(q >> 40); n = (uint32_t)(q >> 16) & 0xffffffu; ch = (uint32_t)q & 0xffffu;
+}
+
+// One stage of the 32 x 32 bit-matrix transpose across a warp (rows = lanes, columns = bits):
+// `y` is the word of lane ^ j.  After the stages j = 16, 8, 4, 2, 1 lane b holds bit b of
+// every lane's input word (bit l of the result <-> input lane l), i.e. 32 ballots at once.
+TA_HD void pr_transpose_consts(int lane, int j, uint32_t& keep, uint32_t& rot) {
+    const uint32_t m = (j == 16) ? 0x0000ffffu : (j == 8) ? 0x00ff00ffu : (j == 4) ? 0x0f0f0f0fu
+                     : (j == 2) ? 0x33333333u : 0x55555555u;
+    // lower half of a 2j block keeps its columns m and receives the partner's columns m moved
+    // up by j; the upper half keeps ~m and receives the partner's columns ~m moved down by j.
+    // Both moves are one rotation (the wrapped-around bits fall outside the receiving mask), so
+    // a stage is SHFL + SHF.W + LOP3 with `keep` / `rot` fixed per lane.
+    const bool hi = (lane & j) != 0;
+    keep = hi ? ~m : m;
+    rot = hi ? (uint32_t)(32 - j) : (uint32_t)j;
+}
+TA_HD uint32_t pr_transpose_apply(uint32_t x, uint32_t y, uint32_t keep, uint32_t rot) {
+    const uint32_t yr = (y << rot) | (y >> (32u - rot));
+    return yr ^ ((x ^ yr) & keep);            // keep ? x : yr, bitwise
+}
+TA_HD uint32_t pr_transpose_stage(uint32_t x, uint32_t y, int lane, int j) {
+    uint32_t keep, rot;
+    pr_transpose_consts(lane, j, keep, rot);
+    return pr_transpose_apply(x, y, keep, rot);
+}
+
+#define TA_PR_WORDS 8          // 32-position words per chunk of 256 detections
+
+// Envelope walk of one (category chunk, range cfg, threshold) cell over the chunk's TRUE
+// POSITIVES only (accumulate, eval.py:527-573).  T[j * stride] / F[j * stride], j < 8, are the
+// cell's TP / FP flags of the chunk's positions 32 j .. 32 j + 31 in descending-score order
+// (bit = position inside the word); tc / fc the running TP / FP counts at the END of the chunk.
+// Walking the true positives backwards keeps the suffix-maximum precision as the exact rational
+// (bt, bn) and stores it (tagged with the chunk) for every recall level k whose tk-th true
+// positive lies in the chunk: q[k * q_stride].  tk[0 .. n_rec) must be non-decreasing
+// (ta_min_tp_for_recall of ascending recall thresholds).  Returns the chunk's best candidate.
+TA_HD unsigned long long ta_pr_walk_bits(const uint32_t* T, const uint32_t* F, int64_t stride,
+                                         uint32_t tc, uint32_t fc, const int32_t* tk, int n_rec,
+                                         uint32_t ch_rel, unsigned long long* q, int64_t q_stride) {
+    uint32_t Tw[TA_PR_WORDS], Fw[TA_PR_WORDS];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = 0; j < TA_PR_WORDS; ++j) { Tw[j] = T[j * stride]; Fw[j] = F[j * stride]; }
+    // last recall level whose (clamped) tk is <= tc: binary search, tk is non-decreasing
+    int lo = -1, hi = n_rec;            // invariant: tk'[lo] <= tc < tk'[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        const int32_t v = tk[mid];
+        if ((uint32_t)(v > 1 ? v : 1) <= tc) lo = mid; else hi = mid;
+    }
+    int kq = lo;
+    uint32_t next_tk = 0u;
+    if (kq >= 0) { const int32_t v = tk[kq]; next_tk = (uint32_t)(v > 1 ? v : 1); }
+    uint32_t bt = 0, bn = 1;            // precision 0: the first true positive always beats it
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int j = TA_PR_WORDS - 1; j >= 0; --j) {
+        uint32_t t = Tw[j];
+        const uint32_t f = Fw[j];
+        while (t) {
+            const int p = 31 - TA_CLZ(t);
+            t ^= 1u << p;
+            // false positives before position p = count at the word's end - those at >= p
+            const uint32_t n = tc + (fc - (uint32_t)TA_POPC(f >> p));
+            // strict ">" is enough: a tie keeps the later detection's pair, and the only
+            // value-changing tie, (1,1) vs (k,k), has (1,1) as the candidate (first TP overall)
+            if ((unsigned long long)tc * bn > (unsigned long long)bt * n) { bt = tc; bn = n; }
+            while (next_tk == tc) {
+                q[kq * q_stride] = pr_pack(bt, bn, ch_rel);
+                --kq;
+                next_tk = 0u;
+                if (kq >= 0) { const int32_t v = tk[kq]; next_tk = (uint32_t)(v > 1 ? v : 1); }
+            }
+            --tc;
+        }
+        fc -= (uint32_t)TA_POPC(f);
+    }
+    return pr_pack(bt, bn, 0);
+}
+
 #endif  // TA_DEVICE_FNS_CUH

@@ -22,10 +22,16 @@
 //                  detections backwards from shared memory: running counts, suffix-maximum
 //                  precision, and the answer of every recall threshold whose tk-th true
 //                  positive lies inside the chunk
+//   k_pr_bits / k_pr_envelope_bits   bit-plane variant of count / envelope (TA_PR_IMPL=1):
+//                  the chunk's TP/FP words are transposed ONCE (32 x 32 bit-matrix transpose
+//                  across the warp) into one 256-bit TP and FP plane per cell; chunk totals
+//                  are popcounts, and the envelope thread of a cell visits only the true
+//                  positives of its plane (clz / popc) instead of all 256 positions
 //   k_pr_suffix    per cell: best precision of all later chunks, for every chunk
 //   k_pr_finalize  per precision entry: merge the in-chunk answer with the later chunks' best,
 //                  divide, write (-1 without GT, 0 for recall levels nobody reaches)
 #include <limits.h>
+#include <stdlib.h>
 #include "ta_internal.h"
 #include "ta_device_fns.cuh"
 
@@ -46,6 +52,10 @@ struct PrArgs {
     uint32_t* cat_tot;           // [n_cat][n_cfg][32] category totals (same bit layout)
     int32_t* tk;                 // [n_cat][n_cfg][n_rec]
     unsigned long long* chunk_best;  // [n_chunks_ub][n_cfg][n_thr] packed (t << 32 | n)
+    int32_t* chunk_cat;          // [n_chunks_ub] category of a chunk            (bit-plane path)
+    uint32_t* bits;              // [n_chunks_ub][2 * TA_PR_WORDS][n_cfg * n_thr] (bit-plane path):
+                                 // word j < 8: TP flags of positions 32 j .. 32 j + 31 of the
+                                 // chunk for one (cfg, threshold) cell, word 8 + j: FP flags
     // outputs
     unsigned long long* prec_bits;   // precision buffer viewed as u64: packed (t << 32 | n) until
                                      // k_pr_finalize turns it into doubles
@@ -195,21 +205,7 @@ __global__ void k_pr_scan(PrArgs a) {
     }
 }
 
-// exact comparison of precisions tp/(fp + tp + eps) given as (t, n = tp + fp): cross products in
-// 64 bits; equal ratios prefer the larger n, which only matters for (1, 1): its rounded value
-// 1/(1 + 2^-52) is below k/k = 1.0 (for n >= 2 the eps term vanishes in fp64, eval.py:550)
-__device__ __forceinline__ bool pr_better(uint32_t t1, uint32_t n1, uint32_t t2, uint32_t n2) {
-    const unsigned long long x = (unsigned long long)t1 * n2, y = (unsigned long long)t2 * n1;
-    return x > y || (x == y && n1 > n2);
-}
-// packed candidate: t (24 bits) | n (24 bits) | chunk index inside the category (16 bits);
-// ta_pr_accumulate rejects categories with 2^24 or more detections
-__device__ __forceinline__ unsigned long long pr_pack(uint32_t t, uint32_t n, uint32_t ch) {
-    return ((unsigned long long)t << 40) | ((unsigned long long)n << 16) | ch;
-}
-__device__ __forceinline__ void pr_unpack(unsigned long long q, uint32_t& t, uint32_t& n, uint32_t& ch) {
-    t = (uint32_t)(q >> 40); n = (uint32_t)(q >> 16) & 0xffffffu; ch = (uint32_t)q & 0xffffu;
-}
+// pr_better / pr_pack / pr_unpack: ta_device_fns.cuh
 
 #define PR_ENV_MAX_CELLS 64   // (cfg, threshold) cells per k_pr_envelope block
 
@@ -281,6 +277,90 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
     *best_out = pr_pack(bt, bn, 0);
 }
 
+
+// ---- bit-plane variant -------------------------------------------------------------------
+static_assert(PR_CHUNK == 32 * TA_PR_WORDS, "chunk = 8 words of 32 positions");
+
+// One block per chunk, thread = position (warp w = positions 32 w .. 32 w + 31).  Per cfg the
+// warp transposes its 32 TP/FP words: lane t then holds the TP plane word of threshold t, lane
+// 16 + t the FP plane word.  Planes are staged in shared memory ([word][cell]: conflict-free),
+// copied out linearly, and summed (popc) into the chunk totals k_pr_scan expects.
+__global__ void __launch_bounds__(PR_CHUNK)
+k_pr_bits(PrArgs a) {
+    extern __shared__ uint32_t plane_s[];          // [2 * TA_PR_WORDS][n_cells]
+    const int chunk = blockIdx.x;
+    if (chunk >= a.chunk_start[a.n_cat]) return;
+    const int cat = pr_find_cat(a.chunk_start, a.n_cat, chunk);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_cells = a.n_cfg * a.n_thr;
+    const int64_t p0 = a.cat_dt_off[cat] + (int64_t)(chunk - a.chunk_start[cat]) * PR_CHUNK;
+    const int n_pos = (int)min((int64_t)PR_CHUNK, a.cat_dt_off[cat + 1] - p0);
+    if (threadIdx.x == 0) a.chunk_cat[chunk] = cat;
+    const int p = threadIdx.x;
+    const bool live = p < n_pos;
+    const uint32_t* row = a.dt_tpfp + (live ? (int64_t)a.acc_perm[p0 + p] * a.n_cfg : 0);
+    const int b = lane & 15;
+    uint32_t* dst = plane_s + ((lane >> 4) * TA_PR_WORDS + warp) * n_cells + b;
+    uint32_t keep[5], rot[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) pr_transpose_consts(lane, 16 >> s, keep[s], rot[s]);
+#pragma unroll 2
+    for (int cfg = 0; cfg < a.n_cfg; ++cfg) {
+        uint32_t x = live ? row[cfg] : 0u;
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+            x = pr_transpose_apply(x, __shfl_xor_sync(0xffffffffu, x, 16 >> s), keep[s], rot[s]);
+        if (b < a.n_thr) dst[cfg * a.n_thr] = x;
+    }
+    __syncthreads();
+    uint32_t* out = a.bits + (int64_t)chunk * (2 * TA_PR_WORDS) * n_cells;
+    for (int i = threadIdx.x; i < 2 * TA_PR_WORDS * n_cells; i += PR_CHUNK) out[i] = plane_s[i];
+    for (int j = threadIdx.x; j < a.n_cfg * 32; j += PR_CHUNK) {
+        const int cfg = j >> 5, bit = j & 31, t = bit & 15;
+        uint32_t cnt = 0;
+        if (t < a.n_thr) {
+            const uint32_t* src = plane_s + (bit >> 4) * TA_PR_WORDS * n_cells + cfg * a.n_thr + t;
+#pragma unroll
+            for (int u = 0; u < TA_PR_WORDS; ++u) cnt += __popc(src[u * n_cells]);
+        }
+        a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg) * 32 + bit] = cnt;
+    }
+}
+
+// One THREAD per (chunk, cfg, threshold) cell, flat over the grid (consecutive lanes =
+// consecutive cells of a chunk: the plane loads are coalesced).  ta_pr_walk_bits visits the
+// cell's true positives only.
+__global__ void __launch_bounds__(128)
+k_pr_envelope_bits(PrArgs a) {
+    const uint32_t n_cells = (uint32_t)(a.n_cfg * a.n_thr);
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)a.chunk_start[a.n_cat] * n_cells;
+    if (gid >= total) return;
+    int chunk;
+    uint32_t cell;
+    if (total < (1ll << 31)) { chunk = (int)((uint32_t)gid / n_cells); cell = (uint32_t)gid - (uint32_t)chunk * n_cells; }
+    else { chunk = (int)(gid / n_cells); cell = (uint32_t)(gid - (int64_t)chunk * n_cells); }
+    const int cfg = (int)(cell / (uint32_t)a.n_thr), b = (int)(cell - (uint32_t)cfg * a.n_thr);
+    const int cat = a.chunk_cat[chunk];
+    if (a.num_gt[(int64_t)cat * a.n_cfg + cfg] == 0) return;
+    const int ch0 = a.chunk_start[cat], ch1 = a.chunk_start[cat + 1];
+    // counts at the END of this chunk = exclusive prefix of the next chunk (category totals
+    // for the last chunk)
+    const uint32_t* nxt = (chunk + 1 < ch1) ? a.chunk_cnt + ((int64_t)(chunk + 1) * a.n_cfg + cfg) * 32
+                                            : a.cat_tot + ((int64_t)cat * a.n_cfg + cfg) * 32;
+    const uint32_t tc = nxt[b], fc = nxt[16 + b];
+    const uint32_t t_begin = a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg) * 32 + b];
+    unsigned long long* best_out = a.chunk_best + (int64_t)chunk * n_cells + cell;
+    if (tc == t_begin) { *best_out = 0ull; return; }          // no TP of this cell in the chunk
+    const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
+    const uint32_t* planes = a.bits + (int64_t)chunk * (2 * TA_PR_WORDS) * n_cells + cell;
+    *best_out = ta_pr_walk_bits(planes, planes + (int64_t)TA_PR_WORDS * n_cells, (int64_t)n_cells, tc, fc,
+                                a.tk + ((int64_t)cat * a.n_cfg + cfg) * a.n_rec, a.n_rec,
+                                (uint32_t)(chunk - ch0),
+                                a.prec_bits + (int64_t)b * a.n_rec * per_t + (int64_t)cat * a.n_cfg + cfg,
+                                per_t);
+}
+
 // per (category, cfg, threshold): chunk_best[ch] <- best precision of all LATER chunks
 __global__ void k_pr_suffix(PrArgs a) {
     const int cat = blockIdx.x;
@@ -342,6 +422,16 @@ __global__ void k_pr_finalize(PrArgs a) {
     a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
 }
 
+// TA_PR_IMPL: 0 = position walk (k_pr_count + k_pr_envelope), 1 = bit planes (k_pr_bits +
+// k_pr_envelope_bits).  Both produce identical tensors (tests/test_gpu_parity.py runs both).
+#ifndef TA_PR_IMPL_DEFAULT
+#define TA_PR_IMPL_DEFAULT 0
+#endif
+static int ta_pr_impl() {
+    const char* e = getenv("TA_PR_IMPL");
+    return (e && *e) ? (e[0] != '0') : TA_PR_IMPL_DEFAULT;
+}
+
 extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
                                 const int32_t* acc_perm, int64_t n_dt, const uint32_t* dt_tpfp,
                                 const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
@@ -366,6 +456,11 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     const size_t o_tot = take((size_t)n_cat * n_cfg * 32 * 4);
     const size_t o_tk = take((size_t)n_cat * n_cfg * n_rec * 4);
     const size_t o_best = take((size_t)n_chunks_ub * n_cfg * n_thr * 8);
+    const size_t n_cells = (size_t)n_cfg * n_thr;
+    // the staged planes of one chunk (64 B per cell) must fit the default 48 KB of shared memory
+    const int impl = (n_cells * 2 * TA_PR_WORDS * 4 <= 48 * 1024) ? ta_pr_impl() : 0;
+    const size_t o_ccat = take(impl ? (size_t)n_chunks_ub * 4 : 0);
+    const size_t o_bits = take(impl ? (size_t)n_chunks_ub * 2 * TA_PR_WORDS * n_cells * 4 : 0);
     void* ws = nullptr;
     int rc = ta_workspace(ctx, st, off, &ws);
     if (rc) return rc;
@@ -380,6 +475,8 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     a.cat_tot = reinterpret_cast<uint32_t*>(base + o_tot);
     a.tk = reinterpret_cast<int32_t*>(base + o_tk);
     a.chunk_best = reinterpret_cast<unsigned long long*>(base + o_best);
+    a.chunk_cat = reinterpret_cast<int32_t*>(base + o_ccat);
+    a.bits = reinterpret_cast<uint32_t*>(base + o_bits);
     a.prec_bits = reinterpret_cast<unsigned long long*>(precision);
     a.precision = precision; a.recall = recall; a.tp_cnt = tp_cnt; a.fp_cnt = fp_cnt;
 
@@ -397,7 +494,10 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
                               "ta_pr_accumulate: a category has 2^24 or more detections");
         }
     }
-    if (n_chunks_ub > 0) {
+    if (n_chunks_ub > 0 && impl) {
+        k_pr_bits<<<n_chunks_ub, PR_CHUNK, 2 * TA_PR_WORDS * n_cells * 4, st>>>(a);
+        if ((rc = ta_check_launch(ctx, "k_pr_bits"))) return rc;
+    } else if (n_chunks_ub > 0) {
         const int warps = n_cfg < PR_COUNT_MAX_CFG ? n_cfg : PR_COUNT_MAX_CFG;
         dim3 grid(n_chunks_ub, (n_cfg + PR_COUNT_MAX_CFG - 1) / PR_COUNT_MAX_CFG);
         k_pr_count<<<grid, warps * 32, 0, st>>>(a);
@@ -405,7 +505,12 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     }
     k_pr_scan<<<n_cat, 128, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_scan"))) return rc;
-    if (n_chunks_ub > 0) {
+    if (n_chunks_ub > 0 && impl) {
+        // grid over the upper bound of chunks: the kernel reads the real count on the device
+        const int64_t threads = (int64_t)n_chunks_ub * (int64_t)n_cells;
+        k_pr_envelope_bits<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a);
+        if ((rc = ta_check_launch(ctx, "k_pr_envelope_bits"))) return rc;
+    } else if (n_chunks_ub > 0) {
         int cpb = PR_ENV_MAX_CELLS / n_thr;
         if (cpb > n_cfg) cpb = n_cfg;
         const size_t smem = (size_t)PR_CHUNK * cpb * 4 + (size_t)cpb * n_rec * 4;

@@ -160,4 +160,142 @@ int hs_pr_accumulate(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* ac
     return 0;
 }
 
+// Serial emulation of the bit-plane PR pipeline of csrc/ta_pr.cu (k_pr_plan -> k_pr_bits ->
+// k_pr_scan -> k_pr_envelope_bits -> k_pr_suffix -> k_pr_finalize) with the SAME per-thread
+// functions (pr_transpose_stage on an emulated 32-lane warp, ta_pr_walk_bits, pr_better, ...).
+int hs_pr_accumulate_bits(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
+                          const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                          int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
+                          int64_t* tp_cnt, int64_t* fp_cnt) {
+    (void)n_dt;
+    const int CH = 32 * TA_PR_WORDS;
+    const int n_cells = n_cfg * n_thr;
+    std::vector<int> chunk_start(n_cat + 1, 0);
+    for (int c = 0; c < n_cat; ++c)
+        chunk_start[c + 1] = chunk_start[c] + (int)((cat_dt_off[c + 1] - cat_dt_off[c] + CH - 1) / CH);
+    const int n_chunks = chunk_start[n_cat];
+    std::vector<int> chunk_cat(n_chunks);
+    std::vector<uint32_t> bits((size_t)n_chunks * 2 * TA_PR_WORDS * n_cells, 0u);
+    std::vector<uint32_t> chunk_cnt((size_t)n_chunks * n_cfg * 32, 0u), cat_tot((size_t)n_cat * n_cfg * 32, 0u);
+    std::vector<int32_t> tk((size_t)n_cat * n_cfg * n_rec);
+    std::vector<unsigned long long> chunk_best((size_t)n_chunks * n_cells, 0ull);
+    const int64_t per_t = (int64_t)n_cat * n_cfg;
+    std::vector<unsigned long long> prec_bits((size_t)n_thr * n_rec * per_t, 0xdeadbeefdeadbeefull);
+    // k_pr_bits
+    for (int cat = 0; cat < n_cat; ++cat)
+        for (int chunk = chunk_start[cat]; chunk < chunk_start[cat + 1]; ++chunk) {
+            chunk_cat[chunk] = cat;
+            const int64_t p0 = cat_dt_off[cat] + (int64_t)(chunk - chunk_start[cat]) * CH;
+            const int n_pos = (int)std::min<int64_t>(CH, cat_dt_off[cat + 1] - p0);
+            uint32_t* out = bits.data() + (size_t)chunk * 2 * TA_PR_WORDS * n_cells;
+            for (int warp = 0; warp < TA_PR_WORDS; ++warp)
+                for (int cfg = 0; cfg < n_cfg; ++cfg) {
+                    uint32_t x[32], y[32];
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int p = warp * 32 + lane;
+                        x[lane] = p < n_pos ? dt_tpfp[(int64_t)acc_perm[p0 + p] * n_cfg + cfg] : 0u;
+                    }
+                    for (int j = 16; j >= 1; j >>= 1) {
+                        for (int lane = 0; lane < 32; ++lane) y[lane] = x[lane ^ j];     // shfl_xor
+                        for (int lane = 0; lane < 32; ++lane) x[lane] = pr_transpose_stage(x[lane], y[lane], lane, j);
+                    }
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int b = lane & 15;
+                        if (b < n_thr) out[((lane >> 4) * TA_PR_WORDS + warp) * n_cells + cfg * n_thr + b] = x[lane];
+                    }
+                }
+            for (int j = 0; j < n_cfg * 32; ++j) {
+                const int cfg = j >> 5, bit = j & 31, t = bit & 15;
+                uint32_t cnt = 0;
+                if (t < n_thr)
+                    for (int u = 0; u < TA_PR_WORDS; ++u)
+                        cnt += (uint32_t)__builtin_popcount(out[((bit >> 4) * TA_PR_WORDS + u) * n_cells + cfg * n_thr + t]);
+                chunk_cnt[((size_t)chunk * n_cfg + cfg) * 32 + bit] = cnt;
+            }
+        }
+    // k_pr_scan
+    for (int cat = 0; cat < n_cat; ++cat) {
+        const bool has_dt = cat_dt_off[cat + 1] > cat_dt_off[cat];
+        for (int j = 0; j < n_cfg * 32; ++j) {
+            const int cfg = j >> 5, bit = j & 31, t = bit & 15;
+            uint32_t run = 0;
+            for (int ch = chunk_start[cat]; ch < chunk_start[cat + 1]; ++ch) {
+                uint32_t& q = chunk_cnt[((size_t)ch * n_cfg) * 32 + j];
+                const uint32_t v = q; q = run; run += v;
+            }
+            cat_tot[((size_t)cat * n_cfg) * 32 + j] = run;
+            const int ngt = num_gt[(int64_t)cat * n_cfg + cfg];
+            if (t < n_thr) {
+                const int64_t cell = ((int64_t)t * n_cat + cat) * n_cfg + cfg;
+                if (bit < 16) {
+                    if (tp_cnt) tp_cnt[cell] = ngt ? (int64_t)run : 0;
+                    recall[cell] = ngt == 0 ? -1.0 : (has_dt ? (double)run / (double)ngt : 0.0);
+                } else if (fp_cnt) fp_cnt[cell] = ngt ? (int64_t)run : 0;
+            }
+        }
+        for (int cfg = 0; cfg < n_cfg; ++cfg)
+            for (int k = 0; k < n_rec; ++k) {
+                const int ngt = num_gt[(int64_t)cat * n_cfg + cfg];
+                tk[((size_t)cat * n_cfg + cfg) * n_rec + k] = ngt ? (int32_t)ta_min_tp_for_recall(rec_thrs[k], ngt) : 0x7fffffff;
+            }
+    }
+    // k_pr_envelope_bits
+    for (int chunk = 0; chunk < n_chunks; ++chunk)
+        for (int cell = 0; cell < n_cells; ++cell) {
+            const int cfg = cell / n_thr, b = cell % n_thr, cat = chunk_cat[chunk];
+            if (num_gt[(int64_t)cat * n_cfg + cfg] == 0) continue;
+            const int ch0 = chunk_start[cat], ch1 = chunk_start[cat + 1];
+            const uint32_t* nxt = (chunk + 1 < ch1) ? &chunk_cnt[((size_t)(chunk + 1) * n_cfg + cfg) * 32]
+                                                    : &cat_tot[((size_t)cat * n_cfg + cfg) * 32];
+            const uint32_t tc = nxt[b], fc = nxt[16 + b];
+            const uint32_t t_begin = chunk_cnt[((size_t)chunk * n_cfg + cfg) * 32 + b];
+            unsigned long long* best_out = &chunk_best[(size_t)chunk * n_cells + cell];
+            if (tc == t_begin) { *best_out = 0ull; continue; }
+            const uint32_t* planes = bits.data() + (size_t)chunk * 2 * TA_PR_WORDS * n_cells + cell;
+            *best_out = ta_pr_walk_bits(planes, planes + (size_t)TA_PR_WORDS * n_cells, n_cells, tc, fc,
+                                        &tk[((size_t)cat * n_cfg + cfg) * n_rec], n_rec, (uint32_t)(chunk - ch0),
+                                        prec_bits.data() + (int64_t)b * n_rec * per_t + (int64_t)cat * n_cfg + cfg, per_t);
+        }
+    // k_pr_suffix
+    for (int cat = 0; cat < n_cat; ++cat)
+        for (int j = 0; j < n_cells; ++j) {
+            if (num_gt[(int64_t)cat * n_cfg + j / n_thr] == 0) continue;
+            uint32_t bt = 0, bn = 0, d;
+            for (int ch = chunk_start[cat + 1] - 1; ch >= chunk_start[cat]; --ch) {
+                unsigned long long& q = chunk_best[(size_t)ch * n_cells + j];
+                uint32_t ct, cn;
+                pr_unpack(q, ct, cn, d);
+                q = pr_pack(bt, bn, 0);
+                if (pr_better(ct, cn, bt, bn)) { bt = ct; bn = cn; }
+            }
+        }
+    // k_pr_finalize
+    for (int64_t idx = 0; idx < (int64_t)n_thr * n_rec * per_t; ++idx) {
+        const int64_t tk_idx = idx / per_t, cc = idx - tk_idx * per_t;
+        const int ngt = num_gt[cc];
+        if (ngt == 0) { precision[idx] = -1.0; continue; }
+        const int t = (int)tk_idx / n_rec, k = (int)tk_idx - t * n_rec;
+        const int cat = (int)(cc / n_cfg), cfg = (int)(cc - (int64_t)cat * n_cfg);
+        const int32_t tkv = tk[cc * n_rec + k];
+        const uint32_t need = (uint32_t)(tkv > 1 ? tkv : 1);
+        if (need > cat_tot[cc * 32 + t]) { precision[idx] = 0.0; continue; }
+        uint32_t qt, qn, ch, bt, bn, d;
+        pr_unpack(prec_bits[idx], qt, qn, ch);
+        pr_unpack(chunk_best[((size_t)(chunk_start[cat] + ch) * n_cfg + cfg) * n_thr + t], bt, bn, d);
+        if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
+        precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
+    }
+    return 0;
+}
+
+void hs_transpose32(const uint32_t* in, uint32_t* out) {
+    uint32_t x[32], y[32];
+    for (int l = 0; l < 32; ++l) x[l] = in[l];
+    for (int j = 16; j >= 1; j >>= 1) {
+        for (int l = 0; l < 32; ++l) y[l] = x[l ^ j];
+        for (int l = 0; l < 32; ++l) x[l] = pr_transpose_stage(x[l], y[l], l, j);
+    }
+    for (int l = 0; l < 32; ++l) out[l] = x[l];
+}
+
 }  // extern "C"

@@ -33,7 +33,8 @@ def _p(a):
     return None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
 
 
-def run_hostsim(plan, iou_mode="3d_iou", iou_thrs=engine.IOU_THRS, rec_thrs=engine.REC_THRS):
+def run_hostsim(plan, iou_mode="3d_iou", iou_thrs=engine.IOU_THRS, rec_thrs=engine.REC_THRS,
+                pr_impl="serial"):
     hs = build_hostsim()
     n_thr, n_rec, n_cfg, n_cat = len(iou_thrs), len(rec_thrs), plan.n_cfg, len(plan.cat_ids)
     n_iou = int(plan.iou_off[-1])
@@ -65,15 +66,17 @@ def run_hostsim(plan, iou_mode="3d_iou", iou_thrs=engine.IOU_THRS, rec_thrs=engi
                        plan.n_gt, _p(plan.gt_attr_a), _p(plan.gt_attr_b),
                        _p(plan.gt_hp), _p(plan.gt_flag), g_max,
                        _p(tpfp), _p(num_gt), _p(match_gt), _p(gt_ig))
-    out = hostsim_pr(n_cat, plan.cat_dt_off, plan.acc_perm, tpfp, num_gt, n_cfg, iou_thrs, rec_thrs)
+    out = hostsim_pr(n_cat, plan.cat_dt_off, plan.acc_perm, tpfp, num_gt, n_cfg, iou_thrs, rec_thrs,
+                     impl=pr_impl)
     out.iou, out.dt_match_gt, out.gt_ignore = iou[:n_iou], match_gt, gt_ig
     return out
 
 
 def hostsim_pr(n_cat, cat_dt_off, acc_perm, tpfp, num_gt, n_cfg, iou_thrs=engine.IOU_THRS,
-               rec_thrs=engine.REC_THRS):
+               rec_thrs=engine.REC_THRS, impl="serial"):
     """PR accumulation of the host simulation on explicit arrays (also used by the
-    multi-process exchange test)."""
+    multi-process exchange test).  impl="serial": the plain per-cell loop; impl="bits": the
+    serial emulation of the bit-plane kernels (chunks, warp transpose, TP-only walk)."""
     hs = build_hostsim()
     I64, I32, P = C.c_int64, C.c_int32, C.c_void_p
     n_thr, n_rec = len(iou_thrs), len(rec_thrs)
@@ -85,11 +88,12 @@ def hostsim_pr(n_cat, cat_dt_off, acc_perm, tpfp, num_gt, n_cfg, iou_thrs=engine
         precision=np.empty((n_thr, n_rec, n_cat, n_cfg)), recall=np.empty((n_thr, n_cat, n_cfg)),
         tp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64),
         fp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64), num_gt=num_gt, dt_tpfp=tpfp)
-    hs.hs_pr_accumulate.argtypes = [I32, P, P, I64, P, P, I32, I32, I32, P, P, P, P, P]
-    hs.hs_pr_accumulate(n_cat, _p(np.asarray(cat_dt_off, dtype=np.int64)),
-                        _p(np.asarray(acc_perm, dtype=np.int32)), n_dt, _p(tpfp),
-                        _p(num_gt), n_thr, n_cfg, n_rec, _p(rec), _p(out.precision),
-                        _p(out.recall), _p(out.tp_cnt), _p(out.fp_cnt))
+    fn = hs.hs_pr_accumulate if impl == "serial" else hs.hs_pr_accumulate_bits
+    fn.argtypes = [I32, P, P, I64, P, P, I32, I32, I32, P, P, P, P, P]
+    fn(n_cat, _p(np.asarray(cat_dt_off, dtype=np.int64)),
+       _p(np.asarray(acc_perm, dtype=np.int32)), n_dt, _p(tpfp),
+       _p(num_gt), n_thr, n_cfg, n_rec, _p(rec), _p(out.precision),
+       _p(out.recall), _p(out.tp_cnt), _p(out.fp_cnt))
     return out
 
 

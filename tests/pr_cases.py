@@ -1,0 +1,36 @@
+"""Random inputs of the precision/recall accumulation (ta_pr_accumulate) shared by the CPU and
+GPU tests: categories spanning many 256-detection chunks, dense / sparse / absent true
+positives, empty categories, categories without GT, exact chunk multiples."""
+import numpy as np
+
+
+def random_pr_case(seed, n_cat=7, n_cfg=6, n_thr=10, max_len=1500, tp_rate=None):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lens = rng.integers(0, max_len, n_cat)
+    lens[rng.integers(0, n_cat)] = 0                       # an empty category
+    lens[rng.integers(0, n_cat)] = 256 * int(rng.integers(1, 4))   # exact chunk multiple
+    if n_cat > 3:
+        lens[3] = 1
+    cat_dt_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    n_dt = int(cat_dt_off[-1])
+    # accumulate order: a permutation inside every category
+    acc_perm = np.concatenate([cat_dt_off[c] + rng.permutation(lens[c]) for c in range(n_cat)]
+                              + [np.zeros(0, dtype=np.int64)]).astype(np.int32)
+    rate = rng.uniform(0.02, 0.9, (n_cat, n_cfg, 1)) if tp_rate is None else np.full((n_cat, n_cfg, 1), tp_rate)
+    thr_decay = np.linspace(1.0, 0.3, n_thr)[None, None, :]
+    cat_of = np.repeat(np.arange(n_cat), lens)
+    u = rng.random((n_dt, n_cfg, n_thr))
+    tp = u < (rate * thr_decay)[cat_of]
+    ignored = rng.random((n_dt, n_cfg, 1)) < 0.2            # neither TP nor FP in this cfg
+    fp = ~tp & ~ignored & (rng.random((n_dt, n_cfg, n_thr)) < 0.9)
+    tp &= ~ignored
+    w = np.zeros((n_dt, n_cfg), dtype=np.uint32)
+    for t in range(n_thr):
+        w |= tp[:, :, t].astype(np.uint32) << t
+        w |= fp[:, :, t].astype(np.uint32) << (16 + t)
+    tp_tot = np.stack([np.bincount(cat_of, weights=tp[:, c, 0], minlength=n_cat) for c in range(n_cfg)], 1)
+    num_gt = (tp_tot + rng.integers(0, 40, (n_cat, n_cfg))).astype(np.int32)
+    num_gt[rng.random((n_cat, n_cfg)) < 0.15] = 0           # cells without GT stay -1
+    num_gt[(num_gt == 0) & (tp_tot > 0) & (rng.random((n_cat, n_cfg)) < 0.5)] = 1   # tp > num_gt never happens in
+    num_gt = np.maximum(num_gt, np.where(num_gt > 0, tp_tot, 0)).astype(np.int32)   # the evaluators; keep tp <= num_gt
+    return dict(n_cat=n_cat, n_cfg=n_cfg, cat_dt_off=cat_dt_off, acc_perm=acc_perm, tpfp=w, num_gt=num_gt)

@@ -182,3 +182,67 @@ def test_random_small_sets_gpu_vs_host_arithmetic(seed, eng):
             assert np.array_equal(o.num_gt, ref.num_gt)
         assert np.array_equal(d.dt_tpfp, ref.dt_tpfp)
         assert np.array_equal(d.dt_match_gt, ref.dt_match_gt)
+
+
+def _gpu_pr(eng, c, iou_thrs, rec_thrs, impl):
+    """ta_pr_accumulate on explicit arrays with TA_PR_IMPL = impl."""
+    import ctypes as C
+    import os
+    import torch
+    from tao_amodal_b200 import _lib
+    dev = torch.device("cuda", eng.device)
+    T, R, n_cat, n_cfg = len(iou_thrs), len(rec_thrs), c["n_cat"], c["n_cfg"]
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev)
+    cat_off, perm = up(c["cat_dt_off"], np.int64), up(c["acc_perm"], np.int32)
+    tpfp, ngt = up(c["tpfp"].view(np.int32), np.int32), up(c["num_gt"], np.int32)
+    rec = up(rec_thrs, np.float64)
+    prec = torch.full((T, R, n_cat, n_cfg), 7.0, dtype=torch.float64, device=dev)
+    rc = torch.full((T, n_cat, n_cfg), 7.0, dtype=torch.float64, device=dev)
+    tp = torch.zeros((T, n_cat, n_cfg), dtype=torch.int64, device=dev)
+    fp = torch.zeros_like(tp)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    old = os.environ.get("TA_PR_IMPL")
+    os.environ["TA_PR_IMPL"] = str(impl)
+    try:
+        st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+        _lib.check(eng.lib.ta_pr_accumulate(
+            eng._ctx, st, n_cat, p(cat_off), p(perm), int(c["tpfp"].shape[0]), p(tpfp), p(ngt),
+            T, n_cfg, R, p(rec), p(prec), p(rc), p(tp), p(fp)))
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("TA_PR_IMPL")
+        else:
+            os.environ["TA_PR_IMPL"] = old
+    return prec.cpu().numpy(), rc.cpu().numpy(), tp.cpu().numpy(), fp.cpu().numpy()
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("seed,kw", [(0, {}), (1, {}), (2, dict(n_cat=5, n_cfg=20, max_len=700)),
+                                     (3, dict(n_cat=40, n_cfg=6, max_len=5000)),
+                                     (100, dict(n_cat=4, n_cfg=3, tp_rate=0.0)),
+                                     (101, dict(n_cat=4, n_cfg=3, tp_rate=1.0))])
+def test_pr_accumulate_both_implementations(eng, seed, kw, impl):
+    """Position-walk (TA_PR_IMPL=0) and bit-plane (TA_PR_IMPL=1) kernels of ta_pr_accumulate on
+    random multi-chunk categories against the plain serial accumulation (tests/hostsim)."""
+    from plan_backends import hostsim_pr
+    from pr_cases import random_pr_case
+    from tao_amodal_b200 import engine
+    c = random_pr_case(seed, **kw)
+    ref = hostsim_pr(c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
+    prec, rc, tp, fp = _gpu_pr(eng, c, engine.IOU_THRS, engine.REC_THRS, impl)
+    assert np.array_equal(ref.precision, prec)
+    assert np.array_equal(ref.recall, rc)
+    assert np.array_equal(ref.tp_cnt, tp)
+    assert np.array_equal(ref.fp_cnt, fp)
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_goldens_with_each_pr_implementation(golden, eng, impl, monkeypatch):
+    monkeypatch.setenv("TA_PR_IMPL", str(impl))
+    gt, res = golden_inputs(golden)
+    tao_plan, lvis_plan = plans_from_json(gt, res)
+    off_grid = golden["_name"] == "small_float"
+    compare_with_golden(golden, "tao_", tao_plan, eng.evaluate_device(eng.upload(tao_plan), detail=True),
+                        exact_iou=not off_grid, iou_atol=1e-12)
+    compare_with_golden(golden, "lvis_", lvis_plan, eng.evaluate_device(eng.upload(lvis_plan), detail=True))

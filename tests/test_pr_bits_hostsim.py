@@ -1,0 +1,64 @@
+"""Bit-plane PR kernels (k_pr_bits / k_pr_envelope_bits, csrc/ta_pr.cu): their per-thread
+functions, emulated serially on the host, against the plain serial accumulation that the
+goldens of the unmodified reference pin."""
+import numpy as np
+import pytest
+
+import plan_backends
+from plan_backends import hostsim_pr
+from pr_cases import random_pr_case
+from tao_amodal_b200 import engine
+
+
+def _same(a, b):
+    for k in ("precision", "recall", "tp_cnt", "fp_cnt"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_multi_chunk(seed):
+    c = random_pr_case(seed)
+    args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
+    _same(hostsim_pr(*args, impl="bits"), hostsim_pr(*args, impl="serial"))
+
+
+@pytest.mark.parametrize("tp_rate", [0.0, 1.0])
+def test_all_or_no_true_positives(tp_rate):
+    c = random_pr_case(100, n_cat=4, n_cfg=3, tp_rate=tp_rate)
+    args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
+    _same(hostsim_pr(*args, impl="bits"), hostsim_pr(*args, impl="serial"))
+
+
+def test_track_shape_and_odd_thresholds():
+    c = random_pr_case(5, n_cat=5, n_cfg=20, n_thr=10, max_len=700)
+    args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
+    _same(hostsim_pr(*args, impl="bits"), hostsim_pr(*args, impl="serial"))
+    c = random_pr_case(6, n_cat=5, n_cfg=2, n_thr=3, max_len=900)
+    args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
+    thr, rec = engine.IOU_THRS[:3], np.array([0.0, 0.25, 0.5, 0.5, 0.99, 1.0])
+    _same(hostsim_pr(*args, iou_thrs=thr, rec_thrs=rec, impl="bits"),
+          hostsim_pr(*args, iou_thrs=thr, rec_thrs=rec, impl="serial"))
+
+
+def test_transpose_is_a_warp_of_ballots():
+    import ctypes as C
+    hs = plan_backends.build_hostsim()
+    rng = np.random.Generator(np.random.PCG64(3))
+    x = rng.integers(0, 2**32, 32, dtype=np.uint64).astype(np.uint32)
+    out = np.zeros(32, dtype=np.uint32)
+    hs.hs_transpose32(x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    for b in range(32):
+        ballot = sum(((int(x[l]) >> b) & 1) << l for l in range(32))
+        assert int(out[b]) == ballot
+
+
+def test_goldens_through_the_bit_plane_emulation(golden):
+    """Every golden of the unmodified reference, PR step done by the bit-plane emulation."""
+    from conftest import golden_inputs
+    from plan_backends import compare_with_golden, plans_from_json, run_hostsim
+    gt, res = golden_inputs(golden)
+    tao_plan, lvis_plan = plans_from_json(gt, res)
+    off_grid = golden["_name"] == "small_float"
+    compare_with_golden(golden, "tao_", tao_plan, run_hostsim(tao_plan, pr_impl="bits"),
+                        exact_iou=not off_grid, iou_atol=1e-12)
+    compare_with_golden(golden, "lvis_", lvis_plan, run_hostsim(lvis_plan, pr_impl="bits"))
