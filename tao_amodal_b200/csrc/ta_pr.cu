@@ -361,6 +361,83 @@ k_pr_envelope_bits(PrArgs a) {
                                 per_t);
 }
 
+
+// tk table of the bit-plane path: one thread per (category, cfg, recall level)
+__global__ void __launch_bounds__(256)
+k_pr_tk(PrArgs a) {
+    const int64_t n = (int64_t)a.n_cat * a.n_cfg * a.n_rec;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t cc = (uint32_t)(i / a.n_rec);
+    const int k = (int)(i - (int64_t)cc * a.n_rec);
+    const int ngt = a.num_gt[cc];
+    a.tk[i] = ngt ? (int32_t)ta_min_tp_for_recall(a.rec_thrs[k], ngt) : INT_MAX;
+}
+
+// Exclusive scan of the chunk totals, bit-plane path: one block per category, thread <->
+// counter (cfg, bit); only the 2 n_thr live counters of a cfg are touched; 16 independent
+// loads in flight per thread (predicated, no serial tail).
+#define PR_SCAN_DEPTH 16
+__global__ void __launch_bounds__(128)
+k_pr_scan_live(PrArgs a) {
+    const int cat = blockIdx.x;
+    const int ch0 = a.chunk_start[cat], ch1 = a.chunk_start[cat + 1];
+    const int n_ctr = a.n_cfg * 32;
+    const bool has_dt = a.cat_dt_off[cat + 1] > a.cat_dt_off[cat];
+    for (int j = threadIdx.x; j < n_ctr; j += blockDim.x) {
+        const int cfg = j >> 5, bit = j & 31, t = bit & 15;
+        uint32_t run = 0;
+        if (t < a.n_thr) {
+            uint32_t* col = a.chunk_cnt + j;
+            const int64_t rs = (int64_t)a.n_cfg * 32;          // row stride (one chunk)
+            for (int ch = ch0; ch < ch1; ch += PR_SCAN_DEPTH) {
+                uint32_t v[PR_SCAN_DEPTH];
+#pragma unroll
+                for (int u = 0; u < PR_SCAN_DEPTH; ++u)
+                    v[u] = (ch + u < ch1) ? __ldcg(col + (int64_t)(ch + u) * rs) : 0u;
+#pragma unroll
+                for (int u = 0; u < PR_SCAN_DEPTH; ++u) {
+                    if (ch + u < ch1) col[(int64_t)(ch + u) * rs] = run;
+                    run += v[u];
+                }
+            }
+            const int ngt = a.num_gt[(int64_t)cat * a.n_cfg + cfg];
+            const int64_t cell = ((int64_t)t * a.n_cat + cat) * a.n_cfg + cfg;
+            if (bit < 16) {
+                if (a.tp_cnt) a.tp_cnt[cell] = ngt ? (int64_t)run : 0;
+                // eval.py:522-525 (cell keeps -1 without GT), :543-547 (rc[-1] or 0)
+                a.recall[cell] = ngt == 0 ? -1.0 : (has_dt ? (double)run / (double)ngt : 0.0);
+            } else if (a.fp_cnt) {
+                a.fp_cnt[cell] = ngt ? (int64_t)run : 0;
+            }
+        }
+        a.cat_tot[((int64_t)cat * a.n_cfg) * 32 + j] = run;
+    }
+}
+
+// k_pr_finalize on a 2-D grid: blockIdx.y = (threshold, recall level), x over (category, cfg)
+// — no per-thread 64-bit index arithmetic; same values as k_pr_finalize.
+__global__ void __launch_bounds__(256)
+k_pr_finalize_2d(PrArgs a) {
+    const uint32_t per_t = (uint32_t)a.n_cat * (uint32_t)a.n_cfg;
+    const uint32_t cc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cc >= per_t) return;
+    const int tk_idx = blockIdx.y;
+    const int t = tk_idx / a.n_rec, k = tk_idx - t * a.n_rec;
+    const int64_t idx = (int64_t)tk_idx * per_t + cc;
+    const int ngt = a.num_gt[cc];
+    if (ngt == 0) { a.precision[idx] = -1.0; return; }        // eval.py:522-525
+    const uint32_t need = (uint32_t)max(a.tk[(int64_t)cc * a.n_rec + k], 1);
+    if (need > a.cat_tot[(int64_t)cc * 32 + t]) { a.precision[idx] = 0.0; return; }   // eval.py:565-573
+    const uint32_t cat = cc / (uint32_t)a.n_cfg, cfg = cc - cat * (uint32_t)a.n_cfg;
+    uint32_t qt, qn, ch, bt, bn, dummy;
+    pr_unpack(a.prec_bits[idx], qt, qn, ch);
+    pr_unpack(a.chunk_best[((int64_t)(a.chunk_start[cat] + ch) * a.n_cfg + cfg) * a.n_thr + t],
+              bt, bn, dummy);
+    if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
+    a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
+}
+
 // per (category, cfg, threshold): chunk_best[ch] <- best precision of all LATER chunks
 __global__ void k_pr_suffix(PrArgs a) {
     const int cat = blockIdx.x;
@@ -503,8 +580,16 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
         k_pr_count<<<grid, warps * 32, 0, st>>>(a);
         if ((rc = ta_check_launch(ctx, "k_pr_count"))) return rc;
     }
-    k_pr_scan<<<n_cat, 128, 0, st>>>(a);
-    if ((rc = ta_check_launch(ctx, "k_pr_scan"))) return rc;
+    if (impl) {
+        const int64_t n_tk = (int64_t)n_cat * n_cfg * n_rec;
+        k_pr_tk<<<(unsigned)((n_tk + 255) / 256), 256, 0, st>>>(a);
+        if ((rc = ta_check_launch(ctx, "k_pr_tk"))) return rc;
+        k_pr_scan_live<<<n_cat, 128, 0, st>>>(a);
+        if ((rc = ta_check_launch(ctx, "k_pr_scan_live"))) return rc;
+    } else {
+        k_pr_scan<<<n_cat, 128, 0, st>>>(a);
+        if ((rc = ta_check_launch(ctx, "k_pr_scan"))) return rc;
+    }
     if (n_chunks_ub > 0 && impl) {
         // grid over the upper bound of chunks: the kernel reads the real count on the device
         const int64_t threads = (int64_t)n_chunks_ub * (int64_t)n_cells;
@@ -525,6 +610,11 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     k_pr_suffix<<<n_cat, 128, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_suffix"))) return rc;
     const size_t n_prec = (size_t)n_thr * n_rec * n_cat * n_cfg;
+    if (impl && (size_t)n_thr * n_rec <= 65535 && (size_t)n_cat * n_cfg < (1u << 31)) {
+        dim3 grid((unsigned)(((size_t)n_cat * n_cfg + 255) / 256), (unsigned)(n_thr * n_rec));
+        k_pr_finalize_2d<<<grid, 256, 0, st>>>(a);
+        return ta_check_launch(ctx, "k_pr_finalize_2d");
+    }
     k_pr_finalize<<<(unsigned)((n_prec + 255) / 256), 256, 0, st>>>(a);
     return ta_check_launch(ctx, "k_pr_finalize");
 }
