@@ -94,6 +94,23 @@ int ta_box_iou(ta_ctx* ctx, void* stream, int64_t n_groups,
                const double* dt_box, const double* gt_box,
                const int64_t* iou_off, double* iou_out);
 
+/* Per-(image, category) MASK IoU, iou_type = "segm".  Replaces LVISEval.compute_iou ->
+ * pycocotools.mask.iou -> rleIou (lvis_amodal/eval.py:168-192; maskApi.c:78-96 in-tree copy),
+ * iscrowd = 0.  Entity e's mask is the column-major run-length list
+ * counts[rle_off[e] .. rle_off[e+1]) (zeros first) on an hw[e] = (height, width) canvas, with
+ * bbox[e] = [x, y, w, h] as rleToBbox derives it from the runs (maskApi.c:133-151; pairs whose
+ * boxes do not overlap are 0 without a walk, :80-82; masks of different size give -1, :85).
+ * The run lists come from the host codec of include/ta_mask.h.  Output layout, grp_list as in
+ * ta_box_iou; the matrices feed ta_match_greedy.                                        */
+int ta_rle_iou(ta_ctx* ctx, void* stream, int64_t n_groups,
+               const int32_t* grp_list, int64_t n_list,
+               const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+               const int64_t* dt_rle_off, const uint32_t* dt_counts,
+               const uint32_t* dt_hw, const double* dt_bbox,
+               const int64_t* gt_rle_off, const uint32_t* gt_counts,
+               const uint32_t* gt_hw, const double* gt_bbox,
+               const int64_t* iou_off, double* iou_out);
+
 /* COCO-style sequential greedy assignment for every group x range cfg x IoU threshold.
  * Replaces TaoEval.evaluate_vid (eval.py:337-457) and LVISEval.evaluate_img
  * (lvis_amodal/eval.py:194-303).  The reference's id tests are carried by flag bits so the

@@ -28,6 +28,7 @@ EXPORTS = [
     "ta_abi_version", "ta_last_error", "ta_ctx_create", "ta_ctx_destroy", "ta_ctx_sm_count",
     "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
     "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
+    "ta_rle_iou",
 ]
 
 
@@ -97,6 +98,7 @@ def load() -> C.CDLL:
                                      P, P, P, P])
     lib.ta_frame_eval.argtypes = ([P, P, I64, P, P, P, P, P, I32, P, I32, P, I64, P,
                                    I64, P, P, I64, P, I32, P, P, I32, P, P, P, P])
+    lib.ta_rle_iou.argtypes = [P, P, I64, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]
     lib.ta_pr_accumulate.argtypes = [P, P, I32, P, P, I64, P, P, I32, I32, I32, P, P, P, P, P]
     lib.ta_eval_plan_host.argtypes = [P, C.POINTER(PlanHost), P, P, P, P, P,
                                       C.POINTER(I64), C.POINTER(I64)]

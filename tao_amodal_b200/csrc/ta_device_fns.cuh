@@ -245,4 +245,32 @@ TA_HD unsigned long long ta_pr_walk_bits(const uint32_t* T, const uint32_t* F, i
     return pr_pack(bt, bn, 0);
 }
 
+// ---- mask IoU of the segm path (ta_rle.cu; host build: tests/hostsim) -----------------------
+
+// IoU of two column-major run-length masks, iscrowd = 0: pycocotools rleIou for one pair
+// (in-tree copy visualization/tao/third_party/pysot/training_dataset/coco/pycocotools/common/
+// maskApi.c:78-96).  db / gb are the masks' boxes as rleToBbox derives them (:133-151): the
+// pair is only walked when their box IoU is positive (:80-82), masks of different size give -1
+// (:85).  Both run lists are consumed in lock step; zero-length runs toggle like the C loop.
+TA_HD double ta_rle_pair_iou(const uint32_t* cd, int64_t md, const uint32_t* cg, int64_t mg,
+                             const double* db, const double* gb,
+                             uint32_t dh, uint32_t dw, uint32_t gh, uint32_t gw) {
+    const double o = ta_bb_iou(db[0], db[1], db[2], db[3], gb[0], gb[1], gb[2], gb[3]);
+    if (!(o > 0.0)) return o;
+    if (dh != gh || dw != gw) return -1.0;
+    uint32_t ca = md > 0 ? cd[0] : 0u, cb = mg > 0 ? cg[0] : 0u;
+    int64_t a = 1, b = 1;
+    bool va = false, vb = false;
+    uint32_t i = 0, u = 0, ct = 1;
+    while (ct > 0) {
+        const uint32_t c = ca < cb ? ca : cb;
+        if (va || vb) { u += c; if (va && vb) i += c; }
+        ct = 0;
+        ca -= c; if (!ca && a < md) { ca = cd[a++]; va = !va; } ct += ca;
+        cb -= c; if (!cb && b < mg) { cb = cg[b++]; vb = !vb; } ct += cb;
+    }
+    if (i == 0) u = 1;
+    return (double)i / (double)u;
+}
+
 #endif  // TA_DEVICE_FNS_CUH

@@ -298,4 +298,21 @@ void hs_transpose32(const uint32_t* in, uint32_t* out) {
     for (int l = 0; l < 32; ++l) out[l] = x[l];
 }
 
+int hs_rle_iou(int64_t n_groups, const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+               const int64_t* dt_off, const uint32_t* dt_cnt, const uint32_t* dt_hw, const double* dt_bb,
+               const int64_t* gt_off, const uint32_t* gt_cnt, const uint32_t* gt_hw, const double* gt_bb,
+               const int64_t* iou_off, double* iou) {
+    for (int64_t grp = 0; grp < n_groups; ++grp) {
+        const int64_t d0 = grp_dt_off[grp], g0 = grp_gt_off[grp];
+        const int64_t D = grp_dt_off[grp + 1] - d0, G = grp_gt_off[grp + 1] - g0;
+        for (int64_t e = 0; e < D * G; ++e) {
+            const int64_t d = d0 + e / G, g = g0 + e % G;
+            iou[iou_off[grp] + e] = ta_rle_pair_iou(
+                dt_cnt + dt_off[d], dt_off[d + 1] - dt_off[d], gt_cnt + gt_off[g], gt_off[g + 1] - gt_off[g],
+                dt_bb + 4 * d, gt_bb + 4 * g, dt_hw[2 * d], dt_hw[2 * d + 1], gt_hw[2 * g], gt_hw[2 * g + 1]);
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

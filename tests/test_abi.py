@@ -38,3 +38,15 @@ def test_struct_layouts_match_header():
     from tao_amodal_b200 import prep
     assert C.sizeof(_lib.RangeCfg) == prep.RANGE_CFG_DTYPE.itemsize == 72
     assert C.sizeof(_lib.PlanHost) == 6 * 8 + 8 * 4 + 23 * 8
+
+
+def test_mask_codec_exports_every_declared_symbol():
+    """include/ta_mask.h (host-side run-length codec, part of libta_ingest.so)."""
+    from tao_amodal_b200 import ingest
+    src = open(os.path.join(ROOT, "include", "ta_mask.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(ta_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) >= 10
+    lib = ingest.load_lib()
+    for n in names:
+        assert getattr(lib, n) is not None, n
