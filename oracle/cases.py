@@ -139,6 +139,72 @@ def case_edge_mix():
     return gt, res
 
 
+def _inset_polygon(b, rng):
+    """A convex-ish polygon inside box b (x, y, w, h): corners cut by random fractions."""
+    x, y, w, h = b
+    c = rng.uniform(0.05, 0.35, 4)
+    return [x + c[0] * w, y, x + w - c[1] * w, y, x + w, y + c[1] * h, x + w, y + h - c[2] * h,
+            x + w - c[2] * w, y + h, x + c[3] * w, y + h, x, y + h - c[3] * h, x, y + c[0] * h]
+
+
+def add_segmentations(gt, res, seed, dt_mode):
+    """GT annotations get a ``segmentation`` in all the forms LVIS.ann_to_rle accepts
+    (lvis.py:165-178): polygon, two-part polygon, list-of-boxes, uncompressed counts, compressed
+    RLE.  dt_mode: "box" results keep only their bbox (results.py:50-52 derives a polygon),
+    "poly" results carry polygons of their own, "rle" results carry ONLY a compressed RLE
+    (results.py:58-66).  The two RLE forms are produced with the run-length codec under test
+    and stored in the golden file, so the reference reads exactly the same bytes."""
+    from tao_amodal_b200.mask import RlePool
+    rng = np.random.Generator(np.random.PCG64(seed))
+    img = {i["id"]: i for i in gt["images"]}
+
+    def rle_of(segm, im, compressed):
+        pool = RlePool()
+        pool.add_segmentation(segm, im["height"], im["width"])
+        if compressed:
+            r = pool.to_rle(0)
+            return {"size": r["size"], "counts": r["counts"].decode()}
+        off, cnt, hw, _, _ = pool.export()
+        return {"size": [int(hw[0, 0]), int(hw[0, 1])], "counts": cnt.tolist()}
+
+    for n, a in enumerate(gt["annotations"]):
+        b = a["bbox"]
+        kind = n % 6
+        if kind in (0, 1):
+            a["segmentation"] = [_inset_polygon(b, rng)]
+        elif kind == 2:      # two parts: left and right half, cut
+            x, y, w, h = b
+            a["segmentation"] = [_inset_polygon([x, y, w * 0.45, h], rng),
+                                 _inset_polygon([x + w * 0.55, y, w * 0.45, h], rng)]
+        elif kind == 3:      # a list whose first element has 4 numbers is a list of BOXES
+            x, y, w, h = b
+            a["segmentation"] = [[x, y, w, h * 0.5], [x + w * 0.25, y + h * 0.5, w * 0.5, h * 0.5]]
+        elif kind == 4:
+            a["segmentation"] = rle_of([_inset_polygon(b, rng)], img[a["image_id"]], False)
+        else:
+            a["segmentation"] = rle_of([_inset_polygon(b, rng)], img[a["image_id"]], True)
+    if dt_mode == "poly":
+        for n, r in enumerate(res):
+            if n % 3:
+                r["segmentation"] = [_inset_polygon(r["bbox"], rng)]
+    elif dt_mode == "rle":
+        for r in res:
+            r["segmentation"] = rle_of([_inset_polygon(r.pop("bbox"), rng)], img[r["image_id"]], True)
+    return gt, res
+
+
+def case_segm(dt_mode, seed):
+    gt, res = synth.generate_named("tiny", seed=seed)
+    gt, res = gt.to_dict(), res.to_list()
+    return add_segmentations(gt, res, seed + 1, dt_mode)
+
+
+SEGM_CASES = {
+    "segm_box": lambda: case_segm("box", 31),
+    "segm_poly": lambda: case_segm("poly", 32),
+    "segm_rle": lambda: case_segm("rle", 33),
+}
+
 CASES = {
     "tiny": case_tiny,
     "small": case_small,
@@ -150,5 +216,5 @@ CASES = {
 
 
 def build(name):
-    gt, res = CASES[name]()
+    gt, res = (CASES.get(name) or SEGM_CASES[name])()
     return gt, res

@@ -169,6 +169,38 @@ def run_alt_iou(name: str, mode: str, ref) -> dict:
     return out
 
 
+def run_segm(name: str, ref) -> dict:
+    """LVISEval(annotation, results, "segm").run() (lvis_amodal/eval.py:54-57, :70-72, :180-191):
+    annotations become masks through the reference tree's own maskApi.c (oracle/_ref)."""
+    import pycocotools.mask as pm
+    assert pm.BACKEND.startswith("reference C"), "segm goldens need oracle/_ref (make -C oracle)"
+    gt, res = cases.build(name)
+    out = {"in_gt_json": np.asarray(json.dumps(gt)), "in_dt_json": np.asarray(json.dumps(res))}
+    with tempfile.TemporaryDirectory() as td:
+        ap, rp = (os.path.join(td, f) for f in ("gt.json", "dt.json"))
+        json.dump(gt, open(ap, "w"))
+        json.dump(res, open(rp, "w"))
+        le = ref.LVISEval(ap, rp, "segm")
+        le.run()
+        n_img, n_r = len(le.params.img_ids), len(le.params.visibility_rng)
+        cells = {}
+        for flat, e in enumerate(le.eval_imgs):
+            if e is not None:
+                c, rem = divmod(flat, n_r * n_img)
+                r, i = divmod(rem, n_img)
+                cells[c, r, i] = e
+        for k, v in golden_io.flatten_cells(cells).items():
+            out["lvis_" + k] = v
+        for k, v in golden_io.flatten_ious(le.ious).items():
+            out["lvis_" + k] = v
+        out["lvis_precision"], out["lvis_recall"] = le.eval["precision"], le.eval["recall"]
+        tp, fp = counts_from_pointers(le.eval, le.eval["recall"].shape)
+        out["lvis_tp_cnt"], out["lvis_fp_cnt"] = tp, fp
+        out["lvis_results"] = golden_io.results_vector(le.results)
+        out["lvis_results_keys"] = np.asarray(golden_io.results_keys(le.results))
+    return out
+
+
 def main(argv):
     names = argv or list(cases.CASES)
     ref = ref_shims.load_reference()
@@ -179,6 +211,15 @@ def main(argv):
             path = os.path.join(GOLDEN_DIR, "small_%s.npz" % mode)
             np.savez_compressed(path, **out)
             print("%-12s -> %s  TAO AP=%.6f" % (mode, path, out["tao_results"][0]))
+        return
+    if names == ["segm"]:
+        for n in cases.SEGM_CASES:
+            out = run_segm(n, ref)
+            path = os.path.join(GOLDEN_DIR, n + ".npz")
+            np.savez_compressed(path, **out)
+            print("%-12s -> %s (%d KB)  LVIS segm AP=%.6f, %d IoU entries, %d positive" % (
+                n, path, os.path.getsize(path) // 1024, out["lvis_results"][0],
+                out["lvis_iou_vals"].size, int((out["lvis_iou_vals"] > 0).sum())))
         return
     if names == ["nocats"]:
         for n in ("small", "edge_mix"):

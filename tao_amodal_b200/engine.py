@@ -243,6 +243,9 @@ class Engine:
 
     def stage_iou(self, dev: "DevicePlan", iou_mode: str = "3d_iou"):
         """compute_iou of every group (eval.py:306-335 / lvis eval.py:168-192)."""
+        if plan.masks is not None:
+            raise NotImplementedError("ta_eval_plan_host carries box plans only; use upload() + "
+                                      "evaluate_device() for iou_type='segm'")
         import torch
         p, plan = dev.ptr, dev.plan
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -251,6 +254,13 @@ class Engine:
                 self._ctx, st, _lib.IOU_MODES[iou_mode], plan.n_groups, p["grp_dt_off"],
                 p["grp_gt_off"], p["dt_trk_off"], p["dt_box"], p["dt_slot"], p["gt_trk_off"],
                 p["gt_box"], p["gt_slot"], dev.n_slots, p["iou_off"], p["iou"]))
+        elif plan.masks is not None:
+            # iou_type="segm": mask IoU (lvis eval.py:180-191 -> rleIou)
+            _lib.check(self.lib.ta_rle_iou(
+                self._ctx, st, plan.n_groups, None, 0, p["grp_dt_off"], p["grp_gt_off"],
+                p["dt_rle_off"], p["dt_rle_counts"], p["dt_rle_hw"], p["dt_rle_bb"],
+                p["gt_rle_off"], p["gt_rle_counts"], p["gt_rle_hw"], p["gt_rle_bb"],
+                p["iou_off"], p["iou"]))
         else:
             _lib.check(self.lib.ta_box_iou(
                 self._ctx, st, plan.n_groups, None, 0, p["grp_dt_off"], p["grp_gt_off"],
@@ -309,7 +319,7 @@ class Engine:
         stream until results are fetched).  The frame path runs the fused kernel unless
         fused=False (then ta_box_iou + ta_match_greedy).  Returns EvalOutput or None."""
         plan = dev.plan
-        if plan.kind == "lvis" and fused:
+        if plan.kind == "lvis" and fused and plan.masks is None:
             self.stage_frame_eval(dev, detail)
         else:
             self.stage_iou(dev, iou_mode)
@@ -363,6 +373,11 @@ class DevicePlan:
         if track:
             host.update(dt_trk_off=plan.dt_trk_box_off, gt_trk_off=plan.gt_trk_box_off,
                         dt_slot=plan.dt_box_slot, gt_slot=plan.gt_box_slot)
+        if plan.masks is not None:
+            for side in ("dt", "gt"):
+                off, cnt, hw, bb = plan.masks[side]
+                host.update({side + "_rle_off": off, side + "_rle_counts": cnt,
+                             side + "_rle_hw": hw, side + "_rle_bb": bb})
         self.t = {}
         self.input_bytes = 0
         self._input_keys = []

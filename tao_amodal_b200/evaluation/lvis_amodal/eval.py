@@ -1,10 +1,12 @@
 """``LVISEval`` — visibility-split frame-AP evaluator on the CUDA library.
 
-Mirror of tao_amodal/evaluation/lvis_amodal/eval.py:14-583 for ``iou_type='bbox'``: same
+Mirror of tao_amodal/evaluation/lvis_amodal/eval.py:14-583 (``iou_type='bbox'`` and ``'segm'``): same
 constructor, ``params``, ``evaluate / accumulate / summarize / run / print_results /
 get_results`` and the public attributes ``ious``, ``eval_imgs``, ``eval``, ``results``,
 ``freq_groups``.  The (image, category, visibility range) Python grid of the reference is one
-fused IoU + matching kernel here (engine.stage_frame_eval).
+fused IoU + matching kernel here (engine.stage_frame_eval); with ``iou_type='segm'`` the
+annotations become run-length masks (mask.RlePool, native codec) and the IoU matrices come from
+the mask-IoU kernel (ta_rle_iou) followed by the generic matcher.
 """
 from __future__ import annotations
 
@@ -107,8 +109,8 @@ class LVISEval:
     def _prepare(self):
         """Columnar equivalent of lvis eval.py:59-113 (prep.prepare_lvis)."""
         p = self.params
-        if p.iou_type != "bbox":
-            raise NotImplementedError("only iou_type='bbox' runs on the CUDA path")
+        if p.iou_type not in ("bbox", "segm"):
+            raise ValueError("Unknown iou_type for iou computation.")        # lvis eval.py:184
         if len(p.iou_thrs) > 16:
             raise ValueError("at most 16 IoU thresholds are supported")
         img_ids = p.img_ids
@@ -130,6 +132,45 @@ class LVISEval:
             vis_rng=p.visibility_rng, img_ids=img_ids,
             cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats))
         self.freq_groups = self._plan.freq_groups
+        if p.iou_type == "segm":
+            self._plan.masks = self._build_masks(self._plan)
+
+    def _build_masks(self, plan):
+        """``_to_mask`` of lvis eval.py:54-57, :70-72 for the entities of the plan: every GT /
+        detection annotation through LVIS.ann_to_rle's conversion (lvis.py:155-178), kept as
+        flat run-length arrays for the device.  Detections that carry no ``segmentation`` get
+        the 4-corner polygon of their box (lvis_amodal/results.py:50-52), converted in one
+        batched call."""
+        from ...mask import RlePool
+        gt_anns, imgs = self.lvis_gt.anns, self.lvis_gt.imgs
+        gpool = RlePool()
+        for aid in plan.gt_id.tolist():
+            ann = gt_anns[aid]
+            img = imgs[ann["image_id"]]
+            gpool.add_segmentation(ann["segmentation"], img["height"], img["width"])
+        dpool = RlePool()
+        given = self.lvis_dt.given_segmentations()
+        if given is None:
+            img_of = np.asarray(plan.unit_ids)[plan.grp_unit[np.repeat(
+                np.arange(plan.n_groups), np.diff(plan.grp_dt_off))]]
+            hh = np.asarray([imgs[i]["height"] for i in img_of.tolist()], dtype=np.int64)
+            ww = np.asarray([imgs[i]["width"] for i in img_of.tolist()], dtype=np.int64)
+            if plan.n_dt:
+                dpool.add_boxes(plan.dt_box, hh, ww)
+        else:
+            dt_anns = self.lvis_dt.dataset["annotations"]
+            for aid in plan.dt_id.tolist():
+                ann = dt_anns[aid - 1]                       # ids are 1 + position, results.py:56
+                img = imgs[ann["image_id"]]
+                dpool.add_segmentation(ann["segmentation"], img["height"], img["width"])
+        out = {}
+        for side, pool in (("dt", dpool), ("gt", gpool)):
+            off, cnt, hw, bb, _ = pool.export()
+            out[side] = (off, np.ascontiguousarray(cnt if cnt.size else np.zeros(1, np.uint32)),
+                         np.ascontiguousarray(hw.reshape(-1, 2) if hw.size else np.zeros((1, 2), np.uint32)),
+                         np.ascontiguousarray(bb.reshape(-1, 4) if bb.size else np.zeros((1, 4))))
+            pool.close()
+        return out
 
     def evaluate(self):
         """Per-image evaluation on the GPU (lvis eval.py:115-145)."""
@@ -139,7 +180,11 @@ class LVISEval:
         self._prepare()
         eng = get_engine(self.device)
         self._dev = eng.upload(self._plan, self.params.iou_thrs, self.params.rec_thrs)
-        eng.stage_frame_eval(self._dev)
+        if self._plan.masks is None:
+            eng.stage_frame_eval(self._dev)
+        else:
+            eng.stage_iou(self._dev)
+            eng.stage_match(self._dev)
         self._detail = None
         self.ious = LazyDict(lambda: materialize.iou_dict(self._plan, self._need_detail().iou))
         plan = self._plan

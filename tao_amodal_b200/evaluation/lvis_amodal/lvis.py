@@ -1,6 +1,6 @@
 """``LVIS`` — annotation index of the frame evaluator (mirror of
-tao_amodal/evaluation/lvis_amodal/lvis.py:18-153; mask helpers :155-205 are out of scope:
-only ``iou_type='bbox'`` runs on the CUDA path)."""
+tao_amodal/evaluation/lvis_amodal/lvis.py:18-205; the mask helpers :155-192 go through the
+native run-length codec, tao_amodal_b200/mask.py)."""
 from __future__ import annotations
 
 import logging
@@ -86,3 +86,27 @@ class LVIS:
 
     def load_imgs(self, ids):
         return self._load_helper(self.imgs, ids)
+
+    def ann_to_rle(self, ann):
+        """lvis.py:155-178: polygons / uncompressed counts / compressed RLE -> compressed RLE
+        dict ({"size": [h, w], "counts": bytes}), through the native codec."""
+        from ...mask import RlePool
+        segm = ann["segmentation"]
+        if not isinstance(segm, list) and not isinstance(segm["counts"], list):
+            return segm
+        img = self.imgs[ann["image_id"]]
+        pool = RlePool()
+        pool.add_segmentation(segm, img["height"], img["width"])
+        return pool.to_rle(0)
+
+    def ann_to_mask(self, ann):
+        """lvis.py:180-192: binary mask uint8 [h, w] of the annotation."""
+        import numpy as np
+        from ...mask import RlePool
+        pool = RlePool()
+        segm = ann["segmentation"]
+        img = self.imgs[ann["image_id"]]
+        pool.add_segmentation(segm, img["height"], img["width"])
+        off, cnt, hw, _, _ = pool.export()
+        vals = np.arange(cnt.size, dtype=np.uint8) & 1
+        return np.repeat(vals, cnt).reshape((int(hw[0, 1]), int(hw[0, 0]))).T.copy()

@@ -1,5 +1,6 @@
 """``LVISResults`` — prediction index of the frame evaluator (mirror of
-tao_amodal/evaluation/lvis_amodal/results.py:9-89, bbox results only).  Predictions are kept
+tao_amodal/evaluation/lvis_amodal/results.py:9-89; results must carry ``bbox``, optionally with
+their own ``segmentation`` for iou_type="segm").  Predictions are kept
 as columns; the reference-shaped ``dataset`` is materialised on demand."""
 from __future__ import annotations
 
@@ -27,17 +28,27 @@ class LVISResults(LVIS):
         self.logger.info("Loading and preparing results.")
         self.max_dets = max_dets
         self._results_path = None
+        self._has_segm = None
+        self._mask_only = False
+        from_file = isinstance(results, str)
+        dt = None
         if isinstance(results, DtColumns):
-            self._result_anns, dt = None, results
-        elif isinstance(results, str):
+            self._result_anns, dt, self._has_segm = None, results, False
+        elif from_file:
             self._results_path, self._result_anns = results, None
-            dt = ingest.load_dt(results)       # native single-pass reader (bbox results)
-        else:
-            self.logger.warn("Assuming user provided the results in correct format.")
+            try:
+                dt = ingest.load_dt(results)       # native single-pass reader (bbox results)
+            except KeyError:                       # mask-only results file: the dict path below
+                results, self._results_path = load_json(results), None
+        if dt is None:
+            if not from_file:
+                self.logger.warn("Assuming user provided the results in correct format.")
             assert isinstance(results, list), "results is not a list."
-            if len(results) and "bbox" not in results[0]:
-                raise NotImplementedError("only bbox results run on the CUDA path")
+            self._mask_only = bool(len(results)) and "bbox" not in results[0]
+            if self._mask_only:
+                self._box_and_area_from_masks(results)
             self._result_anns = results
+            self._has_segm = any("segmentation" in r for r in results)
             dt = DtColumns.from_list(results)
         if dt.n() == 0:
             raise IndexError("list index out of range")                # results.py:42
@@ -59,15 +70,41 @@ class LVISResults(LVIS):
                 anns = self.dt_columns.to_list()
             if self.max_dets >= 0:
                 anns = self.limit_dets_per_image(anns, self.max_dets)
+            if self._has_segm is None:
+                self._has_segm = any("segmentation" in r for r in anns)
             for n, r in enumerate(anns):
                 x1, y1, w, h = r["bbox"]
                 if "segmentation" not in r:
                     r["segmentation"] = [[x1, y1, x1, y1 + h, x1 + w, y1 + h, x1 + w, y1]]
-                r["area"] = w * h
+                if not self._mask_only:
+                    r["area"] = w * h
                 r["id"] = n + 1
             ds["annotations"] = anns
             self.__dict__["_dataset"] = ds
         return self.__dict__["_dataset"]
+
+    @staticmethod
+    def _box_and_area_from_masks(results):
+        """results.py:58-66 — results that carry only a compressed RLE: ``area`` is the mask
+        area, ``bbox`` the box of the mask (pycocotools area / toBbox, here the native codec)."""
+        from ...mask import RlePool
+        pool = RlePool()
+        for r in results:
+            seg = r["segmentation"]
+            pool.add_string(seg["counts"], seg["size"][0], seg["size"][1])
+        _, _, _, bb, area = pool.export()
+        for k, r in enumerate(results):
+            r["area"] = area[k]
+            if "bbox" not in r:
+                r["bbox"] = bb[k].copy()
+        pool.close()
+
+    def given_segmentations(self):
+        """True when some result came with a ``segmentation`` of its own; None when they all get
+        the box polygon of results.py:50-52."""
+        if self._has_segm is None:
+            self.dataset            # a results FILE: the dict form records it while it is built
+        return True if self._has_segm else None
 
     def limit_dets_per_image(self, anns, max_dets):
         """results.py:73-84."""

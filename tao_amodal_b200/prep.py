@@ -127,6 +127,9 @@ class EvalPlan:
     range_cfgs: Optional[np.ndarray] = None
     sentinel: int = -1           # "unmatched" id value: -1 (tao, eval.py:390-391) / 0 (lvis :239-240)
     freq_groups: Optional[list] = None            # lvis: category indices per r/c/f
+    # lvis, iou_type="segm": run-length masks of the entities (mask.RlePool.export()):
+    # {"dt"|"gt": (rle_off int64 [n+1], counts uint32, hw uint32 [n,2], bbox f64 [n,4])}
+    masks: Optional[dict] = None
     stats: Dict[str, float] = field(default_factory=dict)
 
     @property

@@ -46,6 +46,11 @@ def run_hostsim(plan, iou_mode="3d_iou", iou_thrs=engine.IOU_THRS, rec_thrs=engi
                         _p(plan.grp_gt_off), _p(plan.dt_trk_box_off), _p(plan.dt_box),
                         _p(plan.dt_box_slot), _p(plan.gt_trk_box_off), _p(plan.gt_box),
                         _p(plan.gt_box_slot), _p(plan.iou_off), _p(iou))
+    elif plan.masks is not None:
+        (do, dc, dhw, dbb), (go, gc, ghw, gbb) = plan.masks["dt"], plan.masks["gt"]
+        hs.hs_rle_iou.argtypes = [I64] + [C.c_void_p] * 12
+        hs.hs_rle_iou(plan.n_groups, _p(plan.grp_dt_off), _p(plan.grp_gt_off), _p(do), _p(dc),
+                      _p(dhw), _p(dbb), _p(go), _p(gc), _p(ghw), _p(gbb), _p(plan.iou_off), _p(iou))
     else:
         hs.hs_box_iou.argtypes = [I64] + [C.c_void_p] * 6
         hs.hs_box_iou(plan.n_groups, _p(plan.grp_dt_off), _p(plan.grp_gt_off), _p(plan.dt_box),
