@@ -315,4 +315,27 @@ int hs_rle_iou(int64_t n_groups, const int64_t* grp_dt_off, const int64_t* grp_g
     return 0;
 }
 
+// candidate screening of the flat frame kernel (NODIV) next to the exact per-pair quotient
+int hs_frame_candidates(int64_t n_det, const double* det, int G, const double* gt, double thr_min,
+                        int32_t* cnt_nd, int32_t* gs_nd, double* v_nd, int32_t* cnt_ex, int32_t* gs_ex,
+                        double* v_ex) {
+    const double ninf = -__builtin_inf();
+    const double thr_lo = (thr_min > 0.0) ? thr_min * 0.99999999999909050530 : ninf;
+    for (int64_t d = 0; d < n_det; ++d) {
+        const double* b = det + 4 * d;
+        int c, g;
+        double iv, uv;
+        ta_frame_candidates_nodiv(gt, 0, G, b[0], b[1], b[2], b[3], thr_lo, !(thr_min > 0.0), &c, &g, &iv, &uv);
+        cnt_nd[d] = c; gs_nd[d] = g; v_nd[d] = iv / uv;
+        int ce = 0, ge = 0;
+        double ve = 0.0;
+        for (int k = 0; k < G; ++k) {
+            const double v = ta_bb_iou(b[0], b[1], b[2], b[3], gt[4 * k], gt[4 * k + 1], gt[4 * k + 2], gt[4 * k + 3]);
+            if (!(v < thr_min)) { ++ce; ge = k; ve = v; }
+        }
+        cnt_ex[d] = ce; gs_ex[d] = ge; v_ex[d] = ve;
+    }
+    return 0;
+}
+
 }  // extern "C"

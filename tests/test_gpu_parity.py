@@ -246,3 +246,31 @@ def test_goldens_with_each_pr_implementation(golden, eng, impl, monkeypatch):
     compare_with_golden(golden, "tao_", tao_plan, eng.evaluate_device(eng.upload(tao_plan), detail=True),
                         exact_iou=not off_grid, iou_atol=1e-12)
     compare_with_golden(golden, "lvis_", lvis_plan, eng.evaluate_device(eng.upload(lvis_plan), detail=True))
+
+
+@pytest.mark.parametrize("nodiv", [0, 1])
+def test_frame_goldens_with_each_candidate_variant(golden, eng, nodiv, monkeypatch):
+    """Flat frame kernel with a division per pair (TA_FF_NODIV=0) and one per detection (=1):
+    the evaluation route (no per-cell outputs) must give the reference's tensors either way."""
+    monkeypatch.setenv("TA_FF_NODIV", str(nodiv))
+    gt, res = golden_inputs(golden)
+    _, plan = plans_from_json(gt, res)
+    out = eng.evaluate_device(eng.upload(plan), detail=False)
+    assert np.array_equal(golden["lvis_precision"], out.precision)
+    assert np.array_equal(golden["lvis_recall"], out.recall)
+    assert np.array_equal(golden["lvis_tp_cnt"], out.tp_cnt)
+    assert np.array_equal(golden["lvis_fp_cnt"], out.fp_cnt)
+
+
+@pytest.mark.parametrize("nodiv", [0, 1])
+@pytest.mark.parametrize("seed", [21, 22])
+def test_frame_random_sets_with_each_candidate_variant(eng, seed, nodiv, monkeypatch):
+    from tao_amodal_b200 import prep, synth
+    monkeypatch.setenv("TA_FF_NODIV", str(nodiv))
+    gtc, dtc = synth.generate_named("small", seed=seed)
+    plan = prep.prepare_lvis(gtc, dtc)
+    ref = run_hostsim(plan)
+    out = eng.evaluate_device(eng.upload(plan), detail=False)
+    assert np.array_equal(ref.precision, out.precision)
+    assert np.array_equal(ref.tp_cnt, out.tp_cnt) and np.array_equal(ref.fp_cnt, out.fp_cnt)
+    assert np.array_equal(ref.num_gt, out.num_gt)

@@ -79,3 +79,32 @@ def test_codec_matches_reference_c_on_random_annotations():
     off, cnt, hw, bb, ar = pool.export()
     refs = [pool.to_rle(i) for i in range(len(pool))]
     assert np.array_equal(bb, M.toBbox(refs)) and np.array_equal(ar, M.area(refs))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_rle_iou_kernel_matches_host_arithmetic(seed):
+    """ta_rle_iou on the device against the same per-pair function built for the host."""
+    import torch
+    from tao_amodal_b200 import _lib
+    from tao_amodal_b200.engine import Engine
+    dt, gt, d_off, g_off, iou_off, _ = random_mask_groups(seed, n_groups=40)
+    ref = _hs_rle_iou(dt, gt, d_off, g_off, iou_off)
+    eng = Engine(0)
+    dev = torch.device("cuda", 0)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    do, dc, dhw, dbb, _ = dt.export()
+    go, gc, ghw, gbb, _ = gt.export()
+    pad = lambda a, shape, t: a if a.size else np.zeros(shape, dtype=t)
+    ts = [up(x) for x in (d_off, g_off, do, pad(dc, 1, np.uint32).view(np.int32), pad(dhw, (1, 2), np.uint32).view(np.int32),
+                          pad(dbb, (1, 4), np.float64), go, pad(gc, 1, np.uint32).view(np.int32),
+                          pad(ghw, (1, 2), np.uint32).view(np.int32), pad(gbb, (1, 4), np.float64), iou_off)]
+    out = torch.full((max(int(iou_off[-1]), 1),), 9.0, dtype=torch.float64, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream(0).cuda_stream)
+    _lib.check(eng.lib.ta_rle_iou(eng._ctx, st, len(d_off) - 1, None, 0, p(ts[0]), p(ts[1]),
+                                  p(ts[2]), p(ts[3]), p(ts[4]), p(ts[5]), p(ts[6]), p(ts[7]),
+                                  p(ts[8]), p(ts[9]), p(ts[10]), p(out)))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy()[:int(iou_off[-1])], ref)
+    eng.close()
