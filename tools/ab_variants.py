@@ -1,0 +1,104 @@
+"""A/B of the runtime-selectable kernel variants on one GPU, at the bench workload (cfg3).
+
+    python tools/ab_variants.py [--videos N] [--steps K] [--out gpurun_out/ab_variants.json]
+
+Builds the plans once, then for every combination of
+    TA_PR_IMPL   0 position walk (k_pr_count + k_pr_envelope) | 1 bit planes (k_pr_bits + ...)
+    TA_FF_NODIV  0 division per box pair                      | 1 one division per detection
+runs warm-up + K timed steps (CUDA events around the steps, per-kernel events inside the
+library) and compares EVERY output tensor of both evaluators bit for bit with the baseline
+combination (0, 0), which the reference goldens pin — a full-size parity check of the variants.
+Writes one JSON document; prints a short table.
+"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--videos", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ab_variants.json"))
+    args = ap.parse_args()
+    import torch
+    import bench
+    from tao_amodal_b200 import prep
+    from tao_amodal_b200.engine import Engine
+    t0 = time.perf_counter()
+    gt, dt, tao_plan, lvis_plan = bench.make_workload("cfg3", 0, args.videos)
+    pairs = prep.count_box_pair_visits(tao_plan) + prep.count_box_pair_visits(lvis_plan)
+    prep_s = time.perf_counter() - t0
+    eng = Engine(0)
+    d_tao, d_lvis = eng.upload(tao_plan), eng.upload(lvis_plan)
+
+    def step():
+        eng.stage_iou(d_tao)
+        eng.stage_match(d_tao)
+        eng.stage_accumulate(d_tao)
+        eng.stage_frame_eval(d_lvis)
+        eng.stage_accumulate(d_lvis)
+
+    def outputs():
+        out = {}
+        for name, dv in (("tao", d_tao), ("lvis", d_lvis)):
+            for k in ("precision", "recall", "tp_cnt", "fp_cnt", "num_gt"):
+                out[name + "_" + k] = dv.t[k].cpu().numpy().copy()
+            out[name + "_dt_tpfp"] = dv.t["dt_tpfp"].cpu().numpy().copy()
+        return out
+
+    results, base = {}, None
+    combos = [(0, 0), (1, 0), (0, 1), (1, 1)]
+    for pr, nd in combos:
+        os.environ["TA_PR_IMPL"], os.environ["TA_FF_NODIV"] = str(pr), str(nd)
+        key = "pr%d_nodiv%d" % (pr, nd)
+        rec = {"TA_PR_IMPL": pr, "TA_FF_NODIV": nd}
+        try:
+            # poison the outputs so that a kernel that writes nothing cannot pass
+            for dv in (d_tao, d_lvis):
+                dv.t["precision"].fill_(123.0)
+                dv.t["recall"].fill_(123.0)
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+            out = outputs()
+            if base is None:
+                base = out
+            rec["identical_to_baseline"] = {k: bool(np.array_equal(base[k], v)) for k, v in out.items()}
+            rec["all_identical"] = all(rec["identical_to_baseline"].values())
+            rec["sha1_precision"] = {n: hashlib.sha1(out[n + "_precision"].tobytes()).hexdigest()[:16]
+                                     for n in ("tao", "lvis")}
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            eng.timing(True)
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            kms = eng.timing_read()
+            eng.timing(False)
+            rec["ms_per_step"] = e0.elapsed_time(e1) / args.steps
+            rec["box_pairs_per_s"] = pairs / (rec["ms_per_step"] * 1e-3)
+            rec["kernels_ms_per_step"] = {k: v[0] / args.steps for k, v in sorted(kms.items())}
+        except Exception as e:          # noqa: BLE001 - record the failure and go on
+            rec["error"] = "%s: %s" % (type(e).__name__, e)
+        results[key] = rec
+        print(key, json.dumps({k: rec.get(k) for k in ("ms_per_step", "all_identical", "error")}), flush=True)
+        os.makedirs(os.path.dirname(args.out), exist_ok=True)
+        json.dump({"workload": "cfg3", "videos": args.videos or 500, "box_pairs_per_step": pairs,
+                   "host_prep_s": prep_s, "steps": args.steps, "variants": results},
+                  open(args.out, "w"), indent=1)
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
