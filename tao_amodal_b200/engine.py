@@ -191,6 +191,9 @@ class Engine:
                       iou_thrs: np.ndarray = IOU_THRS, rec_thrs: np.ndarray = REC_THRS,
                       out: Optional[EvalOutput] = None, compress_boxes: bool = True,
                       _ctx=None) -> EvalOutput:
+        if plan.masks is not None:
+            raise NotImplementedError("ta_eval_plan_host carries box plans only; use upload() + "
+                                      "evaluate_device() for iou_type='segm'")
         n_thr, n_rec, n_cfg, n_cat = len(iou_thrs), len(rec_thrs), plan.n_cfg, len(plan.cat_ids)
         g_max, n_slots = plan_limits(plan)
         iou_thrs = np.ascontiguousarray(iou_thrs, dtype=np.float64)
@@ -243,9 +246,6 @@ class Engine:
 
     def stage_iou(self, dev: "DevicePlan", iou_mode: str = "3d_iou"):
         """compute_iou of every group (eval.py:306-335 / lvis eval.py:168-192)."""
-        if plan.masks is not None:
-            raise NotImplementedError("ta_eval_plan_host carries box plans only; use upload() + "
-                                      "evaluate_device() for iou_type='segm'")
         import torch
         p, plan = dev.ptr, dev.plan
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -383,6 +383,8 @@ class DevicePlan:
         self._input_keys = []
         for k, v in host.items():
             v = np.ascontiguousarray(v)
+            if v.dtype == np.uint32:        # torch tensors are only memory containers here
+                v = v.view(np.int32)
             self.input_bytes += v.nbytes
             if v.size == 0:
                 self.t[k] = torch.zeros(16, dtype=torch.uint8, device=dev)
