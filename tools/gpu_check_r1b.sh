@@ -10,38 +10,32 @@ date +%s > gpurun_out/t0
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader >> $S 2>&1
 
 # 1. parity of the new code paths (goldens of the unmodified reference, random differential)
-timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_segm.py tests/test_mask_codec.py \
-    -m gpu -q -x > gpurun_out/t_new_r1b.log 2>&1
+timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_segm.py tests/test_mask_codec.py \
+    -m gpu -q -k "pr_accumulate_both or each_pr_implementation or each_candidate_variant or segm or rle_iou" \
+    > gpurun_out/t_new_r1b.log 2>&1
 echo "new_tests rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))" >> $S
 tail -3 gpurun_out/t_new_r1b.log >> $S
 
 # 2. A/B at the bench workload + bit-identity of every output tensor with the pinned baseline
-timeout 240 python tools/ab_variants.py --out gpurun_out/ab_variants.json > gpurun_out/ab_r1b.log 2>&1
+timeout 150 python tools/ab_variants.py --out gpurun_out/ab_variants.json > gpurun_out/ab_r1b.log 2>&1
 echo "ab rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))" >> $S
 cat gpurun_out/ab_r1b.log | tail -5 >> $S
 
 # 3. the bench line with the new variants
-TA_PR_IMPL=1 TA_FF_NODIV=1 timeout 300 python bench.py > gpurun_out/bench_r1b_new.json 2> gpurun_out/bench_r1b_new.err
+TA_PR_IMPL=1 TA_FF_NODIV=1 timeout 180 python bench.py > gpurun_out/bench_r1b_new.json 2> gpurun_out/bench_r1b_new.err
 echo "bench_new rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))" >> $S
 
 # 4. ncu launch list of the same command (shares only: cold caches, serialised)
-TA_PR_IMPL=1 TA_FF_NODIV=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 140 --csv \
+TA_PR_IMPL=1 TA_FF_NODIV=1 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 140 --csv \
     --log-file gpurun_out/launches_r1b.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
     > gpurun_out/ncu_list_r1b.log 2>&1
 echo "ncu_list rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))" >> $S
 
 # 5. the whole GPU suite with the new variants as the process-wide choice (= flipped defaults;
 #    the tests that pin a variant explicitly still run both)
-TA_PR_IMPL=1 TA_FF_NODIV=1 timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/t_all_r1b.log 2>&1
+TA_PR_IMPL=1 TA_FF_NODIV=1 timeout 400 python -m pytest tests -m gpu -q > gpurun_out/t_all_r1b.log 2>&1
 echo "all_tests rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))" >> $S
 tail -3 gpurun_out/t_all_r1b.log >> $S
-
-# 5b. memcheck of the new kernels on the small cases
-timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py \
-    tests/test_mask_codec.py -m gpu -q -k "pr_accumulate_both or random_sets_with_each or rle_iou_kernel" \
-    > gpurun_out/sanitizer_r1b.log 2>&1
-echo "memcheck rc=$? t=$(( $(date +%s) - $(cat gpurun_out/t0) ))" >> $S
-grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_r1b.log | tail -3 >> $S
 
 # 6. one full-set capture of the new kernels
 TA_PR_IMPL=1 TA_FF_NODIV=1 timeout 400 ncu --set full --clock-control none --import-source on \
