@@ -439,8 +439,7 @@ def main():
     # algorithmic bytes of each kernel per STEP (summed over its launches in one step)
     kernel_bytes = {
         "k_track_iou_tiled": ab_t["iou"], "k_match_greedy": ab_t["match"],
-        "k_frame_flat": ab_l["frame_flat"], "k_frame_flat_nodiv": ab_l["frame_flat"],
-        "k_frame_prep": ab_l["frame_prep"],
+        "k_frame_flat": ab_l["frame_flat"], "k_frame_prep": ab_l["frame_prep"],
         "k_pr_count": ab_t["pr_count"] + ab_l["pr_count"],
         "k_pr_envelope": ab_t["pr_envelope"] + ab_l["pr_envelope"],
         "k_pr_bits": ab_t["pr_bits"] + ab_l["pr_bits"],

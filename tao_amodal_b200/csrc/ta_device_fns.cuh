@@ -273,42 +273,4 @@ TA_HD double ta_rle_pair_iou(const uint32_t* cd, int64_t md, const uint32_t* cg,
     return (double)i / (double)u;
 }
 
-// ---- frame path: candidate summary of one detection without a division per pair -------------
-
-// Pairs of a detection with the GT boxes gt_box[4 * (g0 + g)], g < G, that MAY reach the lowest
-// IoU threshold thr_min: the quotient i / u of ta_bb_iou (maskApi.c:109-120) is formed only
-// after the loop, for the last such pair.  A pair is dropped when i < thr_lo * u with
-// thr_lo = thr_min (1 - 2^-40): then i / u < thr_min (1 - 2^-41) and the rounded quotient is
-// below thr_min, so no true candidate is lost; a pair inside that sliver is only counted, and
-// the caller sends counts above one to the general matcher, which is exact.  Pairs without
-// overlap have IoU 0 (reported as i = 0, u = 1): candidates only when thr_min <= 0
-// (all_pairs; thr_lo must then be -inf).
-//   *cnt  number of possible candidates;  *gs  the last one;  *iv, *uv  its intersection / union
-TA_HD void ta_frame_candidates_nodiv(const double* gt_box, int64_t g0, int G,
-                                     double dx, double dy, double dw, double dh, double thr_lo,
-                                     bool all_pairs, int* cnt, int* gs, double* iv, double* uv) {
-    const double da = dw * dh;
-    const double r0 = dw + dx, b0 = dh + dy;
-    int n = 0, last = 0;
-    double li = 0.0, lu = 1.0;
-    for (int g = 0; g < G; ++g) {
-        const double* q = gt_box + 4 * (g0 + g);
-        const double gx = q[0], gy = q[1], gw = q[2], gh = q[3];
-        const double ga = gw * gh;
-        const double r1 = gw + gx, b1 = gh + gy;
-        const double w = ((r0 < r1) ? r0 : r1) - ((dx > gx) ? dx : gx);
-        const double h = ((b0 < b1) ? b0 : b1) - ((dy > gy) ? dy : gy);
-        double i = 0.0, u = 1.0;
-        if (!(w <= 0.0) && !(h <= 0.0)) {          // ta_bb_iou's two early returns
-            i = w * h;
-            u = da + ga - i;
-            if (i < thr_lo * u) continue;
-        } else if (!all_pairs) {
-            continue;
-        }
-        ++n; last = g; li = i; lu = u;
-    }
-    *cnt = n; *gs = last; *iv = li; *uv = lu;
-}
-
 #endif  // TA_DEVICE_FNS_CUH

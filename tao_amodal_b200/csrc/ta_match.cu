@@ -10,12 +10,7 @@
 // lvis_amodal/eval.py:244-290 (see ta_match_one in ta_device_fns.cuh for the equivalence of
 // the "ignored GTs last + break" walk with a two-class search in original GT order).
 #include <limits.h>
-#include <stdlib.h>
 #include "ta_internal.h"
-
-#ifndef TA_FF_NODIV_DEFAULT
-#define TA_FF_NODIV_DEFAULT 0
-#endif
 #include "ta_device_fns.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -185,7 +180,6 @@ struct FrameArgs {
     int32_t* complex_list;        // groups that need the general matcher (route C)
     int32_t* complex_count;
     const FrameRules* rules_g;    // range-test tables built once per call by k_frame_rules
-    int nodiv;                    // flat frame kernel: one division per detection (TA_FF_NODIV)
 };
 
 // per-detection word: bits 0..15 "ignored when unmatched" per cfg, bit 16 locks its GT
@@ -595,25 +589,6 @@ __device__ __forceinline__ FlatCand fe_candidate(const double* __restrict__ gt_b
     return c;
 }
 
-// The same summary with ONE division per detection (ta_frame_candidates_nodiv): pairs are
-// screened by i < thr_lo * u, the quotient is formed for the last survivor only and re-checked
-// exactly; several survivors are reported as "multi" (general matcher).
-__device__ __forceinline__ FlatCand fe_candidate_nodiv(const double* __restrict__ gt_box, int64_t g0, int G,
-                                                       double2 dp, double2 dq, double thr_min, double thr_lo,
-                                                       const double* thr_s, int n_thr) {
-    FlatCand c{0, 0, 0u};
-    double iv, uv;
-    ta_frame_candidates_nodiv(gt_box, g0, G, dp.x, dp.y, dq.x, dq.y, thr_lo, !(thr_min > 0.0),
-                              &c.cnt, &c.gs, &iv, &uv);
-    if (c.cnt == 1) {
-        const double vs = iv / uv;
-        if (vs < thr_min) c.cnt = 0;
-        else
-            for (int k = 0; k < n_thr; ++k) c.ge |= (!(vs < thr_s[k])) ? (1u << k) : 0u;
-    }
-    return c;
-}
-
 #define FF_WARPS 4
 
 // candidate summary from a row of a precomputed IoU matrix (track path)
@@ -632,8 +607,7 @@ __device__ __forceinline__ FlatCand fe_candidate_row(const double* __restrict__ 
 
 // TRACK: detections are tracks; IoUs come from the matrix ta_track_iou wrote (a.iou / a.iou_off),
 // attributes from dt_a / dt_b / gt_b / gt_hp, and groups with more than 32 GT go to the list.
-// NODIV (frame path only): candidates through fe_candidate_nodiv.
-template <int NT, int NC, bool TRACK, bool NODIV = false>
+template <int NT, int NC, bool TRACK>
 __global__ void __launch_bounds__(FF_WARPS * 32, 8)
 k_frame_flat(FrameArgs a) {
     __shared__ ta_range_cfg cfg_s[RR_MAX];
@@ -647,9 +621,6 @@ k_frame_flat(FrameArgs a) {
     for (int i = 1; i < n_thr; ++i) thr_min = (thr_s[i] < thr_min) ? thr_s[i] : thr_min;
     const uint32_t thr_all = (1u << n_thr) - 1u;
     const uint32_t lanes_lt = (1u << lane) - 1u;
-    // thr_min (1 - 2^-40); -inf when every pair is a candidate (thr_min <= 0)
-    const double thr_lo = (thr_min > 0.0) ? thr_min * 0.99999999999909050530
-                                          : __longlong_as_double(0xfff0000000000000LL);
 
     const int64_t n_win = (a.n_dt + 31) / 32;
     const int64_t w0 = (int64_t)blockIdx.x * FF_WARPS + warp;
@@ -697,8 +668,7 @@ k_frame_flat(FrameArgs a) {
                     } else {
                         const double2 rp = *reinterpret_cast<const double2*>(a.dt_box + 4 * rd);
                         const double2 rq = *reinterpret_cast<const double2*>(a.dt_box + 4 * rd + 2);
-                        rc = NODIV ? fe_candidate_nodiv(a.gt_box, g0_f, G_f, rp, rq, thr_min, thr_lo, thr_s, n_thr)
-                                   : fe_candidate(a.gt_box, g0_f, G_f, rp, rq, thr_min, thr_s, n_thr);
+                        rc = fe_candidate(a.gt_box, g0_f, G_f, rp, rq, thr_min, thr_s, n_thr);
                     }
                     if (rc.cnt == 1 && (a.dt_flag[rd] & 2)) { x = rc.ge; rgs = rc.gs; }
                 }
@@ -715,8 +685,7 @@ k_frame_flat(FrameArgs a) {
             if (TRACK)
                 c = fe_candidate_row(a.iou + a.iou_off[grp] + (d - d0) * G, G, thr_min, thr_s, n_thr);
             else
-                c = NODIV ? fe_candidate_nodiv(a.gt_box, g0, G, dp, dq, thr_min, thr_lo, thr_s, n_thr)
-                          : fe_candidate(a.gt_box, g0, G, dp, dq, thr_min, thr_s, n_thr);
+                c = fe_candidate(a.gt_box, g0, G, dp, dq, thr_min, thr_s, n_thr);
             if (c.cnt > 1 && atomicExch(&a.grp_flag[grp], 1) == 0)
                 a.complex_list[atomicAdd(a.complex_count, 1)] = grp;
         }
@@ -958,12 +927,7 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     FrameArgs a{n_groups, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box, n_thr, iou_thrs, n_cfg,
                 cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, iou_off, iou, write_iou,
                 dt_tpfp, num_gt, dt_match_gt, gt_ignore_out,
-                nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
-    {
-        // TA_FF_NODIV: 1 = the flat kernel divides once per detection (ta_frame_candidates_nodiv)
-        const char* e = getenv("TA_FF_NODIV");
-        a.nodiv = (e && *e) ? (e[0] != '0') : TA_FF_NODIV_DEFAULT;
-    }
+                nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs per SM
     int rc;
     // scratch (slot 1): rule tables, detection -> group map, complex-group flags / list
@@ -1008,15 +972,9 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
             int64_t blocks = ((n_dt + 31) / 32 + FF_WARPS - 1) / FF_WARPS;
             const int64_t fcap = (int64_t)ctx->sm_count * 16;
             if (blocks > fcap) blocks = fcap;
-            if (a.nodiv) {
-                if (spec) k_frame_flat<10, 6, false, true><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
-                else k_frame_flat<0, 0, false, true><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
-                if ((rc = ta_check_launch(ctx, "k_frame_flat_nodiv"))) return rc;
-            } else {
-                if (spec) k_frame_flat<10, 6, false><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
-                else k_frame_flat<0, 0, false><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
-                if ((rc = ta_check_launch(ctx, "k_frame_flat"))) return rc;
-            }
+            if (spec) k_frame_flat<10, 6, false><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
+            else k_frame_flat<0, 0, false><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
+            if ((rc = ta_check_launch(ctx, "k_frame_flat"))) return rc;
         }
         if (n_dt > 0) {
             const int64_t blocks = ctx->sm_count * 2;       // list length is only known on the device

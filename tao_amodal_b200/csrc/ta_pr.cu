@@ -52,6 +52,9 @@ struct PrArgs {
     uint32_t* cat_tot;           // [n_cat][n_cfg][32] category totals (same bit layout)
     int32_t* tk;                 // [n_cat][n_cfg][n_rec]
     unsigned long long* chunk_best;  // [n_chunks_ub][n_cfg][n_thr] packed (t << 32 | n)
+    unsigned long long* ans;     // cell-major answers [n_thr][n_cat][n_cfg][n_rec] (TA_PR_IMPL=3): what
+                                 // prec_bits holds, laid out so that one cell's recall levels are
+                                 // contiguous (sequential stores in the envelope, row reads in finalize)
     int32_t* chunk_cat;          // [n_chunks_ub] category of a chunk            (bit-plane path)
     uint32_t* bits;              // [n_chunks_ub][2 * TA_PR_WORDS][n_cfg * n_thr] (bit-plane path):
                                  // word j < 8: TP flags of positions 32 j .. 32 j + 31 of the
@@ -354,11 +357,12 @@ k_pr_envelope_bits(PrArgs a) {
     if (tc == t_begin) { *best_out = 0ull; return; }          // no TP of this cell in the chunk
     const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
     const uint32_t* planes = a.bits + (int64_t)chunk * (2 * TA_PR_WORDS) * n_cells + cell;
+    const int64_t cc = (int64_t)cat * a.n_cfg + cfg;
+    unsigned long long* q = a.ans ? a.ans + ((int64_t)b * per_t + cc) * a.n_rec
+                                  : a.prec_bits + (int64_t)b * a.n_rec * per_t + cc;
     *best_out = ta_pr_walk_bits(planes, planes + (int64_t)TA_PR_WORDS * n_cells, (int64_t)n_cells, tc, fc,
-                                a.tk + ((int64_t)cat * a.n_cfg + cfg) * a.n_rec, a.n_rec,
-                                (uint32_t)(chunk - ch0),
-                                a.prec_bits + (int64_t)b * a.n_rec * per_t + (int64_t)cat * a.n_cfg + cfg,
-                                per_t);
+                                a.tk + cc * a.n_rec, a.n_rec, (uint32_t)(chunk - ch0),
+                                q, a.ans ? (int64_t)1 : per_t);
 }
 
 
@@ -438,6 +442,45 @@ k_pr_finalize_2d(PrArgs a) {
     a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
 }
 
+
+// k_pr_finalize for cell-major answers: one thread per (threshold, category, cfg) row walks the
+// 101 recall levels — the row's totals, chunk table and tk run are read once, its answers
+// sequentially, and a quotient is only formed when the winning rational changes; stores are
+// coalesced across the threads of a warp (cfg fastest).  Same values as k_pr_finalize.
+__global__ void __launch_bounds__(128)
+k_pr_finalize_rows(PrArgs a) {
+    const uint32_t per_t = (uint32_t)a.n_cat * (uint32_t)a.n_cfg;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)a.n_thr * per_t) return;
+    const uint32_t t = (uint32_t)(gid / per_t), cc = (uint32_t)(gid - (int64_t)t * per_t);
+    double* out = a.precision + (int64_t)t * a.n_rec * per_t + cc;
+    const int ngt = a.num_gt[cc];
+    if (ngt == 0) {                                               // eval.py:522-525
+        for (int k = 0; k < a.n_rec; ++k) out[(int64_t)k * per_t] = -1.0;
+        return;
+    }
+    const uint32_t tot = a.cat_tot[(int64_t)cc * 32 + t];
+    const uint32_t cat = cc / (uint32_t)a.n_cfg, cfg = cc - cat * (uint32_t)a.n_cfg;
+    const unsigned long long* best = a.chunk_best + ((int64_t)a.chunk_start[cat] * a.n_cfg + cfg) * a.n_thr + t;
+    const int64_t best_stride = (int64_t)a.n_cfg * a.n_thr;       // one chunk
+    const int32_t* tkp = a.tk + (int64_t)cc * a.n_rec;
+    const unsigned long long* ansp = a.ans + ((int64_t)t * per_t + cc) * a.n_rec;
+    uint32_t pt = 0xffffffffu, pn = 0;
+    double pv = 0.0;
+    for (int k = 0; k < a.n_rec; ++k) {
+        double v = 0.0;                                           // eval.py:565-573
+        if ((uint32_t)max(tkp[k], 1) <= tot) {
+            uint32_t qt, qn, ch, bt, bn, dummy;
+            pr_unpack(ansp[k], qt, qn, ch);
+            pr_unpack(best[(int64_t)ch * best_stride], bt, bn, dummy);
+            if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
+            if (qt != pt || qn != pn) { pt = qt; pn = qn; pv = ta_precision_at((int64_t)qt, (int64_t)(qn - qt)); }
+            v = pv;
+        }
+        out[(int64_t)k * per_t] = v;
+    }
+}
+
 // per (category, cfg, threshold): chunk_best[ch] <- best precision of all LATER chunks
 __global__ void k_pr_suffix(PrArgs a) {
     const int cat = blockIdx.x;
@@ -499,14 +542,16 @@ __global__ void k_pr_finalize(PrArgs a) {
     a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
 }
 
-// TA_PR_IMPL: 0 = position walk (k_pr_count + k_pr_envelope), 1 = bit planes (k_pr_bits +
-// k_pr_envelope_bits).  Both produce identical tensors (tests/test_gpu_parity.py runs both).
+// TA_PR_IMPL: 0 = position walk (k_pr_count + k_pr_envelope + k_pr_scan + k_pr_finalize);
+// 1..3 = bit planes (k_pr_bits + k_pr_tk + k_pr_scan_live + k_pr_envelope_bits) finished by
+//   1: k_pr_finalize_2d, 2: k_pr_finalize, 3: cell-major answers + k_pr_finalize_rows.
+// All produce identical tensors (tests/test_gpu_parity.py runs every variant).
 #ifndef TA_PR_IMPL_DEFAULT
 #define TA_PR_IMPL_DEFAULT 0
 #endif
 static int ta_pr_impl() {
     const char* e = getenv("TA_PR_IMPL");
-    return (e && *e) ? (e[0] != '0') : TA_PR_IMPL_DEFAULT;
+    return (e && *e >= '0' && *e <= '3') ? (e[0] - '0') : TA_PR_IMPL_DEFAULT;
 }
 
 extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
@@ -538,6 +583,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     const int impl = (n_cells * 2 * TA_PR_WORDS * 4 <= 48 * 1024) ? ta_pr_impl() : 0;
     const size_t o_ccat = take(impl ? (size_t)n_chunks_ub * 4 : 0);
     const size_t o_bits = take(impl ? (size_t)n_chunks_ub * 2 * TA_PR_WORDS * n_cells * 4 : 0);
+    const size_t o_ans = take(impl == 3 ? (size_t)n_thr * n_rec * n_cat * n_cfg * 8 : 0);
     void* ws = nullptr;
     int rc = ta_workspace(ctx, st, off, &ws);
     if (rc) return rc;
@@ -554,6 +600,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     a.chunk_best = reinterpret_cast<unsigned long long*>(base + o_best);
     a.chunk_cat = reinterpret_cast<int32_t*>(base + o_ccat);
     a.bits = reinterpret_cast<uint32_t*>(base + o_bits);
+    a.ans = impl == 3 ? reinterpret_cast<unsigned long long*>(base + o_ans) : nullptr;
     a.prec_bits = reinterpret_cast<unsigned long long*>(precision);
     a.precision = precision; a.recall = recall; a.tp_cnt = tp_cnt; a.fp_cnt = fp_cnt;
 
@@ -610,7 +657,12 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     k_pr_suffix<<<n_cat, 128, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_suffix"))) return rc;
     const size_t n_prec = (size_t)n_thr * n_rec * n_cat * n_cfg;
-    if (impl && (size_t)n_thr * n_rec <= 65535 && (size_t)n_cat * n_cfg < (1u << 31)) {
+    if (impl == 3) {
+        const int64_t rows = (int64_t)n_thr * n_cat * n_cfg;
+        k_pr_finalize_rows<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a);
+        return ta_check_launch(ctx, "k_pr_finalize_rows");
+    }
+    if (impl == 1 && (size_t)n_thr * n_rec <= 65535 && (size_t)n_cat * n_cfg < (1u << 31)) {
         dim3 grid((unsigned)(((size_t)n_cat * n_cfg + 255) / 256), (unsigned)(n_thr * n_rec));
         k_pr_finalize_2d<<<grid, 256, 0, st>>>(a);
         return ta_check_launch(ctx, "k_pr_finalize_2d");

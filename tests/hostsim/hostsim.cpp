@@ -163,10 +163,10 @@ int hs_pr_accumulate(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* ac
 // Serial emulation of the bit-plane PR pipeline of csrc/ta_pr.cu (k_pr_plan -> k_pr_bits ->
 // k_pr_scan -> k_pr_envelope_bits -> k_pr_suffix -> k_pr_finalize) with the SAME per-thread
 // functions (pr_transpose_stage on an emulated 32-lane warp, ta_pr_walk_bits, pr_better, ...).
-int hs_pr_accumulate_bits(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
+static int pr_bits_impl(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
                           const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
                           int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
-                          int64_t* tp_cnt, int64_t* fp_cnt) {
+                          int64_t* tp_cnt, int64_t* fp_cnt, bool rows) {
     (void)n_dt;
     const int CH = 32 * TA_PR_WORDS;
     const int n_cells = n_cfg * n_thr;
@@ -252,9 +252,13 @@ int hs_pr_accumulate_bits(int32_t n_cat, const int64_t* cat_dt_off, const int32_
             unsigned long long* best_out = &chunk_best[(size_t)chunk * n_cells + cell];
             if (tc == t_begin) { *best_out = 0ull; continue; }
             const uint32_t* planes = bits.data() + (size_t)chunk * 2 * TA_PR_WORDS * n_cells + cell;
+            const int64_t cc = (int64_t)cat * n_cfg + cfg;
+            // rows: cell-major answers (k_pr_envelope_bits with a.ans), else the precision layout
+            unsigned long long* q = rows ? prec_bits.data() + ((int64_t)b * per_t + cc) * n_rec
+                                         : prec_bits.data() + (int64_t)b * n_rec * per_t + cc;
             *best_out = ta_pr_walk_bits(planes, planes + (size_t)TA_PR_WORDS * n_cells, n_cells, tc, fc,
                                         &tk[((size_t)cat * n_cfg + cfg) * n_rec], n_rec, (uint32_t)(chunk - ch0),
-                                        prec_bits.data() + (int64_t)b * n_rec * per_t + (int64_t)cat * n_cfg + cfg, per_t);
+                                        q, rows ? 1 : per_t);
         }
     // k_pr_suffix
     for (int cat = 0; cat < n_cat; ++cat)
@@ -269,6 +273,36 @@ int hs_pr_accumulate_bits(int32_t n_cat, const int64_t* cat_dt_off, const int32_
                 if (pr_better(ct, cn, bt, bn)) { bt = ct; bn = cn; }
             }
         }
+    // k_pr_finalize_rows
+    if (rows) {
+        for (int64_t gid = 0; gid < (int64_t)n_thr * per_t; ++gid) {
+            const int64_t t = gid / per_t, cc = gid - t * per_t;
+            double* out = precision + t * n_rec * per_t + cc;
+            const int ngt = num_gt[cc];
+            if (ngt == 0) { for (int k = 0; k < n_rec; ++k) out[(int64_t)k * per_t] = -1.0; continue; }
+            const uint32_t tot = cat_tot[cc * 32 + t];
+            const int cat = (int)(cc / n_cfg), cfg = (int)(cc - (int64_t)cat * n_cfg);
+            const unsigned long long* best = &chunk_best[((size_t)chunk_start[cat] * n_cfg + cfg) * n_thr + t];
+            const int64_t best_stride = (int64_t)n_cfg * n_thr;
+            const int32_t* tkp = &tk[cc * n_rec];
+            const unsigned long long* ansp = prec_bits.data() + (t * per_t + cc) * n_rec;
+            uint32_t pt = 0xffffffffu, pn = 0;
+            double pv = 0.0;
+            for (int k = 0; k < n_rec; ++k) {
+                double v = 0.0;
+                if ((uint32_t)(tkp[k] > 1 ? tkp[k] : 1) <= tot) {
+                    uint32_t qt, qn, ch, bt, bn, d;
+                    pr_unpack(ansp[k], qt, qn, ch);
+                    pr_unpack(best[(int64_t)ch * best_stride], bt, bn, d);
+                    if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
+                    if (qt != pt || qn != pn) { pt = qt; pn = qn; pv = ta_precision_at((int64_t)qt, (int64_t)(qn - qt)); }
+                    v = pv;
+                }
+                out[(int64_t)k * per_t] = v;
+            }
+        }
+        return 0;
+    }
     // k_pr_finalize
     for (int64_t idx = 0; idx < (int64_t)n_thr * n_rec * per_t; ++idx) {
         const int64_t tk_idx = idx / per_t, cc = idx - tk_idx * per_t;
@@ -286,6 +320,21 @@ int hs_pr_accumulate_bits(int32_t n_cat, const int64_t* cat_dt_off, const int32_
         precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
     }
     return 0;
+}
+
+int hs_pr_accumulate_bits(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
+                          const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                          int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
+                          int64_t* tp_cnt, int64_t* fp_cnt) {
+    return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
+                        precision, recall, tp_cnt, fp_cnt, false);
+}
+int hs_pr_accumulate_bits_rows(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
+                               const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                               int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
+                               int64_t* tp_cnt, int64_t* fp_cnt) {
+    return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
+                        precision, recall, tp_cnt, fp_cnt, true);
 }
 
 void hs_transpose32(const uint32_t* in, uint32_t* out) {
@@ -311,29 +360,6 @@ int hs_rle_iou(int64_t n_groups, const int64_t* grp_dt_off, const int64_t* grp_g
                 dt_cnt + dt_off[d], dt_off[d + 1] - dt_off[d], gt_cnt + gt_off[g], gt_off[g + 1] - gt_off[g],
                 dt_bb + 4 * d, gt_bb + 4 * g, dt_hw[2 * d], dt_hw[2 * d + 1], gt_hw[2 * g], gt_hw[2 * g + 1]);
         }
-    }
-    return 0;
-}
-
-// candidate screening of the flat frame kernel (NODIV) next to the exact per-pair quotient
-int hs_frame_candidates(int64_t n_det, const double* det, int G, const double* gt, double thr_min,
-                        int32_t* cnt_nd, int32_t* gs_nd, double* v_nd, int32_t* cnt_ex, int32_t* gs_ex,
-                        double* v_ex) {
-    const double ninf = -__builtin_inf();
-    const double thr_lo = (thr_min > 0.0) ? thr_min * 0.99999999999909050530 : ninf;
-    for (int64_t d = 0; d < n_det; ++d) {
-        const double* b = det + 4 * d;
-        int c, g;
-        double iv, uv;
-        ta_frame_candidates_nodiv(gt, 0, G, b[0], b[1], b[2], b[3], thr_lo, !(thr_min > 0.0), &c, &g, &iv, &uv);
-        cnt_nd[d] = c; gs_nd[d] = g; v_nd[d] = iv / uv;
-        int ce = 0, ge = 0;
-        double ve = 0.0;
-        for (int k = 0; k < G; ++k) {
-            const double v = ta_bb_iou(b[0], b[1], b[2], b[3], gt[4 * k], gt[4 * k + 1], gt[4 * k + 2], gt[4 * k + 3]);
-            if (!(v < thr_min)) { ++ce; ge = k; ve = v; }
-        }
-        cnt_ex[d] = ce; gs_ex[d] = ge; v_ex[d] = ve;
     }
     return 0;
 }

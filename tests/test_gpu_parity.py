@@ -217,7 +217,7 @@ def _gpu_pr(eng, c, iou_thrs, rec_thrs, impl):
     return prec.cpu().numpy(), rc.cpu().numpy(), tp.cpu().numpy(), fp.cpu().numpy()
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 @pytest.mark.parametrize("seed,kw", [(0, {}), (1, {}), (2, dict(n_cat=5, n_cfg=20, max_len=700)),
                                      (3, dict(n_cat=40, n_cfg=6, max_len=5000)),
                                      (100, dict(n_cat=4, n_cfg=3, tp_rate=0.0)),
@@ -237,7 +237,7 @@ def test_pr_accumulate_both_implementations(eng, seed, kw, impl):
     assert np.array_equal(ref.fp_cnt, fp)
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_goldens_with_each_pr_implementation(golden, eng, impl, monkeypatch):
     monkeypatch.setenv("TA_PR_IMPL", str(impl))
     gt, res = golden_inputs(golden)
@@ -246,31 +246,3 @@ def test_goldens_with_each_pr_implementation(golden, eng, impl, monkeypatch):
     compare_with_golden(golden, "tao_", tao_plan, eng.evaluate_device(eng.upload(tao_plan), detail=True),
                         exact_iou=not off_grid, iou_atol=1e-12)
     compare_with_golden(golden, "lvis_", lvis_plan, eng.evaluate_device(eng.upload(lvis_plan), detail=True))
-
-
-@pytest.mark.parametrize("nodiv", [0, 1])
-def test_frame_goldens_with_each_candidate_variant(golden, eng, nodiv, monkeypatch):
-    """Flat frame kernel with a division per pair (TA_FF_NODIV=0) and one per detection (=1):
-    the evaluation route (no per-cell outputs) must give the reference's tensors either way."""
-    monkeypatch.setenv("TA_FF_NODIV", str(nodiv))
-    gt, res = golden_inputs(golden)
-    _, plan = plans_from_json(gt, res)
-    out = eng.evaluate_device(eng.upload(plan), detail=False)
-    assert np.array_equal(golden["lvis_precision"], out.precision)
-    assert np.array_equal(golden["lvis_recall"], out.recall)
-    assert np.array_equal(golden["lvis_tp_cnt"], out.tp_cnt)
-    assert np.array_equal(golden["lvis_fp_cnt"], out.fp_cnt)
-
-
-@pytest.mark.parametrize("nodiv", [0, 1])
-@pytest.mark.parametrize("seed", [21, 22])
-def test_frame_random_sets_with_each_candidate_variant(eng, seed, nodiv, monkeypatch):
-    from tao_amodal_b200 import prep, synth
-    monkeypatch.setenv("TA_FF_NODIV", str(nodiv))
-    gtc, dtc = synth.generate_named("small", seed=seed)
-    plan = prep.prepare_lvis(gtc, dtc)
-    ref = run_hostsim(plan)
-    out = eng.evaluate_device(eng.upload(plan), detail=False)
-    assert np.array_equal(ref.precision, out.precision)
-    assert np.array_equal(ref.tp_cnt, out.tp_cnt) and np.array_equal(ref.fp_cnt, out.fp_cnt)
-    assert np.array_equal(ref.num_gt, out.num_gt)

@@ -2,12 +2,11 @@
 
     python tools/ab_variants.py [--videos N] [--steps K] [--out gpurun_out/ab_variants.json]
 
-Builds the plans once, then for every combination of
-    TA_PR_IMPL   0 position walk (k_pr_count + k_pr_envelope) | 1 bit planes (k_pr_bits + ...)
-    TA_FF_NODIV  0 division per box pair                      | 1 one division per detection
+Builds the plans once, then for every value of
+    TA_PR_IMPL   0 position walk | 1..3 bit planes with three finalize variants (csrc/ta_pr.cu)
 runs warm-up + K timed steps (CUDA events around the steps, per-kernel events inside the
 library) and compares EVERY output tensor of both evaluators bit for bit with the baseline
-combination (0, 0), which the reference goldens pin — a full-size parity check of the variants.
+variant 0, which the reference goldens pin — a full-size parity check of the variants.
 Writes one JSON document; prints a short table.
 """
 import argparse
@@ -56,11 +55,10 @@ def main():
         return out
 
     results, base = {}, None
-    combos = [(0, 0), (1, 0), (0, 1), (1, 1)]
-    for pr, nd in combos:
-        os.environ["TA_PR_IMPL"], os.environ["TA_FF_NODIV"] = str(pr), str(nd)
-        key = "pr%d_nodiv%d" % (pr, nd)
-        rec = {"TA_PR_IMPL": pr, "TA_FF_NODIV": nd}
+    for pr in (0, 1, 2, 3):
+        os.environ["TA_PR_IMPL"] = str(pr)
+        key = "pr%d" % pr
+        rec = {"TA_PR_IMPL": pr}
         try:
             # poison the outputs so that a kernel that writes nothing cannot pass
             for dv in (d_tao, d_lvis):
