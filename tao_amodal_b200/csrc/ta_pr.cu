@@ -481,6 +481,59 @@ k_pr_finalize_rows(PrArgs a) {
     }
 }
 
+
+// k_pr_finalize for cell-major answers, tiled: a block owns one threshold and 32 consecutive
+// (category, cfg) cells.  Phase 1 reads the cells' answer rows the way the envelope wrote them
+// (warp per cell, lanes over the recall levels: contiguous), merges the later chunks' best and
+// divides; phase 2 writes the [recall level][cell] tile from shared memory, 256 B per warp.
+// Reads and writes are both coalesced and every entry is independent.  Same values as
+// k_pr_finalize.
+#define PR_TILE_CELLS 32
+__global__ void __launch_bounds__(128)
+k_pr_finalize_tile(PrArgs a) {
+    extern __shared__ double tile_s[];                    // [n_rec][PR_TILE_CELLS + 1]
+    const uint32_t per_t = (uint32_t)a.n_cat * (uint32_t)a.n_cfg;
+    const uint32_t cc0 = blockIdx.x * PR_TILE_CELLS;
+    const int t = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < PR_TILE_CELLS; c += 4) {
+        const uint32_t cc = cc0 + c;
+        if (cc >= per_t) break;
+        const int ngt = a.num_gt[cc];
+        uint32_t tot = 0;
+        const unsigned long long* best = nullptr;
+        if (ngt) {
+            tot = a.cat_tot[(int64_t)cc * 32 + t];
+            const uint32_t cat = cc / (uint32_t)a.n_cfg, cfg = cc - cat * (uint32_t)a.n_cfg;
+            best = a.chunk_best + ((int64_t)a.chunk_start[cat] * a.n_cfg + cfg) * a.n_thr + t;
+        }
+        const int64_t best_stride = (int64_t)a.n_cfg * a.n_thr;
+        const int32_t* tkp = a.tk + (int64_t)cc * a.n_rec;
+        const unsigned long long* ansp = a.ans + ((int64_t)t * per_t + cc) * a.n_rec;
+        for (int k = lane; k < a.n_rec; k += 32) {
+            double v = -1.0;                                       // eval.py:522-525
+            if (ngt) {
+                v = 0.0;                                           // eval.py:565-573
+                if ((uint32_t)max(tkp[k], 1) <= tot) {
+                    uint32_t qt, qn, ch, bt, bn, dummy;
+                    pr_unpack(ansp[k], qt, qn, ch);
+                    pr_unpack(best[(int64_t)ch * best_stride], bt, bn, dummy);
+                    if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
+                    v = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
+                }
+            }
+            tile_s[k * (PR_TILE_CELLS + 1) + c] = v;
+        }
+    }
+    __syncthreads();
+    const uint32_t cc = cc0 + lane;
+    if (cc < per_t) {
+        double* out = a.precision + (int64_t)t * a.n_rec * per_t + cc;
+        for (int k = warp; k < a.n_rec; k += 4)
+            out[(int64_t)k * per_t] = tile_s[k * (PR_TILE_CELLS + 1) + lane];
+    }
+}
+
 // per (category, cfg, threshold): chunk_best[ch] <- best precision of all LATER chunks
 __global__ void k_pr_suffix(PrArgs a) {
     const int cat = blockIdx.x;
@@ -544,14 +597,15 @@ __global__ void k_pr_finalize(PrArgs a) {
 
 // TA_PR_IMPL: 0 = position walk (k_pr_count + k_pr_envelope + k_pr_scan + k_pr_finalize);
 // 1..3 = bit planes (k_pr_bits + k_pr_tk + k_pr_scan_live + k_pr_envelope_bits) finished by
-//   1: k_pr_finalize_2d, 2: k_pr_finalize, 3: cell-major answers + k_pr_finalize_rows.
+//   1: k_pr_finalize_2d, 2: k_pr_finalize, 3: cell-major answers + k_pr_finalize_rows,
+//   4: cell-major answers + k_pr_finalize_tile.
 // All produce identical tensors (tests/test_gpu_parity.py runs every variant).
 #ifndef TA_PR_IMPL_DEFAULT
 #define TA_PR_IMPL_DEFAULT 0
 #endif
 static int ta_pr_impl() {
     const char* e = getenv("TA_PR_IMPL");
-    return (e && *e >= '0' && *e <= '3') ? (e[0] - '0') : TA_PR_IMPL_DEFAULT;
+    return (e && *e >= '0' && *e <= '4') ? (e[0] - '0') : TA_PR_IMPL_DEFAULT;
 }
 
 extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
@@ -583,7 +637,11 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     const int impl = (n_cells * 2 * TA_PR_WORDS * 4 <= 48 * 1024) ? ta_pr_impl() : 0;
     const size_t o_ccat = take(impl ? (size_t)n_chunks_ub * 4 : 0);
     const size_t o_bits = take(impl ? (size_t)n_chunks_ub * 2 * TA_PR_WORDS * n_cells * 4 : 0);
-    const size_t o_ans = take(impl == 3 ? (size_t)n_thr * n_rec * n_cat * n_cfg * 8 : 0);
+    // variant 4 needs its [n_rec][33] tile in the default 48 KB of shared memory, else variant 3
+    int impl_fin = impl;
+    if (impl == 4 && (size_t)n_rec * (PR_TILE_CELLS + 1) * 8 > 48 * 1024) impl_fin = 3;
+    const bool cell_major = impl >= 3;
+    const size_t o_ans = take(cell_major ? (size_t)n_thr * n_rec * n_cat * n_cfg * 8 : 0);
     void* ws = nullptr;
     int rc = ta_workspace(ctx, st, off, &ws);
     if (rc) return rc;
@@ -600,7 +658,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     a.chunk_best = reinterpret_cast<unsigned long long*>(base + o_best);
     a.chunk_cat = reinterpret_cast<int32_t*>(base + o_ccat);
     a.bits = reinterpret_cast<uint32_t*>(base + o_bits);
-    a.ans = impl == 3 ? reinterpret_cast<unsigned long long*>(base + o_ans) : nullptr;
+    a.ans = cell_major ? reinterpret_cast<unsigned long long*>(base + o_ans) : nullptr;
     a.prec_bits = reinterpret_cast<unsigned long long*>(precision);
     a.precision = precision; a.recall = recall; a.tp_cnt = tp_cnt; a.fp_cnt = fp_cnt;
 
@@ -657,7 +715,12 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     k_pr_suffix<<<n_cat, 128, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_suffix"))) return rc;
     const size_t n_prec = (size_t)n_thr * n_rec * n_cat * n_cfg;
-    if (impl == 3) {
+    if (impl_fin == 4) {
+        dim3 grid((unsigned)(((size_t)n_cat * n_cfg + PR_TILE_CELLS - 1) / PR_TILE_CELLS), (unsigned)n_thr);
+        k_pr_finalize_tile<<<grid, 128, (size_t)n_rec * (PR_TILE_CELLS + 1) * 8, st>>>(a);
+        return ta_check_launch(ctx, "k_pr_finalize_tile");
+    }
+    if (impl_fin == 3) {
         const int64_t rows = (int64_t)n_thr * n_cat * n_cfg;
         k_pr_finalize_rows<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a);
         return ta_check_launch(ctx, "k_pr_finalize_rows");

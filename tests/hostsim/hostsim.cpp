@@ -166,8 +166,9 @@ int hs_pr_accumulate(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* ac
 static int pr_bits_impl(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
                           const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
                           int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
-                          int64_t* tp_cnt, int64_t* fp_cnt, bool rows) {
+                          int64_t* tp_cnt, int64_t* fp_cnt, int mode) {
     (void)n_dt;
+    const bool rows = mode >= 1;          // cell-major answers (TA_PR_IMPL >= 3)
     const int CH = 32 * TA_PR_WORDS;
     const int n_cells = n_cfg * n_thr;
     std::vector<int> chunk_start(n_cat + 1, 0);
@@ -274,7 +275,7 @@ static int pr_bits_impl(int32_t n_cat, const int64_t* cat_dt_off, const int32_t*
             }
         }
     // k_pr_finalize_rows
-    if (rows) {
+    if (mode == 1) {
         for (int64_t gid = 0; gid < (int64_t)n_thr * per_t; ++gid) {
             const int64_t t = gid / per_t, cc = gid - t * per_t;
             double* out = precision + t * n_rec * per_t + cc;
@@ -314,7 +315,8 @@ static int pr_bits_impl(int32_t n_cat, const int64_t* cat_dt_off, const int32_t*
         const uint32_t need = (uint32_t)(tkv > 1 ? tkv : 1);
         if (need > cat_tot[cc * 32 + t]) { precision[idx] = 0.0; continue; }
         uint32_t qt, qn, ch, bt, bn, d;
-        pr_unpack(prec_bits[idx], qt, qn, ch);
+        // mode 2 = k_pr_finalize_tile: per-entry finalize reading the cell-major answers
+        pr_unpack(rows ? prec_bits[((int64_t)t * per_t + cc) * n_rec + k] : prec_bits[idx], qt, qn, ch);
         pr_unpack(chunk_best[((size_t)(chunk_start[cat] + ch) * n_cfg + cfg) * n_thr + t], bt, bn, d);
         if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
         precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
@@ -327,14 +329,22 @@ int hs_pr_accumulate_bits(int32_t n_cat, const int64_t* cat_dt_off, const int32_
                           int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
                           int64_t* tp_cnt, int64_t* fp_cnt) {
     return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
-                        precision, recall, tp_cnt, fp_cnt, false);
+                        precision, recall, tp_cnt, fp_cnt, 0);
 }
 int hs_pr_accumulate_bits_rows(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
                                const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
                                int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
                                int64_t* tp_cnt, int64_t* fp_cnt) {
     return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
-                        precision, recall, tp_cnt, fp_cnt, true);
+                        precision, recall, tp_cnt, fp_cnt, 1);
+}
+
+int hs_pr_accumulate_bits_tile(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
+                               const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                               int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
+                               int64_t* tp_cnt, int64_t* fp_cnt) {
+    return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
+                        precision, recall, tp_cnt, fp_cnt, 2);
 }
 
 void hs_transpose32(const uint32_t* in, uint32_t* out) {
