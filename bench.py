@@ -444,6 +444,7 @@ def main():
         "k_pr_envelope": ab_t["pr_envelope"] + ab_l["pr_envelope"],
         "k_pr_bits": ab_t["pr_bits"] + ab_l["pr_bits"],
         "k_pr_envelope_bits": ab_t["pr_envelope_bits"] + ab_l["pr_envelope_bits"],
+        "k_pr_finalize_tile": ab_t["pr_finalize"] + ab_l["pr_finalize"],
         "k_pr_finalize": ab_t["pr_finalize"] + ab_l["pr_finalize"],
     }
     per_kernel = {}

@@ -22,11 +22,15 @@
 //                  detections backwards from shared memory: running counts, suffix-maximum
 //                  precision, and the answer of every recall threshold whose tk-th true
 //                  positive lies inside the chunk
-//   k_pr_bits / k_pr_envelope_bits   bit-plane variant of count / envelope (TA_PR_IMPL=1):
-//                  the chunk's TP/FP words are transposed ONCE (32 x 32 bit-matrix transpose
+// The DEFAULT path (TA_PR_IMPL=1) replaces count / scan / envelope / finalize by
+//   k_pr_bits      the chunk's TP/FP words are transposed ONCE (32 x 32 bit-matrix transpose
 //                  across the warp) into one 256-bit TP and FP plane per cell; chunk totals
-//                  are popcounts, and the envelope thread of a cell visits only the true
-//                  positives of its plane (clz / popc) instead of all 256 positions
+//                  are popcounts
+//   k_pr_tk, k_pr_scan_live   tk table (flat) and scan of the 2 n_thr live counters per cfg
+//   k_pr_envelope_bits   one thread per (chunk, cell) visits only the TRUE POSITIVES of its plane
+//                  (clz / popc) instead of all 256 positions; answers go to a cell-major buffer
+//                  (sequential stores per thread)
+//   k_pr_finalize_tile   coalesced cell-major reads, shared-memory transpose, coalesced writes
 //   k_pr_suffix    per cell: best precision of all later chunks, for every chunk
 //   k_pr_finalize  per precision entry: merge the in-chunk answer with the later chunks' best,
 //                  divide, write (-1 without GT, 0 for recall levels nobody reaches)
@@ -52,7 +56,7 @@ struct PrArgs {
     uint32_t* cat_tot;           // [n_cat][n_cfg][32] category totals (same bit layout)
     int32_t* tk;                 // [n_cat][n_cfg][n_rec]
     unsigned long long* chunk_best;  // [n_chunks_ub][n_cfg][n_thr] packed (t << 32 | n)
-    unsigned long long* ans;     // cell-major answers [n_thr][n_cat][n_cfg][n_rec] (TA_PR_IMPL=3): what
+    unsigned long long* ans;     // cell-major answers [n_thr][n_cat][n_cfg][n_rec] (bit-plane path): what
                                  // prec_bits holds, laid out so that one cell's recall levels are
                                  // contiguous (sequential stores in the envelope, row reads in finalize)
     int32_t* chunk_cat;          // [n_chunks_ub] category of a chunk            (bit-plane path)
@@ -419,69 +423,6 @@ k_pr_scan_live(PrArgs a) {
     }
 }
 
-// k_pr_finalize on a 2-D grid: blockIdx.y = (threshold, recall level), x over (category, cfg)
-// — no per-thread 64-bit index arithmetic; same values as k_pr_finalize.
-__global__ void __launch_bounds__(256)
-k_pr_finalize_2d(PrArgs a) {
-    const uint32_t per_t = (uint32_t)a.n_cat * (uint32_t)a.n_cfg;
-    const uint32_t cc = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cc >= per_t) return;
-    const int tk_idx = blockIdx.y;
-    const int t = tk_idx / a.n_rec, k = tk_idx - t * a.n_rec;
-    const int64_t idx = (int64_t)tk_idx * per_t + cc;
-    const int ngt = a.num_gt[cc];
-    if (ngt == 0) { a.precision[idx] = -1.0; return; }        // eval.py:522-525
-    const uint32_t need = (uint32_t)max(a.tk[(int64_t)cc * a.n_rec + k], 1);
-    if (need > a.cat_tot[(int64_t)cc * 32 + t]) { a.precision[idx] = 0.0; return; }   // eval.py:565-573
-    const uint32_t cat = cc / (uint32_t)a.n_cfg, cfg = cc - cat * (uint32_t)a.n_cfg;
-    uint32_t qt, qn, ch, bt, bn, dummy;
-    pr_unpack(a.prec_bits[idx], qt, qn, ch);
-    pr_unpack(a.chunk_best[((int64_t)(a.chunk_start[cat] + ch) * a.n_cfg + cfg) * a.n_thr + t],
-              bt, bn, dummy);
-    if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
-    a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
-}
-
-
-// k_pr_finalize for cell-major answers: one thread per (threshold, category, cfg) row walks the
-// 101 recall levels — the row's totals, chunk table and tk run are read once, its answers
-// sequentially, and a quotient is only formed when the winning rational changes; stores are
-// coalesced across the threads of a warp (cfg fastest).  Same values as k_pr_finalize.
-__global__ void __launch_bounds__(128)
-k_pr_finalize_rows(PrArgs a) {
-    const uint32_t per_t = (uint32_t)a.n_cat * (uint32_t)a.n_cfg;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (int64_t)a.n_thr * per_t) return;
-    const uint32_t t = (uint32_t)(gid / per_t), cc = (uint32_t)(gid - (int64_t)t * per_t);
-    double* out = a.precision + (int64_t)t * a.n_rec * per_t + cc;
-    const int ngt = a.num_gt[cc];
-    if (ngt == 0) {                                               // eval.py:522-525
-        for (int k = 0; k < a.n_rec; ++k) out[(int64_t)k * per_t] = -1.0;
-        return;
-    }
-    const uint32_t tot = a.cat_tot[(int64_t)cc * 32 + t];
-    const uint32_t cat = cc / (uint32_t)a.n_cfg, cfg = cc - cat * (uint32_t)a.n_cfg;
-    const unsigned long long* best = a.chunk_best + ((int64_t)a.chunk_start[cat] * a.n_cfg + cfg) * a.n_thr + t;
-    const int64_t best_stride = (int64_t)a.n_cfg * a.n_thr;       // one chunk
-    const int32_t* tkp = a.tk + (int64_t)cc * a.n_rec;
-    const unsigned long long* ansp = a.ans + ((int64_t)t * per_t + cc) * a.n_rec;
-    uint32_t pt = 0xffffffffu, pn = 0;
-    double pv = 0.0;
-    for (int k = 0; k < a.n_rec; ++k) {
-        double v = 0.0;                                           // eval.py:565-573
-        if ((uint32_t)max(tkp[k], 1) <= tot) {
-            uint32_t qt, qn, ch, bt, bn, dummy;
-            pr_unpack(ansp[k], qt, qn, ch);
-            pr_unpack(best[(int64_t)ch * best_stride], bt, bn, dummy);
-            if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
-            if (qt != pt || qn != pn) { pt = qt; pn = qn; pv = ta_precision_at((int64_t)qt, (int64_t)(qn - qt)); }
-            v = pv;
-        }
-        out[(int64_t)k * per_t] = v;
-    }
-}
-
-
 // k_pr_finalize for cell-major answers, tiled: a block owns one threshold and 32 consecutive
 // (category, cfg) cells.  Phase 1 reads the cells' answer rows the way the envelope wrote them
 // (warp per cell, lanes over the recall levels: contiguous), merges the later chunks' best and
@@ -595,17 +536,17 @@ __global__ void k_pr_finalize(PrArgs a) {
     a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
 }
 
-// TA_PR_IMPL: 0 = position walk (k_pr_count + k_pr_envelope + k_pr_scan + k_pr_finalize);
-// 1..3 = bit planes (k_pr_bits + k_pr_tk + k_pr_scan_live + k_pr_envelope_bits) finished by
-//   1: k_pr_finalize_2d, 2: k_pr_finalize, 3: cell-major answers + k_pr_finalize_rows,
-//   4: cell-major answers + k_pr_finalize_tile.
-// All produce identical tensors (tests/test_gpu_parity.py runs every variant).
+// TA_PR_IMPL: 0 = position walk (k_pr_count, k_pr_scan, k_pr_envelope, k_pr_finalize);
+//             1 = bit planes (k_pr_bits, k_pr_tk, k_pr_scan_live, k_pr_envelope_bits with
+//                 cell-major answers, k_pr_finalize_tile) — the default.
+// Both produce identical tensors (tests/test_gpu_parity.py runs both; tools/ab_variants.py
+// compares them at the bench size: profiles/r1b_ab_variants.md).
 #ifndef TA_PR_IMPL_DEFAULT
-#define TA_PR_IMPL_DEFAULT 0
+#define TA_PR_IMPL_DEFAULT 1
 #endif
 static int ta_pr_impl() {
     const char* e = getenv("TA_PR_IMPL");
-    return (e && *e >= '0' && *e <= '4') ? (e[0] - '0') : TA_PR_IMPL_DEFAULT;
+    return (e && *e) ? (e[0] != '0') : TA_PR_IMPL_DEFAULT;
 }
 
 extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
@@ -633,15 +574,13 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     const size_t o_tk = take((size_t)n_cat * n_cfg * n_rec * 4);
     const size_t o_best = take((size_t)n_chunks_ub * n_cfg * n_thr * 8);
     const size_t n_cells = (size_t)n_cfg * n_thr;
-    // the staged planes of one chunk (64 B per cell) must fit the default 48 KB of shared memory
-    const int impl = (n_cells * 2 * TA_PR_WORDS * 4 <= 48 * 1024) ? ta_pr_impl() : 0;
+    // the staged planes of one chunk (64 B per cell) and the finalize tile ([n_rec][33] doubles)
+    // must fit the default 48 KB of shared memory
+    const int impl = (n_cells * 2 * TA_PR_WORDS * 4 <= 48 * 1024 &&
+                      (size_t)n_rec * (PR_TILE_CELLS + 1) * 8 <= 48 * 1024) ? ta_pr_impl() : 0;
     const size_t o_ccat = take(impl ? (size_t)n_chunks_ub * 4 : 0);
     const size_t o_bits = take(impl ? (size_t)n_chunks_ub * 2 * TA_PR_WORDS * n_cells * 4 : 0);
-    // variant 4 needs its [n_rec][33] tile in the default 48 KB of shared memory, else variant 3
-    int impl_fin = impl;
-    if (impl == 4 && (size_t)n_rec * (PR_TILE_CELLS + 1) * 8 > 48 * 1024) impl_fin = 3;
-    const bool cell_major = impl >= 3;
-    const size_t o_ans = take(cell_major ? (size_t)n_thr * n_rec * n_cat * n_cfg * 8 : 0);
+    const size_t o_ans = take(impl ? (size_t)n_thr * n_rec * n_cat * n_cfg * 8 : 0);
     void* ws = nullptr;
     int rc = ta_workspace(ctx, st, off, &ws);
     if (rc) return rc;
@@ -658,7 +597,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     a.chunk_best = reinterpret_cast<unsigned long long*>(base + o_best);
     a.chunk_cat = reinterpret_cast<int32_t*>(base + o_ccat);
     a.bits = reinterpret_cast<uint32_t*>(base + o_bits);
-    a.ans = cell_major ? reinterpret_cast<unsigned long long*>(base + o_ans) : nullptr;
+    a.ans = impl ? reinterpret_cast<unsigned long long*>(base + o_ans) : nullptr;
     a.prec_bits = reinterpret_cast<unsigned long long*>(precision);
     a.precision = precision; a.recall = recall; a.tp_cnt = tp_cnt; a.fp_cnt = fp_cnt;
 
@@ -715,20 +654,10 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     k_pr_suffix<<<n_cat, 128, 0, st>>>(a);
     if ((rc = ta_check_launch(ctx, "k_pr_suffix"))) return rc;
     const size_t n_prec = (size_t)n_thr * n_rec * n_cat * n_cfg;
-    if (impl_fin == 4) {
+    if (impl) {
         dim3 grid((unsigned)(((size_t)n_cat * n_cfg + PR_TILE_CELLS - 1) / PR_TILE_CELLS), (unsigned)n_thr);
         k_pr_finalize_tile<<<grid, 128, (size_t)n_rec * (PR_TILE_CELLS + 1) * 8, st>>>(a);
         return ta_check_launch(ctx, "k_pr_finalize_tile");
-    }
-    if (impl_fin == 3) {
-        const int64_t rows = (int64_t)n_thr * n_cat * n_cfg;
-        k_pr_finalize_rows<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(a);
-        return ta_check_launch(ctx, "k_pr_finalize_rows");
-    }
-    if (impl == 1 && (size_t)n_thr * n_rec <= 65535 && (size_t)n_cat * n_cfg < (1u << 31)) {
-        dim3 grid((unsigned)(((size_t)n_cat * n_cfg + 255) / 256), (unsigned)(n_thr * n_rec));
-        k_pr_finalize_2d<<<grid, 256, 0, st>>>(a);
-        return ta_check_launch(ctx, "k_pr_finalize_2d");
     }
     k_pr_finalize<<<(unsigned)((n_prec + 255) / 256), 256, 0, st>>>(a);
     return ta_check_launch(ctx, "k_pr_finalize");

@@ -168,7 +168,7 @@ static int pr_bits_impl(int32_t n_cat, const int64_t* cat_dt_off, const int32_t*
                           int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
                           int64_t* tp_cnt, int64_t* fp_cnt, int mode) {
     (void)n_dt;
-    const bool rows = mode >= 1;          // cell-major answers (TA_PR_IMPL >= 3)
+    const bool rows = mode >= 1;          // cell-major answers (the shipped layout)
     const int CH = 32 * TA_PR_WORDS;
     const int n_cells = n_cfg * n_thr;
     std::vector<int> chunk_start(n_cat + 1, 0);
@@ -274,36 +274,6 @@ static int pr_bits_impl(int32_t n_cat, const int64_t* cat_dt_off, const int32_t*
                 if (pr_better(ct, cn, bt, bn)) { bt = ct; bn = cn; }
             }
         }
-    // k_pr_finalize_rows
-    if (mode == 1) {
-        for (int64_t gid = 0; gid < (int64_t)n_thr * per_t; ++gid) {
-            const int64_t t = gid / per_t, cc = gid - t * per_t;
-            double* out = precision + t * n_rec * per_t + cc;
-            const int ngt = num_gt[cc];
-            if (ngt == 0) { for (int k = 0; k < n_rec; ++k) out[(int64_t)k * per_t] = -1.0; continue; }
-            const uint32_t tot = cat_tot[cc * 32 + t];
-            const int cat = (int)(cc / n_cfg), cfg = (int)(cc - (int64_t)cat * n_cfg);
-            const unsigned long long* best = &chunk_best[((size_t)chunk_start[cat] * n_cfg + cfg) * n_thr + t];
-            const int64_t best_stride = (int64_t)n_cfg * n_thr;
-            const int32_t* tkp = &tk[cc * n_rec];
-            const unsigned long long* ansp = prec_bits.data() + (t * per_t + cc) * n_rec;
-            uint32_t pt = 0xffffffffu, pn = 0;
-            double pv = 0.0;
-            for (int k = 0; k < n_rec; ++k) {
-                double v = 0.0;
-                if ((uint32_t)(tkp[k] > 1 ? tkp[k] : 1) <= tot) {
-                    uint32_t qt, qn, ch, bt, bn, d;
-                    pr_unpack(ansp[k], qt, qn, ch);
-                    pr_unpack(best[(int64_t)ch * best_stride], bt, bn, d);
-                    if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
-                    if (qt != pt || qn != pn) { pt = qt; pn = qn; pv = ta_precision_at((int64_t)qt, (int64_t)(qn - qt)); }
-                    v = pv;
-                }
-                out[(int64_t)k * per_t] = v;
-            }
-        }
-        return 0;
-    }
     // k_pr_finalize
     for (int64_t idx = 0; idx < (int64_t)n_thr * n_rec * per_t; ++idx) {
         const int64_t tk_idx = idx / per_t, cc = idx - tk_idx * per_t;
@@ -331,14 +301,6 @@ int hs_pr_accumulate_bits(int32_t n_cat, const int64_t* cat_dt_off, const int32_
     return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
                         precision, recall, tp_cnt, fp_cnt, 0);
 }
-int hs_pr_accumulate_bits_rows(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
-                               const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
-                               int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
-                               int64_t* tp_cnt, int64_t* fp_cnt) {
-    return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
-                        precision, recall, tp_cnt, fp_cnt, 1);
-}
-
 int hs_pr_accumulate_bits_tile(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
                                const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
                                int32_t n_rec, const double* rec_thrs, double* precision, double* recall,

@@ -80,8 +80,9 @@ def run_hostsim(plan, iou_mode="3d_iou", iou_thrs=engine.IOU_THRS, rec_thrs=engi
 def hostsim_pr(n_cat, cat_dt_off, acc_perm, tpfp, num_gt, n_cfg, iou_thrs=engine.IOU_THRS,
                rec_thrs=engine.REC_THRS, impl="serial"):
     """PR accumulation of the host simulation on explicit arrays (also used by the
-    multi-process exchange test).  impl="serial": the plain per-cell loop; impl="bits": the
-    serial emulation of the bit-plane kernels (chunks, warp transpose, TP-only walk)."""
+    multi-process exchange test).  impl="serial": the plain per-cell loop; impl="bits_tile":
+    the serial emulation of the bit-plane kernels as shipped (chunks, warp transpose, TP-only
+    walk, cell-major answers); impl="bits": the same with answers in the precision layout."""
     hs = build_hostsim()
     I64, I32, P = C.c_int64, C.c_int32, C.c_void_p
     n_thr, n_rec = len(iou_thrs), len(rec_thrs)
@@ -94,7 +95,7 @@ def hostsim_pr(n_cat, cat_dt_off, acc_perm, tpfp, num_gt, n_cfg, iou_thrs=engine
         tp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64),
         fp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64), num_gt=num_gt, dt_tpfp=tpfp)
     fn = {"serial": hs.hs_pr_accumulate, "bits": hs.hs_pr_accumulate_bits,
-          "bits_rows": hs.hs_pr_accumulate_bits_rows, "bits_tile": hs.hs_pr_accumulate_bits_tile}[impl]
+          "bits_tile": hs.hs_pr_accumulate_bits_tile}[impl]
     fn.argtypes = [I32, P, P, I64, P, P, I32, I32, I32, P, P, P, P, P]
     fn(n_cat, _p(np.asarray(cat_dt_off, dtype=np.int64)),
        _p(np.asarray(acc_perm, dtype=np.int32)), n_dt, _p(tpfp),

@@ -15,7 +15,7 @@ def _same(a, b):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
 
 
-@pytest.mark.parametrize("impl", ["bits", "bits_rows", "bits_tile"])
+@pytest.mark.parametrize("impl", ["bits", "bits_tile"])
 @pytest.mark.parametrize("seed", range(8))
 def test_random_multi_chunk(seed, impl):
     c = random_pr_case(seed)
@@ -37,7 +37,7 @@ def test_track_shape_and_odd_thresholds():
     c = random_pr_case(6, n_cat=5, n_cfg=2, n_thr=3, max_len=900)
     args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
     thr, rec = engine.IOU_THRS[:3], np.array([0.0, 0.25, 0.5, 0.5, 0.99, 1.0])
-    for impl in ("bits", "bits_rows", "bits_tile"):
+    for impl in ("bits", "bits_tile"):
         _same(hostsim_pr(*args, iou_thrs=thr, rec_thrs=rec, impl=impl),
               hostsim_pr(*args, iou_thrs=thr, rec_thrs=rec, impl="serial"))
 
@@ -61,7 +61,7 @@ def test_goldens_through_the_bit_plane_emulation(golden):
     gt, res = golden_inputs(golden)
     tao_plan, lvis_plan = plans_from_json(gt, res)
     off_grid = golden["_name"] == "small_float"
-    for impl in ("bits", "bits_rows", "bits_tile"):
+    for impl in ("bits", "bits_tile"):
         compare_with_golden(golden, "tao_", tao_plan, run_hostsim(tao_plan, pr_impl=impl),
                             exact_iou=not off_grid, iou_atol=1e-12)
         compare_with_golden(golden, "lvis_", lvis_plan, run_hostsim(lvis_plan, pr_impl=impl))
