@@ -189,7 +189,7 @@ def _ragged_contains(r: Ragged, row: np.ndarray, val: np.ndarray) -> np.ndarray:
     vmax = int(max(vals.max(), val.max())) + 1
     vmin = int(min(vals.min(), val.min()))
     span = vmax - vmin + 1
-    keys = np.unique(row_of * span + (vals - vmin))
+    keys = np.sort(row_of * span + (vals - vmin))      # membership only: duplicates are harmless
     q = np.where(row >= 0, row, 0) * span + (val - vmin)
     hit = _index_of(keys, q) >= 0
     return hit & (row >= 0)
@@ -495,12 +495,13 @@ def _tao_tracks(rows, rank, trk_key, S_frame, S_slot, bbox, area, vis):
     pos_in_stream[stream] = np.arange(rows.size)
     keys, inv = np.unique(trk_key, return_inverse=True)
     n_trk = keys.size
-    first_key = np.full(n_trk, np.iinfo(np.int64).max, dtype=np.int64)
-    np.minimum.at(first_key, inv, pos_in_stream)
     # inside a track: stable sort by frame_index over the stream order (tao.py:182-184)
     order = np.lexsort((pos_in_stream, S_frame[rank], inv))
     seg = np.zeros(n_trk + 1, dtype=np.int64)
     np.cumsum(np.bincount(inv, minlength=n_trk), out=seg[1:])
+    # first appearance of every track in the stream (tracks are contiguous in `order`)
+    first_key = (np.minimum.reduceat(pos_in_stream[order], seg[:-1]) if n_trk
+                 else np.zeros(0, dtype=np.int64))
     r_sorted = rows[order]
     a_sorted = area[r_sorted].astype(np.float64)
     area_mean = neumaier_segment_sum(a_sorted, seg) / np.diff(seg)
