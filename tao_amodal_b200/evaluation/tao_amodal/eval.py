@@ -84,7 +84,9 @@ class TaoEval:
         """Columnar equivalent of eval.py:178-233 (prep.prepare_tao)."""
         p = self.params
         if p.iou_type != "bbox":
-            raise NotImplementedError("only iou_type='bbox' runs on the CUDA path")
+            # the reference fails here too: _to_mask (eval.py:173-176) calls Tao.ann_to_rle, which
+            # tao.py does not define
+            raise AttributeError("'Tao' object has no attribute 'ann_to_rle'")
         if len(p.iou_thrs) > 16:
             raise ValueError("at most 16 IoU thresholds are supported")
         vid_ids = p.vid_ids
