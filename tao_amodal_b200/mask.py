@@ -138,7 +138,6 @@ class RlePool:
             if r == -(2 ** 63):
                 raise IndexError(self._lib.ta_mask_error().decode())
             cap = -r
-        off, cnt, hw, _, _ = None, None, None, None, None
         hw = np.zeros((len(self), 2), dtype=np.uint32)
         self._lib.ta_rle_pool_export(self._h, None, None, _ptr(hw), None, None)
         return {"size": [int(hw[i, 0]), int(hw[i, 1])], "counts": buf.value}

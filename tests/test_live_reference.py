@@ -84,3 +84,24 @@ def test_accessors_match_the_reference(ref, tmp_path):
     imgs = sorted(lr.get_img_ids())
     assert lr.get_ann_ids(img_ids=imgs[:5], cat_ids=cats) == lm.get_ann_ids(img_ids=imgs[:5], cat_ids=cats)
     assert lr.load_cats(cats[:2]) == lm.load_cats(cats[:2])
+
+
+@pytest.mark.parametrize("seed,dt_mode", [(41, "box"), (42, "poly"), (43, "rle")])
+def test_segm_random_sets_match_the_reference(seed, dt_mode, ref, tmp_path):
+    """LVISEval(iou_type="segm") of the unmodified reference (masks through its own maskApi.c,
+    oracle/_ref) against the plan + mask codec + per-thread kernel arithmetic on the host."""
+    from oracle import cases, maskapi_ref
+    if not maskapi_ref.available():
+        pytest.skip("oracle/_ref not built")
+    gt, res = cases.case_segm(dt_mode, seed)
+    ap, rp = str(tmp_path / "gt.json"), str(tmp_path / "dt.json")
+    json.dump(gt, open(ap, "w"))
+    json.dump(res, open(rp, "w"))
+    le = ref.LVISEval(ap, rp, "segm")
+    le.run()
+    from tao_amodal_b200.evaluation.lvis_amodal import LVIS, LVISEval
+    ev = LVISEval(LVIS(copy.deepcopy(gt)), copy.deepcopy(res), "segm")
+    ev._prepare()
+    out = run_hostsim(ev._plan)
+    assert np.array_equal(le.eval["precision"], out.precision)
+    assert np.array_equal(le.eval["recall"], out.recall)
