@@ -10,6 +10,8 @@ from ..columnar import DtColumns, GtColumns
 _ENGINES: Dict[int, object] = {}
 _JSON_CACHE: Dict[Tuple[str, float, int], object] = {}
 
+import numpy as np
+
 
 def get_engine(device: int = 0):
     """One Engine (ta_ctx) per device per process."""
@@ -100,3 +102,32 @@ def dist_accumulate(eng, dev, rank, world):
     acc.accumulate()
     for k in ("precision", "recall", "tp_cnt", "fp_cnt"):
         dist.broadcast(dev.t[k], src=0)
+
+
+def ascending_rec_thrs(rec_thrs):
+    """The PR kernels take the recall thresholds in ascending order.  Returns (ascending copy,
+    inv) with ``rec_thrs[k] == ascending[inv[k]]``; inv is None when the given order already is
+    ascending (the evaluators' default, np.linspace)."""
+    r = np.ascontiguousarray(rec_thrs, dtype=np.float64)
+    if r.size < 2 or bool(np.all(r[1:] >= r[:-1])):
+        return r, None
+    order = np.argsort(r, kind="stable")
+    inv = np.empty(r.size, dtype=np.int64)
+    inv[order] = np.arange(r.size)
+    return np.ascontiguousarray(r[order]), inv
+
+
+def restore_rec_order(precision, recall, rec_thrs, inv):
+    """Undo ascending_rec_thrs on precision [T, R, C, K] (recall [T, C, K]), including the
+    reference's behaviour for thresholds given out of order: its loop over the recall
+    thresholds stops at the FIRST one no detection reaches (bare ``except: pass`` around the
+    loop, eval.py:565-571 / lvis_amodal/eval.py:405-411), so every later entry of the cell stays
+    0.0 even if its threshold is reachable."""
+    if inv is None:
+        return precision
+    out = np.ascontiguousarray(precision[:, inv])
+    r = np.asarray(rec_thrs, dtype=np.float64)
+    unreachable = r[None, :, None, None] > recall[:, None]
+    stopped = np.maximum.accumulate(unreachable, axis=1)
+    out[stopped & (out != -1)] = 0.0
+    return out

@@ -18,7 +18,8 @@ import numpy as np
 
 from ... import materialize, prep
 from ...columnar import DtColumns
-from .._common import LazyDict, dist_accumulate, dist_info, get_engine
+from .._common import (LazyDict, ascending_rec_thrs, dist_accumulate, dist_info, get_engine,
+                       restore_rec_order)
 from .lvis import LVIS
 from .results import LVISResults
 
@@ -179,7 +180,8 @@ class LVISEval:
         self.params.img_ids = list(np.unique(self.params.img_ids))
         self._prepare()
         eng = get_engine(self.device)
-        self._dev = eng.upload(self._plan, self.params.iou_thrs, self.params.rec_thrs)
+        rec_sorted, self._rec_inv = ascending_rec_thrs(self.params.rec_thrs)
+        self._dev = eng.upload(self._plan, self.params.iou_thrs, rec_sorted)
         if self._plan.masks is None:
             eng.stage_frame_eval(self._dev)
         else:
@@ -220,7 +222,8 @@ class LVISEval:
             "params": p,
             "counts": [T, R, C, NR],
             "date": datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S"),
-            "precision": t["precision"].cpu().numpy(),
+            "precision": restore_rec_order(t["precision"].cpu().numpy(), t["recall"].cpu().numpy(),
+                                           p.rec_thrs, self._rec_inv),
             "recall": t["recall"].cpu().numpy(),
             "dt_pointers": LazyDict(lambda: materialize.dt_pointers(
                 self._plan, T, self._need_detail().dt_tpfp, self._num_gt)),

@@ -17,7 +17,8 @@ import numpy as np
 
 from ... import materialize, prep
 from ...columnar import DtColumns
-from .._common import LazyDict, dist_accumulate, dist_info, get_engine
+from .._common import (LazyDict, ascending_rec_thrs, dist_accumulate, dist_info, get_engine,
+                       restore_rec_order)
 from .results import TaoResults
 from .tao import Tao
 
@@ -109,7 +110,8 @@ class TaoEval:
         self.params.vid_ids = list(np.unique(self.params.vid_ids))
         self._prepare()
         eng = get_engine(self.device)
-        self._dev = eng.upload(self._plan, self.params.iou_thrs, self.params.rec_thrs)
+        rec_sorted, self._rec_inv = ascending_rec_thrs(self.params.rec_thrs)
+        self._dev = eng.upload(self._plan, self.params.iou_thrs, rec_sorted)
         eng.stage_iou(self._dev, self.params.iou_3d_type)
         eng.stage_match(self._dev)
         self._detail = None
@@ -145,8 +147,10 @@ class TaoEval:
         T, R, C = len(p.iou_thrs), len(p.rec_thrs), len(self._plan.cat_ids)
         A, Tm = len(p.area_rng), len(p.time_rng)
         t = self._dev.t
-        precision = t["precision"].cpu().numpy().reshape(T, R, C, A, Tm)
-        recall = t["recall"].cpu().numpy().reshape(T, C, A, Tm)
+        recall = t["recall"].cpu().numpy()
+        precision = restore_rec_order(t["precision"].cpu().numpy(), recall, p.rec_thrs,
+                                      self._rec_inv).reshape(T, R, C, A, Tm)
+        recall = recall.reshape(T, C, A, Tm)
         self._num_gt = t["num_gt"].cpu().numpy()
         self.eval = {
             "params": p,

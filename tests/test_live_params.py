@@ -121,3 +121,25 @@ def test_lvis_params(ref, files, mutate):
 def test_lvis_max_dets(ref, files):
     le, ev, out = _lvis_pair(ref, files, lambda p: None, max_dets=2)
     assert np.array_equal(le.eval["precision"], out.precision)
+
+
+def _odd_thresholds(p):
+    p.rec_thrs = np.array([0.5, 0.1, 0.9, 0.1, 1.0, 0.0])      # unsorted, duplicated
+    p.iou_thrs = np.array([0.75, 0.5, 0.5])
+
+
+@pytest.mark.parametrize("pair", ["tao", "lvis"])
+def test_recall_thresholds_out_of_order(ref, files, pair):
+    """The reference's loop over the recall thresholds stops at the first unreachable one
+    (eval.py:565-571); the evaluators feed the kernels ascending thresholds and restore the
+    given order (evaluation/_common.py)."""
+    from tao_amodal_b200.evaluation._common import ascending_rec_thrs, restore_rec_order
+    fn = _tao_pair if pair == "tao" else _lvis_pair
+    a, ev, _ = fn(ref, files, _odd_thresholds)
+    asc, inv = ascending_rec_thrs(ev.params.rec_thrs)
+    assert inv is not None
+    out = run_hostsim(ev._plan, iou_thrs=ev.params.iou_thrs, rec_thrs=asc)
+    prec = restore_rec_order(out.precision, out.recall, ev.params.rec_thrs, inv)
+    assert np.array_equal(a.eval["precision"].reshape(prec.shape), prec)
+    assert np.array_equal(a.eval["recall"].reshape(out.recall.shape), out.recall)
+    assert (prec == 0.0).any() and (prec > 0.0).any()
