@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """Wall-clock of the drop-in CLI on the headline set (BASELINE.json: 1 M predictions / 100 k GT
-boxes, 5 000 videos, 1203 categories), JSON in -> metrics out, next to the CPU oracle port of
-the reference on the same files (single core).  The real reference cannot travel to the GPU
-box; the port visits only non-empty cells, so it is FASTER than the reference (SURVEY.md §3.4
-estimates ~73 min for the reference on this shape) and the ratio printed here is conservative.
+boxes, 5 000 videos, 1203 categories), JSON in -> metrics out.  The CPU side of the comparison
+is bench.py's business (``cpu_baseline`` / ``--impl reference``: the only places outside tests/
+that may run oracle/); SURVEY.md §3.4 estimates ~73 min for the unmodified reference on this
+shape.
 
-    python tools/bench_cli.py [--config cfg5] [--videos N] [--skip-cpu] [--out gpurun_out/cli.json]
+    python tools/bench_cli.py [--config cfg5] [--videos N] [--out gpurun_out/cli.json]
 """
 import argparse
 import contextlib
@@ -25,13 +25,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="cfg5")
     ap.add_argument("--videos", type=int, default=0)
-    ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--cpu-videos", type=int, default=100,
-                    help="videos of the set given to the CPU port (scaled linearly to the full set)")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     from tao_amodal_b200 import synth
-    from tao_amodal_b200.columnar import subset_videos
     over = {"videos": args.videos} if args.videos else {}
     gt, dt = synth.generate_named(args.config, **over)
     td = tempfile.mkdtemp(prefix="ta_cli_")
@@ -61,24 +57,6 @@ def main():
     res["cli_runs_s"] = runs
     res["log_tail"] = open(lp).read().strip().splitlines()[-1]
 
-    if not args.skip_cpu:
-        import copy
-        from oracle import lvis_frame, tao_track
-        vids = gt.vid_id[:args.cpu_videos]
-        g, d = subset_videos(gt, dt, vids)
-        gd, dl = g.to_dict(), d.to_list()
-        t0 = time.perf_counter()
-        lvis_frame.evaluate_lvis(copy.deepcopy(gd), copy.deepcopy(dl), keep_cells=False)
-        dl2 = copy.deepcopy(dl)
-        tao_track.uniquify_track_ids(dl2)
-        tao_track.evaluate_tao(gd, dl2, keep_cells=False)
-        t_cpu = time.perf_counter() - t0
-        scale = len(gt.vid_id) / float(len(vids))
-        res["cpu_port_subset_s"] = t_cpu
-        res["cpu_port_subset_videos"] = int(len(vids))
-        res["cpu_port_full_estimate_s"] = t_cpu * scale
-        res["speedup_vs_cpu_port"] = t_cpu * scale / res["cli_wall_s"]
-        res["cpu_cores"] = 1
     res["reference_estimate_s"] = 73 * 60 if args.config == "cfg5" and not args.videos else None
     print(json.dumps(res))
     if args.out:
