@@ -7,6 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import threading
 from typing import Dict, Tuple
 
 import numpy as np
@@ -71,12 +72,50 @@ class _Doc:
             self.h = None
 
 
+_LOCK = threading.Lock()
+_INFLIGHT: Dict[Tuple[str, float, int, int], threading.Event] = {}
+
+
 def _cached(path: str, kind: int, build):
+    """One parse per (path, mtime, size, kind), also when a prefetch thread is already on it: a
+    second caller waits for the first instead of parsing again.  Failures are not cached — the
+    waiting caller then parses itself and raises the error in its own thread."""
     st = os.stat(path)
     key = (os.path.abspath(path), st.st_mtime, st.st_size, kind)
-    if key not in _CACHE:
-        _CACHE[key] = build()
-    return _CACHE[key]
+    while True:
+        with _LOCK:
+            if key in _CACHE:
+                return _CACHE[key]
+            ev = _INFLIGHT.get(key)
+            mine = ev is None
+            if mine:
+                ev = _INFLIGHT[key] = threading.Event()
+        if not mine:
+            ev.wait()
+            continue
+        try:
+            val = build()
+            with _LOCK:
+                _CACHE[key] = val
+            return val
+        finally:
+            with _LOCK:
+                _INFLIGHT.pop(key, None)
+            ev.set()
+
+
+def prefetch(path: str, kind: str) -> threading.Thread:
+    """Start parsing a file ("gt" annotations / "dt" results) on a background thread (the native
+    parser runs without the GIL), so that the two files of the CLI are read concurrently.
+    Errors are left to the regular load_gt / load_dt call that follows."""
+    def work():
+        try:
+            (load_gt if kind == "gt" else load_dt)(path)
+        except Exception:           # noqa: BLE001 - reported by the foreground load
+            pass
+    t = threading.Thread(target=work, name="ta-ingest-prefetch", daemon=True)
+    t.start()
+    return t
 
 
 def load_gt(path: str, need_videos_tracks: bool = False) -> GtColumns:

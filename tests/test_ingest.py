@@ -80,3 +80,24 @@ def test_errors_mirror_the_dict_path(tmp_path):
         ingest.load_gt(p, need_videos_tracks=True)      # Tao needs videos and tracks
     with pytest.raises(FileNotFoundError):
         ingest.load_gt(str(tmp_path / "missing.json"))
+
+
+def test_prefetch_shares_one_parse_with_the_foreground_load(tmp_path):
+    """ingest.prefetch + load_dt: the foreground call waits for the background parse and gets
+    the very same columns object; a broken file raises in the foreground as before."""
+    import json
+    from tao_amodal_b200 import ingest, synth
+    gt, dt = synth.generate_named("tiny")
+    p = str(tmp_path / "dt.json")
+    json.dump(dt.to_list(), open(p, "w"))
+    ingest._CACHE.clear()
+    t = ingest.prefetch(p, "dt")
+    a = ingest.load_dt(p)
+    t.join()
+    assert ingest.load_dt(p) is a and len(ingest._INFLIGHT) == 0
+    assert np.array_equal(a.bbox, dt.bbox)
+    bad = str(tmp_path / "bad.json")
+    open(bad, "w").write('[{"image_id": 1, "bbox": [0, 0, 1')
+    ingest.prefetch(bad, "dt").join()
+    with pytest.raises(Exception):
+        ingest.load_dt(bad)

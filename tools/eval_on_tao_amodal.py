@@ -149,6 +149,9 @@ def main(argv=None):
     else:           # other ranks compute their shard silently
         logging.disable(logging.CRITICAL)
         sys.stdout = open(os.devnull, "w")
+    # the results file is parsed on a background thread while the annotation file is read
+    if isinstance(args.track_result, str) and os.path.exists(args.track_result):
+        ingest.prefetch(args.track_result, "dt")
     try:
         evaluate_predictions_on_lvis(args.annotation, args.track_result, "bbox", logger,
                                      device=device)
