@@ -31,6 +31,10 @@ typedef struct ta_json_doc ta_json_doc;
 
 int         ta_json_open(const char* path, int kind, ta_json_doc** out);
 const char* ta_json_error(void);
+/* Workers that parsed the last document opened on the calling thread: > 1 when a large result
+ * list went through the speculative parallel parse (guessed object starts, verified by
+ * chaining; any doubt falls back to the sequential parse), else 1. */
+int         ta_json_last_parse_workers(void);
 int64_t     ta_json_count(const ta_json_doc* doc, const char* column);   /* elements, -1 if unknown */
 int         ta_json_copy(const ta_json_doc* doc, const char* column, void* dst, int64_t bytes);
 void        ta_json_close(ta_json_doc* doc);

@@ -17,7 +17,9 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
@@ -30,6 +32,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local int g_last_workers = 0;       // workers that produced the last document of this thread
 
 struct Fail {
     std::string msg;
@@ -383,30 +386,140 @@ void parse_annotation_file(Parser& P, Doc& D) {
     flags.push<int64_t>(seen);
 }
 
-void parse_result_file(Parser& P, Doc& D) {
-    Column &img = D.c("image_id", 8), &trk = D.c("track_id", 8), &cat = D.c("category_id", 8);
-    Column &vid = D.c("video_id", 8), &bbox = D.c("bbox", 8), &score = D.c("score", 8);
+// One result object at P (just past its '{'): fields into the six columns.
+struct ResultCols {
+    Column img, trk, cat, vid, bbox, score;
+};
+
+inline void parse_result_object(Parser& P, ResultCols& R) {
     int64_t i = 0, t = -1, c = 0, v = -1;
     double s = 0.0;
     int have = 0;
+    if (!P.eat('}')) {
+        do {
+            const char *ks, *ke;
+            P.raw_string(ks, ke);
+            P.need(':');
+            if (P.key_is(ks, ke, "image_id")) { i = P.as_int(); have |= 1; }
+            else if (P.key_is(ks, ke, "category_id")) { c = P.as_int(); have |= 2; }
+            else if (P.key_is(ks, ke, "bbox")) { P.bbox(R.bbox); have |= 4; }
+            else if (P.key_is(ks, ke, "score")) { s = P.as_double(); have |= 8; }
+            else if (P.key_is(ks, ke, "track_id")) t = P.as_int();
+            else if (P.key_is(ks, ke, "video_id")) v = P.as_int();
+            else P.skip_value();
+        } while (P.eat(','));
+        P.need('}');
+    }
+    if (!(have & 1)) key_error("image_id");
+    if (!(have & 2)) key_error("category_id");
+    if (!(have & 4)) key_error("bbox");
+    if (!(have & 8)) key_error("score");
+    R.img.push(i); R.trk.push(t); R.cat.push(c); R.vid.push(v); R.score.push(s);
+}
+
+void store_result_cols(Doc& D, std::vector<ResultCols>& parts) {
+    const char* names[6] = {"image_id", "track_id", "category_id", "video_id", "bbox", "score"};
+    for (int k = 0; k < 6; ++k) {
+        Column& dst = D.c(names[k], 8);
+        size_t total = 0;
+        auto pick = [&](ResultCols& r) -> Column& {
+            return k == 0 ? r.img : k == 1 ? r.trk : k == 2 ? r.cat : k == 3 ? r.vid : k == 4 ? r.bbox : r.score;
+        };
+        for (auto& r : parts) total += pick(r).data.size();
+        dst.data.resize(total);
+        size_t o = 0;
+        for (auto& r : parts) {
+            Column& c = pick(r);
+            if (!c.data.empty()) memcpy(dst.data.data() + o, c.data.data(), c.data.size());
+            o += c.data.size();
+        }
+    }
+}
+
+// Sequential parse: the authority for results and for error messages.
+void parse_result_file(Parser& P, Doc& D) {
+    std::vector<ResultCols> parts(1);
     P.ws();
     if (P.p >= P.end || *P.p != '[') throw Fail{"AssertionError: results is not a list."};
-    each_object(P, [&](const char* ks, const char* ke) {
-        if (P.key_is(ks, ke, "image_id")) { i = P.as_int(); have |= 1; }
-        else if (P.key_is(ks, ke, "category_id")) { c = P.as_int(); have |= 2; }
-        else if (P.key_is(ks, ke, "bbox")) { P.bbox(bbox); have |= 4; }
-        else if (P.key_is(ks, ke, "score")) { s = P.as_double(); have |= 8; }
-        else if (P.key_is(ks, ke, "track_id")) t = P.as_int();
-        else if (P.key_is(ks, ke, "video_id")) v = P.as_int();
-        else P.skip_value();
-    }, [&]() {
-        if (!(have & 1)) key_error("image_id");
-        if (!(have & 2)) key_error("category_id");
-        if (!(have & 4)) key_error("bbox");
-        if (!(have & 8)) key_error("score");
-        img.push(i); trk.push(t); cat.push(c); vid.push(v); score.push(s);
-        t = -1; v = -1; have = 0;
-    });
+    P.need('[');
+    if (!P.eat(']')) {
+        do {
+            P.need('{');
+            parse_result_object(P, parts[0]);
+        } while (P.eat(','));
+        P.need(']');
+    }
+    store_result_cols(D, parts);
+}
+
+// Speculative parallel parse of a large result list.  The list is cut at guessed object starts
+// (the first "{" after a "}" + "," near each cut); worker k parses whole objects from its start
+// until it reaches worker k + 1's start.  The guesses are then VERIFIED by chaining: worker 0
+// starts at the true beginning, so its object boundaries are true; if it ends exactly on
+// worker 1's start, that start was a true boundary too, and so on.  Any mismatch, or any error
+// in any worker, discards everything and the caller parses sequentially (which also produces
+// the reference-compatible error message).  Returns false when it did not succeed.
+bool parse_result_file_parallel(const char* begin, const char* end, Doc& D, int n_workers) {
+    Parser H{begin, end, begin};
+    H.ws();
+    if (H.p >= end || *H.p != '[') return false;
+    ++H.p;
+    H.ws();
+    if (H.p >= end || *H.p != '{') return false;
+    const char* first = H.p;
+    std::vector<const char*> start((size_t)n_workers + 1, nullptr);
+    start[0] = first;
+    const size_t span = (size_t)(end - first);
+    for (int k = 1; k < n_workers; ++k) {
+        const char* q = first + span / n_workers * k;
+        // guess: '}' [ws] ',' [ws] '{'
+        const char* found = nullptr;
+        for (; q < end; ++q) {
+            if (*q != '}') continue;
+            const char* r = q + 1;
+            while (r < end && (*r == ' ' || *r == '\n' || *r == '\t' || *r == '\r')) ++r;
+            if (r >= end || *r != ',') continue;
+            ++r;
+            while (r < end && (*r == ' ' || *r == '\n' || *r == '\t' || *r == '\r')) ++r;
+            if (r < end && *r == '{') { found = r; break; }
+        }
+        if (!found || found <= start[k - 1]) return false;
+        start[k] = found;
+    }
+    start[n_workers] = end;          // the last worker runs to the closing bracket
+    std::vector<ResultCols> parts((size_t)n_workers);
+    std::vector<const char*> stop((size_t)n_workers, nullptr);
+    std::vector<int> ok((size_t)n_workers, 0);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n_workers; ++k)
+        th.emplace_back([&, k]() {
+            try {
+                Parser P{start[k], end, begin};
+                const bool last = k == n_workers - 1;
+                while (true) {
+                    P.need('{');
+                    parse_result_object(P, parts[k]);
+                    if (!P.eat(',')) {               // end of the list: only the last worker may see it
+                        P.need(']');
+                        P.ws();
+                        if (!last || P.p != end) return;
+                        stop[k] = end;
+                        ok[k] = 1;
+                        return;
+                    }
+                    P.ws();
+                    if (!last && P.p >= start[k + 1]) { stop[k] = P.p; ok[k] = 1; return; }
+                }
+            } catch (...) {
+            }
+        });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < n_workers; ++k) {
+        if (!ok[k]) return false;
+        if (k + 1 < n_workers && stop[k] != start[k + 1]) return false;
+    }
+    store_result_cols(D, parts);
+    return true;
 }
 
 }  // namespace
@@ -416,6 +529,7 @@ struct ta_json_doc {
 };
 
 extern "C" const char* ta_json_error(void) { return g_err; }
+extern "C" int ta_json_last_parse_workers(void) { return g_last_workers; }
 
 extern "C" int ta_json_open(const char* path, int kind, ta_json_doc** out) {
     if (!path || !out) { snprintf(g_err, sizeof(g_err), "ta_json_open: NULL argument"); return -1; }
@@ -433,10 +547,27 @@ extern "C" int ta_json_open(const char* path, int kind, ta_json_doc** out) {
     try {
         Parser P{static_cast<const char*>(map), static_cast<const char*>(map) + len,
                  static_cast<const char*>(map)};
-        if (kind == TA_JSON_ANNOTATIONS) parse_annotation_file(P, d->doc);
-        else parse_result_file(P, d->doc);
-        P.ws();
-        if (P.p != P.end) P.fail("extra data");
+        bool done = false;
+        g_last_workers = 1;
+        const char* min_env = getenv("TA_INGEST_PAR_MIN_BYTES");        // testing hook
+        const size_t par_min = min_env ? (size_t)atoll(min_env) : ((size_t)8 << 20);
+        if (kind == TA_JSON_RESULTS && len >= par_min) {
+            // large result lists: speculative parallel parse, verified; else fall through
+            unsigned hw = std::thread::hardware_concurrency();
+            const char* env = getenv("TA_INGEST_THREADS");
+            int nw = env ? atoi(env) : (int)(hw ? (hw > 16 ? 16 : hw) : 1);
+            if (nw > 1) {
+                done = parse_result_file_parallel(P.begin, P.end, d->doc, nw);
+                if (!done) d->doc.col.clear();
+                else g_last_workers = nw;
+            }
+        }
+        if (!done) {
+            if (kind == TA_JSON_ANNOTATIONS) parse_annotation_file(P, d->doc);
+            else parse_result_file(P, d->doc);
+            P.ws();
+            if (P.p != P.end) P.fail("extra data");
+        }
     } catch (const Fail& f) {
         snprintf(g_err, sizeof(g_err), "%s", f.msg.c_str());
         rc = -3;

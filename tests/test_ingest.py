@@ -101,3 +101,63 @@ def test_prefetch_shares_one_parse_with_the_foreground_load(tmp_path):
     ingest.prefetch(bad, "dt").join()
     with pytest.raises(Exception):
         ingest.load_dt(bad)
+
+
+def _dt_equal(a, b):
+    for f in ("image_id", "track_id", "category_id", "video_id", "bbox", "score"):
+        assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True), f
+
+
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_parallel_result_parse_equals_sequential(tmp_path, monkeypatch, threads):
+    """Large result lists are parsed by several workers from GUESSED object starts that are then
+    verified by chaining (csrc/ta_json.cpp); forced here on small files, including values that
+    contain the very byte pattern the guess looks for."""
+    import json
+    from tao_amodal_b200 import ingest, synth
+    from tao_amodal_b200.columnar import DtColumns
+    gt, dt = synth.generate_named("small")
+    clean = dt.to_list()
+    nasty = dt.to_list()
+    for k, r in enumerate(nasty):
+        if k % 5 == 0:      # nested values and strings with '}, {' inside: wrong guesses
+            r["segmentation"] = {"size": [4, 4], "counts": "ab}, {\"image_id\": 7}, {cd"}
+        if k % 7 == 0:
+            r["extra"] = [{"a": [1, 2, {"b": "}, {"}]}, "}, {"]
+    for name, res, indent in (("clean", clean, None), ("clean_indent", clean, 1),
+                              ("nasty", nasty, None), ("nasty_indent", nasty, 1)):
+        p = str(tmp_path / ("dt_%s.json" % name))
+        json.dump(res, open(p, "w"), indent=indent)
+        monkeypatch.setenv("TA_INGEST_THREADS", "1")
+        ingest._CACHE.clear()
+        seq = ingest.load_dt(p)
+        monkeypatch.setenv("TA_INGEST_THREADS", str(threads))
+        monkeypatch.setenv("TA_INGEST_PAR_MIN_BYTES", "0")
+        ingest._CACHE.clear()
+        par = ingest.load_dt(p)
+        if name.startswith("clean"):      # guesses hold: really parsed by `threads` workers
+            assert ingest.load_lib().ta_json_last_parse_workers() == threads
+        _dt_equal(seq, par)
+        _dt_equal(par, DtColumns.from_list(json.load(open(p))))
+    ingest._CACHE.clear()
+
+
+def test_parallel_result_parse_reports_the_sequential_error(tmp_path, monkeypatch):
+    import json
+    from tao_amodal_b200 import ingest, synth
+    gt, dt = synth.generate_named("tiny")
+    res = dt.to_list()
+    del res[len(res) // 2]["score"]
+    p = str(tmp_path / "bad.json")
+    json.dump(res, open(p, "w"))
+    monkeypatch.setenv("TA_INGEST_PAR_MIN_BYTES", "0")
+    monkeypatch.setenv("TA_INGEST_THREADS", "4")
+    ingest._CACHE.clear()
+    with pytest.raises(KeyError, match="score"):
+        ingest.load_dt(p)
+    open(p, "w").write(json.dumps(dt.to_list()) + " trailing")
+    with pytest.raises(json.JSONDecodeError):
+        ingest.load_dt(p)
+    open(p, "w").write("[]")
+    assert ingest.load_dt(p).n() == 0
+    ingest._CACHE.clear()
