@@ -44,8 +44,11 @@ def _worker(rank, world, port, case, kind, q):
         acc = parallel.DistAccumulator(plan, rank, world, torch.device("cpu"))
         rows = acc.exchange_tpfp(torch.from_numpy(local.dt_tpfp.view(np.int32)))
         num_gt, num_gt_own = acc.global_num_gt(torch.from_numpy(local.num_gt))
+        # owner-side PR through the emulation of the shipped (bit-plane) kernels: padded empty
+        # categories and categories without detections included
         out = hostsim_pr(acc.n_loc, acc.cat_dt_off.numpy(), acc.acc_perm.numpy(),
-                         rows.numpy().view(np.uint32), num_gt_own.numpy(), plan.n_cfg)
+                         rows.numpy().view(np.uint32), num_gt_own.numpy(), plan.n_cfg,
+                         impl="bits_tile")
         parts = [torch.from_numpy(x) for x in (out.precision, out.recall, out.tp_cnt, out.fp_cnt)]
         C_, K = len(plan.cat_ids), plan.n_cfg
         pr, rc = torch.empty((10, 101, C_, K), dtype=torch.float64), torch.empty((10, C_, K), dtype=torch.float64)
