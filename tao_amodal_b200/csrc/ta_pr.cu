@@ -13,27 +13,29 @@
 // The category lists are cut into chunks of PR_CHUNK detections so that long categories do not
 // serialise.  Precisions are compared as exact rationals (tp, tp + fp) — rounding is monotone, so
 // the maximum of the rounded quotients is the rounded quotient of the rational maximum — and
-// only the <= 101 winners per cell are divided (ta_precision_at):
+// only the <= 101 winners per cell are divided (ta_precision_at).
+//
+// Shipped kernel set (TA_PR_IMPL=1, default):
 //   k_pr_plan      chunk table: first chunk of every category
-//   k_pr_count     per chunk: TP / FP totals of every (cfg, threshold)  (bit-sliced carry-save
-//                  counters per lane + REDUX across the warp)
-//   k_pr_scan      per category: exclusive scan of the chunk totals, tk tables, recall, counts
-//   k_pr_envelope  per chunk, one THREAD per (cfg, threshold) cell walking the chunk's
-//                  detections backwards from shared memory: running counts, suffix-maximum
-//                  precision, and the answer of every recall threshold whose tk-th true
-//                  positive lies inside the chunk
-// The DEFAULT path (TA_PR_IMPL=1) replaces count / scan / envelope / finalize by
 //   k_pr_bits      the chunk's TP/FP words are transposed ONCE (32 x 32 bit-matrix transpose
-//                  across the warp) into one 256-bit TP and FP plane per cell; chunk totals
-//                  are popcounts
-//   k_pr_tk, k_pr_scan_live   tk table (flat) and scan of the 2 n_thr live counters per cfg
+//                  across the warp) into one 256-bit TP and FP plane per (cfg, threshold) cell;
+//                  chunk totals are popcounts
+//   k_pr_tk, k_pr_scan_live   tk table (flat) and per-category exclusive scan of the 2 n_thr live
+//                  counters per cfg; recall and TP / FP totals
 //   k_pr_envelope_bits   one thread per (chunk, cell) visits only the TRUE POSITIVES of its plane
-//                  (clz / popc) instead of all 256 positions; answers go to a cell-major buffer
-//                  (sequential stores per thread)
-//   k_pr_finalize_tile   coalesced cell-major reads, shared-memory transpose, coalesced writes
+//                  (clz / popc) instead of all 256 positions: running counts, suffix-maximum
+//                  precision, and the answer of every recall level whose tk-th true positive
+//                  lies inside the chunk, stored cell-major (sequential per thread)
 //   k_pr_suffix    per cell: best precision of all later chunks, for every chunk
-//   k_pr_finalize  per precision entry: merge the in-chunk answer with the later chunks' best,
-//                  divide, write (-1 without GT, 0 for recall levels nobody reaches)
+//   k_pr_finalize_tile   merge the in-chunk answer with the later chunks' best, divide, write
+//                  (-1 without GT, 0 for recall levels nobody reaches): coalesced cell-major
+//                  reads, shared-memory transpose, coalesced writes
+// Baseline kernel set (TA_PR_IMPL=0; the A/B reference, tools/ab_variants.py):
+//   k_pr_count     chunk totals with bit-sliced carry-save counters per lane + REDUX
+//   k_pr_scan      scan of all 32 counters per cfg + the tk table
+//   k_pr_envelope  one thread per cell walking ALL positions of the chunk from shared memory,
+//                  answers scattered straight into the precision tensor
+//   k_pr_finalize  one thread per precision entry
 #include <limits.h>
 #include <stdlib.h>
 #include "ta_internal.h"
