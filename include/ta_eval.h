@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 2
+#define TA_ABI_VERSION 3
 #define TA_MAX_THRS 16   /* IoU thresholds packed as 16 TP bits + 16 FP bits per detection */
 
 typedef enum ta_status {
@@ -144,16 +144,35 @@ int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
                     uint32_t* dt_tpfp, int32_t* num_gt,
                     int32_t* dt_match_gt, uint8_t* gt_ignore_out);
 
-/* Fused frame path: box IoU + greedy assignment of every (image, category) group in ONE
- * kernel — LVISEval.compute_iou + evaluate_img (lvis_amodal/eval.py:168-303) — with the
- * group's GT boxes staged in shared memory and its IoU tile kept on chip.  Detection area
+/* Fused frame path: box IoU + greedy assignment of every (image, category) group —
+ * LVISEval.compute_iou + evaluate_img (lvis_amodal/eval.py:168-303).  Detection area
  * (the unmatched-ignore test of :281-283) is w*h of the box, as lvis_amodal/results.py:56
- * defines it.  Groups with GT and more than ta_frame_eval_max_gt() GT boxes, more than
+ * defines it.  gt_attr_a is the GT visibility.
+ *
+ * Evaluation route (no per-cell outputs requested): the (category, image)-sorted detections
+ * are cut into warp tasks at group boundaries by a SCHEDULE that depends only on the CSR
+ * offsets and dt_flag (ta_frame_sched_build, once per plan; sched = NULL builds it into
+ * context scratch on every call).  Each task's GT boxes are staged in shared memory by one
+ * bulk-async copy and every detection is evaluated by one lane; groups in which a detection
+ * reaches the lowest threshold with several GTs are redone by the general matcher.
+ * Groups with GT and more than ta_frame_eval_max_gt() GT boxes, more than
  * ta_frame_eval_max_dt() detections or more than ta_frame_eval_max_pairs() box pairs must
- * be listed in big_list: they are routed through
- * ta_box_iou + ta_match_greedy using `iou` (sized by iou_off) as their IoU storage.  With
- * write_iou != 0 every group's IoU matrix is also written to `iou`.
- * gt_attr_a is the GT visibility.  Outputs as in ta_match_greedy.                       */
+ * be listed in big_list: they are routed through ta_box_iou + ta_match_greedy using `iou`
+ * (sized by iou_off) as their IoU storage.  With write_iou != 0 every group's IoU matrix is
+ * also written to `iou` (detail route, warp-per-group kernel).
+ *
+ * Outputs as in ta_match_greedy, plus the optional COMPACT form: with dt_word != NULL,
+ * n_thr + 3 n_cfg <= 31 and no per-cell outputs, the result of detection d is the single word
+ *     dt_word[d] = M | A << n_thr | B << (n_thr + n_cfg) | U << (n_thr + 2 n_cfg)
+ * (M: thresholds at which d is matched; per cfg c: bit c of A = matched thresholds are TP,
+ * of B = matched thresholds are FP, of U = unmatched thresholds are FP), i.e. row entry c is
+ * (A_c ? M : 0) | ((B_c ? M : 0) | (U_c ? ~M : 0)) << 16; bit 31 set means "read the row
+ * dt_tpfp[d][*]" (groups that went through the general matcher).  dt_tpfp rows of all other
+ * detections are then NOT written.  ta_pr_accumulate takes the same pair.               */
+int64_t ta_frame_sched_bytes(int64_t n_groups, int64_t n_dt, int64_t n_gt);
+int ta_frame_sched_build(ta_ctx* ctx, void* stream, int64_t n_groups,
+                         const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+                         int64_t n_dt, const uint8_t* dt_flag, int64_t n_gt, void* sched);
 int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
                   const int64_t* grp_dt_off, const int64_t* grp_gt_off, const int32_t* grp_cat,
                   const double* dt_box, const double* gt_box,
@@ -162,6 +181,7 @@ int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
                   int64_t n_gt, const double* gt_attr_a, const uint8_t* gt_flag,
                   int64_t n_big, const int32_t* big_list, int32_t g_max_big,
                   const int64_t* iou_off, double* iou, int32_t write_iou,
+                  const void* sched, uint32_t* dt_word,
                   uint32_t* dt_tpfp, int32_t* num_gt,
                   int32_t* dt_match_gt, uint8_t* gt_ignore_out);
 int ta_frame_eval_max_gt(void);
@@ -171,14 +191,16 @@ int ta_frame_eval_max_pairs(void);
 /* Precision / recall accumulation.  Replaces TaoEval.accumulate (eval.py:459-584) and
  * LVISEval.accumulate (lvis_amodal/eval.py:305-426).  acc_perm lists, category by
  * category (cat_dt_off), the detection indices in stable descending-score order.
- * dt_tpfp is the [n_dt][n_cfg] output of the matchers.
+ * dt_tpfp is the [n_dt][n_cfg] output of the matchers; dt_word (optional, may be NULL) the
+ * compact per-detection words of ta_frame_eval, which take precedence over the rows unless
+ * their bit 31 is set.
  * Outputs (reference tensor layouts, -1 where the reference leaves -1):
  *   precision f64 [n_thr][n_rec][n_cat][n_cfg], recall f64 [n_thr][n_cat][n_cfg],
  *   tp_cnt / fp_cnt int64 [n_thr][n_cat][n_cfg] (may be NULL).
  * Scratch (chunk counters) lives in the context and grows on demand.                   */
 int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
                      const int32_t* acc_perm, int64_t n_dt, const uint32_t* dt_tpfp,
-                     const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                     const uint32_t* dt_word, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
                      int32_t n_rec, const double* rec_thrs,
                      double* precision, double* recall, int64_t* tp_cnt, int64_t* fp_cnt);
 

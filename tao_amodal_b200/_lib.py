@@ -28,7 +28,7 @@ EXPORTS = [
     "ta_abi_version", "ta_last_error", "ta_ctx_create", "ta_ctx_destroy", "ta_ctx_sm_count",
     "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
     "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
-    "ta_rle_iou",
+    "ta_rle_iou", "ta_frame_sched_bytes", "ta_frame_sched_build",
 ]
 
 
@@ -97,14 +97,17 @@ def load() -> C.CDLL:
                                      I64, P, P, P, I64, P, P, P, P, I32,
                                      P, P, P, P])
     lib.ta_frame_eval.argtypes = ([P, P, I64, P, P, P, P, P, I32, P, I32, P, I64, P,
-                                   I64, P, P, I64, P, I32, P, P, I32, P, P, P, P])
+                                   I64, P, P, I64, P, I32, P, P, I32, P, P, P, P, P, P])
+    lib.ta_frame_sched_bytes.argtypes = [I64, I64, I64]
+    lib.ta_frame_sched_bytes.restype = I64
+    lib.ta_frame_sched_build.argtypes = [P, P, I64, P, P, I64, P, I64, P]
     lib.ta_rle_iou.argtypes = [P, P, I64, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]
-    lib.ta_pr_accumulate.argtypes = [P, P, I32, P, P, I64, P, P, I32, I32, I32, P, P, P, P, P]
+    lib.ta_pr_accumulate.argtypes = [P, P, I32, P, P, I64, P, P, P, I32, I32, I32, P, P, P, P, P]
     lib.ta_eval_plan_host.argtypes = [P, C.POINTER(PlanHost), P, P, P, P, P,
                                       C.POINTER(I64), C.POINTER(I64)]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("ta_last_error", "ta_ctx_launch_count"):
+        if name not in ("ta_last_error", "ta_ctx_launch_count", "ta_frame_sched_bytes"):
             fn.restype = C.c_int
     _lib = lib
     return lib

@@ -144,6 +144,7 @@ __global__ void k_match_greedy(MatchArgs a) {
 #define FE_MAX_DT 128         // detections of a group handled on chip (when it has GT)
 #define FE_MAX_PAIRS 512      // IoU tile doubles per warp
 #define FE_MAX_CFG 16
+#define TA_WORD_FULL 0x80000000u   // compact result word: the full row in dt_tpfp is authoritative
 
 struct FrameRules;
 struct FrameArgs {
@@ -180,6 +181,14 @@ struct FrameArgs {
     int32_t* complex_list;        // groups that need the general matcher (route C)
     int32_t* complex_count;
     const FrameRules* rules_g;    // range-test tables built once per call by k_frame_rules
+    // streamed flat path (k_frame_flat): per-plan schedule + per-call GT words
+    int64_t n_tasks;
+    const int64_t* task_dt;       // [n_tasks + 1] first detection of every task
+    const int64_t* task_gt;       // [n_tasks + 1] first GT box of every task
+    const uint32_t* dt_desc;      // [n_dt] (GT offset inside the task's 64-box block) << 8 | G << 2 | flag
+    const uint32_t* gt_word;      // [n_gt] bit c = ignored by cfg c, bit 16 = id equals the unmatched value
+    uint32_t* gt_word_out;        // k_gt_words output (same buffer)
+    uint32_t* dt_word;            // [n_dt] compact result words (NULL: full rows in dt_tpfp)
 };
 
 // per-detection word: bits 0..15 "ignored when unmatched" per cfg, bit 16 locks its GT
@@ -362,6 +371,8 @@ k_frame_eval(FrameArgs a) {
             const int D = (int)(__shfl_sync(0xffffffffu, dt_off_r, gi + 1) - d0);
             const int cat = __shfl_sync(0xffffffffu, cat_r, gi);
             if (G > FE_MAX_GT || D > FE_MAX_DT || D * G > FE_MAX_PAIRS) continue;   // big_list route
+            if (LIST && a.dt_word)
+                for (int d = lane; d < D; d += 32) a.dt_word[d0 + d] = TA_WORD_FULL;
             __syncwarp();
             // ---- GT side: boxes to shared memory, ignore masks per cfg, non-ignored counts.
             // All global loads of the group (GT lane data, first detection per lane) are issued
@@ -609,7 +620,7 @@ __device__ __forceinline__ FlatCand fe_candidate_row(const double* __restrict__ 
 // attributes from dt_a / dt_b / gt_b / gt_hp, and groups with more than 32 GT go to the list.
 template <int NT, int NC, bool TRACK>
 __global__ void __launch_bounds__(FF_WARPS * 32, 8)
-k_frame_flat(FrameArgs a) {
+k_track_flat(FrameArgs a) {
     __shared__ ta_range_cfg cfg_s[RR_MAX];
     __shared__ double thr_s[TA_MAX_THRS];
     __shared__ FrameRules rules;
@@ -789,17 +800,354 @@ k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp) {
         }
         int cat = __shfl_sync(0xffffffffu, cat_l, gi);
         uint32_t m = cfg_all;                                  // "ignored everywhere" = counts nothing
-        if (gg < g_end && !((big_mask >> gi) & 1u))
+        if (gg < g_end && !((big_mask >> gi) & 1u)) {
+            const uint8_t gfl = a.gt_flag[gg];
             m = fe_gt_ignore_mask(rules, a.gt_vis[gg], a.gt_b ? a.gt_b[gg] : 0.0,
-                                  a.gt_hp ? a.gt_hp[gg] : 0, a.gt_flag[gg], cfg_all);
-        else
+                                  a.gt_hp ? a.gt_hp[gg] : 0, gfl, cfg_all);
+            // per-GT word of the streamed flat kernel: ignore mask + "id equals the unmatched value"
+            if (a.gt_word_out) a.gt_word_out[gg] = m | ((gfl & 4) ? (1u << 16) : 0u);
+        } else {
             cat = -1 - lane;
+        }
         const uint32_t peers = __match_any_sync(0xffffffffu, cat);
         const bool leader = (__ffs(peers) - 1) == lane;
         for (int c = 0; c < n_cfg; ++c) {
             const int tot = __reduce_add_sync(peers, (int)(!((m >> c) & 1u)));
             if (leader && cat >= 0 && tot) atomicAdd(&a.num_gt[(int64_t)cat * n_cfg + c], tot);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// streamed flat frame path: k_frame_sched (once per plan) + k_frame_flat (every evaluation)
+//
+// Same lane-per-detection scheme as k_track_flat, re-cut so that a warp never needs anything
+// another warp computed and never waits on a global load of GT data:
+//   * the (category, image)-sorted detections are cut into TASKS at group boundaries: a new task
+//     starts at the first group whose detection offset enters a new block of FS_TASK_DT
+//     detections or whose GT offset enters a new block of FS_TASK_GT boxes.  A task therefore
+//     owns whole groups (no replay of a neighbour's detections), about FS_TASK_DT detections,
+//     and GT boxes that all lie in one window of FS_TASK_GT + 32 consecutive boxes.
+//     task index of a group = dt_off / FS_TASK_DT + gt_off / FS_TASK_GT (closed form, no scan).
+//   * one warp per task.  Lane 0 fetches the task's GT window with ONE 1-D bulk copy
+//     (cp.async.bulk global -> shared, completion on an mbarrier) into a double buffer: the
+//     copy of task t+1 is in flight while task t is evaluated.
+//   * the warp walks the task's detections 32 at a time (next window's boxes prefetched into
+//     registers).  Per lane: overlap test and i, u per GT from shared memory; a pair is a
+//     candidate only if i >= (thr_min - margin) * u, which needs no division — the single exact
+//     i / u (bit-identical to pycocotools bbIou, maskApi.c:109-120) is taken once per detection
+//     for its last candidate.  "GT g* is taken at threshold k" lives in a per-task shared table
+//     (taken_s[GT]) across windows and in ballots inside a window, exactly the rule of
+//     k_track_flat: matched(d) = ge(d) & ~OR{ge(d') : d' earlier, same GT, d' locks}.
+//   * result: ONE 32-bit word per detection when n_thr + 3 n_cfg <= 31 (COMPACT):
+//       bits [0, T)            thresholds at which the detection is matched (to its only candidate)
+//       bits [T, T+C)          cfg c: matched thresholds count as TP   (GT regular, id != sentinel)
+//       bits [T+C, T+2C)       cfg c: matched thresholds count as FP   (GT id == sentinel value)
+//       bits [T+2C, T+3C)      cfg c: unmatched thresholds count as FP (else ignored)
+//       bit 31                 the detection's full row in dt_tpfp is authoritative (general matcher)
+//     which ta_pr_accumulate expands on the fly; otherwise the full [n_cfg] row as before.
+// ------------------------------------------------------------------------------------------
+#define FS_TASK_DT 256
+#define FS_TASK_GT 64
+#define FS_GT_SPAN (FS_TASK_GT + FE_MAX_GT)
+#define FS_WARPS 4
+#define FS_SKIP_G 63u
+
+struct SchedLayout {
+    int64_t n_tasks;
+    size_t o_task_dt, o_task_gt, o_desc, o_grp, total;
+};
+static SchedLayout fs_layout(int64_t n_dt, int64_t n_gt) {
+    SchedLayout L;
+    L.n_tasks = n_dt / FS_TASK_DT + n_gt / FS_TASK_GT + 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    L.o_task_dt = take((size_t)(L.n_tasks + 1) * 8);
+    L.o_task_gt = take((size_t)(L.n_tasks + 1) * 8);
+    L.o_desc = take((size_t)(n_dt > 0 ? n_dt : 1) * 4);
+    L.o_grp = take((size_t)(n_dt > 0 ? n_dt : 1) * 4);
+    L.total = off;
+    return L;
+}
+
+// Per 32 consecutive groups (one warp): task table entries of the groups that open a task,
+// and per detection the descriptor word + group index (coalesced over the groups' contiguous
+// detections; the group of a detection is found by a 5-step search over the 33 offsets held
+// one per lane).
+__global__ void __launch_bounds__(256)
+k_frame_sched(int64_t n_groups, const int64_t* __restrict__ grp_dt_off,
+              const int64_t* __restrict__ grp_gt_off, const uint8_t* __restrict__ dt_flag,
+              int64_t n_tasks, int64_t* __restrict__ task_dt, int64_t* __restrict__ task_gt,
+              uint32_t* __restrict__ dt_desc, int32_t* __restrict__ dt_grp) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t grp0 = wid * 32;
+    if (grp0 >= n_groups) return;
+    const int n_in = (int)((grp0 + 32 < n_groups) ? 32 : n_groups - grp0);
+    const int li = lane < n_in ? lane : n_in;
+    const int64_t doff = grp_dt_off[grp0 + li], goff = grp_gt_off[grp0 + li];
+    const int64_t d_end = grp_dt_off[grp0 + n_in], g_end = grp_gt_off[grp0 + n_in];
+    if (lane < n_in) {
+        const int64_t g = grp0 + lane;
+        const int64_t idx = doff / FS_TASK_DT + goff / FS_TASK_GT;
+        int64_t prev = -1;
+        if (g > 0) prev = grp_dt_off[g - 1] / FS_TASK_DT + grp_gt_off[g - 1] / FS_TASK_GT;
+        for (int64_t i = prev + 1; i <= idx; ++i) { task_dt[i] = doff; task_gt[i] = goff; }
+        if (g == n_groups - 1) {
+            const int64_t de = grp_dt_off[n_groups], ge = grp_gt_off[n_groups];
+            for (int64_t i = idx + 1; i <= n_tasks; ++i) { task_dt[i] = de; task_gt[i] = ge; }
+        }
+    }
+    const int64_t gn = __shfl_down_sync(0xffffffffu, goff, 1);
+    const int64_t G_l = (lane + 1 < n_in ? gn : g_end) - goff;
+    const int64_t d_begin = __shfl_sync(0xffffffffu, doff, 0);
+    for (int64_t base = d_begin; base < d_end; base += 32) {
+        const int64_t dd = base + lane;
+        int gi = 0;
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+            const int cnd = gi + step;
+            const int64_t v = __shfl_sync(0xffffffffu, doff, cnd & 31);
+            if (cnd < n_in && v <= dd) gi = cnd;
+        }
+        const int64_t go = __shfl_sync(0xffffffffu, goff, gi);
+        const int64_t Gg = __shfl_sync(0xffffffffu, G_l, gi);
+        if (dd < d_end) {
+            const uint32_t Gf = Gg > FE_MAX_GT ? FS_SKIP_G : (uint32_t)Gg;
+            dt_desc[dd] = ((uint32_t)(go & (FS_TASK_GT - 1)) << 8) | (Gf << 2) | (dt_flag[dd] & 3u);
+            dt_grp[dd] = (int32_t)(grp0 + gi);
+        }
+    }
+}
+
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) --------------------------
+__device__ __forceinline__ uint32_t fs_smem(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void fs_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fs_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void fs_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fs_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fs_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
+// the detection-side rule tables the flat kernel needs (area intervals of the unmatched-ignore
+// test; the b attribute of a frame detection is the constant 0)
+struct FlatRules {
+    int n_da;
+    uint32_t const_mask;          // cfgs whose dt_b interval excludes 0
+    double lo[RR_MAX], hi[RR_MAX];
+    uint32_t mask[RR_MAX];
+};
+
+template <int NT, int NC, bool COMPACT>
+__global__ void __launch_bounds__(FS_WARPS * 32, 8)
+k_frame_flat(FrameArgs a) {
+    __shared__ __align__(128) double gt_s[FS_WARPS][2][FS_GT_SPAN * 4];
+    __shared__ uint32_t taken_s[FS_WARPS][FS_GT_SPAN];
+    __shared__ __align__(8) unsigned long long bar_s[FS_WARPS][2];
+    __shared__ double thr_s[TA_MAX_THRS];
+    __shared__ FlatRules fr;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_thr = NT ? NT : a.n_thr, n_cfg = NC ? NC : a.n_cfg;
+    if (threadIdx.x < n_thr) {
+        const double th = a.thrs[threadIdx.x];
+        thr_s[threadIdx.x] = (th < 1.0 - 1e-10) ? th : 1.0 - 1e-10;
+    }
+    if (threadIdx.x == 32) {
+        const FrameRules* r = a.rules_g;
+        fr.n_da = r->n_da;
+        uint32_t cm = 0;
+        for (int k = 0; k < r->n_db; ++k)
+            if (0.0 < r->db_lo[k] || 0.0 > r->db_hi[k]) cm |= r->db_mask[k];
+        fr.const_mask = cm;
+        for (int k = 0; k < r->n_da; ++k) { fr.lo[k] = r->da_lo[k]; fr.hi[k] = r->da_hi[k]; fr.mask[k] = r->da_mask[k]; }
+    }
+    const uint32_t bar0 = fs_smem(&bar_s[warp][0]), bar1 = fs_smem(&bar_s[warp][1]);
+    if (lane == 0) {
+        fs_mbar_init(bar0, 1);
+        fs_mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const uint32_t cfg_all = (n_cfg == 32) ? 0xffffffffu : ((1u << n_cfg) - 1u);
+    const uint32_t thr_all = (1u << n_thr) - 1u;
+    const uint32_t lanes_lt = (1u << lane) - 1u;
+    double thr_min = thr_s[0];
+    for (int i = 1; i < n_thr; ++i) thr_min = (thr_s[i] < thr_min) ? thr_s[i] : thr_min;
+    // candidate filter: i < lo * u  =>  fl(i / u) < thr_min  (lo sits 2^-20 relative below thr_min,
+    // the rounding errors of lo * u and i / u are 2^-53); thresholds <= 0 (or NaN) make every
+    // pair a candidate, as in the reference's `iou < best` test
+    const bool always = !(thr_min > 0.0);
+    const double lo = thr_min * (1.0 - 1.0 / 1048576.0);
+    uint32_t* taken_w = taken_s[warp];
+
+    const int64_t n_tasks = a.n_tasks;
+    const int64_t w0 = (int64_t)blockIdx.x * FS_WARPS + warp;
+    const int64_t wstride = (int64_t)gridDim.x * FS_WARPS;
+
+    // GT window of a task: boxes [task_gt[t] & ~63, task_gt[t + 1]), at most FS_GT_SPAN of them
+    // (beyond that only oversize groups, which this kernel skips)
+    auto issue = [&](int64_t t, int buf) {
+        const int64_t g_lo = a.task_gt[t] & ~(int64_t)(FS_TASK_GT - 1);
+        int64_t n = a.task_gt[t + 1] - g_lo;
+        if (n > FS_GT_SPAN) n = FS_GT_SPAN;
+        const uint32_t bar = buf ? bar1 : bar0;
+        if (n > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            fs_mbar_expect_tx(bar, (uint32_t)n * 32u);
+            fs_bulk_g2s(fs_smem(&gt_s[warp][buf][0]), a.gt_box + 4 * g_lo, (uint32_t)n * 32u, bar);
+        } else {
+            fs_mbar_arrive(bar);
+        }
+    };
+
+    if (w0 < n_tasks && lane == 0) issue(w0, 0);
+    int it = 0;
+    for (int64_t t = w0; t < n_tasks; t += wstride, ++it) {
+        const int cur = it & 1;
+        if (t + wstride < n_tasks && lane == 0) issue(t + wstride, cur ^ 1);
+        const int64_t d_begin = a.task_dt[t], d_end = a.task_dt[t + 1];
+        const int64_t g_base = a.task_gt[t] & ~(int64_t)(FS_TASK_GT - 1);
+        for (int i = lane; i < FS_GT_SPAN; i += 32) taken_w[i] = 0u;
+        // first window's detections
+        double2 dp = make_double2(0, 0), dq = make_double2(0, 0);
+        uint32_t desc = 0;
+        if (d_begin + lane < d_end) {
+            dp = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d_begin + lane));
+            dq = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d_begin + lane) + 2);
+            desc = a.dt_desc[d_begin + lane];
+        }
+        fs_mbar_wait(cur ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+        const double* gt_cur = gt_s[warp][cur];
+        for (int64_t base = d_begin; base < d_end; base += 32) {
+            const int64_t d = base + lane;
+            const bool valid = d < d_end;
+            // next window's loads are in flight while this one is evaluated
+            double2 pn = make_double2(0, 0), qn = make_double2(0, 0);
+            uint32_t descn = 0;
+            if (d + 32 < d_end) {
+                pn = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d + 32));
+                qn = *reinterpret_cast<const double2*>(a.dt_box + 4 * (d + 32) + 2);
+                descn = a.dt_desc[d + 32];
+            }
+            const uint32_t G = (desc >> 2) & 63u, rel = desc >> 8, dfl = desc & 3u;
+            const bool skip = G == FS_SKIP_G;
+            const bool work = valid && !skip && G > 0u;
+            const double da = dq.x * dq.y;
+            const double r0 = dq.x + dp.x, b0 = dq.y + dp.y;
+            int cnt = 0;
+            uint32_t gs = 0;
+            double ci = 0.0, cu = 1.0;
+            const int Gm = __reduce_max_sync(0xffffffffu, work ? (int)G : 0);
+            uint32_t M = 0;
+            __syncwarp();                      // taken_w updates of the previous window are visible
+            if (Gm > 0) {
+                const double* gb = gt_cur + 4 * rel;
+                for (int j = 0; j < Gm; ++j) {
+                    if (work && j < (int)G) {
+                        const double2 p = *reinterpret_cast<const double2*>(gb + 4 * j);
+                        const double2 q = *reinterpret_cast<const double2*>(gb + 4 * j + 2);
+                        // maskApi.c:109-120 without the division
+                        const double ga = q.x * q.y;
+                        const double r1 = q.x + p.x, b1 = q.y + p.y;
+                        const double w = ((r0 < r1) ? r0 : r1) - ((dp.x > p.x) ? dp.x : p.x);
+                        const double h = ((b0 < b1) ? b0 : b1) - ((dp.y > p.y) ? dp.y : p.y);
+                        const bool ov = !(w <= 0.0) && !(h <= 0.0);
+                        const double ii = w * h;
+                        const double uu = da + ga - ii;
+                        const uint32_t ex = ((uint32_t)__double2hiint(uu) >> 20) & 0x7ffu;
+                        const bool mb = always || (ov && (!(ii < lo * uu) || (ex - 200u) > 1600u));
+                        if (mb) { ++cnt; gs = (uint32_t)j; ci = ov ? ii : 0.0; cu = ov ? uu : 1.0; }
+                    }
+                }
+                uint32_t ge = 0;
+                if (cnt == 1) {
+                    const double v = ci / cu;
+                    if (v < thr_min) cnt = 0;
+                    else
+                        for (int k = 0; k < n_thr; ++k) ge |= (!(v < thr_s[k])) ? (1u << k) : 0u;
+                }
+                if (cnt > 1) {
+                    const int grp = a.dt_grp[d];
+                    if (atomicExch(&a.grp_flag[grp], 1) == 0)
+                        a.complex_list[atomicAdd(a.complex_count, 1)] = grp;
+                }
+                const bool single = cnt == 1;
+                const bool locks = single && (dfl & 2u);
+                const uint32_t gidx = rel + gs;                // GT position inside the task window
+                const uint32_t key = single ? gidx : (0x100u | (uint32_t)lane);
+                if (__any_sync(0xffffffffu, single)) {
+                    const uint32_t same = __match_any_sync(0xffffffffu, key);
+                    const uint32_t earlier = same & lanes_lt;
+                    uint32_t taken = single ? taken_w[gidx] : 0u;
+                    for (int k = 0; k < n_thr; ++k) {
+                        const uint32_t bk = __ballot_sync(0xffffffffu, locks && ((ge >> k) & 1u));
+                        if (bk & earlier) taken |= 1u << k;
+                    }
+                    __syncwarp();              // every lane has read taken_w
+                    if (locks) atomicOr(&taken_w[gidx], ge);
+                    M = single ? (ge & ~taken) : 0u;
+                }
+            }
+            // ---- result
+            if (valid) {
+                uint32_t dm = ((dfl & 1u) ? cfg_all : 0u) | fr.const_mask;
+                for (int k = 0; k < fr.n_da; ++k)
+                    if (da < fr.lo[k] || da > fr.hi[k]) dm |= fr.mask[k];
+                uint32_t gmask = 0;
+                bool sent = false;
+                if (M) {
+                    const uint32_t gw = a.gt_word[g_base + rel + gs];
+                    gmask = gw & 0xffffu;
+                    sent = (gw >> 16) & 1u;
+                }
+                if (COMPACT) {
+                    uint32_t word;
+                    if (skip || cnt > 1) {
+                        word = TA_WORD_FULL;
+                    } else {
+                        const uint32_t nig = ~gmask & cfg_all, ndc = ~dm & cfg_all;
+                        const uint32_t A = (M && !sent) ? nig : 0u;
+                        const uint32_t B = (M && sent) ? (nig & ndc) : 0u;
+                        word = M | (A << n_thr) | (B << (n_thr + n_cfg)) | (ndc << (n_thr + 2 * n_cfg));
+                    }
+                    a.dt_word[d] = word;
+                } else if (!skip) {
+                    uint32_t* o = a.dt_tpfp + d * n_cfg;
+                    for (int cf = 0; cf < n_cfg; ++cf) {
+                        const bool gi = (gmask >> cf) & 1u, dc = (dm >> cf) & 1u;
+                        const uint32_t tp = (!sent && !gi) ? M : 0u;
+                        const uint32_t fp = ((sent && !gi && !dc) ? M : 0u) | (dc ? 0u : (thr_all & ~M));
+                        o[cf] = tp | (fp << 16);
+                    }
+                }
+            }
+            dp = pn; dq = qn; desc = descn;
+        }
+        __syncwarp();                          // buffer `cur` and taken_w fully consumed
     }
 }
 
@@ -879,7 +1227,7 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
         int64_t blocks = ((n_dt + 31) / 32 + FF_WARPS - 1) / FF_WARPS;
         const int64_t fcap = (int64_t)ctx->sm_count * 16;
         if (blocks > fcap) blocks = fcap;
-        k_frame_flat<0, 0, true><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(f);
+        k_track_flat<0, 0, true><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(f);
         if ((rc = ta_check_launch(ctx, "k_track_flat"))) return rc;
         a.dev_list = f.complex_list;
         a.dev_count = f.complex_count;
@@ -893,14 +1241,50 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
     return ta_check_launch(ctx, "k_match_greedy");
 }
 
-// dt area for the big-group route of the frame path: w*h of the box (lvis results.py:56)
+// dt area for the big-group route of the frame path: w*h of the box (lvis results.py:56);
+// with compact result words the detections of these groups point to their full rows
 __global__ void k_box_area_list(int64_t n_list, const int32_t* __restrict__ grp_list,
                                 const int64_t* __restrict__ grp_dt_off,
-                                const double* __restrict__ dt_box, double* __restrict__ area) {
+                                const double* __restrict__ dt_box, double* __restrict__ area,
+                                uint32_t* __restrict__ dt_word) {
     const int64_t grp = grp_list[blockIdx.x];
     const int64_t d0 = grp_dt_off[grp], d1 = grp_dt_off[grp + 1];
-    for (int64_t d = d0 + threadIdx.x; d < d1; d += blockDim.x)
+    for (int64_t d = d0 + threadIdx.x; d < d1; d += blockDim.x) {
         area[d] = dt_box[4 * d + 2] * dt_box[4 * d + 3];
+        if (dt_word) dt_word[d] = TA_WORD_FULL;
+    }
+}
+
+extern "C" int64_t ta_frame_sched_bytes(int64_t n_groups, int64_t n_dt, int64_t n_gt) {
+    (void)n_groups;
+    if (n_dt < 0 || n_gt < 0) return 0;
+    return (int64_t)fs_layout(n_dt, n_gt).total;
+}
+
+static int fs_build(ta_ctx* ctx, cudaStream_t st, int64_t n_groups, const int64_t* grp_dt_off,
+                    const int64_t* grp_gt_off, int64_t n_dt, const uint8_t* dt_flag, int64_t n_gt,
+                    void* sched) {
+    const SchedLayout L = fs_layout(n_dt, n_gt);
+    char* b = static_cast<char*>(sched);
+    const int64_t warps = (n_groups + 31) / 32;
+    k_frame_sched<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
+        n_groups, grp_dt_off, grp_gt_off, dt_flag, L.n_tasks,
+        reinterpret_cast<int64_t*>(b + L.o_task_dt), reinterpret_cast<int64_t*>(b + L.o_task_gt),
+        reinterpret_cast<uint32_t*>(b + L.o_desc), reinterpret_cast<int32_t*>(b + L.o_grp));
+    return ta_check_launch(ctx, "k_frame_sched");
+}
+
+extern "C" int ta_frame_sched_build(ta_ctx* ctx, void* stream, int64_t n_groups,
+                                    const int64_t* grp_dt_off, const int64_t* grp_gt_off,
+                                    int64_t n_dt, const uint8_t* dt_flag, int64_t n_gt, void* sched) {
+    if (!ctx || !sched) return ta_set_err(TA_ERR_INVALID, "ta_frame_sched_build: NULL argument");
+    if (n_groups < 0 || n_dt < 0 || n_gt < 0)
+        return ta_set_err(TA_ERR_INVALID, "ta_frame_sched_build: negative size");
+    if (n_groups > INT_MAX) return ta_set_err(TA_ERR_TOO_LARGE, "ta_frame_sched_build: too many groups");
+    if (n_groups == 0) return TA_OK;
+    TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
+    return fs_build(ctx, (cudaStream_t)stream, n_groups, grp_dt_off, grp_gt_off, n_dt, dt_flag, n_gt, sched);
 }
 
 extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
@@ -911,6 +1295,7 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
                              int64_t n_gt, const double* gt_attr_a, const uint8_t* gt_flag,
                              int64_t n_big, const int32_t* big_list, int32_t g_max_big,
                              const int64_t* iou_off, double* iou, int32_t write_iou,
+                             const void* sched, uint32_t* dt_word,
                              uint32_t* dt_tpfp, int32_t* num_gt,
                              int32_t* dt_match_gt, uint8_t* gt_ignore_out) {
     if (!ctx) return ta_set_err(TA_ERR_INVALID, "ta_frame_eval: ctx is NULL");
@@ -921,6 +1306,7 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     if ((write_iou || n_big > 0) && (!iou || !iou_off))
         return ta_set_err(TA_ERR_INVALID, "ta_frame_eval: iou storage required");
     if (n_groups == 0) return TA_OK;
+    if (n_groups > INT_MAX) return ta_set_err(TA_ERR_TOO_LARGE, "ta_frame_eval: too many groups");
     TA_CUDA(cudaSetDevice(ctx->device));
     ta_begin(ctx, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
@@ -929,14 +1315,20 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
                 dt_tpfp, num_gt, dt_match_gt, gt_ignore_out,
                 nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int64_t cap = (int64_t)ctx->sm_count * 8;      // persistent: 8 CTAs per SM
+    const bool detail = write_iou || dt_match_gt || gt_ignore_out;
+    // compact result words: only the evaluation route, and only when a word holds T + 3 C bits
+    const bool compact = !detail && dt_word != nullptr && n_thr + 3 * n_cfg <= 31;
     int rc;
-    // scratch (slot 1): rule tables, detection -> group map, complex-group flags / list
+    // scratch (slot 1): rule tables, per-GT words, complex-group flags / list, and the schedule
+    // when the caller did not build one (ta_frame_sched_build)
+    const SchedLayout L = fs_layout(n_dt, n_gt);
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_rules = take(sizeof(FrameRules));
-    const size_t o_grp = take((size_t)(n_dt > 0 ? n_dt : 1) * 4);
+    const size_t o_gtw = take((size_t)(n_gt > 0 ? n_gt : 1) * 4);
     const size_t o_flag = take((size_t)n_groups * 4 + 4);      // flags + the list counter
     const size_t o_list = take((size_t)n_groups * 4);
+    const size_t o_sched = take((detail || sched) ? 0 : L.total);
     void* ws2 = nullptr;
     if ((rc = ta_workspace(ctx, st, off, &ws2, 1))) return rc;
     char* base = static_cast<char*>(ws2);
@@ -944,7 +1336,7 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     k_frame_rules<<<1, 32, 0, st>>>(cfgs, n_cfg, rules_g);
     if ((rc = ta_check_launch(ctx, "k_frame_rules"))) return rc;
     a.rules_g = rules_g;
-    if (write_iou || dt_match_gt || gt_ignore_out) {
+    if (detail) {
         // detail outputs: the warp-per-group kernel does everything
         const int64_t n_tasks = (n_groups + FE_RUN - 1) / FE_RUN;
         int64_t blocks = (n_tasks + FE_WARPS - 1) / FE_WARPS;
@@ -952,10 +1344,25 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
         k_frame_eval<true, 0, 0, false><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
         rc = ta_check_launch(ctx, "k_frame_eval");
     } else {
-        // evaluation path: lane-per-detection kernel, GT counts, then the general matcher on the
-        // (few) groups whose detections have several candidate GTs
-        int32_t* dt_grp = reinterpret_cast<int32_t*>(base + o_grp);
-        a.dt_grp = dt_grp;
+        // evaluation path: GT counts + per-GT words, the streamed lane-per-detection kernel, then
+        // the general matcher on the (few) groups whose detections have several candidate GTs
+        if (!sched && n_dt > 0) {
+            if ((rc = fs_build(ctx, st, n_groups, grp_dt_off, grp_gt_off, n_dt, dt_flag, n_gt,
+                               base + o_sched)))
+                return rc;
+            sched = base + o_sched;
+        }
+        const char* sb = static_cast<const char*>(sched);
+        a.n_tasks = L.n_tasks;
+        if (sb) {
+            a.task_dt = reinterpret_cast<const int64_t*>(sb + L.o_task_dt);
+            a.task_gt = reinterpret_cast<const int64_t*>(sb + L.o_task_gt);
+            a.dt_desc = reinterpret_cast<const uint32_t*>(sb + L.o_desc);
+            a.dt_grp = reinterpret_cast<const int32_t*>(sb + L.o_grp);
+        }
+        a.gt_word_out = reinterpret_cast<uint32_t*>(base + o_gtw);
+        a.gt_word = a.gt_word_out;
+        a.dt_word = compact ? dt_word : nullptr;
         a.grp_flag = reinterpret_cast<int32_t*>(base + o_flag);
         a.complex_count = a.grp_flag + n_groups;
         a.complex_list = reinterpret_cast<int32_t*>(base + o_list);
@@ -964,16 +1371,19 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
         {
             const int64_t prep_warps = (n_groups + 31) / 32;
             const unsigned pb = (unsigned)((prep_warps + 7) / 8);
-            if (spec) k_frame_prep<6><<<pb, 256, 0, st>>>(a, n_dt > 0 ? dt_grp : nullptr);
-            else k_frame_prep<0><<<pb, 256, 0, st>>>(a, n_dt > 0 ? dt_grp : nullptr);
+            if (spec) k_frame_prep<6><<<pb, 256, 0, st>>>(a, nullptr);
+            else k_frame_prep<0><<<pb, 256, 0, st>>>(a, nullptr);
             if ((rc = ta_check_launch(ctx, "k_frame_prep"))) return rc;
         }
         if (n_dt > 0) {
-            int64_t blocks = ((n_dt + 31) / 32 + FF_WARPS - 1) / FF_WARPS;
-            const int64_t fcap = (int64_t)ctx->sm_count * 16;
+            int64_t blocks = (L.n_tasks + FS_WARPS - 1) / FS_WARPS;
+            const int64_t fcap = (int64_t)ctx->sm_count * 8;
             if (blocks > fcap) blocks = fcap;
-            if (spec) k_frame_flat<10, 6, false><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
-            else k_frame_flat<0, 0, false><<<(unsigned)blocks, FF_WARPS * 32, 0, st>>>(a);
+            const unsigned nb = (unsigned)blocks, nt = FS_WARPS * 32;
+            if (spec && compact) k_frame_flat<10, 6, true><<<nb, nt, 0, st>>>(a);
+            else if (spec) k_frame_flat<10, 6, false><<<nb, nt, 0, st>>>(a);
+            else if (compact) k_frame_flat<0, 0, true><<<nb, nt, 0, st>>>(a);
+            else k_frame_flat<0, 0, false><<<nb, nt, 0, st>>>(a);
             if ((rc = ta_check_launch(ctx, "k_frame_flat"))) return rc;
         }
         if (n_dt > 0) {
@@ -988,7 +1398,8 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     void* ws = nullptr;
     rc = ta_workspace(ctx, st, (size_t)n_dt * sizeof(double), &ws);
     if (rc) return rc;
-    k_box_area_list<<<(unsigned)n_big, 128, 0, st>>>(n_big, big_list, grp_dt_off, dt_box, (double*)ws);
+    k_box_area_list<<<(unsigned)n_big, 128, 0, st>>>(n_big, big_list, grp_dt_off, dt_box, (double*)ws,
+                                                       compact ? dt_word : nullptr);
     rc = ta_check_launch(ctx, "k_box_area_list");
     if (rc) return rc;
     rc = ta_box_iou(ctx, stream, n_groups, big_list, n_big, grp_dt_off, grp_gt_off, dt_box, gt_box,

@@ -115,10 +115,11 @@ extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
         const int64_t n_iou = pl->iou_off[G];
         const size_t n_cell = (size_t)pl->n_thr * pl->n_cat * pl->n_cfg;
         const size_t n_prec = n_cell * pl->n_rec;
-        void *d_iou, *d_tpfp, *d_numgt, *d_prec, *d_rec, *d_tp, *d_fp;
+        void *d_iou, *d_tpfp, *d_numgt, *d_prec, *d_rec, *d_tp, *d_fp, *d_word = nullptr;
         // the frame path keeps IoU tiles on chip; only oversize groups use the global buffer
         TA_CUDA(ar.alloc(&d_iou, (track || pl->n_big > 0) ? (size_t)n_iou * 8 : 16));
         TA_CUDA(ar.alloc(&d_tpfp, (size_t)pl->n_cfg * pl->n_dt * 4));
+        if (!track) TA_CUDA(ar.alloc(&d_word, (size_t)pl->n_dt * 4));
         TA_CUDA(ar.alloc(&d_numgt, (size_t)pl->n_cat * pl->n_cfg * 4));
         TA_CUDA(ar.alloc(&d_prec, n_prec * 8));
         TA_CUDA(ar.alloc(&d_rec, n_cell * 8));
@@ -140,11 +141,13 @@ extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
             rc = ta_frame_eval(ctx, st, G, grp_dt_off, grp_gt_off, grp_cat, dt_box, gt_box,
                                pl->n_thr, thrs, pl->n_cfg, cfgs, pl->n_dt, dt_flag, pl->n_gt, gt_a,
                                gt_flag, pl->n_big, big_list, pl->g_max, iou_off, (double*)d_iou, 0,
-                               (uint32_t*)d_tpfp, (int32_t*)d_numgt, nullptr, nullptr);
+                               nullptr, (uint32_t*)d_word, (uint32_t*)d_tpfp, (int32_t*)d_numgt,
+                               nullptr, nullptr);
         }
         if (rc == TA_OK)
             rc = ta_pr_accumulate(ctx, st, pl->n_cat, cat_dt_off, acc_perm, pl->n_dt,
-                                  (const uint32_t*)d_tpfp, (const int32_t*)d_numgt, pl->n_thr,
+                                  (const uint32_t*)d_tpfp, (const uint32_t*)d_word,
+                                  (const int32_t*)d_numgt, pl->n_thr,
                                   pl->n_cfg, pl->n_rec, recs, (double*)d_prec, (double*)d_rec,
                                   (int64_t*)d_tp, (int64_t*)d_fp);
         int64_t d2h = 0;

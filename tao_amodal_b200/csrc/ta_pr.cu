@@ -50,6 +50,8 @@ struct PrArgs {
     const int64_t* cat_dt_off;
     const int32_t* acc_perm;
     const uint32_t* dt_tpfp;     // [n_dt][n_cfg]
+    const uint32_t* dt_word;     // [n_dt] compact result words of ta_frame_eval (or NULL): bit 31
+                                 // set = use the detection's row in dt_tpfp
     const int32_t* num_gt;       // [n_cat][n_cfg]
     const double* rec_thrs;
     // scratch
@@ -76,6 +78,24 @@ struct PrArgs {
 };
 
 #define PR_MAX_CAT_DT (1 << 24)  // detections per category (packed candidates: 24-bit counts)
+
+// TP/FP word of (detection idx, cfg): the row entry, or the expansion of the compact word
+// (layout: ta_match.cu, k_frame_flat): M | A << T | B << (T + C) | Cu << (T + 2 C).
+__device__ __forceinline__ uint32_t pr_expand(uint32_t w, int cfg, int n_thr, int n_cfg) {
+    const uint32_t thr_all = (1u << n_thr) - 1u;
+    const uint32_t M = w & thr_all;
+    const uint32_t s = w >> (n_thr + cfg);
+    const uint32_t tp = (s & 1u) ? M : 0u;
+    const uint32_t fp = (((s >> n_cfg) & 1u) ? M : 0u) | (((s >> (2 * n_cfg)) & 1u) ? (thr_all & ~M) : 0u);
+    return tp | (fp << 16);
+}
+__device__ __forceinline__ uint32_t pr_word(const PrArgs& a, int64_t idx, int cfg) {
+    if (a.dt_word) {
+        const uint32_t w = a.dt_word[idx];
+        if (!(w >> 31)) return pr_expand(w, cfg, a.n_thr, a.n_cfg);
+    }
+    return a.dt_tpfp[idx * a.n_cfg + cfg];
+}
 
 __global__ void __launch_bounds__(1024)
 k_pr_plan(PrArgs a) {
@@ -148,7 +168,7 @@ k_pr_count(PrArgs a) {
         for (int u = 0; u < PR_CHUNK / 32; ++u) {
             const int p = u * 32 + lane;               // coalesced permutation reads
             uint32_t w = 0;
-            if (p < n_pos) w = a.dt_tpfp[(int64_t)a.acc_perm[p0 + p] * a.n_cfg + cfg];
+            if (p < n_pos) w = pr_word(a, (int64_t)a.acc_perm[p0 + p], cfg);
             const uint32_t k0 = c0 & w;  c0 ^= w;
             const uint32_t k1 = c1 & k0; c1 ^= k0;
             const uint32_t k2 = c2 & k1; c2 ^= k1;
@@ -235,7 +255,7 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
     // ---- stage the chunk's TP/FP words (rows gathered through the score permutation) and tk
     for (int i = threadIdx.x; i < n_pos * ncf; i += blockDim.x) {
         const int p = i / ncf, c = i - p * ncf;
-        words[p * ncf + c] = a.dt_tpfp[(int64_t)a.acc_perm[p0 + p] * a.n_cfg + cfg0 + c];
+        words[p * ncf + c] = pr_word(a, (int64_t)a.acc_perm[p0 + p], cfg0 + c);
     }
     for (int i = threadIdx.x; i < ncf * a.n_rec; i += blockDim.x)
         tk_s[i] = a.tk[((int64_t)cat * a.n_cfg + cfg0) * a.n_rec + i];
@@ -307,7 +327,11 @@ k_pr_bits(PrArgs a) {
     if (threadIdx.x == 0) a.chunk_cat[chunk] = cat;
     const int p = threadIdx.x;
     const bool live = p < n_pos;
-    const uint32_t* row = a.dt_tpfp + (live ? (int64_t)a.acc_perm[p0 + p] * a.n_cfg : 0);
+    const int64_t didx = live ? (int64_t)a.acc_perm[p0 + p] : 0;
+    const uint32_t* row = a.dt_tpfp + didx * a.n_cfg;
+    // compact word (ta_frame_eval): expanded per cfg in registers, 4 B instead of 4 n_cfg B read
+    const uint32_t cw = (a.dt_word && live) ? a.dt_word[didx] : 0x80000000u;
+    const bool full = (cw >> 31) != 0;
     const int b = lane & 15;
     uint32_t* dst = plane_s + ((lane >> 4) * TA_PR_WORDS + warp) * n_cells + b;
     uint32_t keep[5], rot[5];
@@ -315,7 +339,8 @@ k_pr_bits(PrArgs a) {
     for (int s = 0; s < 5; ++s) pr_transpose_consts(lane, 16 >> s, keep[s], rot[s]);
 #pragma unroll 2
     for (int cfg = 0; cfg < a.n_cfg; ++cfg) {
-        uint32_t x = live ? row[cfg] : 0u;
+        uint32_t x = 0u;
+        if (live) x = full ? row[cfg] : pr_expand(cw, cfg, a.n_thr, a.n_cfg);
 #pragma unroll
         for (int s = 0; s < 5; ++s)
             x = pr_transpose_apply(x, __shfl_xor_sync(0xffffffffu, x, 16 >> s), keep[s], rot[s]);
@@ -553,7 +578,7 @@ static int ta_pr_impl() {
 
 extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* cat_dt_off,
                                 const int32_t* acc_perm, int64_t n_dt, const uint32_t* dt_tpfp,
-                                const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                                const uint32_t* dt_word, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
                                 int32_t n_rec, const double* rec_thrs,
                                 double* precision, double* recall, int64_t* tp_cnt, int64_t* fp_cnt) {
     if (!ctx) return ta_set_err(TA_ERR_INVALID, "ta_pr_accumulate: ctx is NULL");
@@ -591,6 +616,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     a.n_cat = n_cat; a.n_thr = n_thr; a.n_cfg = n_cfg; a.n_rec = n_rec; a.n_dt = n_dt;
     a.n_chunks_ub = n_chunks_ub;
     a.cat_dt_off = cat_dt_off; a.acc_perm = acc_perm; a.dt_tpfp = dt_tpfp; a.num_gt = num_gt;
+    a.dt_word = (dt_word && n_thr + 3 * n_cfg <= 31) ? dt_word : nullptr;
     a.rec_thrs = rec_thrs;
     a.chunk_start = reinterpret_cast<int32_t*>(base + o_start);
     a.chunk_cnt = reinterpret_cast<uint32_t*>(base + o_cnt);

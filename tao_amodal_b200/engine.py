@@ -89,6 +89,24 @@ def lossless_f32_boxes(plan: EvalPlan):
     return got
 
 
+def expand_words(dt_word: np.ndarray, dt_tpfp: np.ndarray, n_thr: int, n_cfg: int) -> np.ndarray:
+    """Full [n_dt, n_cfg] TP/FP rows from the compact result words of ta_frame_eval
+    (include/ta_eval.h): rows of detections whose word has bit 31 set are taken from dt_tpfp."""
+    w = dt_word.view(np.uint32).astype(np.uint32)
+    thr_all = np.uint32((1 << n_thr) - 1)
+    M = (w & thr_all)[:, None]
+    c = np.arange(n_cfg, dtype=np.uint32)[None, :]
+    A = (w[:, None] >> (n_thr + c)) & 1
+    B = (w[:, None] >> (n_thr + n_cfg + c)) & 1
+    U = (w[:, None] >> (n_thr + 2 * n_cfg + c)) & 1
+    tp = np.where(A == 1, M, 0)
+    fp = np.where(B == 1, M, 0) | np.where(U == 1, thr_all & ~M, 0)
+    rows = (tp | (fp << 16)).astype(np.uint32)
+    full = (w >> 31) == 1
+    rows[full] = dt_tpfp.view(np.uint32).reshape(-1, n_cfg)[full]
+    return rows
+
+
 def _ptr(a: Optional[np.ndarray]):
     if a is None:
         return None
@@ -101,7 +119,7 @@ class Engine:
 
     def __init__(self, device: int = 0):
         self.lib = _lib.load()
-        if self.lib.ta_abi_version() != 2:
+        if self.lib.ta_abi_version() != 3:
             raise RuntimeError("libta_eval.so ABI version mismatch")
         self.device = int(device)
         h = C.c_void_p()
@@ -276,6 +294,7 @@ class Engine:
         if detail:
             dev.ensure_detail()
         p = dev.ptr
+        dev.words_valid = False
         _lib.check(self.lib.ta_match_greedy(
             self._ctx, st, plan.n_groups, None, 0, p["grp_dt_off"], p["grp_gt_off"], p["grp_cat"],
             p["iou_off"], p["iou"], dev.n_thr, p["iou_thrs"], plan.n_cfg, p["cfgs"],
@@ -286,7 +305,8 @@ class Engine:
 
     def stage_frame_eval(self, dev: "DevicePlan", detail: bool = False):
         """Fused frame path: LVISEval.compute_iou + evaluate_img in one kernel
-        (lvis_amodal/eval.py:168-303)."""
+        (lvis_amodal/eval.py:168-303).  Without `detail` the result of a detection is one compact
+        word (dev.t["dt_word"]) unless dev.compact is False (full rows in dt_tpfp)."""
         import torch
         plan = dev.plan
         assert plan.kind == "lvis"
@@ -295,12 +315,15 @@ class Engine:
         if detail:
             dev.ensure_detail()
         p = dev.ptr
+        dev.words_valid = bool(dev.compact and not detail and "dt_word" in dev.t)
         _lib.check(self.lib.ta_frame_eval(
             self._ctx, st, plan.n_groups, p["grp_dt_off"], p["grp_gt_off"], p["grp_cat"],
             p["dt_box"], p["gt_box"], dev.n_thr, p["iou_thrs"], plan.n_cfg, p["cfgs"],
             plan.n_dt, p["dt_flag"], plan.n_gt, p["gt_attr_a"], p["gt_flag"],
             dev.n_big, p["big_list"] if dev.n_big else None, dev.g_max,
-            p["iou_off"], p["iou"], 1 if detail else 0, p["dt_tpfp"], p["num_gt"],
+            p["iou_off"], p["iou"], 1 if detail else 0,
+            p.get("sched"), p["dt_word"] if dev.words_valid else None,
+            p["dt_tpfp"], p["num_gt"],
             p["dt_match_gt"] if detail else None, p["gt_ignore"] if detail else None))
 
     def stage_accumulate(self, dev: "DevicePlan"):
@@ -310,6 +333,7 @@ class Engine:
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         _lib.check(self.lib.ta_pr_accumulate(
             self._ctx, st, dev.n_cat, p["cat_dt_off"], p["acc_perm"], plan.n_dt, p["dt_tpfp"],
+            p["dt_word"] if dev.words_valid else None,
             p["num_gt"], dev.n_thr, plan.n_cfg, dev.n_rec, p["rec_thrs"],
             p["precision"], p["recall"], p["tp_cnt"], p["fp_cnt"]))
 
@@ -403,6 +427,21 @@ class DevicePlan:
         self.t["iou"] = torch.empty(max(n_iou, 1), dtype=torch.float64, device=dev)
         self.t["dt_tpfp"] = torch.zeros(max(n_cfg * plan.n_dt, 1), dtype=torch.int32, device=dev)
         self.t["num_gt"] = torch.zeros((C_, n_cfg), dtype=torch.int32, device=dev)
+        # frame path: compact per-detection result words + the per-plan task schedule of
+        # ta_frame_eval (depends on the CSR offsets only: built once, here)
+        self.compact = True
+        self.words_valid = False
+        if not track and plan.masks is None:
+            self.t["dt_word"] = torch.zeros(max(plan.n_dt, 1), dtype=torch.int32, device=dev)
+            if plan.n_groups > 0 and plan.n_dt > 0:
+                nb = int(eng.lib.ta_frame_sched_bytes(plan.n_groups, plan.n_dt, plan.n_gt))
+                self.t["sched"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+                st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+                _lib.check(eng.lib.ta_frame_sched_build(
+                    eng._ctx, st, plan.n_groups, C.c_void_p(self.t["grp_dt_off"].data_ptr()),
+                    C.c_void_p(self.t["grp_gt_off"].data_ptr()), plan.n_dt,
+                    C.c_void_p(self.t["dt_flag"].data_ptr()), plan.n_gt,
+                    C.c_void_p(self.t["sched"].data_ptr())))
         self.t["precision"] = torch.empty((T, R, C_, n_cfg), dtype=torch.float64, device=dev)
         self.t["recall"] = torch.empty((T, C_, n_cfg), dtype=torch.float64, device=dev)
         self.t["tp_cnt"] = torch.empty((T, C_, n_cfg), dtype=torch.int64, device=dev)

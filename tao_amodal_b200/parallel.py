@@ -137,6 +137,7 @@ class DeviceDistAccumulator(DistAccumulator):
         import torch
         super().__init__(dev.plan, rank, world, dev.dev, group)
         self.eng, self.dev = eng, dev
+        dev.compact = False          # the exchange ships full TP/FP rows
         T, R, L, K = dev.n_thr, dev.n_rec, self.n_loc, self.n_cfg
         d = dev.dev
         self.part = {"precision": torch.empty((T, R, L, K), dtype=torch.float64, device=d),
@@ -158,7 +159,7 @@ class DeviceDistAccumulator(DistAccumulator):
         q = self.part
         _lib.check(eng.lib.ta_pr_accumulate(
             eng._ctx, st, self.n_loc, P(self.cat_dt_off), P(self.acc_perm), self.n_recv, P(rows),
-            P(num_gt_own), dev.n_thr, n_cfg, dev.n_rec, dev.ptr["rec_thrs"],
+            None, P(num_gt_own), dev.n_thr, n_cfg, dev.n_rec, dev.ptr["rec_thrs"],
             P(q["precision"]), P(q["recall"]), P(q["tp_cnt"]), P(q["fp_cnt"])))
         names = ("precision", "recall", "tp_cnt", "fp_cnt")
         self.merge_to_root([q[k] for k in names], [t[k] for k in names])

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_null_ctx_errors():
     lib = _lib.load()
-    assert lib.ta_abi_version() == 2
+    assert lib.ta_abi_version() == 3
     rc = lib.ta_track_iou(None, None, 0, 0, None, None, None, None, None, None, None, None, 0,
                           None, None)
     assert rc == _lib.TA_ERR_INVALID

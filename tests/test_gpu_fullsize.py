@@ -40,7 +40,27 @@ def test_counts_identity_and_kernel_variants_agree(big):
     # the evaluation route (lane-per-detection kernels, no per-cell outputs) against the
     # warp-per-group kernels that produce the per-cell outputs
     for plan, ref in ((lvis, a),):
-        q = eng.evaluate_device(eng.upload(plan), detail=False)
+        dv = eng.upload(plan)
+        q = eng.evaluate_device(dv, detail=False)
+        # compact per-detection words of the streamed flat kernel == rows of the detail kernel
+        from tao_amodal_b200.engine import expand_words
+        assert dv.words_valid
+        rows = expand_words(dv.t["dt_word"].cpu().numpy()[:plan.n_dt],
+                            dv.t["dt_tpfp"].cpu().numpy()[:plan.n_dt * plan.n_cfg], 10, plan.n_cfg)
+        assert np.array_equal(rows, ref.dt_tpfp)
+        # ... and the full-row mode of the same kernel
+        dv2 = eng.upload(plan)
+        dv2.compact = False
+        q2 = eng.evaluate_device(dv2, detail=False)
+        assert np.array_equal(dv2.t["dt_tpfp"].cpu().numpy().view(np.uint32)[:plan.n_dt * plan.n_cfg]
+                              .reshape(plan.n_dt, plan.n_cfg), ref.dt_tpfp)
+        assert np.array_equal(q2.precision, ref.precision)
+        # ... and with the schedule built inside the call (sched = NULL)
+        dv3 = eng.upload(plan)
+        dv3.t.pop("sched")
+        dv3._refresh()
+        q3 = eng.evaluate_device(dv3, detail=False)
+        assert np.array_equal(q3.precision, ref.precision) and np.array_equal(q3.num_gt, ref.num_gt)
         h = eng.evaluate_host(plan)
         for o in (q, h):
             for k in ("num_gt", "precision", "recall", "tp_cnt", "fp_cnt"):

@@ -206,7 +206,7 @@ def _gpu_pr(eng, c, iou_thrs, rec_thrs, impl):
     try:
         st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
         _lib.check(eng.lib.ta_pr_accumulate(
-            eng._ctx, st, n_cat, p(cat_off), p(perm), int(c["tpfp"].shape[0]), p(tpfp), p(ngt),
+            eng._ctx, st, n_cat, p(cat_off), p(perm), int(c["tpfp"].shape[0]), p(tpfp), None, p(ngt),
             T, n_cfg, R, p(rec), p(prec), p(rc), p(tp), p(fp)))
         torch.cuda.synchronize()
     finally:
