@@ -204,46 +204,107 @@ def run_cpu_port(samples, cores: int):
 
 CPU_SAMPLE_FRAMES = 0     # 0 = whole videos (cfg3 videos have 300 frames)
 
+# The reference arm and the cpu_baseline leg time the UNMODIFIED reference (baseline/_ref, a
+# verbatim copy made by __graft_entry__.build(); oracle/ref_bench.py) on ONE core — it is
+# single-threaded — over this FIXED sample of the bench workload: one video, its first 150
+# frames, all 1203 categories (the reference's cost is the (image x category) grid walk, linear
+# in images: ~8 s per pass, so --steps 20 --warmup 5 ends in a few minutes).
+REF_SAMPLE_VIDEOS = 1
+REF_SAMPLE_FRAMES = 150
+
+
+def reference_sample(workload, td):
+    from oracle import ref_bench
+    return ref_bench.write_sample(workload, REF_SAMPLE_VIDEOS, td, REF_SAMPLE_FRAMES)
+
 
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from tao_amodal_b200 import synth
-    cores = os.cpu_count() or 1
-    cfg = synth.CONFIGS[args.workload]
-    gt, dt = synth.generate_named(args.workload, videos=max(cores, 2), seed=cfg.seed)
-    # size the per-step sample so that K steps end within ~2.5 minutes: calibrate on the first
-    # 60 frames, then take the largest prefix of frames whose projected cost fits
-    t_cal = run_cpu_port(cpu_samples(gt, dt, cores, 60), cores)[1]
-    frames = 0
-    for cand in (300, 200, 150, 100, 60):
-        if args.steps * t_cal * (cand / 60.0) ** 1.5 <= 150.0 or cand == 60:
-            frames = 0 if cand >= cfg.frames else cand
-            break
-    samples = cpu_samples(gt, dt, cores, frames)
-    for _ in range(min(args.warmup, 1)):
-        run_cpu_port(samples, cores)
-    pairs, wall = 0, 0.0
-    for _ in range(args.steps):
-        p, w = run_cpu_port(samples, cores)
-        pairs += p
-        wall += w
+    import tempfile
+    from oracle import ref_bench
+    ref_root = ref_bench.find_reference()
+    extra = {}
+    if ref_root is not None:
+        with tempfile.TemporaryDirectory() as td:
+            ap, rp, pairs_1, sample = reference_sample(args.workload, td)
+            for _ in range(args.warmup):
+                ref_bench.run_once(ap, rp)
+            wall, res = 0.0, None
+            for _ in range(args.steps):
+                s, res = ref_bench.run_once(ap, rp)
+                wall += s
+            pairs = pairs_1 * args.steps
+            try:        # best-case CPU variant: numba's per-call dispatch switched off
+                nj = ref_bench.run_subprocess(ap, rp, True, 1)[0]
+                extra["value_numba_disabled"] = pairs_1 / nj
+            except Exception as e:      # noqa: BLE001
+                extra["value_numba_disabled"] = None
+                extra["numba_disabled_error"] = str(e)[:200]
+        cores, kind, warm = 1, "reference", args.warmup
+        extra["reference_results"] = res
+        extra["reference_root"] = os.path.relpath(ref_root, ROOT) if ref_root.startswith(ROOT) else ref_root
+        sample = "per step: " + sample + "; unmodified reference through its CLI call sequence, 1 process"
+    else:
+        # no reference tree on this box: the oracle port on all cores (round-1 behaviour)
+        from tao_amodal_b200 import synth
+        cores = os.cpu_count() or 1
+        cfg = synth.CONFIGS[args.workload]
+        gt, dt = synth.generate_named(args.workload, videos=max(cores, 2), seed=cfg.seed)
+        samples = cpu_samples(gt, dt, cores, REF_SAMPLE_FRAMES)
+        warm = min(args.warmup, 1)
+        for _ in range(warm):
+            run_cpu_port(samples, cores)
+        pairs, wall = 0, 0.0
+        for _ in range(args.steps):
+            p, w = run_cpu_port(samples, cores)
+            pairs += p
+            wall += w
+        kind = "port"
+        sample = "%d one-video samples per step (first %d of %d frames of %s-shaped videos), one per core" % (
+            len(samples), REF_SAMPLE_FRAMES, cfg.frames, args.workload)
     value = pairs / wall
-    sample = "%d one-video samples per step (first %d of %d frames of %s-shaped videos), one per core" % (
-        len(samples), frames or cfg.frames, cfg.frames, args.workload)
+    cb = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    cb.update(extra)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * wall / args.steps,
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def cpu_baseline_leg(args, gt, dt):
+    """cpu_baseline of the main arm (rank 0, N = 1): the unmodified reference, one warm-up pass
+    (numba JIT compile) + one timed pass over the fixed sample; the oracle port on all cores
+    when the reference tree is absent."""
+    import tempfile
+    from oracle import ref_bench
+    if ref_bench.find_reference() is not None:
+        with tempfile.TemporaryDirectory() as td:
+            ap, rp, pairs, sample = reference_sample(args.workload, td)
+            ref_bench.run_once(ap, rp)
+            s, _ = ref_bench.run_once(ap, rp)
+            out = {"value": pairs / s, "unit": UNIT, "cores": 1, "kind": "reference",
+                   "sample": sample + "; unmodified reference (baseline/_ref), 1 process, %.1f s" % s}
+            try:
+                nj = ref_bench.run_subprocess(ap, rp, True, 1)[0]
+                out["value_numba_disabled"] = pairs / nj
+            except Exception:           # noqa: BLE001
+                out["value_numba_disabled"] = None
+        return out
+    cores = os.cpu_count() or 1
+    samples = cpu_samples(gt, dt, cores, CPU_SAMPLE_FRAMES)
+    pairs, wall = run_cpu_port(samples, cores)
+    return {"value": pairs / wall, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d whole one-video samples of the same workload, one per core, %.1f s wall"
+                      % (len(samples), wall)}
 
 
 def workload_config(args, world):
@@ -491,13 +552,7 @@ def main():
         "host_prep_s": t_prep,
     }
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        samples = cpu_samples(gt, dt, cores, CPU_SAMPLE_FRAMES)
-        pairs, wall = run_cpu_port(samples, cores)
-        line["cpu_baseline"] = {
-            "value": pairs / wall, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d whole one-video samples of the same workload, one per core, %.1f s wall"
-                      % (len(samples), wall)}
+        line["cpu_baseline"] = cpu_baseline_leg(args, gt, dt)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -235,6 +235,44 @@ int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* plan,
                       int64_t* tp_cnt, int64_t* fp_cnt, int32_t* num_gt,
                       int64_t* h2d_bytes, int64_t* d2h_bytes);
 
+/* ---- multi-GPU exchange (one process per GPU; NCCL over NVLink / NVSwitch) ---------------
+ * Videos (and their images) shard across ranks: ta_track_iou / ta_match_greedy / ta_frame_eval
+ * run on each rank's own groups with no communication.  accumulate, however, orders all
+ * detections of a category by score across ALL videos (tao_amodal/evaluation/tao_amodal/
+ * eval.py:498-518, lvis_amodal/eval.py:340-361), so before ta_pr_accumulate one record per
+ * detection (its compact word, or its full TP/FP row) travels to the rank that owns the
+ * category, and the non-ignored GT counts are summed.  The reference is single-process; these
+ * entry points are what a multi-GPU maintainer-side driver calls between evaluate and
+ * accumulate (tao_amodal_b200/parallel.py is that driver here).
+ *
+ *   ta_exchange_unique_id   rank 0 draws an NCCL id (128 bytes) and hands it to the other ranks
+ *                           by any host channel; every rank then calls ta_exchange_create.
+ *   ta_exchange_gather      out[i] = src[index[i]]   records of `words` uint32 (send-side pack:
+ *                           index = local records grouped by destination rank)
+ *   ta_exchange_alltoallv   byte ranges send[send_off[r]..send_off[r+1]) -> rank r, received
+ *                           into recv[recv_off[r]..); offsets are HOST arrays of world+1 entries;
+ *                           one grouped ncclSend/ncclRecv, asynchronous on `stream`
+ *   ta_exchange_scatter     dst[index[i]] = src[i]   (received full rows -> dense row table)
+ *   ta_exchange_allreduce_sum   in-place sum over ranks; dtype 0 = int32, 1 = int64, 2 = float64
+ *   ta_exchange_group_begin / _end   calls issued in between are fused into ONE NCCL launch
+ * All pointers except the offset arrays are device pointers.  NCCL is loaded at run time
+ * (libnccl.so.2; a copy already in the process is reused): TA_ERR_NCCL when absent or failing. */
+typedef struct ta_exchange ta_exchange;
+int ta_exchange_unique_id(void* id, int32_t id_bytes);
+int ta_exchange_create(ta_ctx* ctx, int32_t rank, int32_t world, const void* id, ta_exchange** out);
+int ta_exchange_destroy(ta_exchange* x);
+int ta_exchange_rank(const ta_exchange* x);
+int ta_exchange_world(const ta_exchange* x);
+int ta_exchange_gather(ta_ctx* ctx, void* stream, int64_t n, int32_t words, const int32_t* index,
+                       const uint32_t* src, uint32_t* out);
+int ta_exchange_scatter(ta_ctx* ctx, void* stream, int64_t n, int32_t words, const int32_t* index,
+                        const uint32_t* src, uint32_t* dst);
+int ta_exchange_alltoallv(ta_exchange* x, void* stream, const void* send, const int64_t* send_off,
+                          void* recv, const int64_t* recv_off);
+int ta_exchange_allreduce_sum(ta_exchange* x, void* stream, void* buf, int64_t count, int32_t dtype);
+int ta_exchange_group_begin(ta_exchange* x);
+int ta_exchange_group_end(ta_exchange* x);
+
 /* Optional per-kernel timing for benchmarks.  While enabled the context records a CUDA event
  * after every kernel launch (and a marker at every API entry); ta_ctx_timing_read waits for
  * them, aggregates the intervals by kernel name and resets the log.  names receives the

@@ -40,24 +40,35 @@ def find_reference():
     return None
 
 
-def write_sample(workload: str, videos: int, out_dir: str):
-    """The first `videos` videos of the workload (its own seed) as annotation.json /
-    results.json.  Returns (annotation path, results path, box_pairs, description)."""
+def write_sample(workload: str, videos: int, out_dir: str, frames: int = 0):
+    """The first `videos` videos of the workload (its own seed), optionally only their first
+    `frames` frames, as annotation.json / results.json.  Returns (annotation path, results
+    path, box_pairs, description); box_pairs is counted on exactly the data written."""
     sys.path.insert(0, ROOT)
     from tao_amodal_b200 import prep, synth
+    from tao_amodal_b200.columnar import DtColumns, GtColumns
     cfg = synth.CONFIGS[workload]
     gt, dt = synth.generate_named(workload, videos=videos, seed=cfg.seed)
+    gd, dl = gt.to_dict(), dt.to_list()
+    if frames and frames < cfg.frames:
+        keep = {im["id"] for im in gd["images"] if im["frame_index"] < frames}
+        gd["images"] = [im for im in gd["images"] if im["id"] in keep]
+        gd["annotations"] = [a for a in gd["annotations"] if a["image_id"] in keep]
+        live = {a["track_id"] for a in gd["annotations"]}
+        gd["tracks"] = [t for t in gd["tracks"] if t["id"] in live]
+        dl = [r for r in dl if r["image_id"] in keep]
+        gt, dt = GtColumns.from_dict(gd), DtColumns.from_list(dl)
     lvis_plan = prep.prepare_lvis(gt, dt)
     d2 = dt.copy()
     prep.make_track_ids_unique(d2)
     tao_plan = prep.prepare_tao(gt, d2)
     pairs = prep.count_box_pair_visits(tao_plan) + prep.count_box_pair_visits(lvis_plan)
     ap, rp = os.path.join(out_dir, "annotation.json"), os.path.join(out_dir, "results.json")
-    json.dump(gt.to_dict(), open(ap, "w"))
-    json.dump(dt.to_list(), open(rp, "w"))
-    desc = ("%d whole %s-shaped video(s) (%d frames, %d predicted + %d GT tracks, %d categories), "
-            "seed %d" % (videos, workload, cfg.frames, cfg.pred_tracks, cfg.gt_tracks,
-                         cfg.categories, cfg.seed))
+    json.dump(gd, open(ap, "w"))
+    json.dump(dl, open(rp, "w"))
+    desc = ("first %d of %d frames of %d %s-shaped video(s) (%d predicted + %d GT tracks per video, "
+            "%d categories), seed %d" % (frames or cfg.frames, cfg.frames, videos, workload,
+                                         cfg.pred_tracks, cfg.gt_tracks, cfg.categories, cfg.seed))
     return ap, rp, int(pairs), desc
 
 
@@ -119,8 +130,9 @@ def run_subprocess(ap: str, rp: str, numba_disable_jit: bool, repeats: int = 1):
 if __name__ == "__main__":
     wl = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
     nv = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    fr = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     with tempfile.TemporaryDirectory() as td:
-        ap, rp, pairs, desc = write_sample(wl, nv, td)
+        ap, rp, pairs, desc = write_sample(wl, nv, td, fr)
         print(desc, "box pairs", pairs, "reference at", find_reference())
         s, res = run_once(ap, rp)
         print("first pass (numba JIT compile included) %.2f s" % s, res)

@@ -21,6 +21,7 @@ TA_ERR_INVALID = -1
 TA_ERR_CUDA = -2
 TA_ERR_TOO_LARGE = -3
 TA_ERR_ASSERT = -4
+TA_ERR_NCCL = -5
 
 IOU_MODES = {"3d_iou": 0, "avg_iou": 1, "imagenetvid": 2, "3d_iou_seq": 3}
 
@@ -29,6 +30,9 @@ EXPORTS = [
     "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
     "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
     "ta_rle_iou", "ta_frame_sched_bytes", "ta_frame_sched_build",
+    "ta_exchange_unique_id", "ta_exchange_create", "ta_exchange_destroy", "ta_exchange_rank",
+    "ta_exchange_world", "ta_exchange_gather", "ta_exchange_scatter", "ta_exchange_alltoallv",
+    "ta_exchange_allreduce_sum", "ta_exchange_group_begin", "ta_exchange_group_end",
 ]
 
 
@@ -101,6 +105,17 @@ def load() -> C.CDLL:
     lib.ta_frame_sched_bytes.argtypes = [I64, I64, I64]
     lib.ta_frame_sched_bytes.restype = I64
     lib.ta_frame_sched_build.argtypes = [P, P, I64, P, P, I64, P, I64, P]
+    lib.ta_exchange_unique_id.argtypes = [P, I32]
+    lib.ta_exchange_create.argtypes = [P, I32, I32, P, C.POINTER(C.c_void_p)]
+    lib.ta_exchange_destroy.argtypes = [P]
+    lib.ta_exchange_rank.argtypes = [P]
+    lib.ta_exchange_world.argtypes = [P]
+    lib.ta_exchange_gather.argtypes = [P, P, I64, I32, P, P, P]
+    lib.ta_exchange_scatter.argtypes = [P, P, I64, I32, P, P, P]
+    lib.ta_exchange_alltoallv.argtypes = [P, P, P, P, P, P]
+    lib.ta_exchange_allreduce_sum.argtypes = [P, P, P, I64, I32]
+    lib.ta_exchange_group_begin.argtypes = [P]
+    lib.ta_exchange_group_end.argtypes = [P]
     lib.ta_rle_iou.argtypes = [P, P, I64, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]
     lib.ta_pr_accumulate.argtypes = [P, P, I32, P, P, I64, P, P, P, I32, I32, I32, P, P, P, P, P]
     lib.ta_eval_plan_host.argtypes = [P, C.POINTER(PlanHost), P, P, P, P, P,

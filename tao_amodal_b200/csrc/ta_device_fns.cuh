@@ -191,6 +191,25 @@ TA_HD uint32_t pr_transpose_stage(uint32_t x, uint32_t y, int lane, int j) {
 
 #define TA_PR_WORDS 8          // 32-position words per chunk of 256 detections
 
+// Compact per-detection result word of ta_frame_eval (include/ta_eval.h):
+//   w = M | A << T | B << (T + C) | U << (T + 2 C),  bit 31 = "use the full row instead".
+// TP/FP row entry of range cfg `cfg`: (A_cfg ? M : 0) | ((B_cfg ? M : 0) | (U_cfg ? ~M : 0)) << 16.
+TA_HD uint32_t pr_expand(uint32_t w, int cfg, int n_thr, int n_cfg) {
+    const uint32_t thr_all = (1u << n_thr) - 1u;
+    const uint32_t M = w & thr_all;
+    const uint32_t s = w >> (n_thr + cfg);
+    const uint32_t tp = (s & 1u) ? M : 0u;
+    const uint32_t fp = (((s >> n_cfg) & 1u) ? M : 0u) | (((s >> (2 * n_cfg)) & 1u) ? (thr_all & ~M) : 0u);
+    return tp | (fp << 16);
+}
+// The same per (cfg, threshold) CELL over 32 detections at once: Mk / A / B / U are the ballots
+// of the word bits k / T + cfg / T + C + cfg / T + 2 C + cfg (one 32 x 32 bit transpose of the
+// compact words gives all of them).  Lanes whose word is 0 contribute nothing.
+TA_HD void pr_cell_planes(uint32_t Mk, uint32_t A, uint32_t B, uint32_t U, uint32_t& tp, uint32_t& fp) {
+    tp = A & Mk;
+    fp = (B & Mk) | (U & ~Mk);
+}
+
 // Envelope walk of one (category chunk, range cfg, threshold) cell over the chunk's TRUE
 // POSITIVES only (accumulate, eval.py:527-573).  T[j * stride] / F[j * stride], j < 8, are the
 // cell's TP / FP flags of the chunk's positions 32 j .. 32 j + 31 in descending-score order

@@ -1232,7 +1232,7 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
         a.dev_list = f.complex_list;
         a.dev_count = f.complex_count;
         a.skip_num_gt = 1;
-        int64_t lblocks = (int64_t)ctx->sm_count * 2;
+        int64_t lblocks = (int64_t)ctx->sm_count * 4;
         if (lblocks > n_groups) lblocks = n_groups;
         k_match_greedy<<<(unsigned)lblocks, threads, smem, st>>>(a);
         return ta_check_launch(ctx, "k_match_greedy_list");
@@ -1387,7 +1387,7 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
             if ((rc = ta_check_launch(ctx, "k_frame_flat"))) return rc;
         }
         if (n_dt > 0) {
-            const int64_t blocks = ctx->sm_count * 2;       // list length is only known on the device
+            const int64_t blocks = ctx->sm_count * 8;       // list length is only known on the device
             if (spec) k_frame_eval<false, 10, 6, true><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
             else k_frame_eval<false, 0, 0, true><<<(unsigned)blocks, FE_WARPS * 32, 0, st>>>(a);
             rc = ta_check_launch(ctx, "k_frame_eval_list");

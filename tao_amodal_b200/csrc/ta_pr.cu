@@ -20,8 +20,8 @@
 //   k_pr_bits      the chunk's TP/FP words are transposed ONCE (32 x 32 bit-matrix transpose
 //                  across the warp) into one 256-bit TP and FP plane per (cfg, threshold) cell;
 //                  chunk totals are popcounts
-//   k_pr_tk, k_pr_scan_live   tk table (flat) and per-category exclusive scan of the 2 n_thr live
-//                  counters per cfg; recall and TP / FP totals
+//   k_pr_scan_live   per-category exclusive scan of the 2 n_thr live counters per cfg; recall
+//                  and TP / FP totals; the category's tk table
 //   k_pr_envelope_bits   one thread per (chunk, cell) visits only the TRUE POSITIVES of its plane
 //                  (clz / popc) instead of all 256 positions: running counts, suffix-maximum
 //                  precision, and the answer of every recall level whose tk-th true positive
@@ -59,14 +59,17 @@ struct PrArgs {
     uint32_t* chunk_cnt;         // [n_chunks_ub][n_cfg][32]: bit t -> TP count, bit 16+t -> FP count
     uint32_t* cat_tot;           // [n_cat][n_cfg][32] category totals (same bit layout)
     int32_t* tk;                 // [n_cat][n_cfg][n_rec]
-    unsigned long long* chunk_best;  // [n_chunks_ub][n_cfg][n_thr] packed (t << 32 | n)
+    unsigned long long* chunk_best;  // [n_chunks_ub][n_cfg][n_thr] packed candidates
+    int best_cell_major;             // (alternative layout [cell][chunk]; measured slower, unused)
     unsigned long long* ans;     // cell-major answers [n_thr][n_cat][n_cfg][n_rec] (bit-plane path): what
                                  // prec_bits holds, laid out so that one cell's recall levels are
                                  // contiguous (sequential stores in the envelope, row reads in finalize)
     int32_t* chunk_cat;          // [n_chunks_ub] category of a chunk            (bit-plane path)
-    uint32_t* bits;              // [n_chunks_ub][2 * TA_PR_WORDS][n_cfg * n_thr] (bit-plane path):
-                                 // word j < 8: TP flags of positions 32 j .. 32 j + 31 of the
-                                 // chunk for one (cfg, threshold) cell, word 8 + j: FP flags
+    int64_t* chunk_p0;           // [n_chunks_ub] first position (accumulate order) of a chunk
+    int32_t* chunk_np;           // [n_chunks_ub] positions in the chunk (<= PR_CHUNK)
+    uint32_t* bits;              // [n_cfg * n_thr][n_chunks_ub][2 * TA_PR_WORDS] (bit-plane path):
+                                 // 64 B per (cell, chunk): word j < 8 = TP flags of positions
+                                 // 32 j .. 32 j + 31 of the chunk, word 8 + j = FP flags
     // outputs
     unsigned long long* prec_bits;   // precision buffer viewed as u64: packed (t << 32 | n) until
                                      // k_pr_finalize turns it into doubles
@@ -80,15 +83,7 @@ struct PrArgs {
 #define PR_MAX_CAT_DT (1 << 24)  // detections per category (packed candidates: 24-bit counts)
 
 // TP/FP word of (detection idx, cfg): the row entry, or the expansion of the compact word
-// (layout: ta_match.cu, k_frame_flat): M | A << T | B << (T + C) | Cu << (T + 2 C).
-__device__ __forceinline__ uint32_t pr_expand(uint32_t w, int cfg, int n_thr, int n_cfg) {
-    const uint32_t thr_all = (1u << n_thr) - 1u;
-    const uint32_t M = w & thr_all;
-    const uint32_t s = w >> (n_thr + cfg);
-    const uint32_t tp = (s & 1u) ? M : 0u;
-    const uint32_t fp = (((s >> n_cfg) & 1u) ? M : 0u) | (((s >> (2 * n_cfg)) & 1u) ? (thr_all & ~M) : 0u);
-    return tp | (fp << 16);
-}
+// (pr_expand, ta_device_fns.cuh)
 __device__ __forceinline__ uint32_t pr_word(const PrArgs& a, int64_t idx, int cfg) {
     if (a.dt_word) {
         const uint32_t w = a.dt_word[idx];
@@ -146,6 +141,21 @@ __device__ __forceinline__ int pr_find_cat(const int32_t* chunk_start, int n_cat
         if (chunk_start[mid] <= chunk) lo = mid; else hi = mid;
     }
     return lo;
+}
+
+// Chunk table of the bit-plane path, one thread per chunk: category, first position, length —
+// so that no later kernel has to search or chase offsets.
+__global__ void __launch_bounds__(256)
+k_pr_chunks(PrArgs a) {
+    const int n_chunks = a.chunk_start[a.n_cat];
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_chunks) return;
+    const int cat = pr_find_cat(a.chunk_start, a.n_cat, ch);
+    const int rel = ch - a.chunk_start[cat];
+    const int64_t p0 = a.cat_dt_off[cat] + (int64_t)rel * PR_CHUNK;
+    a.chunk_cat[ch] = cat;
+    a.chunk_p0[ch] = p0;
+    a.chunk_np[ch] = (int)min((int64_t)PR_CHUNK, a.cat_dt_off[cat + 1] - p0);
 }
 
 // One warp per range cfg, lane = 8 consecutive positions of the chunk.  Each lane adds its 8
@@ -236,6 +246,11 @@ __global__ void k_pr_scan(PrArgs a) {
 
 // pr_better / pr_pack / pr_unpack: ta_device_fns.cuh
 
+__device__ __forceinline__ int64_t pr_best_idx(const PrArgs& a, int chunk, int cell) {
+    return a.best_cell_major ? (int64_t)cell * a.n_chunks_ub + chunk
+                             : (int64_t)chunk * (a.n_cfg * a.n_thr) + cell;
+}
+
 #define PR_ENV_MAX_CELLS 64   // (cfg, threshold) cells per k_pr_envelope block
 
 __global__ void __launch_bounds__(PR_ENV_MAX_CELLS)
@@ -271,7 +286,7 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
                                             : a.cat_tot + ((int64_t)cat * a.n_cfg + cfg) * 32;
     uint32_t tc = nxt[b], fc = nxt[16 + b];
     const uint32_t t_begin = a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg) * 32 + b];
-    unsigned long long* best_out = a.chunk_best + ((int64_t)chunk * a.n_cfg + cfg) * a.n_thr + b;
+    unsigned long long* best_out = a.chunk_best + pr_best_idx(a, chunk, cfg * a.n_thr + b);
     if (tc == t_begin) { *best_out = 0ull; return; }          // no TP of this cell in the chunk
     const int32_t* tkc = tk_s + c * a.n_rec;
     // last recall threshold whose (clamped) tk is <= tc
@@ -309,71 +324,132 @@ k_pr_envelope(PrArgs a, int cfgs_per_block) {
 
 // ---- bit-plane variant -------------------------------------------------------------------
 static_assert(PR_CHUNK == 32 * TA_PR_WORDS, "chunk = 8 words of 32 positions");
+#define PR_PS 17              // shared-memory stride of one cell's 16 plane words
 
-// One block per chunk, thread = position (warp w = positions 32 w .. 32 w + 31).  Per cfg the
-// warp transposes its 32 TP/FP words: lane t then holds the TP plane word of threshold t, lane
-// 16 + t the FP plane word.  Planes are staged in shared memory ([word][cell]: conflict-free),
-// copied out linearly, and summed (popc) into the chunk totals k_pr_scan expects.
+// One block per chunk, thread = position (warp w = positions 32 w .. 32 w + 31).
+//   compact words (ta_frame_eval): ONE 32 x 32 bit transpose of the warp's words turns lane b
+//     into the ballot of word bit b; the (cfg, threshold) cells then are
+//     TP = A_cfg & M_k, FP = (B_cfg & M_k) | (U_cfg & ~M_k) (pr_cell_planes), two or three cells
+//     per lane, their four operands fetched with shuffles.  Detections whose word points to a
+//     full row (general matcher) are patched in one by one.
+//   full rows (track path, exchanged rows): per cfg the warp transposes its 32 TP/FP words:
+//     lane t then holds the TP plane word of threshold t, lane 16 + t the FP plane word.
+// Planes are staged in shared memory cell-major ([cell][16 words]) and written as one 64-byte
+// piece per cell; chunk totals are popcounts.
 __global__ void __launch_bounds__(PR_CHUNK)
 k_pr_bits(PrArgs a) {
-    extern __shared__ uint32_t plane_s[];          // [2 * TA_PR_WORDS][n_cells]
-    const int chunk = blockIdx.x;
-    if (chunk >= a.chunk_start[a.n_cat]) return;
-    const int cat = pr_find_cat(a.chunk_start, a.n_cat, chunk);
+    extern __shared__ uint32_t plane_s[];    // [n_cells][PR_PS]: 16 plane words + 1 pad (bank-conflict-free)
+    __shared__ uint32_t rowstage[PR_CHUNK / 32][32];
+    const int n_chunks = a.chunk_start[a.n_cat];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_cells = a.n_cfg * a.n_thr;
-    const int64_t p0 = a.cat_dt_off[cat] + (int64_t)(chunk - a.chunk_start[cat]) * PR_CHUNK;
-    const int n_pos = (int)min((int64_t)PR_CHUNK, a.cat_dt_off[cat + 1] - p0);
-    if (threadIdx.x == 0) a.chunk_cat[chunk] = cat;
+    const int n_thr = a.n_thr, n_cfg = a.n_cfg;
+    const int n_cells = n_cfg * n_thr;
     const int p = threadIdx.x;
-    const bool live = p < n_pos;
-    const int64_t didx = live ? (int64_t)a.acc_perm[p0 + p] : 0;
-    const uint32_t* row = a.dt_tpfp + didx * a.n_cfg;
-    // compact word (ta_frame_eval): expanded per cfg in registers, 4 B instead of 4 n_cfg B read
-    const uint32_t cw = (a.dt_word && live) ? a.dt_word[didx] : 0x80000000u;
-    const bool full = (cw >> 31) != 0;
-    const int b = lane & 15;
-    uint32_t* dst = plane_s + ((lane >> 4) * TA_PR_WORDS + warp) * n_cells + b;
+    const int g = gridDim.x;
     uint32_t keep[5], rot[5];
 #pragma unroll
     for (int s = 0; s < 5; ++s) pr_transpose_consts(lane, 16 >> s, keep[s], rot[s]);
+    // Persistent blocks with a three-deep software pipeline over their chunks: the chunk table
+    // entry of chunk c + 3g, the permutation entries of c + 2g and the result words of c + g
+    // are in flight while chunk c is transposed (each is a dependent load of the previous one).
+    auto desc_p0 = [&](int ch) { return ch < n_chunks ? a.chunk_p0[ch] : (int64_t)0; };
+    auto desc_np = [&](int ch) { return ch < n_chunks ? a.chunk_np[ch] : 0; };
+    auto perm_of = [&](int64_t p0, int np) { return p < np ? a.acc_perm[p0 + p] : -1; };
+    auto word_of = [&](int pm) { return (a.dt_word && pm >= 0) ? a.dt_word[pm] : 0u; };
+    int c = blockIdx.x;
+    int64_t p0_1 = desc_p0(c + g), p0_2 = desc_p0(c + 2 * g);
+    int np_1 = desc_np(c + g), np_2 = desc_np(c + 2 * g);
+    int perm0 = perm_of(desc_p0(c), desc_np(c)), perm1 = perm_of(p0_1, np_1);
+    uint32_t w0 = word_of(perm0);
+    for (; c < n_chunks; c += g) {
+        const uint32_t w1 = word_of(perm1);
+        const int perm2 = perm_of(p0_2, np_2);
+        const int64_t p0_3 = desc_p0(c + 3 * g);
+        const int np_3 = desc_np(c + 3 * g);
+        const bool live = perm0 >= 0;
+        const uint32_t* row = a.dt_tpfp + (int64_t)(live ? perm0 : 0) * n_cfg;
+        if (a.dt_word) {
+            const uint32_t cw = w0;
+            const bool full = (cw >> 31) != 0;
+            uint32_t x = full ? 0u : cw;
+#pragma unroll
+            for (int s = 0; s < 5; ++s)
+                x = pr_transpose_apply(x, __shfl_xor_sync(0xffffffffu, x, 16 >> s), keep[s], rot[s]);
+            for (int c0 = 0; c0 < n_cells; c0 += 32) {
+                const int cell = min(c0 + lane, n_cells - 1);
+                const int cfg = cell / n_thr, k = cell - cfg * n_thr;
+                const uint32_t Mk = __shfl_sync(0xffffffffu, x, k);
+                const uint32_t A = __shfl_sync(0xffffffffu, x, n_thr + cfg);
+                const uint32_t B = __shfl_sync(0xffffffffu, x, n_thr + n_cfg + cfg);
+                const uint32_t U = __shfl_sync(0xffffffffu, x, n_thr + 2 * n_cfg + cfg);
+                uint32_t tp, fp;
+                pr_cell_planes(Mk, A, B, U, tp, fp);
+                if (c0 + lane < n_cells) {
+                    plane_s[cell * PR_PS + warp] = tp;
+                    plane_s[cell * PR_PS + TA_PR_WORDS + warp] = fp;
+                }
+            }
+            uint32_t fm = __ballot_sync(0xffffffffu, full);
+            while (fm) {                              // warp-uniform: detections with a full row
+                const int src = __ffs(fm) - 1;
+                fm &= fm - 1;
+                __syncwarp();
+                if (lane == src)
+                    for (int q = 0; q < n_cfg; ++q) rowstage[warp][q] = row[q];
+                __syncwarp();
+                for (int cell = lane; cell < n_cells; cell += 32) {
+                    const int cfg = cell / n_thr, k = cell - cfg * n_thr;
+                    const uint32_t rw = rowstage[warp][cfg];
+                    plane_s[cell * PR_PS + warp] |= ((rw >> k) & 1u) << src;
+                    plane_s[cell * PR_PS + TA_PR_WORDS + warp] |= ((rw >> (16 + k)) & 1u) << src;
+                }
+            }
+        } else {
+            const int b = lane & 15;
+            uint32_t* dst = plane_s + (lane >> 4) * TA_PR_WORDS + warp;
 #pragma unroll 2
-    for (int cfg = 0; cfg < a.n_cfg; ++cfg) {
-        uint32_t x = 0u;
-        if (live) x = full ? row[cfg] : pr_expand(cw, cfg, a.n_thr, a.n_cfg);
+            for (int cfg = 0; cfg < n_cfg; ++cfg) {
+                uint32_t x = live ? row[cfg] : 0u;
 #pragma unroll
-        for (int s = 0; s < 5; ++s)
-            x = pr_transpose_apply(x, __shfl_xor_sync(0xffffffffu, x, 16 >> s), keep[s], rot[s]);
-        if (b < a.n_thr) dst[cfg * a.n_thr] = x;
-    }
-    __syncthreads();
-    uint32_t* out = a.bits + (int64_t)chunk * (2 * TA_PR_WORDS) * n_cells;
-    for (int i = threadIdx.x; i < 2 * TA_PR_WORDS * n_cells; i += PR_CHUNK) out[i] = plane_s[i];
-    for (int j = threadIdx.x; j < a.n_cfg * 32; j += PR_CHUNK) {
-        const int cfg = j >> 5, bit = j & 31, t = bit & 15;
-        uint32_t cnt = 0;
-        if (t < a.n_thr) {
-            const uint32_t* src = plane_s + (bit >> 4) * TA_PR_WORDS * n_cells + cfg * a.n_thr + t;
-#pragma unroll
-            for (int u = 0; u < TA_PR_WORDS; ++u) cnt += __popc(src[u * n_cells]);
+                for (int s = 0; s < 5; ++s)
+                    x = pr_transpose_apply(x, __shfl_xor_sync(0xffffffffu, x, 16 >> s), keep[s], rot[s]);
+                if (b < n_thr) dst[(cfg * n_thr + b) * PR_PS] = x;
+            }
         }
-        a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg) * 32 + bit] = cnt;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_cells * 16; i += PR_CHUNK) {
+            const int cell = i >> 4, w = i & 15;          // 16 consecutive threads write one 64-byte piece
+            a.bits[((int64_t)cell * a.n_chunks_ub + c) * 16 + w] = plane_s[cell * PR_PS + w];
+        }
+        for (int j = threadIdx.x; j < n_cfg * 32; j += PR_CHUNK) {
+            const int cfg = j >> 5, bit = j & 31, t = bit & 15;
+            uint32_t cnt = 0;
+            if (t < n_thr) {
+                const uint32_t* src = plane_s + (cfg * n_thr + t) * PR_PS + (bit >> 4) * TA_PR_WORDS;
+#pragma unroll
+                for (int u = 0; u < TA_PR_WORDS; ++u) cnt += __popc(src[u]);
+            }
+            a.chunk_cnt[((int64_t)c * n_cfg + cfg) * 32 + bit] = cnt;
+        }
+        __syncthreads();                 // planes consumed before the next chunk overwrites them
+        w0 = w1; perm0 = perm1; perm1 = perm2;
+        p0_2 = p0_3; np_2 = np_3;
     }
 }
 
-// One THREAD per (chunk, cfg, threshold) cell, flat over the grid (consecutive lanes =
-// consecutive cells of a chunk: the plane loads are coalesced).  ta_pr_walk_bits visits the
-// cell's true positives only.
+// One THREAD per (chunk, cell), cells fastest: the lanes of a warp walk consecutive cells of one
+// chunk (shared tk rows and counters: L1 hits).  Measured alternatives, both slower (0.71 / 0.73
+// vs 0.47 ms at the bench size): lanes = consecutive chunks of one cell, lanes = chunks of equal
+// rank inside their categories.
+// ta_pr_walk_bits visits the cell's true positives only.
 __global__ void __launch_bounds__(128)
 k_pr_envelope_bits(PrArgs a) {
     const uint32_t n_cells = (uint32_t)(a.n_cfg * a.n_thr);
+    const uint32_t n_chunks = (uint32_t)a.chunk_start[a.n_cat];
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = (int64_t)a.chunk_start[a.n_cat] * n_cells;
-    if (gid >= total) return;
-    int chunk;
-    uint32_t cell;
-    if (total < (1ll << 31)) { chunk = (int)((uint32_t)gid / n_cells); cell = (uint32_t)gid - (uint32_t)chunk * n_cells; }
-    else { chunk = (int)(gid / n_cells); cell = (uint32_t)(gid - (int64_t)chunk * n_cells); }
+    if (gid >= (int64_t)n_chunks * n_cells) return;
+    const int chunk = (int)(gid / n_cells);
+    const uint32_t cell = (uint32_t)(gid - (int64_t)chunk * n_cells);
     const int cfg = (int)(cell / (uint32_t)a.n_thr), b = (int)(cell - (uint32_t)cfg * a.n_thr);
     const int cat = a.chunk_cat[chunk];
     if (a.num_gt[(int64_t)cat * a.n_cfg + cfg] == 0) return;
@@ -384,34 +460,25 @@ k_pr_envelope_bits(PrArgs a) {
                                             : a.cat_tot + ((int64_t)cat * a.n_cfg + cfg) * 32;
     const uint32_t tc = nxt[b], fc = nxt[16 + b];
     const uint32_t t_begin = a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg) * 32 + b];
-    unsigned long long* best_out = a.chunk_best + (int64_t)chunk * n_cells + cell;
+    unsigned long long* best_out = a.chunk_best + pr_best_idx(a, chunk, (int)cell);
     if (tc == t_begin) { *best_out = 0ull; return; }          // no TP of this cell in the chunk
     const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
-    const uint32_t* planes = a.bits + (int64_t)chunk * (2 * TA_PR_WORDS) * n_cells + cell;
+    const uint4* pl = reinterpret_cast<const uint4*>(a.bits + ((int64_t)cell * a.n_chunks_ub + chunk) * 16);
+    uint32_t w[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = pl[q];
+        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+    }
     const int64_t cc = (int64_t)cat * a.n_cfg + cfg;
-    unsigned long long* q = a.ans ? a.ans + ((int64_t)b * per_t + cc) * a.n_rec
-                                  : a.prec_bits + (int64_t)b * a.n_rec * per_t + cc;
-    *best_out = ta_pr_walk_bits(planes, planes + (int64_t)TA_PR_WORDS * n_cells, (int64_t)n_cells, tc, fc,
-                                a.tk + cc * a.n_rec, a.n_rec, (uint32_t)(chunk - ch0),
-                                q, a.ans ? (int64_t)1 : per_t);
+    unsigned long long* q = a.ans + ((int64_t)b * per_t + cc) * a.n_rec;
+    *best_out = ta_pr_walk_bits(w, w + TA_PR_WORDS, (int64_t)1, tc, fc, a.tk + cc * a.n_rec, a.n_rec,
+                                (uint32_t)(chunk - ch0), q, (int64_t)1);
 }
 
-
-// tk table of the bit-plane path: one thread per (category, cfg, recall level)
-__global__ void __launch_bounds__(256)
-k_pr_tk(PrArgs a) {
-    const int64_t n = (int64_t)a.n_cat * a.n_cfg * a.n_rec;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t cc = (uint32_t)(i / a.n_rec);
-    const int k = (int)(i - (int64_t)cc * a.n_rec);
-    const int ngt = a.num_gt[cc];
-    a.tk[i] = ngt ? (int32_t)ta_min_tp_for_recall(a.rec_thrs[k], ngt) : INT_MAX;
-}
-
-// Exclusive scan of the chunk totals, bit-plane path: one block per category, thread <->
-// counter (cfg, bit); only the 2 n_thr live counters of a cfg are touched; 16 independent
-// loads in flight per thread (predicated, no serial tail).
+// Exclusive scan of the chunk totals + the tk table, bit-plane path: one block per category,
+// thread <-> counter (cfg, bit); only the 2 n_thr live counters of a cfg are touched; 16
+// independent loads in flight per thread (predicated, no serial tail).
 #define PR_SCAN_DEPTH 16
 __global__ void __launch_bounds__(128)
 k_pr_scan_live(PrArgs a) {
@@ -448,6 +515,13 @@ k_pr_scan_live(PrArgs a) {
         }
         a.cat_tot[((int64_t)cat * a.n_cfg) * 32 + j] = run;
     }
+    // tk table of the category: smallest TP count that reaches each recall level
+    for (int j = threadIdx.x; j < a.n_cfg * a.n_rec; j += blockDim.x) {
+        const int cfg = j / a.n_rec, k = j - cfg * a.n_rec;
+        const int ngt = a.num_gt[(int64_t)cat * a.n_cfg + cfg];
+        a.tk[((int64_t)cat * a.n_cfg + cfg) * a.n_rec + k] =
+            ngt ? (int32_t)ta_min_tp_for_recall(a.rec_thrs[k], ngt) : INT_MAX;
+    }
 }
 
 // k_pr_finalize for cell-major answers, tiled: a block owns one threshold and 32 consecutive
@@ -457,14 +531,15 @@ k_pr_scan_live(PrArgs a) {
 // Reads and writes are both coalesced and every entry is independent.  Same values as
 // k_pr_finalize.
 #define PR_TILE_CELLS 32
-__global__ void __launch_bounds__(128)
+#define PR_FIN_WARPS 8
+__global__ void __launch_bounds__(PR_FIN_WARPS * 32)
 k_pr_finalize_tile(PrArgs a) {
     extern __shared__ double tile_s[];                    // [n_rec][PR_TILE_CELLS + 1]
     const uint32_t per_t = (uint32_t)a.n_cat * (uint32_t)a.n_cfg;
     const uint32_t cc0 = blockIdx.x * PR_TILE_CELLS;
     const int t = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < PR_TILE_CELLS; c += 4) {
+    for (int c = warp; c < PR_TILE_CELLS; c += PR_FIN_WARPS) {
         const uint32_t cc = cc0 + c;
         if (cc >= per_t) break;
         const int ngt = a.num_gt[cc];
@@ -473,9 +548,9 @@ k_pr_finalize_tile(PrArgs a) {
         if (ngt) {
             tot = a.cat_tot[(int64_t)cc * 32 + t];
             const uint32_t cat = cc / (uint32_t)a.n_cfg, cfg = cc - cat * (uint32_t)a.n_cfg;
-            best = a.chunk_best + ((int64_t)a.chunk_start[cat] * a.n_cfg + cfg) * a.n_thr + t;
+            best = a.chunk_best + pr_best_idx(a, a.chunk_start[cat], (int)(cfg * a.n_thr + t));
         }
-        const int64_t best_stride = (int64_t)a.n_cfg * a.n_thr;
+        const int64_t best_stride = a.best_cell_major ? 1 : (int64_t)a.n_cfg * a.n_thr;
         const int32_t* tkp = a.tk + (int64_t)cc * a.n_rec;
         const unsigned long long* ansp = a.ans + ((int64_t)t * per_t + cc) * a.n_rec;
         for (int k = lane; k < a.n_rec; k += 32) {
@@ -497,7 +572,7 @@ k_pr_finalize_tile(PrArgs a) {
     const uint32_t cc = cc0 + lane;
     if (cc < per_t) {
         double* out = a.precision + (int64_t)t * a.n_rec * per_t + cc;
-        for (int k = warp; k < a.n_rec; k += 4)
+        for (int k = warp; k < a.n_rec; k += PR_FIN_WARPS)
             out[(int64_t)k * per_t] = tile_s[k * (PR_TILE_CELLS + 1) + lane];
     }
 }
@@ -514,17 +589,17 @@ __global__ void k_pr_suffix(PrArgs a) {
         for (; ch - 7 >= ch0; ch -= 8) {              // 8 independent loads in flight
             unsigned long long v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = a.chunk_best[(int64_t)(ch - u) * n_cell + j];
+            for (int u = 0; u < 8; ++u) v[u] = a.chunk_best[pr_best_idx(a, ch - u, j)];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 uint32_t ct, cn;
                 pr_unpack(v[u], ct, cn, dummy);
-                a.chunk_best[(int64_t)(ch - u) * n_cell + j] = pr_pack(bt, bn, 0);
+                a.chunk_best[pr_best_idx(a, ch - u, j)] = pr_pack(bt, bn, 0);
                 if (pr_better(ct, cn, bt, bn)) { bt = ct; bn = cn; }
             }
         }
         for (; ch >= ch0; --ch) {
-            unsigned long long* q = a.chunk_best + (int64_t)ch * n_cell + j;
+            unsigned long long* q = a.chunk_best + pr_best_idx(a, ch, j);
             uint32_t ct, cn;
             pr_unpack(*q, ct, cn, dummy);
             *q = pr_pack(bt, bn, 0);
@@ -557,7 +632,7 @@ __global__ void k_pr_finalize(PrArgs a) {
     if (need > a.cat_tot[cc * 32 + t]) { a.precision[idx] = 0.0; return; }   // eval.py:565-573
     uint32_t qt, qn, ch, bt, bn, dummy;
     pr_unpack(a.prec_bits[idx], qt, qn, ch);
-    pr_unpack(a.chunk_best[((int64_t)(a.chunk_start[cat] + ch) * a.n_cfg + cfg) * a.n_thr + t],
+    pr_unpack(a.chunk_best[pr_best_idx(a, a.chunk_start[cat] + (int)ch, cfg * a.n_thr + t)],
               bt, bn, dummy);
     if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
     a.precision[idx] = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
@@ -603,9 +678,12 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     const size_t n_cells = (size_t)n_cfg * n_thr;
     // the staged planes of one chunk (64 B per cell) and the finalize tile ([n_rec][33] doubles)
     // must fit the default 48 KB of shared memory
-    const int impl = (n_cells * 2 * TA_PR_WORDS * 4 <= 48 * 1024 &&
+    const int impl = (n_cells * PR_PS * 4 <= 48 * 1024 &&
                       (size_t)n_rec * (PR_TILE_CELLS + 1) * 8 <= 48 * 1024) ? ta_pr_impl() : 0;
     const size_t o_ccat = take(impl ? (size_t)n_chunks_ub * 4 : 0);
+    const size_t o_cp0 = take(impl ? (size_t)n_chunks_ub * 8 : 0);
+    const size_t o_cnp = take(impl ? (size_t)n_chunks_ub * 4 : 0);
+
     const size_t o_bits = take(impl ? (size_t)n_chunks_ub * 2 * TA_PR_WORDS * n_cells * 4 : 0);
     const size_t o_ans = take(impl ? (size_t)n_thr * n_rec * n_cat * n_cfg * 8 : 0);
     void* ws = nullptr;
@@ -623,7 +701,11 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     a.cat_tot = reinterpret_cast<uint32_t*>(base + o_tot);
     a.tk = reinterpret_cast<int32_t*>(base + o_tk);
     a.chunk_best = reinterpret_cast<unsigned long long*>(base + o_best);
-    a.chunk_cat = reinterpret_cast<int32_t*>(base + o_ccat);
+    a.chunk_cat = impl ? reinterpret_cast<int32_t*>(base + o_ccat) : nullptr;
+    a.best_cell_major = 0;
+    a.chunk_p0 = reinterpret_cast<int64_t*>(base + o_cp0);
+    a.chunk_np = reinterpret_cast<int32_t*>(base + o_cnp);
+
     a.bits = reinterpret_cast<uint32_t*>(base + o_bits);
     a.ans = impl ? reinterpret_cast<unsigned long long*>(base + o_ans) : nullptr;
     a.prec_bits = reinterpret_cast<unsigned long long*>(precision);
@@ -644,7 +726,11 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
         }
     }
     if (n_chunks_ub > 0 && impl) {
-        k_pr_bits<<<n_chunks_ub, PR_CHUNK, 2 * TA_PR_WORDS * n_cells * 4, st>>>(a);
+        k_pr_chunks<<<(n_chunks_ub + 255) / 256, 256, 0, st>>>(a);
+        if ((rc = ta_check_launch(ctx, "k_pr_chunks"))) return rc;
+        int bits_blocks = ctx->sm_count * 8;           // persistent: 8 CTAs of 256 threads per SM
+        if (bits_blocks > n_chunks_ub) bits_blocks = n_chunks_ub;
+        k_pr_bits<<<bits_blocks, PR_CHUNK, (size_t)PR_PS * n_cells * 4, st>>>(a);
         if ((rc = ta_check_launch(ctx, "k_pr_bits"))) return rc;
     } else if (n_chunks_ub > 0) {
         const int warps = n_cfg < PR_COUNT_MAX_CFG ? n_cfg : PR_COUNT_MAX_CFG;
@@ -653,9 +739,6 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
         if ((rc = ta_check_launch(ctx, "k_pr_count"))) return rc;
     }
     if (impl) {
-        const int64_t n_tk = (int64_t)n_cat * n_cfg * n_rec;
-        k_pr_tk<<<(unsigned)((n_tk + 255) / 256), 256, 0, st>>>(a);
-        if ((rc = ta_check_launch(ctx, "k_pr_tk"))) return rc;
         k_pr_scan_live<<<n_cat, 128, 0, st>>>(a);
         if ((rc = ta_check_launch(ctx, "k_pr_scan_live"))) return rc;
     } else {
@@ -684,7 +767,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     const size_t n_prec = (size_t)n_thr * n_rec * n_cat * n_cfg;
     if (impl) {
         dim3 grid((unsigned)(((size_t)n_cat * n_cfg + PR_TILE_CELLS - 1) / PR_TILE_CELLS), (unsigned)n_thr);
-        k_pr_finalize_tile<<<grid, 128, (size_t)n_rec * (PR_TILE_CELLS + 1) * 8, st>>>(a);
+        k_pr_finalize_tile<<<grid, PR_FIN_WARPS * 32, (size_t)n_rec * (PR_TILE_CELLS + 1) * 8, st>>>(a);
         return ta_check_launch(ctx, "k_pr_finalize_tile");
     }
     k_pr_finalize<<<(unsigned)((n_prec + 255) / 256), 256, 0, st>>>(a);

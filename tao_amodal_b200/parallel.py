@@ -7,25 +7,33 @@ order and then in-group order (tao_amodal/evaluation/tao_amodal/eval.py:498-511,
 lvis_amodal/eval.py:340-361) — a histogram all-reduce cannot reproduce that, so the exchange
 moves one compact record per detection to the rank that owns its category:
 
-  setup (once per plan — the multi-GPU part of "building the plan", like ``acc_perm`` in prep):
-      all_to_all of (score f64, order key i64, category i32); the owner orders its records by
-      (category, -score, key) and keeps that permutation as its ``acc_perm``.
-      key = unit_id * 2**24 + position in the group  (unit_id = video id / image id: the
-      reference iterates units in sorted-id order, so this is its tie order).
-  every evaluation:
-      all_to_all of the TP/FP words  u32 [n_dt][n_cfg]   (the only per-step payload)
-      all_reduce(SUM) of num_gt      i32 [C][n_cfg]
-      ta_pr_accumulate on the owner's categories, renumbered densely (local index =
-      category index // world), so each rank produces a [T, R, ceil(C / world), n_cfg] slice
-      gather of the slices to rank 0, which interleaves them back into [T, R, C, n_cfg].
+  ownership   contiguous BLOCKS of categories, balanced by the global number of detections
+              (one all-reduce of the per-category counts at setup).  A rank's detections are
+              stored category-major (prep.py), so the records bound for one owner are one
+              contiguous slice of the local result arrays: the send side needs no packing.
+  setup       (once per plan — the multi-GPU part of "building the plan", like ``acc_perm``):
+              all-to-all of (score f64, order key i64, category i32); the owner orders its records
+              by (category, -score, key) and keeps that permutation as its ``acc_perm``.
+              key = unit_id * 2**24 + position in the group  (unit_id = video id / image id: the
+              reference iterates units in sorted-id order, so this is its tie order).
+  every evaluation  (ONE fused NCCL launch per plan, ``ta_exchange_*`` of include/ta_eval.h):
+              all-to-all of the result records — frame path: the compact 4-byte words of
+              ta_frame_eval plus the full rows of the few detections the general matcher
+              handled; track path: the full rows u32 [n_cfg] — and the all-reduce(SUM) of
+              num_gt i32 [C][n_cfg];
+              ta_pr_accumulate on the owner's category block, which yields the owner's
+              [T, R, C_own, n_cfg] slice of precision (and recall / counts).
+  results     stay with their owners (each copies its own slice out);  ``gather_to_root``
+              assembles the reference's full tensors on rank 0 when a caller wants them.
 
-Categories are dealt round-robin (owner = category index mod world) to spread the skew of
-category sizes.  Works with the NCCL backend on CUDA tensors and with gloo on CPU tensors (the
-world_size-2 CPU tests inject a host PR function).
+Two transports carry the same logic: ``AbiTransport`` (the C ABI over NCCL, CUDA tensors — the
+product path) and ``TorchTransport`` (``torch.distributed``; the world_size-2 gloo tests on CPU,
+which inject a host PR function).
 """
 from __future__ import annotations
 
-from typing import Callable, Optional
+import ctypes as C
+from typing import List
 
 import numpy as np
 
@@ -51,119 +59,274 @@ def category_of_dt(plan: EvalPlan) -> np.ndarray:
     return np.repeat(plan.grp_cat.astype(np.int32), np.diff(plan.grp_dt_off))
 
 
-class DistAccumulator:
-    """Exchange state of one plan on one rank."""
+def balanced_blocks(weights: np.ndarray, world: int) -> np.ndarray:
+    """int64 [world + 1]: category block boundaries such that every block holds about the same
+    total weight (number of detections); all-zero weights split by category count."""
+    w = np.asarray(weights, dtype=np.float64)
+    n = w.size
+    if w.sum() <= 0:
+        w = np.ones(n)
+    pre = np.concatenate([[0.0], np.cumsum(w)])
+    targets = pre[-1] * np.arange(1, world) / world
+    inner = np.searchsorted(pre, targets, side="left")
+    b = np.concatenate([[0], np.minimum(inner, n), [n]]).astype(np.int64)
+    return np.maximum.accumulate(b)
 
-    def __init__(self, plan: EvalPlan, rank: int, world: int, device, group=None):
+
+# ------------------------------------------------------------------------------ transports
+class TorchTransport:
+    """torch.distributed (gloo on CPU tensors for the tests, or nccl)."""
+
+    def __init__(self, rank: int, world: int, device, group=None):
+        self.rank, self.world, self.device, self.group = rank, world, device, group
+
+    def counts(self, send_counts: List[int]) -> List[int]:
         import torch
         import torch.distributed as dist
-        self.plan, self.rank, self.world, self.group = plan, rank, world, group
-        self.device = device
+        s = torch.tensor(send_counts, dtype=torch.int64, device=self.device)
+        r = torch.empty_like(s)
+        dist.all_to_all_single(r, s, group=self.group)
+        return [int(v) for v in r.cpu().tolist()]
+
+    def all_to_all(self, send, send_counts, recv_counts, out=None):
+        import torch
+        import torch.distributed as dist
+        n = int(sum(recv_counts))
+        if out is None:
+            out = torch.empty((n,) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(out[:n], send.contiguous(), list(recv_counts), list(send_counts),
+                               group=self.group)
+        return out[:n]
+
+    def all_reduce(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def begin(self):
+        pass
+
+    def end(self):
+        pass
+
+
+class AbiTransport:
+    """The C ABI over NCCL (ta_exchange_*): device tensors, torch's current stream."""
+
+    _DT = {"torch.int32": 0, "torch.int64": 1, "torch.float64": 2}
+
+    def __init__(self, eng, rank: int, world: int, unique_id: bytes):
+        import torch
+        from . import _lib
+        self.eng, self.rank, self.world = eng, rank, world
+        self.lib = eng.lib
+        h = C.c_void_p()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _lib.check(self.lib.ta_exchange_create(eng._ctx, rank, world, buf, C.byref(h)))
+        self._h = h
+        self.device = torch.device("cuda", eng.device)
+
+    @staticmethod
+    def unique_id(lib) -> bytes:
+        from . import _lib
+        buf = C.create_string_buffer(128)
+        _lib.check(lib.ta_exchange_unique_id(buf, 128))
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ta_exchange_destroy(self._h)
+            self._h = None
+
+    def _stream(self):
+        import torch
+        return C.c_void_p(torch.cuda.current_stream(self.eng.device).cuda_stream)
+
+    def counts(self, send_counts):
+        import torch
+        s = torch.tensor(send_counts, dtype=torch.int64, device=self.device)
+        r = self.all_to_all(s, [1] * self.world, [1] * self.world)
+        return [int(v) for v in r.cpu().tolist()]
+
+    def all_to_all(self, send, send_counts, recv_counts, out=None):
+        import torch
+        from . import _lib
+        row = int(np.prod(send.shape[1:], dtype=np.int64)) * send.element_size()
+        n = int(sum(recv_counts))
+        if out is None:
+            out = torch.empty((max(n, 1),) + tuple(send.shape[1:]), dtype=send.dtype, device=self.device)
+        so = np.concatenate([[0], np.cumsum(send_counts)]).astype(np.int64) * row
+        ro = np.concatenate([[0], np.cumsum(recv_counts)]).astype(np.int64) * row
+        assert send.is_contiguous() and out.is_contiguous()
+        _lib.check(self.lib.ta_exchange_alltoallv(
+            self._h, self._stream(), C.c_void_p(send.data_ptr()), so.ctypes.data_as(C.c_void_p),
+            C.c_void_p(out.data_ptr()), ro.ctypes.data_as(C.c_void_p)))
+        return out[:n]
+
+    def all_reduce(self, t):
+        from . import _lib
+        assert t.is_contiguous()
+        _lib.check(self.lib.ta_exchange_allreduce_sum(self._h, self._stream(), C.c_void_p(t.data_ptr()),
+                                                      t.numel(), self._DT[str(t.dtype)]))
+        return t
+
+    def begin(self):
+        from . import _lib
+        _lib.check(self.lib.ta_exchange_group_begin(self._h))
+
+    def end(self):
+        from . import _lib
+        _lib.check(self.lib.ta_exchange_group_end(self._h))
+
+
+# ------------------------------------------------------------------------------ routing
+class ExchangePlan:
+    """Routing state of one plan on one rank (built once per plan): category ownership, the
+    contiguous send slices, and the owner-side accumulate order of the received records."""
+
+    def __init__(self, plan: EvalPlan, tr, device):
+        import torch
+        self.plan, self.tr, self.device = plan, tr, device
+        self.rank, self.world = tr.rank, tr.world
         self.n_cat, self.n_cfg = len(plan.cat_ids), plan.n_cfg
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
-        cat = t(category_of_dt(plan)).to(torch.int64)
-        score = t(plan.dt_score)
-        key = t(order_keys(plan))
-        owner = cat % world
-        # records grouped by destination rank, local order preserved inside a destination
-        self.send_order = torch.sort(owner, stable=True).indices
-        send_counts = torch.bincount(owner, minlength=world).to(torch.int64)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts, group=group)
-        self.send_splits = send_counts.cpu().tolist()
-        self.recv_splits = recv_counts.cpu().tolist()
-        self.n_recv = int(sum(self.recv_splits))
-
-        def xchg(x):
-            out = torch.empty((self.n_recv,) + tuple(x.shape[1:]), dtype=x.dtype, device=device)
-            dist.all_to_all_single(out, x.index_select(0, self.send_order).contiguous(),
-                                   self.recv_splits, self.send_splits, group=group)
-            return out
-
-        r_cat, r_score, r_key = xchg(cat), xchg(score), xchg(key)
-        r_loc = r_cat // world              # dense local category index on the owner
+        cnt = t(np.diff(plan.cat_dt_off).astype(np.int64))
+        tr.all_reduce(cnt)
+        self.bounds = balanced_blocks(cnt.cpu().numpy(), self.world)        # [world + 1] categories
+        dt_b = np.asarray(plan.cat_dt_off, dtype=np.int64)[self.bounds]     # local detection slices
+        self.send_counts = [int(v) for v in np.diff(dt_b)]
+        self.recv_counts = tr.counts(self.send_counts)
+        self.n_recv = int(sum(self.recv_counts))
+        self.c_lo, self.c_hi = int(self.bounds[self.rank]), int(self.bounds[self.rank + 1])
+        self.n_loc = self.c_hi - self.c_lo
+        r_cat = tr.all_to_all(t(category_of_dt(plan)).to(torch.int64), self.send_counts, self.recv_counts)
+        r_score = tr.all_to_all(t(plan.dt_score), self.send_counts, self.recv_counts)
+        r_key = tr.all_to_all(t(order_keys(plan)), self.send_counts, self.recv_counts)
+        r_loc = r_cat - self.c_lo                # dense local category index on the owner
         # (category, -score, key) order through three stable sorts, least significant first
         p = torch.sort(r_key, stable=True).indices
         p = p[torch.sort(-r_score[p], stable=True).indices]
         p = p[torch.sort(r_loc[p], stable=True).indices]
         self.acc_perm = p.to(torch.int32).contiguous()
-        self.n_loc = -(-self.n_cat // world)                        # ceil(C / world), padded
-        self.n_own = len(range(rank, self.n_cat, world))
-        cnt = torch.bincount(r_loc, minlength=self.n_loc)
+        cnt_loc = torch.bincount(r_loc, minlength=max(self.n_loc, 1))
         self.cat_dt_off = torch.zeros(self.n_loc + 1, dtype=torch.int64, device=device)
-        self.cat_dt_off[1:] = torch.cumsum(cnt, 0)
-        self.recv_rows = torch.empty((max(self.n_recv, 1), self.n_cfg), dtype=torch.int32,
-                                     device=device)
+        if self.n_loc:
+            self.cat_dt_off[1:] = torch.cumsum(cnt_loc[:self.n_loc], 0)
 
     # ---------------------------------------------------------------------------- per step
-    def exchange_tpfp(self, tpfp_local):
-        """tpfp_local: int32 [n_dt, n_cfg] (device order) -> this rank's received rows."""
-        import torch.distributed as dist
-        send = tpfp_local.index_select(0, self.send_order).contiguous()
-        out = self.recv_rows[:self.n_recv]
-        dist.all_to_all_single(out, send, self.recv_splits, self.send_splits, group=self.group)
-        return out
+    def exchange(self, records, out=None):
+        """records: [n_dt, ...] in local detection order -> this owner's received records."""
+        return self.tr.all_to_all(records, self.send_counts, self.recv_counts, out=out)
 
     def global_num_gt(self, num_gt_local):
-        """Sum over ranks; returns (global counts [C, n_cfg], this rank's categories
-        [ceil(C / world), n_cfg], zero-padded)."""
-        import torch
-        import torch.distributed as dist
-        g = num_gt_local.clone()
-        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
-        own = torch.zeros((self.n_loc, g.shape[1]), dtype=g.dtype, device=g.device)
-        own[:self.n_own] = g[self.rank::self.world]
-        return g, own
+        """Sum over ranks (in place); returns (global counts [C, n_cfg], the owner's block)."""
+        g = self.tr.all_reduce(num_gt_local)
+        return g, g[self.c_lo:self.c_hi]
 
-    def merge_to_root(self, parts, full=None):
+    def gather_to_root(self, parts, full=None):
         """parts: this rank's [.., n_loc, n_cfg] tensors (category axis = -2).  Rank 0 receives
-        every rank's slice and interleaves them into the matching `full` tensors."""
-        import torch
-        import torch.distributed as dist
+        every owner's slice and places it at the owner's category block of the matching `full`
+        tensor.  Not part of an evaluation step: results live with their owners."""
         for i, x in enumerate(parts):
             x = x.contiguous()
-            recv = [torch.empty_like(x) for _ in range(self.world)] if self.rank == 0 else None
-            dist.gather(x, recv, dst=0, group=self.group)
+            lead = int(np.prod(x.shape[:-2], dtype=np.int64))
+            per_cat = lead * x.shape[-1]
+            sizes = [int(self.bounds[r + 1] - self.bounds[r]) * per_cat for r in range(self.world)]
+            send_counts = [x.numel()] + [0] * (self.world - 1)
+            recv_counts = sizes if self.rank == 0 else [0] * self.world
+            got = self.tr.all_to_all(x.reshape(-1), send_counts, recv_counts)
             if self.rank == 0:
+                off = 0
                 for r in range(self.world):
-                    n_r = len(range(r, self.n_cat, self.world))
-                    full[i][..., r::self.world, :] = recv[r][..., :n_r, :]
+                    lo, hi = int(self.bounds[r]), int(self.bounds[r + 1])
+                    if hi > lo:
+                        blk = got[off:off + sizes[r]].reshape(tuple(x.shape[:-2]) + (hi - lo, x.shape[-1]))
+                        full[i][..., lo:hi, :] = blk
+                    off += sizes[r]
 
 
-class DeviceDistAccumulator(DistAccumulator):
-    """DistAccumulator driving ta_pr_accumulate on the owner's slice (CUDA / NCCL)."""
+class DeviceExchange(ExchangePlan):
+    """ExchangePlan driving ta_pr_accumulate on the owner's block (CUDA, AbiTransport)."""
 
-    def __init__(self, eng, dev, rank: int, world: int, group=None):
+    def __init__(self, eng, dev, tr):
         import torch
-        super().__init__(dev.plan, rank, world, dev.dev, group)
+        super().__init__(dev.plan, tr, dev.dev)
         self.eng, self.dev = eng, dev
-        dev.compact = False          # the exchange ships full TP/FP rows
         T, R, L, K = dev.n_thr, dev.n_rec, self.n_loc, self.n_cfg
         d = dev.dev
         self.part = {"precision": torch.empty((T, R, L, K), dtype=torch.float64, device=d),
                      "recall": torch.empty((T, L, K), dtype=torch.float64, device=d),
                      "tp_cnt": torch.empty((T, L, K), dtype=torch.int64, device=d),
                      "fp_cnt": torch.empty((T, L, K), dtype=torch.int64, device=d)}
+        n_dt, n = dev.plan.n_dt, max(self.n_recv, 1)
+        self.compact = bool(dev.compact and "dt_word" in dev.t)
+        self.recv_rows = torch.zeros((n, K), dtype=torch.int32, device=d)
+        self.num_gt_global = torch.zeros_like(dev.t["num_gt"])
+        if self.compact:
+            # one dry run of the local matcher tells which detections carry a full row (groups
+            # the general matcher handled): their rows travel next to the compact words
+            eng.stage_frame_eval(dev)
+            words = dev.t["dt_word"][:n_dt]
+            self.flag_idx = torch.nonzero(words < 0).flatten().to(torch.int32).contiguous()
+            b = np.asarray(dev.plan.cat_dt_off, dtype=np.int64)[self.bounds]
+            pos = np.searchsorted(self.flag_idx.cpu().numpy(), b, side="left")
+            self.flag_send = [int(v) for v in np.diff(pos)]
+            self.flag_recv = tr.counts(self.flag_send)
+            self.recv_words = torch.zeros(n, dtype=torch.int32, device=d)
+            self.exchange(words, out=self.recv_words)
+            self.recv_flag_idx = (torch.nonzero(self.recv_words[:self.n_recv] < 0).flatten()
+                                  .to(torch.int32).contiguous())
+            assert int(self.recv_flag_idx.numel()) == int(sum(self.flag_recv))
+            nf, nr = max(int(self.flag_idx.numel()), 1), max(int(self.recv_flag_idx.numel()), 1)
+            self.send_flag_rows = torch.zeros((nf, K), dtype=torch.int32, device=d)
+            self.recv_flag_rows = torch.zeros((nr, K), dtype=torch.int32, device=d)
 
     def accumulate(self):
-        import ctypes as C
+        """Exchange + owner-side PR of the matcher outputs currently in dev's buffers."""
         import torch
         from . import _lib
-        dev, eng = self.dev, self.eng
+        dev, eng, tr = self.dev, self.eng, self.tr
         t = dev.t
-        n_dt, n_cfg = dev.plan.n_dt, self.n_cfg
-        rows = self.exchange_tpfp(t["dt_tpfp"][:n_dt * n_cfg].view(n_dt, n_cfg))
-        num_gt, num_gt_own = self.global_num_gt(t["num_gt"])
+        n_dt, K = dev.plan.n_dt, self.n_cfg
         st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
         P = lambda x: C.c_void_p(x.data_ptr())
+        rows_all = t["dt_tpfp"][:n_dt * K].view(n_dt, K)
+        self.num_gt_global.copy_(t["num_gt"])
+        use_words = self.compact and dev.words_valid
+        if use_words:
+            nf = int(self.flag_idx.numel())
+            if nf:
+                _lib.check(eng.lib.ta_exchange_gather(eng._ctx, st, nf, K, P(self.flag_idx),
+                                                      P(rows_all), P(self.send_flag_rows)))
+            tr.begin()
+            self.exchange(t["dt_word"][:n_dt], out=self.recv_words)
+            tr.all_to_all(self.send_flag_rows[:nf], self.flag_send, self.flag_recv,
+                          out=self.recv_flag_rows)
+            tr.all_reduce(self.num_gt_global)
+            tr.end()
+            nr = int(self.recv_flag_idx.numel())
+            if nr:
+                _lib.check(eng.lib.ta_exchange_scatter(eng._ctx, st, nr, K, P(self.recv_flag_idx),
+                                                       P(self.recv_flag_rows), P(self.recv_rows)))
+        else:
+            tr.begin()
+            self.exchange(rows_all, out=self.recv_rows)
+            tr.all_reduce(self.num_gt_global)
+            tr.end()
+        own = self.num_gt_global[self.c_lo:self.c_hi]
         q = self.part
-        _lib.check(eng.lib.ta_pr_accumulate(
-            eng._ctx, st, self.n_loc, P(self.cat_dt_off), P(self.acc_perm), self.n_recv, P(rows),
-            None, P(num_gt_own), dev.n_thr, n_cfg, dev.n_rec, dev.ptr["rec_thrs"],
-            P(q["precision"]), P(q["recall"]), P(q["tp_cnt"]), P(q["fp_cnt"])))
+        if self.n_loc:
+            _lib.check(eng.lib.ta_pr_accumulate(
+                eng._ctx, st, self.n_loc, P(self.cat_dt_off), P(self.acc_perm), self.n_recv,
+                P(self.recv_rows), P(self.recv_words) if use_words else None, P(own),
+                dev.n_thr, K, dev.n_rec, dev.ptr["rec_thrs"],
+                P(q["precision"]), P(q["recall"]), P(q["tp_cnt"]), P(q["fp_cnt"])))
+
+    def to_root(self):
+        """Assemble the reference's full tensors in dev.t on rank 0 (API / parity checks)."""
         names = ("precision", "recall", "tp_cnt", "fp_cnt")
-        self.merge_to_root([q[k] for k in names], [t[k] for k in names])
-        t["num_gt"].copy_(num_gt)
+        self.gather_to_root([self.part[k] for k in names], [self.dev.t[k] for k in names])
+        self.dev.t["num_gt"].copy_(self.num_gt_global)
 
 
 def shard_videos(video_ids, world: int, weights=None):

@@ -34,7 +34,10 @@ class SynthConfig:
     categories: int
     seed: int
     gt_span: Optional[int] = None     # fixed alive span for every GT track (cfg5 uses 10)
-    pred_full_length: bool = False    # every predicted track covers all frames (cfg5)
+    pred_full_length: bool = False    # predicted tracks that are not copies of a GT track cover
+                                      # all frames (cfg5); copies always live on the GT's span —
+                                      # a 40-frame copy of a 10-frame GT track would have 3-D IoU
+                                      # <= 0.25 and the set's AP would be identically 0
     score_quantum: float = 0.0        # >0: scores are multiples of this (tie stress)
     sparse_image_ids: bool = False    # non-consecutive ids -> CPython set order != ascending
     keep_prob: float = 0.9            # per-frame keep probability of a copied track
@@ -53,7 +56,9 @@ CONFIGS = {
                         categories=100, seed=1001),
     "cfg3": SynthConfig("cfg3", videos=500, frames=300, pred_tracks=200, gt_tracks=30,
                         categories=1203, seed=1002),
-    "cfg5": SynthConfig("cfg5", videos=5000, frames=40, pred_tracks=5, gt_tracks=2,
+    # 1 M predicted boxes: 8 tracks per video, half of them 10-frame copies of a GT track, the
+    # others 40-frame static boxes -> 5000 x 8 x 25 boxes on average
+    "cfg5": SynthConfig("cfg5", videos=5000, frames=40, pred_tracks=8, gt_tracks=2,
                         categories=1203, seed=1004, gt_span=10, pred_full_length=True),
 }
 
@@ -166,19 +171,11 @@ def generate(cfg: SynthConfig) -> Tuple[GtColumns, DtColumns]:
             next_pred_track += 1
             if kind == 0:
                 s, e, cat, path = gt_paths[int(rng.integers(0, G))]
-                if cfg.pred_full_length:
-                    full = np.empty((F, 4))
-                    full[:s] = path[0]
-                    full[s:e] = path
-                    full[e:] = path[-1]
-                    frames = np.arange(F)
-                    boxes = full
-                else:
-                    keep = rng.uniform(size=e - s) < cfg.keep_prob
-                    if not keep.any():
-                        keep[0] = True
-                    frames = np.arange(s, e)[keep]
-                    boxes = path[keep]
+                keep = rng.uniform(size=e - s) < cfg.keep_prob
+                if not keep.any():
+                    keep[0] = True
+                frames = np.arange(s, e)[keep]
+                boxes = path[keep]
                 boxes = boxes + _quant(rng.uniform(-3.0, 3.0, size=boxes.shape))
                 boxes[:, 2:] = np.maximum(boxes[:, 2:], 1.0)
             else:

@@ -336,4 +336,34 @@ int hs_rle_iou(int64_t n_groups, const int64_t* grp_dt_off, const int64_t* grp_g
     return 0;
 }
 
+// Plane words of one warp (32 detections) from COMPACT result words, the way k_pr_bits builds
+// them (one 32 x 32 bit transpose + pr_cell_planes), next to the per-cfg expansion + transpose
+// of the full-row path.  tp / fp: [n_cfg * n_thr] words each.  Returns 0 when both agree.
+int hs_pr_compact_planes(const uint32_t* words32, int n_thr, int n_cfg, uint32_t* tp, uint32_t* fp) {
+    uint32_t x[32], y[32];
+    for (int l = 0; l < 32; ++l) x[l] = (words32[l] >> 31) ? 0u : words32[l];
+    for (int j = 16; j >= 1; j >>= 1) {
+        for (int l = 0; l < 32; ++l) y[l] = x[l ^ j];
+        for (int l = 0; l < 32; ++l) x[l] = pr_transpose_stage(x[l], y[l], l, j);
+    }
+    int bad = 0;
+    for (int cfg = 0; cfg < n_cfg; ++cfg) {
+        // reference: expand every lane's word for this cfg and transpose
+        uint32_t r[32], q[32];
+        for (int l = 0; l < 32; ++l) r[l] = (words32[l] >> 31) ? 0u : pr_expand(words32[l], cfg, n_thr, n_cfg);
+        for (int j = 16; j >= 1; j >>= 1) {
+            for (int l = 0; l < 32; ++l) q[l] = r[l ^ j];
+            for (int l = 0; l < 32; ++l) r[l] = pr_transpose_stage(r[l], q[l], l, j);
+        }
+        for (int k = 0; k < n_thr; ++k) {
+            uint32_t a, b;
+            pr_cell_planes(x[k], x[n_thr + cfg], x[n_thr + n_cfg + cfg], x[n_thr + 2 * n_cfg + cfg], a, b);
+            tp[cfg * n_thr + k] = a;
+            fp[cfg * n_thr + k] = b;
+            if (a != r[k] || b != r[16 + k]) ++bad;
+        }
+    }
+    return bad;
+}
+
 }  // extern "C"

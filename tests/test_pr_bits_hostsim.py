@@ -65,3 +65,30 @@ def test_goldens_through_the_bit_plane_emulation(golden):
         compare_with_golden(golden, "tao_", tao_plan, run_hostsim(tao_plan, pr_impl=impl),
                             exact_iou=not off_grid, iou_atol=1e-12)
         compare_with_golden(golden, "lvis_", lvis_plan, run_hostsim(lvis_plan, pr_impl=impl))
+
+
+@pytest.mark.parametrize("n_thr,n_cfg", [(10, 6), (16, 5), (1, 10), (3, 2), (13, 6)])
+def test_compact_words_give_the_planes_of_the_expanded_rows(n_thr, n_cfg):
+    """k_pr_bits, compact-word path: one bit transpose of the words + pr_cell_planes per cell
+    equals expanding every word into its full TP/FP row (pr_expand) and transposing per cfg;
+    and pr_expand equals the host-side expansion (engine.expand_words)."""
+    import ctypes as C
+    hs = plan_backends.build_hostsim()
+    rng = np.random.Generator(np.random.PCG64(n_thr * 100 + n_cfg))
+    assert n_thr + 3 * n_cfg <= 31
+    for _ in range(50):
+        w = rng.integers(0, 1 << (n_thr + 3 * n_cfg), size=32, dtype=np.uint64).astype(np.uint32)
+        w[rng.uniform(size=32) < 0.1] |= np.uint32(1 << 31)      # detections with a full row
+        w[rng.uniform(size=32) < 0.1] = 0                       # dead lanes
+        tp = np.zeros(n_thr * n_cfg, dtype=np.uint32)
+        fp = np.zeros_like(tp)
+        bad = hs.hs_pr_compact_planes(w.ctypes.data_as(C.c_void_p), n_thr, n_cfg,
+                                      tp.ctypes.data_as(C.c_void_p), fp.ctypes.data_as(C.c_void_p))
+        assert bad == 0
+        rows = engine.expand_words(w, np.zeros((32, n_cfg), dtype=np.uint32), n_thr, n_cfg)
+        live = (w >> 31) == 0
+        for cfg in range(n_cfg):
+            for k in range(n_thr):
+                want_tp = sum(int((rows[l, cfg] >> k) & 1) << l for l in range(32) if live[l])
+                want_fp = sum(int((rows[l, cfg] >> (16 + k)) & 1) << l for l in range(32) if live[l])
+                assert int(tp[cfg * n_thr + k]) == want_tp and int(fp[cfg * n_thr + k]) == want_fp
