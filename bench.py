@@ -63,8 +63,9 @@ def make_workload(name: str, rank: int, videos: int = 0):
 
 def algorithmic_bytes(plan, cells_with_gt: int = 0) -> dict:
     """Algorithmic HBM bytes of each kernel for one launch on this plan (DESIGN.md §4,
-    SURVEY §8d).  cells_with_gt = number of (category, cfg) cells with non-ignored GT (only
-    those produce precision values other than the -1 fill)."""
+    SURVEY §8d): every array a kernel has to read or write, counted once.  cells_with_gt =
+    number of (category, cfg) cells with non-ignored GT (only those produce precision values
+    other than the -1 fill)."""
     nd_box, ng_box = plan.dt_box.shape[0], plan.gt_box.shape[0]
     n_iou = int(plan.iou_off[-1])
     n_cfg, n_dt, n_gt = plan.n_cfg, plan.n_dt, plan.n_gt
@@ -79,26 +80,26 @@ def algorithmic_bytes(plan, cells_with_gt: int = 0) -> dict:
         nd_box = int((db[1:] - db[:-1])[act].sum())
         ng_box = int((gb[1:] - gb[:-1])[act].sum())
     n_chunks = int(np.ceil(np.diff(plan.cat_dt_off) / 256.0).sum())
+    n_tasks = n_dt // 256 + n_gt // 64 + 1
+    compact = plan.kind == "lvis" and T + 3 * n_cfg <= 31
+    word_bytes = 4 if compact else 4 * n_cfg          # result bytes per detection
     return {
         "iou": per_box * (nd_box + ng_box) + 8 * n_iou,
         # IoU matrix + dt (area, n_anns, flag) + gt (attr a, b, hp, flag) read, TP/FP words written
         "match": 8 * n_iou + 17 * n_dt + 21 * n_gt + 4 * n_cfg * n_dt,
-        # lane-per-detection frame kernel: boxes, flags, detection->group map, group offsets of
-        # the groups with detections, GT visibility; TP/FP words written
-        "frame_flat": 32 * (nd_box + ng_box) + 5 * n_dt + 9 * n_gt + 16 * plan.n_groups
-                      + 4 * n_cfg * n_dt,
-        # group table + GT visibility/flags read, detection->group map written
-        "frame_prep": 20 * plan.n_groups + 9 * n_gt + 4 * n_dt,
+        # streamed lane-per-detection frame kernel: boxes (each once), the per-detection
+        # descriptor word, the per-GT word, the task table; one result word per detection
+        "frame_flat": 32 * (nd_box + ng_box) + 4 * n_dt + 4 * n_gt + 16 * n_tasks + word_bytes * n_dt,
+        # group table + GT visibility/flags read, per-GT words written
+        "frame_prep": 20 * plan.n_groups + 9 * n_gt + 4 * n_gt,
         # permutation + TP/FP words read, chunk counters written
         "pr_count": n_dt * (4 + 4 * n_cfg) + 128 * n_cfg * n_chunks,
-        # permutation + TP/FP words + chunk counters read; chunk bests and the answered recall
-        # levels of the cells that have GT written
         "pr_envelope": n_dt * (4 + 4 * n_cfg) + (128 + 8 * T) * n_cfg * n_chunks
                        + 8 * T * R * cells_with_gt,
-        # bit-plane variant (TA_PR_IMPL=1): k_pr_bits reads permutation + words, writes the TP / FP
-        # planes (64 B per cell and chunk) and the chunk counters; k_pr_envelope_bits reads the
-        # planes + counters and writes what k_pr_envelope writes
-        "pr_bits": n_dt * (4 + 4 * n_cfg) + (128 + 64 * T) * n_cfg * n_chunks,
+        # bit-plane path: k_pr_bits reads permutation + result words, writes the TP / FP planes
+        # (64 B per cell and chunk) and the chunk counters; k_pr_envelope_bits reads the planes +
+        # counters and writes chunk bests + the answered recall levels of the cells with GT
+        "pr_bits": n_dt * (4 + word_bytes) + (128 + 64 * T) * n_cfg * n_chunks,
         "pr_envelope_bits": (128 + 64 * T + 8 * T) * n_cfg * n_chunks + 8 * T * R * cells_with_gt,
         # precision tensor written once, answered entries read once
         "pr_finalize": 8 * T * R * n_cat * n_cfg + 8 * T * R * cells_with_gt,
@@ -280,17 +281,18 @@ def reference_arm(args):
     return 0
 
 
-def cpu_baseline_leg(args, gt, dt):
+def cpu_baseline_leg(args, gt, dt, eng=None):
     """cpu_baseline of the main arm (rank 0, N = 1): the unmodified reference, one warm-up pass
     (numba JIT compile) + one timed pass over the fixed sample; the oracle port on all cores
-    when the reference tree is absent."""
+    when the reference tree is absent.  With an engine the same sample also runs through this
+    repo's pipeline and the summary metrics of both are compared (parity.reference_sample_*)."""
     import tempfile
     from oracle import ref_bench
     if ref_bench.find_reference() is not None:
         with tempfile.TemporaryDirectory() as td:
             ap, rp, pairs, sample = reference_sample(args.workload, td)
             ref_bench.run_once(ap, rp)
-            s, _ = ref_bench.run_once(ap, rp)
+            s, ref_res = ref_bench.run_once(ap, rp)
             out = {"value": pairs / s, "unit": UNIT, "cores": 1, "kind": "reference",
                    "sample": sample + "; unmodified reference (baseline/_ref), 1 process, %.1f s" % s}
             try:
@@ -298,6 +300,22 @@ def cpu_baseline_leg(args, gt, dt):
                 out["value_numba_disabled"] = pairs / nj
             except Exception:           # noqa: BLE001
                 out["value_numba_disabled"] = None
+            if eng is not None:
+                from tao_amodal_b200 import engine, ingest, materialize, prep
+                g, d = ingest.load_gt(ap), ingest.load_dt(rp)
+                lp = prep.prepare_lvis(g, d)
+                d2 = d.copy()
+                prep.make_track_ids_unique(d2)
+                tp = prep.prepare_tao(g, d2)
+                o_t, o_l = eng.evaluate_host(tp), eng.evaluate_host(lp)
+                mine = {
+                    "tao_AP": float(materialize.summarize_tao(
+                        o_t.precision.reshape(o_t.precision.shape[:3] + (5, 4)),
+                        o_t.recall.reshape(o_t.recall.shape[:2] + (5, 4)), engine.IOU_THRS)["AP"]),
+                    "lvis_AP": float(materialize.summarize_lvis(
+                        o_l.precision, o_l.recall, engine.IOU_THRS, lp.freq_groups)["AP"])}
+                out["parity"] = {"reference_sample_AP": ref_res, "ours_sample_AP": mine,
+                                 "reference_sample_identical": bool(mine == ref_res)}
         return out
     cores = os.cpu_count() or 1
     samples = cpu_samples(gt, dt, cores, CPU_SAMPLE_FRAMES)
@@ -319,6 +337,95 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------ main arm
+OUT_KEYS = ("precision", "recall", "tp_cnt", "fp_cnt", "num_gt")
+
+
+def plans_of(gt, dt):
+    from tao_amodal_b200 import prep
+    lvis_plan = prep.prepare_lvis(gt, dt, allow_empty=True)
+    dt2 = dt.copy()
+    prep.make_track_ids_unique(dt2)
+    tao_plan = prep.prepare_tao(gt, dt2, vid_ids=np.unique(gt.vid_id), allow_empty=True)
+    return tao_plan, lvis_plan
+
+
+class Pipeline:
+    """The bench step on one rank: both evaluators on resident plans, with the cross-rank
+    exchange when world > 1."""
+
+    STAGES = ["tao_iou", "tao_match", "tao_acc", "lvis_eval", "lvis_acc"]
+
+    def __init__(self, eng, tao_plan, lvis_plan, transport=None):
+        self.eng = eng
+        self.d_tao, self.d_lvis = eng.upload(tao_plan), eng.upload(lvis_plan)
+        self.exch = None
+        if transport is not None:
+            from tao_amodal_b200 import parallel
+            self.exch = {id(d): parallel.DeviceExchange(eng, d, transport)
+                         for d in (self.d_tao, self.d_lvis)}
+        eng_, d_tao, d_lvis = eng, self.d_tao, self.d_lvis
+        self.stages = [lambda: eng_.stage_iou(d_tao), lambda: eng_.stage_match(d_tao),
+                       lambda: self.acc(d_tao), lambda: eng_.stage_frame_eval(d_lvis),
+                       lambda: self.acc(d_lvis)]
+
+    def acc(self, dev):
+        if self.exch is None:
+            self.eng.stage_accumulate(dev)
+        else:
+            self.exch[id(dev)].accumulate()
+
+    def step(self, record=None):
+        for k, fn in enumerate(self.stages):
+            if record is not None:
+                record[k][0].record()
+            fn()
+            if record is not None:
+                record[k][1].record()
+
+    def outputs(self, root_only=True):
+        """The reference-layout tensors as numpy (after to_root when sharded); None off-root."""
+        if self.exch is not None:
+            for d in (self.d_tao, self.d_lvis):
+                self.exch[id(d)].to_root()
+            if root_only and self.exch[id(self.d_tao)].rank != 0:
+                return None
+        return {n + "_" + k: d.t[k].cpu().numpy().copy()
+                for n, d in (("tao", self.d_tao), ("lvis", self.d_lvis)) for k in OUT_KEYS}
+
+
+def timed(torch, dist, world, pipe, steps, warmup, eng, local, clock=True):
+    """W warm-up + K timed steps: CUDA events on the launch stream around the region and around
+    every stage, per-kernel events inside the library; barrier + synchronize on both sides."""
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+    for _ in range(warmup):
+        pipe.step()
+    sync()
+    sampler = ClockSampler(local) if clock else None
+    if sampler:
+        sampler.start()
+    ev = [[[torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+           for _ in pipe.STAGES] for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launches
+    eng.timing(True)           # per-kernel CUDA events inside the library (ta_ctx_timing)
+    e0.record()
+    for s in range(steps):
+        pipe.step(ev[s])
+    e1.record()
+    sync()
+    kernel_ms = eng.timing_read()
+    eng.timing(False)
+    clocks = sampler.stop() if sampler else None
+    stage_ms = {n: float(np.mean([ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(steps)]))
+                for i, n in enumerate(pipe.STAGES)}
+    return {"dev_ms": e0.elapsed_time(e1), "launches": eng.launches - l0, "kernel_ms": kernel_ms,
+            "clocks": clocks, "stage_ms": stage_ms}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -328,6 +435,8 @@ def main():
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--videos", type=int, default=0, help="override videos per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true",
+                    help="N > 1: skip the strong-scaling section (same set sharded + parity)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -344,7 +453,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from tao_amodal_b200.engine import Engine
-    from tao_amodal_b200 import prep
+    from tao_amodal_b200 import prep, synth
     t_prep = time.perf_counter()
     gt, dt, tao_plan, lvis_plan = make_workload(args.workload, rank, args.videos)
     pairs_trk = prep.count_box_pair_visits(tao_plan)
@@ -353,63 +462,40 @@ def main():
     t_prep = time.perf_counter() - t_prep
 
     eng = Engine(local)
-    d_tao, d_lvis = eng.upload(tao_plan), eng.upload(lvis_plan)
-    exch = None
+    transport = None
     if world > 1:
+        # the C ABI's own NCCL communicator (ta_exchange_*): rank 0 draws the id
         from tao_amodal_b200 import parallel
-        exch = {id(d): parallel.DeviceDistAccumulator(eng, d, rank, world) for d in (d_tao, d_lvis)}
+        box = [parallel.AbiTransport.unique_id(eng.lib) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        transport = parallel.AbiTransport(eng, rank, world, box[0])
+    pipe = Pipeline(eng, tao_plan, lvis_plan, transport)
+    d_tao, d_lvis = pipe.d_tao, pipe.d_lvis
 
-    cells_with_gt = [int((eng.evaluate_device(dv).num_gt > 0).sum()) for dv in (d_tao, d_lvis)]
-    stage_names = ["tao_iou", "tao_match", "tao_acc", "lvis_eval", "lvis_acc"]
-    ev = None
-
-    def acc(dev):
-        if exch is None:
-            eng.stage_accumulate(dev)
-        else:
-            exch[id(dev)].accumulate()
-
-    stages = [lambda: eng.stage_iou(d_tao), lambda: eng.stage_match(d_tao), lambda: acc(d_tao),
-              lambda: eng.stage_frame_eval(d_lvis), lambda: acc(d_lvis)]
-
-    def step(record=None):
-        for k, fn in enumerate(stages):
-            if record is not None:
-                record[k][0].record()
-            fn()
-            if record is not None:
-                record[k][1].record()
-
-    def sync():
-        torch.cuda.synchronize()
+    res = timed(torch, dist, world, pipe, args.steps, args.warmup, eng, local)
+    dev_ms, kernel_ms, clocks, launches, stage_ms = (res["dev_ms"], res["kernel_ms"], res["clocks"],
+                                                     res["launches"], res["stage_ms"])
+    parity = {}
+    single = None
+    if world == 1 or rank == 0:
+        # what was just timed, on this rank's own (whole) set, single GPU: the comparator of the
+        # host-buffer call (N = 1) and of the sharded run of the same set (N > 1)
         if world > 1:
-            dist.barrier()
+            eng.stage_iou(d_tao)
+            eng.stage_match(d_tao)
+            eng.stage_accumulate(d_tao)
+            eng.stage_frame_eval(d_lvis)
+            eng.stage_accumulate(d_lvis)
             torch.cuda.synchronize()
+            single = {n + "_" + k: d.t[k].cpu().numpy().copy()
+                      for n, d in (("tao", d_tao), ("lvis", d_lvis)) for k in OUT_KEYS}
+        else:
+            single = pipe.outputs()
+    cells_with_gt = [0, 0]
+    if single is not None:
+        cells_with_gt = [int((single["tao_num_gt"] > 0).sum()), int((single["lvis_num_gt"] > 0).sum())]
 
-    for _ in range(args.warmup):
-        step()
-    sync()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev = [[[torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
-           for _ in stage_names] for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = eng.launches
-    eng.timing(True)           # per-kernel CUDA events inside the library (ta_ctx_timing)
-    e0.record()
-    for s in range(args.steps):
-        step(ev[s])
-    e1.record()
-    sync()
-    kernel_ms = eng.timing_read()
-    eng.timing(False)
-    clocks = sampler.stop()
-    launches = eng.launches - l0
-    dev_ms = e0.elapsed_time(e1)
-    stage_ms = {n: float(np.mean([ev[s][i][0].elapsed_time(ev[s][i][1]) for s in range(args.steps)]))
-                for i, n in enumerate(stage_names)}
-
-    # ---- e2e: host buffers (pinned) through the single C call, H2D + D2H inside the region
+    # ---- e2e: host buffers (pinned) through the C call(s), H2D + D2H inside the region
     def pin(plan):
         import dataclasses
         rep = {}
@@ -445,10 +531,14 @@ def main():
             eng.evaluate_host_many([p_tao, p_lvis], outs=outs)
             return (outs[0].h2d_bytes + outs[1].h2d_bytes, outs[0].d2h_bytes + outs[1].d2h_bytes)
     else:
+        # pinned host slices for every owner's results: each rank copies its OWN category block out
+        host_part = {id(dv): {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                              for k, v in pipe.exch[id(dv)].part.items()} for dv in (d_tao, d_lvis)}
+
         def e2e_step():
-            # pinned host plan -> HBM, local IoU + matching, cross-rank exchange of the TP/FP
-            # records, owner-side PR, merged tensors back on rank 0's host.  (The exchange's
-            # routing tables are part of the plan, like acc_perm, and stay resident.)
+            # pinned host plan -> HBM, local IoU + matching, cross-rank exchange of the result
+            # records, owner-side PR, every owner's slice back to ITS host (pinned).  (The
+            # exchange's routing tables are part of the plan, like acc_perm, and stay resident.)
             h2d = d2h = 0
             for plan, dev in ((p_tao, d_tao), (p_lvis, d_lvis)):
                 h2d += dev.reload(plan)
@@ -457,19 +547,85 @@ def main():
                     eng.stage_match(dev)
                 else:
                     eng.stage_frame_eval(dev)
-                exch[id(dev)].accumulate()
-                if rank == 0:
-                    for k in ("precision", "recall", "tp_cnt", "fp_cnt", "num_gt"):
-                        d2h += dev.t[k].cpu().numpy().nbytes
+                ex = pipe.exch[id(dev)]
+                ex.accumulate()
+                for k, v in ex.part.items():
+                    host_part[id(dev)][k].copy_(v, non_blocking=True)
+                    d2h += v.numel() * v.element_size()
             torch.cuda.synchronize()
             return h2d, d2h
     for _ in range(2):
         e2e_step()
-    sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         h2d, d2h = e2e_step()
     e2e_s = time.perf_counter() - t0
+    if world == 1:
+        # the host-buffer call and the resident route must agree bit for bit
+        host_out = {n + "_" + k: getattr(o, k) for n, o in (("tao", outs[0]), ("lvis", outs[1]))
+                    for k in OUT_KEYS}
+        parity["host_call_equals_resident"] = bool(all(
+            np.array_equal(host_out[k].reshape(single[k].shape), single[k]) for k in single))
+
+    # ---- N > 1: the SAME set sharded per video over the ranks (BASELINE configs[3] / [4]):
+    # strong-scaling time and bit-identity of the merged tensors with the 1-GPU ones
+    strong = None
+    if world > 1 and not args.no_strong:
+        from tao_amodal_b200 import parallel
+        from tao_amodal_b200.columnar import subset_videos
+        cfg = synth.CONFIGS[args.workload]
+        over = {"seed": cfg.seed}
+        if args.videos:
+            over["videos"] = args.videos
+        t_s = time.perf_counter()
+        gt0, dt0 = (gt, dt) if rank == 0 else synth.generate_named(args.workload, **over)
+        shards = parallel.shard_videos(np.unique(gt0.vid_id), world)
+        g_s, d_s = subset_videos(gt0, dt0, shards[rank])
+        s_tao, s_lvis = plans_of(g_s, d_s)
+        t_s = time.perf_counter() - t_s
+        del pipe.exch
+        spipe = Pipeline(eng, s_tao, s_lvis, transport)
+        sres = timed(torch, dist, world, spipe, args.steps, args.warmup, eng, local, clock=False)
+        merged = spipe.outputs()
+        tt = torch.tensor([sres["dev_ms"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ok = torch.tensor([1], device="cuda", dtype=torch.int64)
+        if rank == 0:
+            ident = {k: bool(np.array_equal(merged[k], single[k])) for k in single}
+            parity.update({"ranks": world, "identical": bool(all(ident.values())),
+                           "tensors": ident, "compared_with": "the same %d-video set evaluated on one GPU"
+                                                              % (args.videos or cfg.videos)})
+            fx_path = os.path.join(ROOT, "tests", "golden", "full_%s_tao.npz" % args.workload)
+            if os.path.exists(fx_path) and not args.videos:
+                # configs[4]: the full TrackAP table against the unmodified reference's
+                import hashlib
+                from tao_amodal_b200 import engine, materialize
+                fx = np.load(fx_path)
+                prec = merged["tao_precision"]
+                tab = materialize.summarize_tao(prec.reshape(prec.shape[:3] + (5, 4)),
+                                                merged["tao_recall"].reshape(merged["tao_recall"].shape[:2] + (5, 4)),
+                                                engine.IOU_THRS)
+                vec = np.asarray([float(v) for v in tab.values()])
+                parity["trackap_table_max_abs_diff_vs_reference"] = float(np.abs(vec - fx["tao_results"]).max())
+                parity["trackap_precision_sha256_equal"] = bool(
+                    hashlib.sha256(np.ascontiguousarray(prec).tobytes()).hexdigest() == str(fx["tao_precision_sha256"]))
+                parity["track_AP"] = float(vec[0])
+            ok[0] = 1 if parity["identical"] else 0
+            strong_ms = float(tt[0]) / args.steps
+            strong = {"scaling": "strong", "videos_total": int(np.unique(gt0.vid_id).size),
+                      "ms_per_step": strong_ms, "value": pairs_local / (strong_ms * 1e-3),
+                      "unit": UNIT, "stages_ms": sres["stage_ms"], "host_prep_s": t_s,
+                      "note": "the rank-0 set of the weak run sharded per video over all ranks; "
+                              "value = its box-pairs / max-over-ranks device time"}
+        dist.broadcast(ok, src=0)
+        if int(ok[0]) != 1:
+            if rank == 0:
+                sys.stderr.write("PARITY FAILURE: sharded tensors differ from the 1-GPU ones: %s\n" % parity)
+            dist.destroy_process_group()
+            return 3
 
     # ---- reduce over ranks: max time, sum units
     if world > 1:
@@ -511,29 +667,34 @@ def main():
     per_kernel = {}
     for name, (ms_tot, n_launch) in kernel_ms.items():
         ms_step = ms_tot / args.steps
-        b = kernel_bytes.get(name)
+        b = kernel_bytes.get(name) if world == 1 else None
         per_kernel[name] = {"ms_per_step": ms_step, "launches_per_step": n_launch / args.steps,
                             "alg_bytes_per_step": b,
                             "gbs": (b / (ms_step * 1e-3) / 1e9) if (b and ms_step > 0) else None}
     ranked = [k for k in sorted(per_kernel, key=lambda k: -per_kernel[k]["ms_per_step"])
               if per_kernel[k]["gbs"] is not None]
-    dom = ranked[0]
-    achieved = per_kernel[dom]["gbs"]
-    traffic = None
-    tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tr_path):
-        tr = json.load(open(tr_path)).get(dom)
-        if isinstance(tr, list):     # ncu dram bytes of the kernel's launches of one step
-            traffic = float(sum(tr[:max(1, int(round(per_kernel[dom]["launches_per_step"])))]))
-        else:
-            traffic = tr
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
-                "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic,
-                "note": "achieved = algorithmic bytes of the kernel's launches in one step / their "
-                        "summed CUDA-event time (events recorded by the library after every launch)",
-                "kernels": per_kernel,
-                "stages_ms": stage_ms}
+    roofline = None
+    if ranked:
+        dom = ranked[0]
+        achieved = per_kernel[dom]["gbs"]
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr_path):
+            tr = json.load(open(tr_path)).get(dom)
+            if isinstance(tr, list):     # ncu dram bytes of the kernel's launches of one step
+                traffic = float(sum(tr[:max(1, int(round(per_kernel[dom]["launches_per_step"])))]))
+            else:
+                traffic = tr
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic,
+                    "note": "achieved = algorithmic bytes of the kernel's launches in one step / their "
+                            "summed CUDA-event time (events recorded by the library after every launch)",
+                    "kernels": per_kernel,
+                    "stages_ms": stage_ms}
+    else:
+        roofline = {"bound": "hbm", "kernels": per_kernel, "stages_ms": stage_ms,
+                    "note": "per-kernel byte accounting is reported at N = 1"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -546,13 +707,17 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "api": ("Engine.evaluate_host_many -> ta_eval_plan_host per plan (pinned host plans -> precision/recall on host)" if world == 1
-                        else "DevicePlan.reload (pinned host plan) + stages + cross-rank exchange + merged tensors on rank 0's host")},
+                        else "per rank: DevicePlan.reload (pinned host plan) + stages + ta_exchange_* + owner-side PR + the owner's slice to its pinned host buffer")},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "parity": parity,
         "host_prep_s": t_prep,
     }
+    if strong is not None:
+        line["strong"] = strong
     if not args.no_cpu_baseline and world == 1:
-        line["cpu_baseline"] = cpu_baseline_leg(args, gt, dt)
+        line["cpu_baseline"] = cpu_baseline_leg(args, gt, dt, eng)
+        line["parity"].update(line["cpu_baseline"].pop("parity", {}))
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -150,9 +150,13 @@ int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
  * defines it.  gt_attr_a is the GT visibility.
  *
  * Evaluation route (no per-cell outputs requested): the (category, image)-sorted detections
- * are cut into warp tasks at group boundaries by a SCHEDULE that depends only on the CSR
- * offsets and dt_flag (ta_frame_sched_build, once per plan; sched = NULL builds it into
- * context scratch on every call).  Each task's GT boxes are staged in shared memory by one
+ * are cut into warp tasks at group boundaries by a SCHEDULE (ta_frame_sched_build, once per
+ * plan).  It holds everything that does not depend on the boxes: the task table and the
+ * per-detection descriptors (from the CSR offsets and dt_flag) and the GT side of the range
+ * cfgs — per-GT ignore words and the non-ignored GT counts, from gt_attr_a / gt_flag / cfgs —
+ * so a call with a schedule makes no pass over the GT attributes; the cfgs / GT attributes
+ * given to ta_frame_eval must then be the ones the schedule was built with.  sched = NULL
+ * derives all of it into context scratch on every call.  Each task's GT boxes are staged in shared memory by one
  * bulk-async copy and every detection is evaluated by one lane; groups in which a detection
  * reaches the lowest threshold with several GTs are redone by the general matcher.
  * Groups with GT and more than ta_frame_eval_max_gt() GT boxes, more than
@@ -169,10 +173,13 @@ int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
  * (A_c ? M : 0) | ((B_c ? M : 0) | (U_c ? ~M : 0)) << 16; bit 31 set means "read the row
  * dt_tpfp[d][*]" (groups that went through the general matcher).  dt_tpfp rows of all other
  * detections are then NOT written.  ta_pr_accumulate takes the same pair.               */
-int64_t ta_frame_sched_bytes(int64_t n_groups, int64_t n_dt, int64_t n_gt);
+int64_t ta_frame_sched_bytes(int64_t n_groups, int64_t n_dt, int64_t n_gt, int32_t n_cat,
+                             int32_t n_cfg);
 int ta_frame_sched_build(ta_ctx* ctx, void* stream, int64_t n_groups,
                          const int64_t* grp_dt_off, const int64_t* grp_gt_off,
-                         int64_t n_dt, const uint8_t* dt_flag, int64_t n_gt, void* sched);
+                         const int32_t* grp_cat, int64_t n_dt, const uint8_t* dt_flag,
+                         int64_t n_gt, const double* gt_attr_a, const uint8_t* gt_flag,
+                         int32_t n_cat, int32_t n_cfg, const ta_range_cfg* cfgs, void* sched);
 int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
                   const int64_t* grp_dt_off, const int64_t* grp_gt_off, const int32_t* grp_cat,
                   const double* dt_box, const double* gt_box,

@@ -102,9 +102,9 @@ def load() -> C.CDLL:
                                      P, P, P, P])
     lib.ta_frame_eval.argtypes = ([P, P, I64, P, P, P, P, P, I32, P, I32, P, I64, P,
                                    I64, P, P, I64, P, I32, P, P, I32, P, P, P, P, P, P])
-    lib.ta_frame_sched_bytes.argtypes = [I64, I64, I64]
+    lib.ta_frame_sched_bytes.argtypes = [I64, I64, I64, I32, I32]
     lib.ta_frame_sched_bytes.restype = I64
-    lib.ta_frame_sched_build.argtypes = [P, P, I64, P, P, I64, P, I64, P]
+    lib.ta_frame_sched_build.argtypes = [P, P, I64, P, P, P, I64, P, I64, P, P, I32, I32, P, P]
     lib.ta_exchange_unique_id.argtypes = [P, I32]
     lib.ta_exchange_create.argtypes = [P, I32, I32, P, C.POINTER(C.c_void_p)]
     lib.ta_exchange_destroy.argtypes = [P]

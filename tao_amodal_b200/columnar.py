@@ -259,17 +259,24 @@ class DtColumns:
     video_id: np.ndarray
     bbox: np.ndarray     # f64 [N,4]
     score: np.ndarray    # f64
+    # number of result objects that lack the key (their column entry is -1).  The frame
+    # evaluator never reads these keys; the track path raises KeyError like the reference
+    # (tools/eval_on_tao_amodal.py:57, tao_amodal/results.py:71) — prep.require_track_keys.
+    missing_track_id: int = 0
+    missing_video_id: int = 0
+
+    _ARRAYS = ("image_id", "track_id", "category_id", "video_id", "bbox", "score")
 
     def n(self) -> int:
         return int(self.image_id.shape[0])
 
     def save_npz(self, path: str) -> None:
-        np.savez(path, **{f.name: getattr(self, f.name) for f in fields(self)})
+        np.savez(path, **{k: getattr(self, k) for k in self._ARRAYS})
 
     @classmethod
     def load_npz(cls, path: str) -> "DtColumns":
         z = np.load(path)
-        return cls(**{f.name: z[f.name] for f in fields(cls)})
+        return cls(**{k: z[k] for k in cls._ARRAYS})
 
     @classmethod
     def from_list(cls, results: list) -> "DtColumns":
@@ -282,6 +289,8 @@ class DtColumns:
             video_id=_i64([r.get("video_id", -1) for r in results]),
             bbox=_f64([r["bbox"] for r in results]).reshape(-1, 4),
             score=_f64([r["score"] for r in results]),
+            missing_track_id=sum(1 for r in results if "track_id" not in r),
+            missing_video_id=sum(1 for r in results if "video_id" not in r),
         )
 
     def to_list(self) -> list:
@@ -295,7 +304,9 @@ class DtColumns:
         ]
 
     def copy(self) -> "DtColumns":
-        return DtColumns(**{f.name: getattr(self, f.name).copy() for f in fields(self)})
+        return DtColumns(**{k: getattr(self, k).copy() for k in self._ARRAYS},
+                         missing_track_id=self.missing_track_id,
+                         missing_video_id=self.missing_video_id)
 
 
 def _ragged_take(r: Ragged, rows: np.ndarray) -> Ragged:
@@ -334,5 +345,6 @@ def subset_videos(gt: GtColumns, dt: DtColumns, video_ids) -> Tuple[GtColumns, D
     drow = np.nonzero(np.isin(dt.video_id, vids))[0]
     d = DtColumns(image_id=dt.image_id[drow], track_id=dt.track_id[drow],
                   category_id=dt.category_id[drow], video_id=dt.video_id[drow],
-                  bbox=np.ascontiguousarray(dt.bbox[drow]), score=dt.score[drow])
+                  bbox=np.ascontiguousarray(dt.bbox[drow]), score=dt.score[drow],
+                  missing_track_id=dt.missing_track_id, missing_video_id=dt.missing_video_id)
     return g, d

@@ -389,6 +389,7 @@ void parse_annotation_file(Parser& P, Doc& D) {
 // One result object at P (just past its '{'): fields into the six columns.
 struct ResultCols {
     Column img, trk, cat, vid, bbox, score;
+    int64_t missing_trk = 0, missing_vid = 0;     // objects without "track_id" / "video_id"
 };
 
 inline void parse_result_object(Parser& P, ResultCols& R) {
@@ -404,12 +405,16 @@ inline void parse_result_object(Parser& P, ResultCols& R) {
             else if (P.key_is(ks, ke, "category_id")) { c = P.as_int(); have |= 2; }
             else if (P.key_is(ks, ke, "bbox")) { P.bbox(R.bbox); have |= 4; }
             else if (P.key_is(ks, ke, "score")) { s = P.as_double(); have |= 8; }
-            else if (P.key_is(ks, ke, "track_id")) t = P.as_int();
-            else if (P.key_is(ks, ke, "video_id")) v = P.as_int();
+            else if (P.key_is(ks, ke, "track_id")) { t = P.as_int(); have |= 16; }
+            else if (P.key_is(ks, ke, "video_id")) { v = P.as_int(); have |= 32; }
             else P.skip_value();
         } while (P.eat(','));
         P.need('}');
     }
+    // the frame evaluator needs neither key (lvis_amodal/results.py); the track path raises
+    // KeyError for them (tools/eval_on_tao_amodal.py:57, tao_amodal/results.py:71) — counted here
+    if (!(have & 16)) ++R.missing_trk;
+    if (!(have & 32)) ++R.missing_vid;
     if (!(have & 1)) key_error("image_id");
     if (!(have & 2)) key_error("category_id");
     if (!(have & 4)) key_error("bbox");
@@ -419,6 +424,13 @@ inline void parse_result_object(Parser& P, ResultCols& R) {
 
 void store_result_cols(Doc& D, std::vector<ResultCols>& parts) {
     const char* names[6] = {"image_id", "track_id", "category_id", "video_id", "bbox", "score"};
+    {
+        int64_t mt = 0, mv = 0;
+        for (auto& r : parts) { mt += r.missing_trk; mv += r.missing_vid; }
+        Column& m = D.c("dt_missing", 8);
+        m.push(mt);
+        m.push(mv);
+    }
     for (int k = 0; k < 6; ++k) {
         Column& dst = D.c(names[k], 8);
         size_t total = 0;

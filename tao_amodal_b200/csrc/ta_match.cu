@@ -275,7 +275,17 @@ __device__ __forceinline__ void fe_build_rules(const ta_range_cfg* cfg_s, int n_
 // one thread, once per API call: the tables every other kernel of the call copies into shared
 // memory (building them per CTA costs tens of microseconds of serial work with 20 cfgs)
 __global__ void k_frame_rules(const ta_range_cfg* cfgs, int n_cfg, FrameRules* out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) fe_build_rules(cfgs, n_cfg, *out);
+    // the serial table build runs on shared-memory copies (a single thread chasing global
+    // memory took ~25 us); the warp copies in and out
+    __shared__ ta_range_cfg cfg_s[RR_MAX];
+    __shared__ FrameRules rules_s;
+    for (int i = threadIdx.x; i < n_cfg && i < RR_MAX; i += blockDim.x) cfg_s[i] = cfgs[i];
+    __syncthreads();
+    if (threadIdx.x == 0) fe_build_rules(cfg_s, n_cfg < RR_MAX ? n_cfg : RR_MAX, rules_s);
+    __syncthreads();
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&rules_s);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out);
+    for (int i = threadIdx.x; i < (int)(sizeof(FrameRules) / 4); i += blockDim.x) dst[i] = src[i];
 }
 
 __device__ __forceinline__ void fe_setup(const FrameArgs& a, int n_thr, int n_cfg,
@@ -855,9 +865,10 @@ k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp) {
 
 struct SchedLayout {
     int64_t n_tasks;
-    size_t o_task_dt, o_task_gt, o_desc, o_grp, total;
+    size_t o_task_dt, o_task_gt, o_desc, o_grp, o_gtw, o_numgt, total;
 };
-static SchedLayout fs_layout(int64_t n_dt, int64_t n_gt) {
+// n_cells = n_cat * n_cfg of the plan's range cfgs (0: no GT-side section, internal schedules)
+static SchedLayout fs_layout(int64_t n_dt, int64_t n_gt, int64_t n_cells = 0) {
     SchedLayout L;
     L.n_tasks = n_dt / FS_TASK_DT + n_gt / FS_TASK_GT + 1;
     size_t off = 0;
@@ -866,6 +877,9 @@ static SchedLayout fs_layout(int64_t n_dt, int64_t n_gt) {
     L.o_task_gt = take((size_t)(L.n_tasks + 1) * 8);
     L.o_desc = take((size_t)(n_dt > 0 ? n_dt : 1) * 4);
     L.o_grp = take((size_t)(n_dt > 0 ? n_dt : 1) * 4);
+    // GT side (depends on the range cfgs): per-GT words and the non-ignored GT counts
+    L.o_gtw = take((size_t)(n_gt > 0 ? n_gt : 1) * 4);
+    L.o_numgt = take(16 + (size_t)n_cells * 4);        // int32 n, then int32 [n_cat][n_cfg]
     L.total = off;
     return L;
 }
@@ -1255,16 +1269,16 @@ __global__ void k_box_area_list(int64_t n_list, const int32_t* __restrict__ grp_
     }
 }
 
-extern "C" int64_t ta_frame_sched_bytes(int64_t n_groups, int64_t n_dt, int64_t n_gt) {
+extern "C" int64_t ta_frame_sched_bytes(int64_t n_groups, int64_t n_dt, int64_t n_gt,
+                                        int32_t n_cat, int32_t n_cfg) {
     (void)n_groups;
-    if (n_dt < 0 || n_gt < 0) return 0;
-    return (int64_t)fs_layout(n_dt, n_gt).total;
+    if (n_dt < 0 || n_gt < 0 || n_cat < 0 || n_cfg < 0) return 0;
+    return (int64_t)fs_layout(n_dt, n_gt, (int64_t)n_cat * n_cfg).total;
 }
 
 static int fs_build(ta_ctx* ctx, cudaStream_t st, int64_t n_groups, const int64_t* grp_dt_off,
                     const int64_t* grp_gt_off, int64_t n_dt, const uint8_t* dt_flag, int64_t n_gt,
-                    void* sched) {
-    const SchedLayout L = fs_layout(n_dt, n_gt);
+                    void* sched, const SchedLayout& L) {
     char* b = static_cast<char*>(sched);
     const int64_t warps = (n_groups + 31) / 32;
     k_frame_sched<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(
@@ -1274,17 +1288,52 @@ static int fs_build(ta_ctx* ctx, cudaStream_t st, int64_t n_groups, const int64_
     return ta_check_launch(ctx, "k_frame_sched");
 }
 
+// num_gt[i] += part[i], i < part_hdr[0] (the schedule's precomputed non-ignored GT counts)
+__global__ void k_add_counts(const int32_t* __restrict__ hdr, int32_t* __restrict__ num_gt) {
+    const int n = hdr[0];
+    const int32_t* part = hdr + 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (part[i]) num_gt[i] += part[i];
+}
+__global__ void k_set_header(int32_t* hdr, int n) { hdr[0] = n; hdr[1] = hdr[2] = hdr[3] = 0; }
+
 extern "C" int ta_frame_sched_build(ta_ctx* ctx, void* stream, int64_t n_groups,
                                     const int64_t* grp_dt_off, const int64_t* grp_gt_off,
-                                    int64_t n_dt, const uint8_t* dt_flag, int64_t n_gt, void* sched) {
+                                    const int32_t* grp_cat, int64_t n_dt, const uint8_t* dt_flag,
+                                    int64_t n_gt, const double* gt_attr_a, const uint8_t* gt_flag,
+                                    int32_t n_cat, int32_t n_cfg, const ta_range_cfg* cfgs,
+                                    void* sched) {
     if (!ctx || !sched) return ta_set_err(TA_ERR_INVALID, "ta_frame_sched_build: NULL argument");
-    if (n_groups < 0 || n_dt < 0 || n_gt < 0)
+    if (n_groups < 0 || n_dt < 0 || n_gt < 0 || n_cat < 0)
         return ta_set_err(TA_ERR_INVALID, "ta_frame_sched_build: negative size");
+    if (n_cfg < 1 || n_cfg > FE_MAX_CFG) return ta_set_err(TA_ERR_INVALID, "ta_frame_sched_build: bad n_cfg");
     if (n_groups > INT_MAX) return ta_set_err(TA_ERR_TOO_LARGE, "ta_frame_sched_build: too many groups");
     if (n_groups == 0) return TA_OK;
     TA_CUDA(cudaSetDevice(ctx->device));
-    ta_begin(ctx, (cudaStream_t)stream);
-    return fs_build(ctx, (cudaStream_t)stream, n_groups, grp_dt_off, grp_gt_off, n_dt, dt_flag, n_gt, sched);
+    cudaStream_t st = (cudaStream_t)stream;
+    ta_begin(ctx, st);
+    const SchedLayout L = fs_layout(n_dt, n_gt, (int64_t)n_cat * n_cfg);
+    int rc = fs_build(ctx, st, n_groups, grp_dt_off, grp_gt_off, n_dt, dt_flag, n_gt, sched, L);
+    if (rc) return rc;
+    // GT side: per-GT words + non-ignored GT counts of the groups the streamed kernel evaluates
+    char* b = static_cast<char*>(sched);
+    int32_t* hdr = reinterpret_cast<int32_t*>(b + L.o_numgt);
+    TA_CUDA(cudaMemsetAsync(hdr, 0, 16 + (size_t)n_cat * n_cfg * 4, st));
+    k_set_header<<<1, 1, 0, st>>>(hdr, n_cat * n_cfg);
+    if ((rc = ta_check_launch(ctx, "k_set_header"))) return rc;
+    void* ws2 = nullptr;
+    if ((rc = ta_workspace(ctx, st, sizeof(FrameRules) + 256, &ws2, 1))) return rc;
+    FrameRules* rules_g = reinterpret_cast<FrameRules*>(ws2);
+    k_frame_rules<<<1, 32, 0, st>>>(cfgs, n_cfg, rules_g);
+    if ((rc = ta_check_launch(ctx, "k_frame_rules"))) return rc;
+    FrameArgs a{n_groups, grp_dt_off, grp_gt_off, grp_cat, nullptr, nullptr, 0, nullptr, n_cfg,
+                cfgs, n_dt, n_gt, dt_flag, gt_attr_a, gt_flag, nullptr, nullptr, 0,
+                nullptr, hdr + 4, nullptr, nullptr,
+                nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, rules_g};
+    a.gt_word_out = reinterpret_cast<uint32_t*>(b + L.o_gtw);
+    const int64_t prep_warps = (n_groups + 31) / 32;
+    k_frame_prep<0><<<(unsigned)((prep_warps + 7) / 8), 256, 0, st>>>(a, nullptr);
+    return ta_check_launch(ctx, "k_frame_prep");
 }
 
 extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
@@ -1321,7 +1370,7 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     int rc;
     // scratch (slot 1): rule tables, per-GT words, complex-group flags / list, and the schedule
     // when the caller did not build one (ta_frame_sched_build)
-    const SchedLayout L = fs_layout(n_dt, n_gt);
+    const SchedLayout L = fs_layout(n_dt, n_gt);       // the offsets used here do not depend on n_cells
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_rules = take(sizeof(FrameRules));
@@ -1346,9 +1395,10 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
     } else {
         // evaluation path: GT counts + per-GT words, the streamed lane-per-detection kernel, then
         // the general matcher on the (few) groups whose detections have several candidate GTs
+        const bool own_sched = sched != nullptr;     // built by ta_frame_sched_build: GT side included
         if (!sched && n_dt > 0) {
             if ((rc = fs_build(ctx, st, n_groups, grp_dt_off, grp_gt_off, n_dt, dt_flag, n_gt,
-                               base + o_sched)))
+                               base + o_sched, L)))
                 return rc;
             sched = base + o_sched;
         }
@@ -1360,15 +1410,23 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
             a.dt_desc = reinterpret_cast<const uint32_t*>(sb + L.o_desc);
             a.dt_grp = reinterpret_cast<const int32_t*>(sb + L.o_grp);
         }
-        a.gt_word_out = reinterpret_cast<uint32_t*>(base + o_gtw);
-        a.gt_word = a.gt_word_out;
+        if (own_sched) {
+            a.gt_word = reinterpret_cast<const uint32_t*>(sb + L.o_gtw);
+        } else {
+            a.gt_word_out = reinterpret_cast<uint32_t*>(base + o_gtw);
+            a.gt_word = a.gt_word_out;
+        }
         a.dt_word = compact ? dt_word : nullptr;
         a.grp_flag = reinterpret_cast<int32_t*>(base + o_flag);
         a.complex_count = a.grp_flag + n_groups;
         a.complex_list = reinterpret_cast<int32_t*>(base + o_list);
         TA_CUDA(cudaMemsetAsync(a.grp_flag, 0, (size_t)n_groups * 4 + 4, st));
         const bool spec = (n_thr == 10 && n_cfg == 6);
-        {
+        if (own_sched) {
+            // the schedule holds the GT side: add its counts, no per-call pass over the GT
+            k_add_counts<<<64, 256, 0, st>>>(reinterpret_cast<const int32_t*>(sb + L.o_numgt), num_gt);
+            if ((rc = ta_check_launch(ctx, "k_add_counts"))) return rc;
+        } else {
             const int64_t prep_warps = (n_groups + 31) / 32;
             const unsigned pb = (unsigned)((prep_warps + 7) / 8);
             if (spec) k_frame_prep<6><<<pb, 256, 0, st>>>(a, nullptr);

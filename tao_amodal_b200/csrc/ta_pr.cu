@@ -437,20 +437,29 @@ k_pr_bits(PrArgs a) {
     }
 }
 
-// One THREAD per (chunk, cell), cells fastest: the lanes of a warp walk consecutive cells of one
-// chunk (shared tk rows and counters: L1 hits).  Measured alternatives, both slower (0.71 / 0.73
-// vs 0.47 ms at the bench size): lanes = consecutive chunks of one cell, lanes = chunks of equal
-// rank inside their categories.
+// One THREAD per (chunk, cell); a warp takes the n_thr cells of ONE range cfg for 32 / n_thr
+// consecutive chunks, so lanes share tk rows and counters (L1 hits) and walk similar numbers of
+// true positives.  Measured alternatives at the bench size: lanes = 32 consecutive cells of one
+// chunk (mixes cfgs whose densities differ 10 x) 0.47 ms; lanes = consecutive chunks of one
+// cell 0.73 ms; lanes = chunks of equal rank inside their categories 0.71 ms.
 // ta_pr_walk_bits visits the cell's true positives only.
 __global__ void __launch_bounds__(128)
 k_pr_envelope_bits(PrArgs a) {
-    const uint32_t n_cells = (uint32_t)(a.n_cfg * a.n_thr);
+    // a warp = ONE range cfg, all its thresholds, of 32 / n_thr consecutive chunks: the lanes'
+    // true-positive counts (= trip counts) differ by the threshold only, not by the cfg
     const uint32_t n_chunks = (uint32_t)a.chunk_start[a.n_cat];
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (int64_t)n_chunks * n_cells) return;
-    const int chunk = (int)(gid / n_cells);
-    const uint32_t cell = (uint32_t)(gid - (int64_t)chunk * n_cells);
-    const int cfg = (int)(cell / (uint32_t)a.n_thr), b = (int)(cell - (uint32_t)cfg * a.n_thr);
+    const int lane = (int)(gid & 31);
+    const int cpw = 32 / a.n_thr;
+    const int64_t wg = gid >> 5;
+    const int cfg = (int)(wg % a.n_cfg);
+    const int64_t trip = wg / a.n_cfg;
+    if (lane >= cpw * a.n_thr) return;
+    const int64_t chunk64 = trip * cpw + lane / a.n_thr;
+    if (chunk64 >= (int64_t)n_chunks) return;
+    const int chunk = (int)chunk64;
+    const int b = lane % a.n_thr;
+    const uint32_t cell = (uint32_t)(cfg * a.n_thr + b);
     const int cat = a.chunk_cat[chunk];
     if (a.num_gt[(int64_t)cat * a.n_cfg + cfg] == 0) return;
     const int ch0 = a.chunk_start[cat], ch1 = a.chunk_start[cat + 1];
@@ -747,7 +756,8 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     }
     if (n_chunks_ub > 0 && impl) {
         // grid over the upper bound of chunks: the kernel reads the real count on the device
-        const int64_t threads = (int64_t)n_chunks_ub * (int64_t)n_cells;
+        const int cpw = 32 / n_thr;
+        const int64_t threads = (((int64_t)n_chunks_ub + cpw - 1) / cpw) * n_cfg * 32;
         k_pr_envelope_bits<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a);
         if ((rc = ta_check_launch(ctx, "k_pr_envelope_bits"))) return rc;
     } else if (n_chunks_ub > 0) {

@@ -434,14 +434,15 @@ class DevicePlan:
         if not track and plan.masks is None:
             self.t["dt_word"] = torch.zeros(max(plan.n_dt, 1), dtype=torch.int32, device=dev)
             if plan.n_groups > 0 and plan.n_dt > 0:
-                nb = int(eng.lib.ta_frame_sched_bytes(plan.n_groups, plan.n_dt, plan.n_gt))
+                nb = int(eng.lib.ta_frame_sched_bytes(plan.n_groups, plan.n_dt, plan.n_gt,
+                                                      self.n_cat, n_cfg))
                 self.t["sched"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
                 st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+                P = lambda k: C.c_void_p(self.t[k].data_ptr())
                 _lib.check(eng.lib.ta_frame_sched_build(
-                    eng._ctx, st, plan.n_groups, C.c_void_p(self.t["grp_dt_off"].data_ptr()),
-                    C.c_void_p(self.t["grp_gt_off"].data_ptr()), plan.n_dt,
-                    C.c_void_p(self.t["dt_flag"].data_ptr()), plan.n_gt,
-                    C.c_void_p(self.t["sched"].data_ptr())))
+                    eng._ctx, st, plan.n_groups, P("grp_dt_off"), P("grp_gt_off"), P("grp_cat"),
+                    plan.n_dt, P("dt_flag"), plan.n_gt, P("gt_attr_a"), P("gt_flag"),
+                    self.n_cat, n_cfg, P("cfgs"), P("sched")))
         self.t["precision"] = torch.empty((T, R, C_, n_cfg), dtype=torch.float64, device=dev)
         self.t["recall"] = torch.empty((T, C_, n_cfg), dtype=torch.float64, device=dev)
         self.t["tp_cnt"] = torch.empty((T, C_, n_cfg), dtype=torch.int64, device=dev)

@@ -24,13 +24,17 @@ def get_engine(device: int = 0):
 def load_json(path: str):
     """json.load with a per-process cache keyed by (path, mtime, size): the reference's CLI
     parses the annotation file twice and the result file twice
-    (tools/eval_on_tao_amodal.py:100,122,127; lvis.py:27, results.py:29-30)."""
+    (tools/eval_on_tao_amodal.py:100,122,127; lvis.py:27, results.py:29-30).  Every caller gets
+    its OWN deep copy: the dataset views mutate the parsed objects in place (merged categories,
+    averaged track scores, added id / area / segmentation — results.py:47-98, lvis
+    results.py:44-66), and the reference parses a fresh copy for each class."""
+    import copy
     st = os.stat(path)
     key = (os.path.abspath(path), st.st_mtime, st.st_size)
     if key not in _JSON_CACHE:
         with open(path, "r") as f:
             _JSON_CACHE[key] = json.load(f)
-    return _JSON_CACHE[key]
+    return copy.deepcopy(_JSON_CACHE[key])
 
 
 class LazyDict(dict):
@@ -94,12 +98,47 @@ def dist_info():
     return 0, 1
 
 
-def dist_accumulate(eng, dev, rank, world):
-    """Cross-rank PR accumulation; every rank ends up with the merged tensors."""
+_TRANSPORTS = {}
+
+
+def dist_transport(eng, rank, world):
+    """The NCCL communicator of the C ABI (ta_exchange_*) for this engine, created once: rank 0
+    draws the id, torch.distributed (already initialised by the caller) hands it round."""
     import torch.distributed as dist
     from .. import parallel
-    acc = parallel.DeviceDistAccumulator(eng, dev, rank, world)
-    acc.accumulate()
+    tr = _TRANSPORTS.get(id(eng))
+    if tr is None:
+        box = [parallel.AbiTransport.unique_id(eng.lib) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        tr = parallel.AbiTransport(eng, rank, world, box[0])
+        _TRANSPORTS[id(eng)] = tr
+    return tr
+
+
+def dist_check_nonempty(dev, what_gt, what_dt):
+    """The reference's "found no ... annotations" errors (eval.py:188-192) on the WHOLE set: a
+    shard alone may be empty (prep allow_empty), the sum over ranks may not."""
+    import torch
+    import torch.distributed as dist
+    n = torch.tensor([dev.plan.n_gt, dev.plan.n_dt], dtype=torch.int64, device=dev.dev)
+    dist.all_reduce(n)
+    n_gt, n_dt = (int(v) for v in n.cpu().tolist())
+    if n_gt == 0:
+        raise ValueError(what_gt)
+    if n_dt == 0:
+        raise ValueError(what_dt)
+
+
+def dist_accumulate(eng, dev, rank, world):
+    """Cross-rank PR accumulation (parallel.DeviceExchange over the C ABI's NCCL exchange);
+    every rank ends up with the merged tensors, as the single-process API promises."""
+    import torch.distributed as dist
+    from .. import parallel
+    ex = parallel.DeviceExchange(eng, dev, dist_transport(eng, rank, world))
+    if dev.plan.kind == "lvis" and ex.compact:
+        pass                     # the setup's dry run left this evaluation's words in place
+    ex.accumulate()
+    ex.to_root()
     for k in ("precision", "recall", "tp_cnt", "fp_cnt"):
         dist.broadcast(dev.t[k], src=0)
 

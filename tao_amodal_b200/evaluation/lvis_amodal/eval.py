@@ -131,7 +131,8 @@ class LVISEval:
         self._plan = prep.prepare_lvis(
             self.lvis_gt.columns, self.lvis_dt.dt_columns, max_dets=self.lvis_dt.max_dets,
             vis_rng=p.visibility_rng, img_ids=img_ids,
-            cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats))
+            cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats),
+            allow_empty=self._world > 1)
         self.freq_groups = self._plan.freq_groups
         if p.iou_type == "segm":
             self._plan.masks = self._build_masks(self._plan)
@@ -195,7 +196,14 @@ class LVISEval:
             len(plan.cat_ids), plan.n_cfg, len(plan.unit_ids))
 
     def _need_detail(self):
+        if self._world > 1:
+            # every rank holds the cells of its own videos only; a merged view would have to
+            # gather per-cell arrays that the reference builds in one process
+            raise RuntimeError("ious / eval_imgs / dt_pointers are per-process structures: "
+                               "not available in multi-GPU mode (run single-GPU to read them)")
         if self._detail is None:
+            # a second pass over the same buffers; the accumulated tensors it rewrites are
+            # identical (same plan, same kernels)
             self._detail = get_engine(self.device).evaluate_device(self._dev, detail=True)
         return self._detail
 

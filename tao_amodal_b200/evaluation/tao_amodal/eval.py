@@ -17,7 +17,7 @@ import numpy as np
 
 from ... import materialize, prep
 from ...columnar import DtColumns
-from .._common import (LazyDict, ascending_rec_thrs, dist_accumulate, dist_info, get_engine,
+from .._common import (LazyDict, ascending_rec_thrs, dist_accumulate, dist_check_nonempty, dist_info, get_engine,
                        restore_rec_order)
 from .results import TaoResults
 from .tao import Tao
@@ -100,7 +100,8 @@ class TaoEval:
         self._plan = prep.prepare_tao(
             self.tao_gt.columns, self.tao_dt.dt_columns, max_dets=self.tao_dt.max_dets,
             area_rng=p.area_rng, time_rng=p.time_rng, vid_ids=vid_ids,
-            cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats))
+            cat_ids=p.cat_ids if p.cat_ids else None, use_cats=bool(p.use_cats),
+            allow_empty=self._world > 1)
 
     def evaluate(self, show_progress=False):
         """Per-video evaluation: IoU matrices + greedy matching of every (video, category,
@@ -112,6 +113,9 @@ class TaoEval:
         eng = get_engine(self.device)
         rec_sorted, self._rec_inv = ascending_rec_thrs(self.params.rec_thrs)
         self._dev = eng.upload(self._plan, self.params.iou_thrs, rec_sorted)
+        if self._world > 1:
+            dist_check_nonempty(self._dev, "Found no groundtruth annotations for given params",
+                                "Found no predicted annotations for given params")
         eng.stage_iou(self._dev, self.params.iou_3d_type)
         eng.stage_match(self._dev)
         self._detail = None
@@ -122,6 +126,9 @@ class TaoEval:
     def _need_detail(self):
         """Second pass with the optional per-cell outputs switched on (only when someone
         reads ``ious`` / ``eval_vids`` / ``dt_pointers``)."""
+        if self._world > 1:
+            raise RuntimeError("ious / eval_vids / dt_pointers are per-process structures: "
+                               "not available in multi-GPU mode (run single-GPU to read them)")
         if self._detail is None:
             eng = get_engine(self.device)
             self._detail = eng.evaluate_device(self._dev, detail=True,

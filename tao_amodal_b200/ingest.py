@@ -170,9 +170,12 @@ def load_dt(path: str) -> DtColumns:
         d = _Doc(path, 1)
         try:
             i64, f64 = np.int64, np.float64
+            miss = d.col("dt_missing", i64)
             return DtColumns(image_id=d.col("image_id", i64), track_id=d.col("track_id", i64),
                              category_id=d.col("category_id", i64), video_id=d.col("video_id", i64),
-                             bbox=d.col("bbox", f64).reshape(-1, 4), score=d.col("score", f64))
+                             bbox=d.col("bbox", f64).reshape(-1, 4), score=d.col("score", f64),
+                             missing_track_id=int(miss[0]) if miss.size else 0,
+                             missing_video_id=int(miss[1]) if miss.size > 1 else 0)
         finally:
             d.close()
     return _cached(path, 1, build)

@@ -250,8 +250,19 @@ def limit_dets_per_image(image_id: np.ndarray, score: np.ndarray, max_dets: int)
     return sel[order]
 
 
+def require_track_keys(dt: DtColumns) -> None:
+    """The track path reads res['track_id'] / res['video_id'] of every result
+    (tools/eval_on_tao_amodal.py:57, tao_amodal/results.py:71-76): a file that lacks them raises
+    KeyError there, and so does this repo instead of scoring each video as one giant track."""
+    if getattr(dt, "missing_track_id", 0):
+        raise KeyError("track_id")
+    if getattr(dt, "missing_video_id", 0):
+        raise KeyError("video_id")
+
+
 def make_track_ids_unique(dt: DtColumns) -> int:
     """tools/eval_on_tao_amodal.py:44-66 on columns (in place). Returns #clashing ids."""
+    require_track_keys(dt)
     t, v = dt.track_id, dt.video_id
     if t.size == 0:
         return 0
@@ -322,10 +333,14 @@ def _acc_perm(n_cat, cat_dt_off, dt_score):
 # ---- TAO track path ----------------------------------------------------------------------
 def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
                 area_rng=TAO_AREA_RNG, time_rng=TAO_TIME_RNG,
-                vid_ids=None, cat_ids=None, use_cats: bool = True) -> EvalPlan:
+                vid_ids=None, cat_ids=None, use_cats: bool = True,
+                allow_empty: bool = False) -> EvalPlan:
     """Plan of the track path.  vid_ids / cat_ids default to everything in the annotation
     file (TaoEval.__init__, eval.py:169-170); subsets mirror assigning Params.vid_ids /
-    Params.cat_ids before evaluate()."""
+    Params.cat_ids before evaluate().  allow_empty: a video SHARD of a multi-GPU run may hold
+    no ground truth / no predictions (or no videos); the reference's "found no ... annotations"
+    errors (eval.py:188-192) then apply to the whole set, not to the shard (the caller checks
+    the summed counts)."""
     cat_ids = np.unique(gt.cat_id if cat_ids is None else np.asarray(cat_ids, dtype=np.int64))
     vid_ids = np.unique(gt.vid_id if vid_ids is None else np.asarray(vid_ids, dtype=np.int64))
     n_cat, n_vid = cat_ids.size, vid_ids.size
@@ -370,7 +385,7 @@ def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
     g_valid = ((g_rank >= 0) & (_index_of(cat_ids, g_cat_raw) >= 0)
                & (gt.ann_area > 0) & (gt.ann_area < INF))
     g_rows = np.nonzero(g_valid)[0]
-    if g_rows.size == 0:
+    if g_rows.size == 0 and not allow_empty:
         raise ValueError("Found no groundtruth annotations for given params")    # eval.py:188-190
     gt_ent = _tao_tracks(
         rows=g_rows, rank=g_rank[g_rows], trk_key=a_trk_row[g_rows],
@@ -384,11 +399,11 @@ def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
         raise KeyError("visibility")
 
     # --- detections (results.py:12-109)
-    if dt.n() == 0:
+    require_track_keys(dt)
+    if dt.n() == 0 and not allow_empty:
         raise IndexError("list index out of range")                              # results.py:63
-    first_vid_chk = {}
     tu, tfirst = np.unique(dt.track_id, return_index=True)
-    if (dt.video_id != dt.video_id[tfirst][np.searchsorted(tu, dt.track_id)]).any():
+    if dt.n() and (dt.video_id != dt.video_id[tfirst][np.searchsorted(tu, dt.track_id)]).any():
         bad = np.nonzero(dt.video_id != dt.video_id[tfirst][np.searchsorted(tu, dt.track_id)])[0][0]
         raise AssertionError("Track id %d appears in more than one video" % int(dt.track_id[bad]))
     sel = limit_dets_per_image(dt.image_id, dt.score, max_dets)
@@ -412,15 +427,15 @@ def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
     seg = np.zeros(tu.size + 1, dtype=np.int64)
     np.cumsum(np.bincount(tinv, minlength=tu.size), out=seg[1:])
     sc_sorted = d_score[o]
-    smin = np.minimum.reduceat(sc_sorted, seg[:-1])
-    smax = np.maximum.reduceat(sc_sorted, seg[:-1])
+    smin = np.minimum.reduceat(sc_sorted, seg[:-1]) if tu.size else np.zeros(0)
+    smax = np.maximum.reduceat(sc_sorted, seg[:-1]) if tu.size else np.zeros(0)
     t_score = smin.copy()
     for k in np.nonzero(smin != smax)[0]:
         t_score[k] = np.mean(sc_sorted[seg[k]:seg[k + 1]].tolist())
     d_rank = s_rank(d_img)
     d_valid = ((d_rank >= 0) & (_index_of(cat_ids, d_cat) >= 0) & (d_area > 0) & (d_area < INF))
     d_rows = np.nonzero(d_valid)[0]
-    if d_rows.size == 0:
+    if d_rows.size == 0 and not allow_empty:
         raise ValueError("Found no predicted annotations for given params")      # eval.py:191-192
     dt_ent = _tao_tracks(
         rows=d_rows, rank=d_rank[d_rows], trk_key=tinv[d_rows],
@@ -563,8 +578,9 @@ def _gather_track_boxes(ent, perm):
 # ---- LVIS frame path ---------------------------------------------------------------------
 def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
                  vis_rng=LVIS_VIS_RNG, img_ids=None, cat_ids=None,
-                 use_cats: bool = True) -> EvalPlan:
-    """Plan of the frame path; img_ids / cat_ids as in prepare_tao (lvis eval.py:51-52)."""
+                 use_cats: bool = True, allow_empty: bool = False) -> EvalPlan:
+    """Plan of the frame path; img_ids / cat_ids as in prepare_tao (lvis eval.py:51-52);
+    allow_empty as in prepare_tao (a shard without predictions)."""
     cat_ids = np.unique(gt.cat_id if cat_ids is None else np.asarray(cat_ids, dtype=np.int64))
     all_img_ids = np.unique(gt.img_id)
     img_ids = all_img_ids if img_ids is None else np.unique(np.asarray(img_ids, dtype=np.int64))
@@ -584,7 +600,7 @@ def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
         raise KeyError("out_of_frame")                                 # eval.py:213
 
     # detections (lvis results.py:29-71)
-    if dt.n() == 0:
+    if dt.n() == 0 and not allow_empty:
         raise IndexError("list index out of range")
     sel = limit_dets_per_image(dt.image_id, dt.score, max_dets)
     d_img = dt.image_id[sel]

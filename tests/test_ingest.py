@@ -161,3 +161,29 @@ def test_parallel_result_parse_reports_the_sequential_error(tmp_path, monkeypatc
     open(p, "w").write("[]")
     assert ingest.load_dt(p).n() == 0
     ingest._CACHE.clear()
+
+
+def test_results_without_track_or_video_id_raise_like_the_reference(tmp_path):
+    """a results file that lacks track_id (but has video_id) must raise
+    KeyError('track_id') on the track path (tools/eval_on_tao_amodal.py:57) instead of scoring
+    every video as one giant track; the frame path never reads those keys."""
+    import json
+    import pytest
+    from tao_amodal_b200 import ingest, prep, synth
+    from tao_amodal_b200.columnar import DtColumns
+    gt, dt = synth.generate_named("tiny")
+    res = dt.to_list()
+    for drop, want in (("track_id", "track_id"), ("video_id", "video_id")):
+        lst = [{k: v for k, v in r.items() if k != drop} for r in res]
+        p = tmp_path / ("no_%s.json" % drop)
+        json.dump(lst, open(p, "w"))
+        for cols in (ingest.load_dt(str(p)), DtColumns.from_list(lst)):
+            assert (cols.missing_track_id > 0) == (drop == "track_id")
+            assert (cols.missing_video_id > 0) == (drop == "video_id")
+            prep.prepare_lvis(gt, cols)                          # frame path: fine
+            with pytest.raises(KeyError, match=want):
+                prep.make_track_ids_unique(cols.copy())
+            with pytest.raises(KeyError, match=want):
+                prep.prepare_tao(gt, cols)
+    full = ingest.load_dt(_write(tmp_path, res))
+    assert full.missing_track_id == 0 and full.missing_video_id == 0

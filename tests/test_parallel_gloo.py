@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, kind, q):
+def _worker(rank, world, port, case, kind, q, only_video=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -37,48 +37,99 @@ def _worker(rank, world, port, case, kind, q):
         gt, dt = GtColumns.from_dict(gt_d), DtColumns.from_list(res)
         if kind == "tao":
             prep.make_track_ids_unique(dt)
+        if only_video is not None:
+            # predictions of ONE video only: every other shard is prediction-free
+            keep = dt.video_id == only_video
+            for f in ("image_id", "track_id", "category_id", "video_id", "bbox", "score"):
+                setattr(dt, f, np.ascontiguousarray(getattr(dt, f)[keep]))
         shards = parallel.shard_videos(np.unique(gt.vid_id), world)
         g_s, d_s = subset_videos(gt, dt, shards[rank])
-        plan = prep.prepare_tao(g_s, d_s) if kind == "tao" else prep.prepare_lvis(g_s, d_s)
+        if kind == "tao":
+            plan = prep.prepare_tao(g_s, d_s, vid_ids=shards[rank], allow_empty=True)
+        else:
+            plan = prep.prepare_lvis(g_s, d_s, img_ids=g_s.img_id, allow_empty=True)
         local = run_hostsim(plan)                       # per-rank IoU + matching
-        acc = parallel.DistAccumulator(plan, rank, world, torch.device("cpu"))
-        rows = acc.exchange_tpfp(torch.from_numpy(local.dt_tpfp.view(np.int32)))
-        num_gt, num_gt_own = acc.global_num_gt(torch.from_numpy(local.num_gt))
-        # owner-side PR through the emulation of the shipped (bit-plane) kernels: padded empty
-        # categories and categories without detections included
-        out = hostsim_pr(acc.n_loc, acc.cat_dt_off.numpy(), acc.acc_perm.numpy(),
-                         rows.numpy().view(np.uint32), num_gt_own.numpy(), plan.n_cfg,
-                         impl="bits_tile")
-        parts = [torch.from_numpy(x) for x in (out.precision, out.recall, out.tp_cnt, out.fp_cnt)]
-        C_, K = len(plan.cat_ids), plan.n_cfg
-        pr, rc = torch.empty((10, 101, C_, K), dtype=torch.float64), torch.empty((10, C_, K), dtype=torch.float64)
-        tp, fp = torch.empty((10, C_, K), dtype=torch.int64), torch.empty((10, C_, K), dtype=torch.int64)
-        acc.merge_to_root(parts, [pr, rc, tp, fp])
+        tr = parallel.TorchTransport(rank, world, torch.device("cpu"))
+        ex = parallel.ExchangePlan(plan, tr, torch.device("cpu"))
+        rows = ex.exchange(torch.from_numpy(np.ascontiguousarray(local.dt_tpfp).view(np.int32)))
+        num_gt, num_gt_own = ex.global_num_gt(torch.from_numpy(local.num_gt.copy()))
+        # owner-side PR through the emulation of the shipped (bit-plane) kernels: categories
+        # without detections and owners without categories included
+        T, R, K = 10, 101, plan.n_cfg
+        if ex.n_loc:
+            out = hostsim_pr(ex.n_loc, ex.cat_dt_off.numpy(), ex.acc_perm.numpy(),
+                             rows.numpy().view(np.uint32).reshape(-1, K),
+                             np.ascontiguousarray(num_gt_own.numpy()), K, impl="bits_tile")
+            parts = [torch.from_numpy(x) for x in (out.precision, out.recall, out.tp_cnt, out.fp_cnt)]
+        else:
+            parts = [torch.empty((T, R, 0, K), dtype=torch.float64), torch.empty((T, 0, K), dtype=torch.float64),
+                     torch.empty((T, 0, K), dtype=torch.int64), torch.empty((T, 0, K), dtype=torch.int64)]
+        C_ = len(plan.cat_ids)
+        pr, rc = torch.empty((T, R, C_, K), dtype=torch.float64), torch.empty((T, C_, K), dtype=torch.float64)
+        tp, fp = torch.empty((T, C_, K), dtype=torch.int64), torch.empty((T, C_, K), dtype=torch.int64)
+        ex.gather_to_root(parts, [pr, rc, tp, fp])
         if rank == 0:
-            shape = g[kind + "_precision"].shape
-            ok = (np.array_equal(g[kind + "_precision"], pr.numpy().reshape(shape))
-                  and np.array_equal(g[kind + "_recall"], rc.numpy().reshape(g[kind + "_recall"].shape))
-                  and np.array_equal(g[kind + "_tp_cnt"], tp.numpy().reshape(g[kind + "_tp_cnt"].shape))
-                  and np.array_equal(g[kind + "_fp_cnt"], fp.numpy().reshape(g[kind + "_fp_cnt"].shape)))
+            if only_video is None:
+                want = {k: g[kind + "_" + k] for k in ("precision", "recall", "tp_cnt", "fp_cnt")}
+            else:
+                # single-process plan of the same reduced input through the same emulation
+                if kind == "tao":
+                    whole = prep.prepare_tao(gt, dt)
+                else:
+                    whole = prep.prepare_lvis(gt, dt)
+                w = run_hostsim(whole)
+                want = {"precision": w.precision, "recall": w.recall, "tp_cnt": w.tp_cnt, "fp_cnt": w.fp_cnt}
+            got = {"precision": pr, "recall": rc, "tp_cnt": tp, "fp_cnt": fp}
+            ok = all(np.array_equal(np.asarray(want[k]).reshape(got[k].shape), got[k].numpy()) for k in got)
             q.put(bool(ok))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["tao", "lvis"])
-@pytest.mark.parametrize("case", ["small", "small_ties", "edge_mix"])
-def test_two_rank_exchange_matches_reference(case, kind):
+def _run(world, case, kind, **kw):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, case, kind, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, kind, q), kwargs=kw)
+             for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=180)
+        p.join(timeout=240)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+@pytest.mark.parametrize("kind", ["tao", "lvis"])
+@pytest.mark.parametrize("case", ["small", "small_ties", "edge_mix"])
+def test_two_rank_exchange_matches_reference(case, kind):
+    _run(2, case, kind)
+
+
+@pytest.mark.parametrize("kind", ["tao", "lvis"])
+def test_prediction_free_shard_takes_part_in_the_exchange(kind):
+    """Only one video has predictions: the other rank's shard has ground truth but nothing to
+    send; the merged result equals the single-process one (no deadlock, no per-shard error)."""
+    _run(2, "small", kind, only_video=1)
+
+
+@pytest.mark.parametrize("kind", ["tao", "lvis"])
+def test_more_ranks_than_videos(kind):
+    """world = 4 over the 3 videos of `tiny`: one rank holds no video at all."""
+    _run(4, "tiny", kind)
+
+
+def test_balanced_blocks_cover_and_balance():
+    from tao_amodal_b200.parallel import balanced_blocks
+    w = np.array([0, 5, 0, 0, 7, 1, 1, 1, 9, 0, 3, 0])
+    for world in (1, 2, 3, 5, 20):
+        b = balanced_blocks(w, world)
+        assert b[0] == 0 and b[-1] == w.size and (np.diff(b) >= 0).all() and b.size == world + 1
+    b = balanced_blocks(w, 3)
+    loads = [w[b[i]:b[i + 1]].sum() for i in range(3)]
+    assert max(loads) <= 16
+    assert (np.diff(balanced_blocks(np.zeros(6), 3)) == 2).all()
 
 
 def test_shard_videos_balances_and_covers():
