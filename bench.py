@@ -535,11 +535,16 @@ def main():
         host_part = {id(dv): {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
                               for k, v in pipe.exch[id(dv)].part.items()} for dv in (d_tao, d_lvis)}
 
+        copy_out = torch.cuda.Stream()
+
         def e2e_step():
-            # pinned host plan -> HBM, local IoU + matching, cross-rank exchange of the result
-            # records, owner-side PR, every owner's slice back to ITS host (pinned).  (The
-            # exchange's routing tables are part of the plan, like acc_perm, and stay resident.)
+            # pinned host plan -> HBM (boxes as lossless float), local IoU + matching, cross-rank
+            # exchange of the result records, owner-side PR, every owner's slice back to ITS
+            # host (pinned) on a second stream, so the download of the track results overlaps
+            # the upload of the frame plan.  (The exchange's routing tables are part of the
+            # plan, like acc_perm, and stay resident.)
             h2d = d2h = 0
+            main = torch.cuda.current_stream()
             for plan, dev in ((p_tao, d_tao), (p_lvis, d_lvis)):
                 h2d += dev.reload(plan)
                 if plan.kind == "tao":
@@ -549,9 +554,13 @@ def main():
                     eng.stage_frame_eval(dev)
                 ex = pipe.exch[id(dev)]
                 ex.accumulate()
-                for k, v in ex.part.items():
-                    host_part[id(dev)][k].copy_(v, non_blocking=True)
-                    d2h += v.numel() * v.element_size()
+                done = torch.cuda.Event()
+                done.record(main)
+                copy_out.wait_event(done)
+                with torch.cuda.stream(copy_out):
+                    for k, v in ex.part.items():
+                        host_part[id(dev)][k].copy_(v, non_blocking=True)
+                        d2h += v.numel() * v.element_size()
             torch.cuda.synchronize()
             return h2d, d2h
     for _ in range(2):

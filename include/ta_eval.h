@@ -70,6 +70,11 @@ const char* ta_last_error(void);
 int         ta_ctx_create(int device, ta_ctx** out);
 int         ta_ctx_destroy(ta_ctx* ctx);
 int         ta_ctx_sm_count(const ta_ctx* ctx);
+/* TA_IOU_3D (tiled kernel) counts the track pairs whose summed intersection exceeds their summed
+ * union — the reference asserts i <= u there (eval.py:95).  ta_eval_plan_host returns
+ * TA_ERR_ASSERT for them; callers of the staged API read (and reset) the counter here, which
+ * waits for `stream`. */
+int         ta_ctx_take_assert_count(ta_ctx* ctx, void* stream, int32_t* count);
 
 /* Spatio-temporal IoU of every (predicted track, GT track) pair of every (video, category)
  * group.  Replaces TaoEval.compute_iou + compute_track_box_iou / compute_avg_track_iou /
@@ -241,6 +246,11 @@ int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* plan,
                       double* precision, double* recall,
                       int64_t* tp_cnt, int64_t* fp_cnt, int32_t* num_gt,
                       int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* float [n,4] -> double [n,4] on the device: lossless transport of box coordinates that are
+ * exactly representable in float (what TA_PLAN_BOX_F32 does inside ta_eval_plan_host), for
+ * callers that refresh resident plans from host memory. */
+int ta_widen_boxes(ta_ctx* ctx, void* stream, int64_t n, const float* src, double* dst);
 
 /* ---- multi-GPU exchange (one process per GPU; NCCL over NVLink / NVSwitch) ---------------
  * Videos (and their images) shard across ranks: ta_track_iou / ta_match_greedy / ta_frame_eval

@@ -145,5 +145,19 @@ extern "C" int ta_ctx_destroy(ta_ctx* c) {
     return TA_OK;
 }
 
+// Number of track pairs whose intersection exceeded their union since the last call (the
+// reference raises AssertionError there, eval.py:95); waits for `stream` and resets the counter.
+extern "C" int ta_ctx_take_assert_count(ta_ctx* c, void* stream, int32_t* count) {
+    if (!c || !count) return ta_set_err(TA_ERR_INVALID, "ta_ctx_take_assert_count: NULL argument");
+    TA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int v = 0;
+    TA_CUDA(cudaMemcpyAsync(&v, c->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaMemsetAsync(c->d_flags, 0, sizeof(int), st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    *count = v;
+    return TA_OK;
+}
+
 extern "C" int ta_ctx_sm_count(const ta_ctx* c) { return c ? c->sm_count : 0; }
 extern "C" int64_t ta_ctx_launch_count(const ta_ctx* c) { return c ? c->launches : 0; }

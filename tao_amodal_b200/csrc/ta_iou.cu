@@ -50,6 +50,7 @@ struct TrackIouArgs {
     const int64_t* iou_off;
     double* iou;
     int S;  // slots per window
+    int* flags;   // [0]: pairs whose intersection exceeds their union (the reference asserts, eval.py:95)
 };
 
 __global__ void __launch_bounds__(TI_WARPS * 32, 2)
@@ -168,6 +169,7 @@ k_track_iou_tiled(TrackIouArgs a) {
                     if (win > 0) inter += *o;
                     if (win == n_win - 1) {
                         const double uni = (da + ga_sh[lane]) - inter;
+                        if (!(inter <= uni) && a.flags) atomicAdd(a.flags, 1);      // eval.py:95
                         *o = uni > 0.0 ? inter / uni : 0.0;
                     } else {
                         *o = inter;
@@ -249,7 +251,7 @@ extern "C" int ta_track_iou(ta_ctx* ctx, void* stream, int mode, int64_t n_group
     ta_begin(ctx, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     TrackIouArgs a{grp_dt_off, grp_gt_off, dt_trk_off, dt_box, dt_slot,
-                   gt_trk_off, gt_box, gt_slot, iou_off, iou_out, 0};
+                   gt_trk_off, gt_box, gt_slot, iou_off, iou_out, 0, ctx->d_flags};
     if (mode == TA_IOU_3D) {
         // slots per shared-memory window: the whole video when it fits (2 CTAs of 16 warps per SM
         // need <= ~110 KB each), else 384-slot windows

@@ -13,6 +13,20 @@ __global__ void k_widen_boxes(const float4* __restrict__ src, double* __restrict
     o[1] = make_double2((double)v.z, (double)v.w);
 }
 
+// Lossless transport of box coordinates: float [n,4] -> double [n,4] on the device (the fp64
+// arithmetic then starts from the identical values; TA_PLAN_BOX_F32 of ta_eval_plan_host does
+// the same internally).  For callers that keep plans resident and refresh them from host memory.
+extern "C" int ta_widen_boxes(ta_ctx* ctx, void* stream, int64_t n, const float* src, double* dst) {
+    if (!ctx) return ta_set_err(TA_ERR_INVALID, "ta_widen_boxes: ctx is NULL");
+    if (n < 0) return ta_set_err(TA_ERR_INVALID, "ta_widen_boxes: negative size");
+    if (n == 0) return TA_OK;
+    TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
+    k_widen_boxes<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(src), dst, n);
+    return ta_check_launch(ctx, "k_widen_boxes");
+}
+
 namespace {
 struct DevArena {
     cudaStream_t st;
@@ -162,6 +176,14 @@ extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
         if (h2d_bytes) *h2d_bytes = ar.h2d;
         if (d2h_bytes) *d2h_bytes = d2h;
     }   // arena frees are stream-ordered after the kernels
+    int bad = 0;
+    if (rc == TA_OK && track && pl->iou_mode == TA_IOU_3D) {
+        // the tiled IoU kernel counted the pairs with intersection > union (eval.py:95)
+        TA_CUDA(cudaMemcpyAsync(&bad, ctx->d_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int), st));
+    }
     TA_CUDA(cudaStreamSynchronize(st));
+    if (bad)
+        return ta_set_err(TA_ERR_ASSERT, "track IoU: intersection exceeds union in %s%lld pairs", "", bad);
     return rc;
 }

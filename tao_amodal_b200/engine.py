@@ -351,6 +351,13 @@ class Engine:
         self.stage_accumulate(dev)
         if not fetch:
             return None
+        if plan.kind == "tao" and iou_mode == "3d_iou":
+            import torch
+            bad = C.c_int32(0)
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            _lib.check(self.lib.ta_ctx_take_assert_count(self._ctx, st, C.byref(bad)))
+            if bad.value:                       # the reference asserts i <= u (eval.py:95)
+                raise AssertionError("track IoU: intersection exceeds union in %d pairs" % bad.value)
         t = dev.t
         out = EvalOutput(
             precision=t["precision"].cpu().numpy(), recall=t["recall"].cpu().numpy(),
@@ -454,10 +461,24 @@ class DevicePlan:
         the existing device buffers, asynchronously on the current stream.  Returns the bytes."""
         import torch
         src = self._host_of(plan)
+        f32 = lossless_f32_boxes(plan)
+        st = C.c_void_p(torch.cuda.current_stream(self.eng.device).cuda_stream)
         n = 0
         for k in self._input_keys:
             v = src.get(k)
             if v is None:
+                continue
+            if f32 is not None and k in ("dt_box", "gt_box"):
+                # lossless float transport: half the PCIe bytes, widened on the device
+                h = f32[0] if k == "dt_box" else f32[1]
+                stage = self.t.get(k + "_f32")
+                if stage is None:
+                    stage = self.t[k + "_f32"] = torch.empty(h.shape, dtype=torch.float32, device=self.dev)
+                stage.copy_(torch.from_numpy(h), non_blocking=True)
+                _lib.check(self.eng.lib.ta_widen_boxes(
+                    self.eng._ctx, st, h.shape[0], C.c_void_p(stage.data_ptr()),
+                    C.c_void_p(self.t[k].data_ptr())))
+                n += h.nbytes
                 continue
             self.t[k].copy_(torch.from_numpy(v), non_blocking=True)
             n += v.nbytes

@@ -13,12 +13,54 @@ _JSON_CACHE: Dict[Tuple[str, float, int], object] = {}
 import numpy as np
 
 
+import threading
+
+_ENGINE_LOCK = threading.Lock()
+
+
 def get_engine(device: int = 0):
-    """One Engine (ta_ctx) per device per process."""
+    """One Engine (ta_ctx) per device per process (thread-safe: the CLI creates it on a
+    background thread while the JSON files are parsed — CUDA context creation takes a few
+    hundred milliseconds)."""
     from ..engine import Engine
-    if device not in _ENGINES:
-        _ENGINES[device] = Engine(device)
-    return _ENGINES[device]
+    with _ENGINE_LOCK:
+        if device not in _ENGINES:
+            _ENGINES[device] = Engine(device)
+        return _ENGINES[device]
+
+
+def warm_engine(device: int = 0):
+    t = threading.Thread(target=get_engine, args=(device,), daemon=True)
+    t.start()
+    return t
+
+
+class BackgroundPlan:
+    """Builds the track evaluator's plan on a worker thread while the frame evaluator runs
+    (numpy's sorts / searches release the GIL).  Any exception is swallowed here: the consumer
+    then builds the plan itself and raises at the place the reference would."""
+
+    def __init__(self, annotation: str, results: str):
+        self.annotation, self.results = annotation, results
+        self.gt = self.dt = self.plan = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        try:
+            from .. import ingest, prep
+            g = ingest.load_gt(self.annotation)
+            d = ingest.load_dt(self.results).copy()
+            prep.make_track_ids_unique(d)
+            plan = prep.prepare_tao(g, d)
+            self.gt, self.dt, self.plan = g, d, plan
+        except BaseException:       # noqa: BLE001 - the foreground path reports errors
+            self.gt = self.dt = self.plan = None
+
+    def take(self):
+        """(gt columns, uniquified dt columns, plan) or (None, None, None)."""
+        self._thread.join()
+        return self.gt, self.dt, self.plan
 
 
 def load_json(path: str):
@@ -89,6 +131,9 @@ class LazyDict(dict):
 def dist_info():
     """(rank, world) of the default torch.distributed group, (0, 1) when not initialised.
     With world > 1 the evaluators shard videos across ranks (parallel.py)."""
+    import sys
+    if "torch.distributed" not in sys.modules and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return 0, 1          # single process: never import torch (seconds of start-up time)
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -115,18 +160,19 @@ def dist_transport(eng, rank, world):
     return tr
 
 
-def dist_check_nonempty(dev, what_gt, what_dt):
-    """The reference's "found no ... annotations" errors (eval.py:188-192) on the WHOLE set: a
-    shard alone may be empty (prep allow_empty), the sum over ranks may not."""
+def dist_check_nonempty(dev, what_gt, what_dt, dt_error=ValueError):
+    """The reference's "found no ... annotations" errors (eval.py:188-192; an empty result list
+    is an IndexError in lvis_amodal/results.py) on the WHOLE set: a shard alone may be empty
+    (prep allow_empty), the sum over ranks may not."""
     import torch
     import torch.distributed as dist
     n = torch.tensor([dev.plan.n_gt, dev.plan.n_dt], dtype=torch.int64, device=dev.dev)
     dist.all_reduce(n)
     n_gt, n_dt = (int(v) for v in n.cpu().tolist())
-    if n_gt == 0:
+    if n_gt == 0 and dt_error is ValueError:
         raise ValueError(what_gt)
     if n_dt == 0:
-        raise ValueError(what_dt)
+        raise dt_error(what_dt)
 
 
 def dist_accumulate(eng, dev, rank, world):

@@ -18,7 +18,7 @@ import numpy as np
 
 from ... import materialize, prep
 from ...columnar import DtColumns
-from .._common import (LazyDict, ascending_rec_thrs, dist_accumulate, dist_info, get_engine,
+from .._common import (LazyDict, ascending_rec_thrs, dist_accumulate, dist_check_nonempty, dist_info, get_engine,
                        restore_rec_order)
 from .lvis import LVIS
 from .results import LVISResults
@@ -104,7 +104,7 @@ class LVISEval:
         self.params.img_ids = sorted(self.lvis_gt.get_img_ids())
         self.params.cat_ids = sorted(self.lvis_gt.get_cat_ids())
         self.device = device
-        self._plan = self._dev = self._detail = None
+        self._plan = self._dev = self._detail = self._host_out = None
         self._rank, self._world = 0, 1
 
     def _prepare(self):
@@ -182,13 +182,24 @@ class LVISEval:
         self._prepare()
         eng = get_engine(self.device)
         rec_sorted, self._rec_inv = ascending_rec_thrs(self.params.rec_thrs)
-        self._dev = eng.upload(self._plan, self.params.iou_thrs, rec_sorted)
-        if self._plan.masks is None:
-            eng.stage_frame_eval(self._dev)
-        else:
-            eng.stage_iou(self._dev)
-            eng.stage_match(self._dev)
+        self._rec_sorted = rec_sorted
         self._detail = None
+        self._dev = self._host_out = None
+        if self._world == 1 and self._plan.masks is None:
+            # single GPU, boxes: ONE C call from host buffers (ta_eval_plan_host) — no torch
+            self._host_out = eng.evaluate_host(
+                self._plan, iou_thrs=np.ascontiguousarray(self.params.iou_thrs, dtype=np.float64),
+                rec_thrs=rec_sorted)
+        else:
+            self._dev = eng.upload(self._plan, self.params.iou_thrs, rec_sorted)
+            if self._world > 1:
+                dist_check_nonempty(self._dev, "Found no groundtruth annotations for given params",
+                                    "list index out of range", dt_error=IndexError)
+            if self._plan.masks is None:
+                eng.stage_frame_eval(self._dev)
+            else:
+                eng.stage_iou(self._dev)
+                eng.stage_match(self._dev)
         self.ious = LazyDict(lambda: materialize.iou_dict(self._plan, self._need_detail().iou))
         plan = self._plan
         self.eval_imgs = _CellList(
@@ -202,9 +213,12 @@ class LVISEval:
             raise RuntimeError("ious / eval_imgs / dt_pointers are per-process structures: "
                                "not available in multi-GPU mode (run single-GPU to read them)")
         if self._detail is None:
-            # a second pass over the same buffers; the accumulated tensors it rewrites are
+            # a second pass over the same plan; the accumulated tensors it rewrites are
             # identical (same plan, same kernels)
-            self._detail = get_engine(self.device).evaluate_device(self._dev, detail=True)
+            eng = get_engine(self.device)
+            if self._dev is None:
+                self._dev = eng.upload(self._plan, self.params.iou_thrs, self._rec_sorted)
+            self._detail = eng.evaluate_device(self._dev, detail=True)
         return self._detail
 
     def compute_iou(self, img_id, cat_id):
@@ -213,26 +227,30 @@ class LVISEval:
     def accumulate(self):
         """PR accumulation on the GPU (lvis eval.py:305-426)."""
         self.logger.info("Accumulating evaluation results.")
-        if self._dev is None:
+        if self._plan is None:
             self.logger.warn("Please run evaluate first.")
             return
-        eng = get_engine(self.device)
-        if self._world > 1:
-            dist_accumulate(eng, self._dev, self._rank, self._world)
-        else:
-            eng.stage_accumulate(self._dev)
         p = self.params
         T, R, C, NR = len(p.iou_thrs), len(p.rec_thrs), len(self._plan.cat_ids), \
             len(p.visibility_rng)
-        t = self._dev.t
-        self._num_gt = t["num_gt"].cpu().numpy()
+        if self._host_out is not None:
+            prec_raw, recall = self._host_out.precision, self._host_out.recall
+            self._num_gt = self._host_out.num_gt
+        else:
+            eng = get_engine(self.device)
+            if self._world > 1:
+                dist_accumulate(eng, self._dev, self._rank, self._world)
+            else:                               # segm plans: staged device path
+                eng.stage_accumulate(self._dev)
+            t = self._dev.t
+            prec_raw, recall = t["precision"].cpu().numpy(), t["recall"].cpu().numpy()
+            self._num_gt = t["num_gt"].cpu().numpy()
         self.eval = {
             "params": p,
             "counts": [T, R, C, NR],
             "date": datetime.datetime.now().strftime("%Y-%m-%d %H:%M:%S"),
-            "precision": restore_rec_order(t["precision"].cpu().numpy(), t["recall"].cpu().numpy(),
-                                           p.rec_thrs, self._rec_inv),
-            "recall": t["recall"].cpu().numpy(),
+            "precision": restore_rec_order(prec_raw, recall, p.rec_thrs, self._rec_inv),
+            "recall": recall,
             "dt_pointers": LazyDict(lambda: materialize.dt_pointers(
                 self._plan, T, self._need_detail().dt_tpfp, self._num_gt)),
         }

@@ -46,7 +46,7 @@ class Params:
 
 class TaoEval:
     def __init__(self, tao_gt, tao_dt, logger=None, iou_type="bbox", iou_3d_type="3d_iou",
-                 device=0):
+                 device=0, _plan=None):
         if not logger:
             self.logger = logging.getLogger('tao.eval')
         elif isinstance(logger, str):
@@ -78,7 +78,17 @@ class TaoEval:
         self._plan = None
         self._dev = None
         self._detail = None
+        self._host_out = None
         self._rank, self._world = 0, 1
+        # a plan built ahead of time for exactly these inputs and the default Params (the CLI's
+        # BackgroundPlan); used only if the Params that shape the plan are still the defaults
+        self._given_plan = _plan
+        self._plan_defaults = self._plan_signature()
+
+    def _plan_signature(self):
+        p = self.params
+        return (tuple(p.vid_ids), tuple(p.cat_ids), repr(p.area_rng), repr(p.time_rng),
+                int(p.use_cats), int(self.tao_dt.max_dets))
 
     # ------------------------------------------------------------------------ device stages
     def _prepare(self):
@@ -97,6 +107,10 @@ class TaoEval:
             # exchanges the per-track records (parallel.py)
             from ... import parallel
             vid_ids = parallel.shard_videos(np.unique(vid_ids), self._world)[self._rank]
+        if (self._given_plan is not None and self._world == 1
+                and self._plan_signature() == self._plan_defaults):
+            self._plan = self._given_plan
+            return
         self._plan = prep.prepare_tao(
             self.tao_gt.columns, self.tao_dt.dt_columns, max_dets=self.tao_dt.max_dets,
             area_rng=p.area_rng, time_rng=p.time_rng, vid_ids=vid_ids,
@@ -112,13 +126,22 @@ class TaoEval:
         self._prepare()
         eng = get_engine(self.device)
         rec_sorted, self._rec_inv = ascending_rec_thrs(self.params.rec_thrs)
-        self._dev = eng.upload(self._plan, self.params.iou_thrs, rec_sorted)
-        if self._world > 1:
+        self._rec_sorted = rec_sorted
+        self._detail = None
+        self._dev = self._host_out = None
+        if self._world == 1:
+            # single GPU: ONE C call from host buffers (ta_eval_plan_host: H2D, IoU, matching,
+            # accumulation, D2H) — no torch anywhere on this path
+            self._host_out = eng.evaluate_host(
+                self._plan, iou_mode=self.params.iou_3d_type,
+                iou_thrs=np.ascontiguousarray(self.params.iou_thrs, dtype=np.float64),
+                rec_thrs=rec_sorted)
+        else:
+            self._dev = eng.upload(self._plan, self.params.iou_thrs, rec_sorted)
             dist_check_nonempty(self._dev, "Found no groundtruth annotations for given params",
                                 "Found no predicted annotations for given params")
-        eng.stage_iou(self._dev, self.params.iou_3d_type)
-        eng.stage_match(self._dev)
-        self._detail = None
+            eng.stage_iou(self._dev, self.params.iou_3d_type)
+            eng.stage_match(self._dev)
         self.ious = LazyDict(lambda: materialize.iou_dict(self._plan, self._need_detail().iou))
         self.eval_vids = LazyDict(lambda: materialize.cells_dict(
             self._plan, len(self.params.iou_thrs), self._need_detail()))
@@ -131,6 +154,8 @@ class TaoEval:
                                "not available in multi-GPU mode (run single-GPU to read them)")
         if self._detail is None:
             eng = get_engine(self.device)
+            if self._dev is None:
+                self._dev = eng.upload(self._plan, self.params.iou_thrs, self._rec_sorted)
             self._detail = eng.evaluate_device(self._dev, detail=True,
                                                iou_mode=self.params.iou_3d_type)
         return self._detail
@@ -142,23 +167,24 @@ class TaoEval:
     def accumulate(self):
         """PR accumulation on the GPU (eval.py:459-584)."""
         self.logger.info("Accumulating evaluation results.")
-        if self._dev is None:
+        if self._plan is None:
             self.logger.warn("Please run evaluate first.")
             return
-        eng = get_engine(self.device)
-        if self._world > 1:
-            dist_accumulate(eng, self._dev, self._rank, self._world)
-        else:
-            eng.stage_accumulate(self._dev)
         p = self.params
         T, R, C = len(p.iou_thrs), len(p.rec_thrs), len(self._plan.cat_ids)
         A, Tm = len(p.area_rng), len(p.time_rng)
-        t = self._dev.t
-        recall = t["recall"].cpu().numpy()
-        precision = restore_rec_order(t["precision"].cpu().numpy(), recall, p.rec_thrs,
+        if self._host_out is not None:
+            recall, prec_raw = self._host_out.recall, self._host_out.precision
+            self._num_gt = self._host_out.num_gt
+        else:
+            eng = get_engine(self.device)
+            dist_accumulate(eng, self._dev, self._rank, self._world)
+            t = self._dev.t
+            recall, prec_raw = t["recall"].cpu().numpy(), t["precision"].cpu().numpy()
+            self._num_gt = t["num_gt"].cpu().numpy()
+        precision = restore_rec_order(prec_raw, recall, p.rec_thrs,
                                       self._rec_inv).reshape(T, R, C, A, Tm)
         recall = recall.reshape(T, C, A, Tm)
-        self._num_gt = t["num_gt"].cpu().numpy()
         self.eval = {
             "params": p,
             "counts": [T, R, C, A, Tm],

@@ -185,5 +185,7 @@ def test_results_without_track_or_video_id_raise_like_the_reference(tmp_path):
                 prep.make_track_ids_unique(cols.copy())
             with pytest.raises(KeyError, match=want):
                 prep.prepare_tao(gt, cols)
-    full = ingest.load_dt(_write(tmp_path, res))
+    p = tmp_path / "full.json"
+    json.dump(res, open(p, "w"))
+    full = ingest.load_dt(str(p))
     assert full.missing_track_id == 0 and full.missing_video_id == 0

@@ -5,7 +5,11 @@ is bench.py's business (``cpu_baseline`` / ``--impl reference``: the only places
 that may run oracle/); SURVEY.md §3.4 estimates ~73 min for the unmodified reference on this
 shape.
 
-    python tools/bench_cli.py [--config cfg5] [--videos N] [--out gpurun_out/cli.json]
+    python tools/bench_cli.py [--config cfg5] [--videos N] [--out gpurun_out/cli.json] [--cold]
+
+--cold: what a user sees — every run is a FRESH `python tools/eval_on_tao_amodal.py ...`
+subprocess, wall-clock around it: interpreter start, imports, CUDA context creation, both JSON
+parses, host prep, GPU work and printing all included.
 """
 import argparse
 import contextlib
@@ -26,6 +30,8 @@ def main():
     ap.add_argument("--config", default="cfg5")
     ap.add_argument("--videos", type=int, default=0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--cold", action="store_true")
+    ap.add_argument("--runs", type=int, default=3)
     args = ap.parse_args()
     from tao_amodal_b200 import synth
     over = {"videos": args.videos} if args.videos else {}
@@ -37,6 +43,38 @@ def main():
     res = {"config": args.config, "videos": int(len(gt.vid_id)), "pred_boxes": int(dt.n()),
            "gt_boxes": int(gt.n_anns()), "annotation_mb": os.path.getsize(ap_) / 1e6,
            "prediction_mb": os.path.getsize(rp) / 1e6}
+
+    if args.cold:
+        import subprocess
+        cli_py = os.path.join(ROOT, "tools", "eval_on_tao_amodal.py")
+        runs = []
+        for _ in range(args.runs):
+            t0 = time.perf_counter()
+            p = subprocess.run([sys.executable, cli_py, "--track_result", rp, "--output_log", lp,
+                                "--annotation", ap_], capture_output=True, text=True)
+            runs.append(time.perf_counter() - t0)
+            if p.returncode != 0:
+                res["error"] = p.stderr[-2000:]
+                break
+        res["cold_runs_s"] = runs
+        res["cold_wall_s"] = min(runs) if runs else None
+        res["cold_first_run_s"] = runs[0] if runs else None
+        if os.path.exists(lp):
+            res["log_tail"] = open(lp).read().strip().splitlines()[-1]
+        res["torch_imported_by_cli"] = None
+        chk = subprocess.run([sys.executable, "-c",
+                              "import sys; sys.argv=['x','--track_result',%r,'--output_log',%r,'--annotation',%r];"
+                              "sys.path.insert(0,%r); import contextlib, io\n"
+                              "import eval_on_tao_amodal as c\n"
+                              "with contextlib.redirect_stdout(io.StringIO()): c.main()\n"
+                              "print('TORCH' if 'torch' in sys.modules else 'NOTORCH', file=sys.stderr)"
+                              % (rp, lp, ap_, os.path.join(ROOT, "tools"))],
+                             capture_output=True, text=True)
+        res["torch_imported_by_cli"] = "NOTORCH" not in chk.stderr
+        print(json.dumps(res))
+        if args.out:
+            json.dump(res, open(args.out, "w"), indent=1)
+        return
 
     import eval_on_tao_amodal as cli
     import torch

@@ -24,7 +24,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from tao_amodal_b200.columnar import DtColumns                      # noqa: E402
-from tao_amodal_b200.evaluation._common import load_json           # noqa: E402
+from tao_amodal_b200.evaluation._common import BackgroundPlan, load_json, warm_engine   # noqa: E402
 from tao_amodal_b200.evaluation.lvis_amodal import LVISEval        # noqa: E402
 from tao_amodal_b200.evaluation.tao_amodal import Tao, TaoEval     # noqa: E402
 from tao_amodal_b200 import ingest, prep                           # noqa: E402
@@ -87,19 +87,23 @@ def evaluate_predictions_on_lvis(lvis_gt, lvis_results, iou_type, logger, device
     return results
 
 
-def eval_tao_track(ann_path, results_path, logger, device=0):
-    """tools/eval_on_tao_amodal.py:118-151."""
+def eval_tao_track(ann_path, results_path, logger, device=0, background=None):
+    """tools/eval_on_tao_amodal.py:118-151.  `background`: a BackgroundPlan that has been
+    building the track plan of these two files while the frame evaluation ran."""
     logger.setLevel(logging.INFO)
     results = {}
     logger.info("Loading gt {}...".format(ann_path))
     tao_gt = Tao(ann_path)
     logger.info('Done')
     logger.info('Loading results...')
-    dt = ingest.load_dt(results_path).copy()      # native reader; the cached columns stay intact
-    prep.make_track_ids_unique(dt)
+    bg_gt, dt, plan = background.take() if background is not None else (None, None, None)
+    if plan is None or bg_gt is not tao_gt.columns:
+        plan = None
+        dt = ingest.load_dt(results_path).copy()  # native reader; the cached columns stay intact
+        prep.make_track_ids_unique(dt)
     logger.info('Done')
     logger.info('Building')
-    tao_eval = TaoEval(tao_gt, dt, logger=logger, device=device)
+    tao_eval = TaoEval(tao_gt, dt, logger=logger, device=device, _plan=plan)
     logger.info('Done')
     tao_eval.run()
     tao_eval.print_results()
@@ -149,13 +153,21 @@ def main(argv=None):
     else:           # other ranks compute their shard silently
         logging.disable(logging.CRITICAL)
         sys.stdout = open(os.devnull, "w")
-    # the results file is parsed on a background thread while the annotation file is read
+    # the results file is parsed on a background thread while the annotation file is read; the
+    # CUDA context is created meanwhile; single-GPU runs also build the track evaluator's plan
+    # in the background while the frame evaluator works
+    background = None
     if isinstance(args.track_result, str) and os.path.exists(args.track_result):
         ingest.prefetch(args.track_result, "dt")
+        if world == 1:
+            warm_engine(device)
+            if os.path.exists(args.annotation):
+                background = BackgroundPlan(args.annotation, args.track_result)
     try:
         evaluate_predictions_on_lvis(args.annotation, args.track_result, "bbox", logger,
                                      device=device)
-        eval_tao_track(args.annotation, args.track_result, logger, device=device)
+        eval_tao_track(args.annotation, args.track_result, logger, device=device,
+                       background=background)
     finally:
         if handler is not None:
             handler.close()
