@@ -512,6 +512,9 @@ def main():
         f32 = lossless_f32_boxes(out)
         if f32 is not None:      # the transport copies must be pinned too
             out._f32_boxes = tuple(torch.from_numpy(x).pin_memory().numpy() for x in f32)
+        if plan.kind == "tao" and plan.dt_box_slot.size and int(plan.dt_box_slot.max()) < 65536:
+            out._u16_slots = tuple(torch.from_numpy(np.ascontiguousarray(x.astype(np.uint16))).pin_memory().numpy()
+                                   for x in (plan.dt_box_slot, plan.gt_box_slot))
         return out
 
     e2e_steps = max(3, min(args.steps, 10))

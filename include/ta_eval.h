@@ -222,6 +222,7 @@ int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* ca
  * TaoEval.run()/LVISEval.run() replacement makes (evaluate + accumulate, eval.py:662-665).
  * Track path when the *_trk_off pointers are non-NULL, frame path (fused) otherwise.   */
 #define TA_PLAN_BOX_F32 1
+#define TA_PLAN_SLOT_U16 2
 typedef struct ta_plan_host {
     int64_t n_groups, n_dt, n_gt, n_dt_boxes, n_gt_boxes, n_big;
     int32_t n_cat, n_cfg, n_thr, n_rec, n_slots_max, g_max, iou_mode;
@@ -234,7 +235,9 @@ typedef struct ta_plan_host {
     const int32_t *grp_cat, *acc_perm, *big_list;
     const void    *dt_box, *gt_box;           /* double[N,4], or float[N,4] with TA_PLAN_BOX_F32 */
     const int64_t *dt_trk_off, *gt_trk_off;   /* NULL on the frame path */
-    const int32_t *dt_slot, *gt_slot;         /* NULL on the frame path */
+    const void    *dt_slot, *gt_slot;         /* int32[N] (uint16[N] with TA_PLAN_SLOT_U16: slots
+                                                 below 65536 shipped in half the bytes); NULL on the
+                                                 frame path */
     const double  *dt_attr_a, *dt_attr_b, *gt_attr_a, *gt_attr_b;
     const uint8_t *dt_flag, *gt_flag;
     const int32_t *gt_hp;
@@ -298,6 +301,10 @@ int ta_exchange_group_end(ta_exchange* x);
 int ta_ctx_timing(ta_ctx* ctx, int enable);
 int ta_ctx_timing_read(ta_ctx* ctx, char* names, int names_cap, double* total_ms, int* launches,
                        int cap);
+
+/* Diagnostics: number of groups the most recent evaluation call of ta_match_greedy /
+ * ta_frame_eval on this context handed to the general matcher (-1: none yet). */
+int ta_ctx_debug_list_count(ta_ctx* ctx, void* stream, int32_t* count);
 
 /* Number of kernel launches issued through this context since creation. */
 int64_t ta_ctx_launch_count(const ta_ctx* ctx);

@@ -159,5 +159,18 @@ extern "C" int ta_ctx_take_assert_count(ta_ctx* c, void* stream, int32_t* count)
     return TA_OK;
 }
 
+// Diagnostics: how many groups the most recent ta_match_greedy / ta_frame_eval evaluation call
+// on this context handed to the general matcher (waits for `stream`).
+extern "C" int ta_ctx_debug_list_count(ta_ctx* c, void* stream, int32_t* count) {
+    if (!c || !count) return ta_set_err(TA_ERR_INVALID, "ta_ctx_debug_list_count: NULL argument");
+    *count = -1;
+    if (!c->last_list_count) return TA_OK;
+    TA_CUDA(cudaSetDevice(c->device));
+    TA_CUDA(cudaMemcpyAsync(count, c->last_list_count, sizeof(int32_t), cudaMemcpyDeviceToHost,
+                            (cudaStream_t)stream));
+    TA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return TA_OK;
+}
+
 extern "C" int ta_ctx_sm_count(const ta_ctx* c) { return c ? c->sm_count : 0; }
 extern "C" int64_t ta_ctx_launch_count(const ta_ctx* c) { return c ? c->launches : 0; }

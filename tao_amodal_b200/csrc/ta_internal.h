@@ -31,6 +31,9 @@ struct ta_ctx {
     int n_ev;
     cudaEvent_t* ev;
     const char** ev_name;      // NULL = entry marker
+    // diagnostics: device counter of the groups the most recent flat-kernel call handed to the
+    // general matcher (ta_ctx_debug_list_count)
+    const int32_t* last_list_count;
 };
 
 #define TA_MAX_EVENTS 16384

@@ -1245,6 +1245,7 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
         if ((rc = ta_check_launch(ctx, "k_track_flat"))) return rc;
         a.dev_list = f.complex_list;
         a.dev_count = f.complex_count;
+        ctx->last_list_count = f.complex_count;
         a.skip_num_gt = 1;
         int64_t lblocks = (int64_t)ctx->sm_count * 4;
         if (lblocks > n_groups) lblocks = n_groups;
@@ -1421,6 +1422,7 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
         a.complex_count = a.grp_flag + n_groups;
         a.complex_list = reinterpret_cast<int32_t*>(base + o_list);
         TA_CUDA(cudaMemsetAsync(a.grp_flag, 0, (size_t)n_groups * 4 + 4, st));
+        ctx->last_list_count = a.complex_count;
         const bool spec = (n_thr == 10 && n_cfg == 6);
         if (own_sched) {
             // the schedule holds the GT side: add its counts, no per-call pass over the GT

@@ -3,6 +3,12 @@
 // the pool's release threshold so repeated calls reuse the same pages).
 #include "ta_internal.h"
 
+// frame slots shipped as uint16 (TA_PLAN_SLOT_U16) -> int32
+__global__ void k_widen_slots(const uint16_t* __restrict__ src, int32_t* __restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (int32_t)src[i];
+}
+
 // lossless fp32 -> fp64 widening of box coordinates shipped as float (TA_PLAN_BOX_F32)
 __global__ void k_widen_boxes(const float4* __restrict__ src, double* __restrict__ dst, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -80,7 +86,9 @@ extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
         const ta_range_cfg* cfgs;
         TA_CUDA(ar.upload(&grp_dt_off, pl->grp_dt_off, G + 1));
         TA_CUDA(ar.upload(&grp_gt_off, pl->grp_gt_off, G + 1));
-        TA_CUDA(ar.upload(&iou_off, pl->iou_off, G + 1));
+        // the frame path keeps its IoU tiles on chip: iou_off is only read for oversize groups
+        if (track || pl->n_big > 0) TA_CUDA(ar.upload(&iou_off, pl->iou_off, G + 1));
+        else iou_off = nullptr;
         TA_CUDA(ar.upload(&cat_dt_off, pl->cat_dt_off, (size_t)pl->n_cat + 1));
         TA_CUDA(ar.upload(&grp_cat, pl->grp_cat, G));
         TA_CUDA(ar.upload(&acc_perm, pl->acc_perm, pl->n_dt));
@@ -113,8 +121,28 @@ extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
         if (track) {
             TA_CUDA(ar.upload(&dt_trk_off, pl->dt_trk_off, pl->n_dt + 1));
             TA_CUDA(ar.upload(&gt_trk_off, pl->gt_trk_off, pl->n_gt + 1));
-            TA_CUDA(ar.upload(&dt_slot, pl->dt_slot, pl->n_dt_boxes));
-            TA_CUDA(ar.upload(&gt_slot, pl->gt_slot, pl->n_gt_boxes));
+            if (pl->flags & TA_PLAN_SLOT_U16) {
+                // slots < 65536 travel as uint16 (half the bytes) and are widened on the device
+                const uint16_t *s_dt, *s_gt;
+                void *w_dt, *w_gt;
+                TA_CUDA(ar.upload(&s_dt, (const uint16_t*)pl->dt_slot, (size_t)pl->n_dt_boxes));
+                TA_CUDA(ar.upload(&s_gt, (const uint16_t*)pl->gt_slot, (size_t)pl->n_gt_boxes));
+                TA_CUDA(ar.alloc(&w_dt, (size_t)pl->n_dt_boxes * 4));
+                TA_CUDA(ar.alloc(&w_gt, (size_t)pl->n_gt_boxes * 4));
+                if (pl->n_dt_boxes) {
+                    k_widen_slots<<<(unsigned)((pl->n_dt_boxes + 255) / 256), 256, 0, st>>>(s_dt, (int32_t*)w_dt, pl->n_dt_boxes);
+                    if ((rc = ta_check_launch(ctx, "k_widen_slots"))) return rc;
+                }
+                if (pl->n_gt_boxes) {
+                    k_widen_slots<<<(unsigned)((pl->n_gt_boxes + 255) / 256), 256, 0, st>>>(s_gt, (int32_t*)w_gt, pl->n_gt_boxes);
+                    if ((rc = ta_check_launch(ctx, "k_widen_slots"))) return rc;
+                }
+                dt_slot = (const int32_t*)w_dt;
+                gt_slot = (const int32_t*)w_gt;
+            } else {
+                TA_CUDA(ar.upload(&dt_slot, (const int32_t*)pl->dt_slot, pl->n_dt_boxes));
+                TA_CUDA(ar.upload(&gt_slot, (const int32_t*)pl->gt_slot, pl->n_gt_boxes));
+            }
             TA_CUDA(ar.upload(&dt_a, pl->dt_attr_a, pl->n_dt));
             TA_CUDA(ar.upload(&dt_b, pl->dt_attr_b, pl->n_dt));
             TA_CUDA(ar.upload(&gt_b, pl->gt_attr_b, pl->n_gt));
@@ -126,7 +154,7 @@ extern "C" int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* pl,
         TA_CUDA(ar.upload(&recs, pl->rec_thrs, pl->n_rec));
         TA_CUDA(ar.upload(&cfgs, pl->cfgs, pl->n_cfg));
 
-        const int64_t n_iou = pl->iou_off[G];
+        const int64_t n_iou = pl->iou_off ? pl->iou_off[G] : 0;
         const size_t n_cell = (size_t)pl->n_thr * pl->n_cat * pl->n_cfg;
         const size_t n_prec = n_cell * pl->n_rec;
         void *d_iou, *d_tpfp, *d_numgt, *d_prec, *d_rec, *d_tp, *d_fp, *d_word = nullptr;

@@ -228,6 +228,14 @@ class Engine:
         f32 = lossless_f32_boxes(plan) if compress_boxes else None
         ph.flags = 1 if f32 is not None else 0
         dt_box, gt_box = f32 if f32 is not None else (plan.dt_box, plan.gt_box)
+        dt_slot, gt_slot = (plan.dt_box_slot, plan.gt_box_slot) if track else (None, None)
+        if track and compress_boxes and n_slots <= 65536:
+            u16 = getattr(plan, "_u16_slots", None)
+            if u16 is None:
+                u16 = plan._u16_slots = (np.ascontiguousarray(plan.dt_box_slot.astype(np.uint16)),
+                                         np.ascontiguousarray(plan.gt_box_slot.astype(np.uint16)))
+            dt_slot, gt_slot = u16
+            ph.flags |= 2
         keep = dict(
             grp_dt_off=plan.grp_dt_off, grp_gt_off=plan.grp_gt_off, iou_off=plan.iou_off,
             cat_dt_off=plan.cat_dt_off, grp_cat=plan.grp_cat, acc_perm=plan.acc_perm,
@@ -235,8 +243,7 @@ class Engine:
             dt_box=dt_box, gt_box=gt_box,
             dt_trk_off=plan.dt_trk_box_off if track else None,
             gt_trk_off=plan.gt_trk_box_off if track else None,
-            dt_slot=plan.dt_box_slot if track else None,
-            gt_slot=plan.gt_box_slot if track else None,
+            dt_slot=dt_slot, gt_slot=gt_slot,
             dt_attr_a=plan.dt_attr_a, dt_attr_b=plan.dt_attr_b,
             gt_attr_a=plan.gt_attr_a, gt_attr_b=plan.gt_attr_b,
             dt_flag=plan.dt_flag, gt_flag=plan.gt_flag, gt_hp=plan.gt_hp,
@@ -464,9 +471,15 @@ class DevicePlan:
         f32 = lossless_f32_boxes(plan)
         st = C.c_void_p(torch.cuda.current_stream(self.eng.device).cuda_stream)
         n = 0
+        # the fused frame path reads neither the per-detection attributes (area = w * h of the
+        # box) nor, without oversize groups, the IoU offsets: ta_eval_plan_host does not ship
+        # them either
+        unused = set()
+        if plan.kind == "lvis" and plan.masks is None:
+            unused = {"dt_attr_a", "dt_attr_b", "gt_attr_b", "gt_hp"} | ({"iou_off"} if not self.n_big else set())
         for k in self._input_keys:
             v = src.get(k)
-            if v is None:
+            if v is None or k in unused:
                 continue
             if f32 is not None and k in ("dt_box", "gt_box"):
                 # lossless float transport: half the PCIe bytes, widened on the device

@@ -40,6 +40,21 @@ def main():
     eng = Engine(0)
     d_tao, d_lvis = eng.upload(tao_plan), eng.upload(lvis_plan)
 
+    def list_count():
+        import ctypes as C
+        n = C.c_int32(0)
+        st = C.c_void_p(torch.cuda.current_stream(0).cuda_stream)
+        eng.lib.ta_ctx_debug_list_count(eng._ctx, st, C.byref(n))
+        return int(n.value)
+
+    eng.stage_iou(d_tao)
+    eng.stage_match(d_tao)
+    n_list_tao = list_count()
+    eng.stage_frame_eval(d_lvis)
+    n_list_lvis = list_count()
+    print("groups handed to the general matcher: track path %d of %d, frame path %d of %d" % (
+        n_list_tao, tao_plan.n_groups, n_list_lvis, lvis_plan.n_groups), flush=True)
+
     def step():
         eng.stage_iou(d_tao)
         eng.stage_match(d_tao)
