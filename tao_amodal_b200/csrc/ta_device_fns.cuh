@@ -210,39 +210,50 @@ TA_HD void pr_cell_planes(uint32_t Mk, uint32_t A, uint32_t B, uint32_t U, uint3
     fp = (B & Mk) | (U & ~Mk);
 }
 
-// Envelope walk of one (category chunk, range cfg, threshold) cell over the chunk's TRUE
-// POSITIVES only (accumulate, eval.py:527-573).  T[j * stride] / F[j * stride], j < 8, are the
-// cell's TP / FP flags of the chunk's positions 32 j .. 32 j + 31 in descending-score order
-// (bit = position inside the word); tc / fc the running TP / FP counts at the END of the chunk.
-// Walking the true positives backwards keeps the suffix-maximum precision as the exact rational
-// (bt, bn) and stores it (tagged with the chunk) for every recall level k whose tk-th true
-// positive lies in the chunk: q[k * q_stride].  tk[0 .. n_rec) must be non-decreasing
-// (ta_min_tp_for_recall of ascending recall thresholds).  Returns the chunk's best candidate.
-TA_HD unsigned long long ta_pr_walk_bits(const uint32_t* T, const uint32_t* F, int64_t stride,
-                                         uint32_t tc, uint32_t fc, const int32_t* tk, int n_rec,
-                                         uint32_t ch_rel, unsigned long long* q, int64_t q_stride) {
-    uint32_t Tw[TA_PR_WORDS], Fw[TA_PR_WORDS];
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int j = 0; j < TA_PR_WORDS; ++j) { Tw[j] = T[j * stride]; Fw[j] = F[j * stride]; }
-    // last recall level whose (clamped) tk is <= tc: binary search, tk is non-decreasing
-    int lo = -1, hi = n_rec;            // invariant: tk'[lo] <= tc < tk'[hi]
+// Envelope walk of one (range cfg, threshold) cell over the TRUE POSITIVES of its chunks, last
+// chunk first (accumulate, eval.py:527-573).  The state carries the running TP / FP counts, the
+// suffix-maximum precision as the exact rational (bt, bn) and the next recall level to answer.
+//   ta_pr_state_init   counts at the END of the last chunk to be walked; finds the last recall
+//                      level whose tk is already reached (tk[0 .. n_rec) non-decreasing:
+//                      ta_min_tp_for_recall of ascending recall thresholds)
+//   ta_pr_walk_chunk   w[0..8) / w[8..16): the cell's TP / FP flags of the chunk's positions
+//                      32 j .. 32 j + 31 in descending-score order (bit = position inside the
+//                      word).  Stores the suffix maximum (tagged with the chunk) for every recall
+//                      level k whose tk-th true positive lies in the chunk: q[k].
+struct ta_pr_state {
+    uint32_t tc, fc, bt, bn, next_tk;
+    uint32_t after_tk;      // the level after next_tk, loaded one event ahead (breaks the chain
+                            // store -> dependent load -> compare of consecutive recall levels)
+    int kq;
+};
+TA_HD uint32_t ta_pr_tk_at(const int32_t* tk, int k) {
+    if (k < 0) return 0u;
+    const int32_t v = tk[k];
+    return (uint32_t)(v > 1 ? v : 1);
+}
+TA_HD void ta_pr_state_init(ta_pr_state& s, uint32_t tc, uint32_t fc, const int32_t* tk, int n_rec) {
+    s.tc = tc; s.fc = fc;
+    s.bt = 0; s.bn = 1;                  // precision 0: the first true positive always beats it
+    int lo = -1, hi = n_rec;             // invariant: tk'[lo] <= tc < tk'[hi]
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         const int32_t v = tk[mid];
         if ((uint32_t)(v > 1 ? v : 1) <= tc) lo = mid; else hi = mid;
     }
-    int kq = lo;
-    uint32_t next_tk = 0u;
-    if (kq >= 0) { const int32_t v = tk[kq]; next_tk = (uint32_t)(v > 1 ? v : 1); }
-    uint32_t bt = 0, bn = 1;            // precision 0: the first true positive always beats it
+    s.kq = lo;
+    s.next_tk = ta_pr_tk_at(tk, lo);
+    s.after_tk = ta_pr_tk_at(tk, lo - 1);
+}
+TA_HD void ta_pr_walk_chunk(ta_pr_state& s, const uint32_t* w, const int32_t* tk, uint32_t ch_rel,
+                            unsigned long long* q, int64_t q_stride) {
+    uint32_t tc = s.tc, fc = s.fc, bt = s.bt, bn = s.bn, next_tk = s.next_tk, after_tk = s.after_tk;
+    int kq = s.kq;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int j = TA_PR_WORDS - 1; j >= 0; --j) {
-        uint32_t t = Tw[j];
-        const uint32_t f = Fw[j];
+        uint32_t t = w[j];
+        const uint32_t f = w[TA_PR_WORDS + j];
         while (t) {
             const int p = 31 - TA_CLZ(t);
             t ^= 1u << p;
@@ -251,17 +262,31 @@ TA_HD unsigned long long ta_pr_walk_bits(const uint32_t* T, const uint32_t* F, i
             // strict ">" is enough: a tie keeps the later detection's pair, and the only
             // value-changing tie, (1,1) vs (k,k), has (1,1) as the candidate (first TP overall)
             if ((unsigned long long)tc * bn > (unsigned long long)bt * n) { bt = tc; bn = n; }
-            while (next_tk == tc) {
-                q[kq * q_stride] = pr_pack(bt, bn, ch_rel);
-                --kq;
-                next_tk = 0u;
-                if (kq >= 0) { const int32_t v = tk[kq]; next_tk = (uint32_t)(v > 1 ? v : 1); }
+            if (next_tk == tc) {
+                const unsigned long long packed = pr_pack(bt, bn, ch_rel);
+                do {
+                    q[kq * q_stride] = packed;
+                    --kq;
+                    next_tk = after_tk;
+                    after_tk = ta_pr_tk_at(tk, kq - 1);
+                } while (next_tk == tc);
             }
             --tc;
         }
         fc -= (uint32_t)TA_POPC(f);
     }
-    return pr_pack(bt, bn, 0);
+    s.tc = tc; s.fc = fc; s.bt = bt; s.bn = bn; s.next_tk = next_tk; s.after_tk = after_tk; s.kq = kq;
+}
+// One chunk on its own (tests/hostsim; the kernel carries the state over several chunks)
+TA_HD unsigned long long ta_pr_walk_bits(const uint32_t* T, const uint32_t* F, int64_t stride,
+                                         uint32_t tc, uint32_t fc, const int32_t* tk, int n_rec,
+                                         uint32_t ch_rel, unsigned long long* q, int64_t q_stride) {
+    uint32_t w[2 * TA_PR_WORDS];
+    for (int j = 0; j < TA_PR_WORDS; ++j) { w[j] = T[j * stride]; w[TA_PR_WORDS + j] = F[j * stride]; }
+    ta_pr_state s;
+    ta_pr_state_init(s, tc, fc, tk, n_rec);
+    ta_pr_walk_chunk(s, w, tk, ch_rel, q, q_stride);
+    return pr_pack(s.bt, s.bn, 0);
 }
 
 // ---- mask IoU of the segm path (ta_rle.cu; host build: tests/hostsim) -----------------------

@@ -44,6 +44,8 @@ struct MatchArgs {
     const int32_t* dev_list;
     const int32_t* dev_count;
     int skip_num_gt;              // the GT counts of these groups were taken by k_frame_prep
+    int iou_cap;                  // doubles of shared memory behind the taken / ignore tables: the
+                                  // group's IoU matrix is staged there when it fits
 };
 
 __global__ void k_match_greedy(MatchArgs a) {
@@ -87,6 +89,15 @@ __global__ void k_match_greedy(MatchArgs a) {
 
         const double thr = active ? a.thrs[t] : 2.0;
         const double* iou = a.iou + a.iou_off[grp];
+        if (D * G <= a.iou_cap) {
+            // every matcher lane walks the same rows one after the other: stage the matrix once
+            // (coalesced) instead of chasing it through L2 row by row
+            double* iou_s = reinterpret_cast<double*>(
+                smem_raw + (((size_t)words * nthreads * sizeof(uint32_t) + (size_t)a.n_cfg * G + 7) & ~(size_t)7));
+            for (int i = threadIdx.x; i < D * G; i += nthreads) iou_s[i] = iou[i];
+            __syncthreads();
+            iou = iou_s;
+        }
         const uint8_t* my_ig = gt_ig + (active ? cfg : 0) * G;
         ta_range_cfg rc;
         if (active) rc = a.cfgs[cfg];
@@ -200,6 +211,7 @@ struct FrameSmem {
     uint32_t dmask[FE_WARPS][FE_MAX_DT];
     uint32_t cand[FE_WARPS][FE_MAX_DT];
     uint32_t gig[FE_WARPS][FE_MAX_CFG];       // per cfg: bit g = GT g ignored
+    uint32_t csum[FE_WARPS][FE_MAX_DT];       // route C: per detection, "same outcome in every cfg"
 };
 
 // Range tests evaluated once per DISTINCT interval instead of once per cfg: the distinct
@@ -381,8 +393,6 @@ k_frame_eval(FrameArgs a) {
             const int D = (int)(__shfl_sync(0xffffffffu, dt_off_r, gi + 1) - d0);
             const int cat = __shfl_sync(0xffffffffu, cat_r, gi);
             if (G > FE_MAX_GT || D > FE_MAX_DT || D * G > FE_MAX_PAIRS) continue;   // big_list route
-            if (LIST && a.dt_word)
-                for (int d = lane; d < D; d += 32) a.dt_word[d0 + d] = TA_WORD_FULL;
             __syncwarp();
             // ---- GT side: boxes to shared memory, ignore masks per cfg, non-ignored counts.
             // All global loads of the group (GT lane data, first detection per lane) are issued
@@ -497,12 +507,22 @@ k_frame_eval(FrameArgs a) {
                     const int gs = (cd >> 16) & 31;
                     const bool sent = (gsent >> gs) & 1u;
                     uint32_t* o = a.dt_tpfp + (d0 + d) * n_cfg;
+                    uint32_t nig = 0;                  // cfgs in which the matched GT is not ignored
                     for (int c = 0; c < n_cfg; ++c) {
                         const bool gi2 = (gig_s[c] >> gs) & 1u;
                         const bool dc = (dm >> c) & 1u;
                         const uint32_t tp = (!sent && !gi2) ? M : 0u;
                         const uint32_t fp = ((sent && !gi2 && !dc) ? M : 0u) | (dc ? 0u : (thr_all & ~M));
                         o[c] = tp | (fp << 16);
+                        nig |= gi2 ? 0u : (1u << c);
+                    }
+                    if (LIST && a.dt_word) {
+                        // a group the flat kernel passed on that turns out to be simple: its
+                        // detections keep compact words (layout: k_frame_flat)
+                        const uint32_t ndc = ~dm & cfg_all;
+                        const uint32_t A = (M && !sent) ? nig : 0u;
+                        const uint32_t B = (M && sent) ? (nig & ndc) : 0u;
+                        a.dt_word[d0 + d] = M | (A << n_thr) | (B << (n_thr + n_cfg)) | (ndc << (n_thr + 2 * n_cfg));
                     }
                     if (DETAIL && a.dt_match_gt)
                         for (int c = 0; c < n_cfg; ++c)
@@ -513,6 +533,11 @@ k_frame_eval(FrameArgs a) {
                 continue;
             }
             // ---- route C: lane = (cfg within round, threshold)
+            // With compact result words (LIST): a detection keeps a compact word when it is matched
+            // at the same thresholds, to the same GT, under every range cfg — true for most
+            // detections even of these groups — and points to its full row otherwise.
+            const bool want_word = LIST && a.dt_word != nullptr;
+            uint32_t* csum_s = sm.csum[warp];
             const uint32_t gall = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
             for (int c0 = 0; c0 < n_cfg; c0 += cpw) {
                 const int cfg = c0 + cw;
@@ -554,6 +579,41 @@ k_frame_eval(FrameArgs a) {
                             ((bt >> sh) & thr_all) | (((bf >> sh) & thr_all) << 16);
                     if (DETAIL && a.dt_match_gt && active)
                         a.dt_match_gt[((int64_t)cfg * n_thr + t) * a.n_dt + d0 + d] = m;
+                    if (want_word) {
+                        const uint32_t bm = __ballot_sync(0xffffffffu, active && m >= 0);
+                        const int g1 = bm ? __shfl_sync(0xffffffffu, m, __ffs(bm) - 1) : -1;
+                        const bool same_g = __ballot_sync(0xffffffffu, active && m >= 0 && m != g1) == 0u;
+                        const uint32_t M0 = bm & thr_all;
+                        uint32_t rep = 0;
+                        for (int q = 0; q < cpw && c0 + q < n_cfg; ++q) rep |= M0 << (q * n_thr);
+                        const bool ok = same_g && bm == rep;
+                        if (lane == 0) {
+                            const uint32_t mine = M0 | ((uint32_t)(g1 + 1) << 16);
+                            if (c0 == 0) csum_s[d] = ok ? mine : 0xffffffffu;
+                            else if (csum_s[d] != 0xffffffffu &&
+                                     (!ok || (csum_s[d] & 0xffffu) != M0 || (M0 && csum_s[d] != mine)))
+                                csum_s[d] = 0xffffffffu;
+                        }
+                    }
+                }
+            }
+            if (want_word) {
+                __syncwarp();
+                for (int d = lane; d < D; d += 32) {
+                    const uint32_t cs = csum_s[d];
+                    uint32_t word = TA_WORD_FULL;
+                    if (cs != 0xffffffffu) {
+                        const uint32_t M = cs & 0xffffu, dm = dmask_s[d];
+                        const int gs = M ? (int)(cs >> 16) - 1 : 0;
+                        const bool sent = (gsent >> gs) & 1u;
+                        uint32_t nig = 0;
+                        for (int c = 0; c < n_cfg; ++c) nig |= ((gig_s[c] >> gs) & 1u) ? 0u : (1u << c);
+                        const uint32_t ndc = ~dm & cfg_all;
+                        const uint32_t A = (M && !sent) ? nig : 0u;
+                        const uint32_t B = (M && sent) ? (nig & ndc) : 0u;
+                        word = M | (A << n_thr) | (B << (n_thr + n_cfg)) | (ndc << (n_thr + 2 * n_cfg));
+                    }
+                    a.dt_word[d0 + d] = word;
                 }
             }
         }
@@ -1199,14 +1259,21 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
     if (warps * 32 > 1024) return ta_set_err(TA_ERR_TOO_LARGE, "ta_match_greedy: too many range cfgs");
     const int threads = warps * 32;
     const int words = (g_max + 31) / 32;
-    const size_t smem = (size_t)words * threads * sizeof(uint32_t) + (size_t)n_cfg * g_max;
+    const size_t smem_tab = (size_t)words * threads * sizeof(uint32_t) + (size_t)n_cfg * g_max;
+    // room for the IoU matrix of a group behind the tables (up to 32 KB)
+    size_t smem = smem_tab;
+    int iou_cap = 0;
+    if (smem_tab + 8 + 4096 * 8 <= (size_t)ctx->smem_optin) {
+        iou_cap = 4096;
+        smem = ((smem_tab + 7) & ~(size_t)7) + (size_t)iou_cap * 8;
+    }
     if (smem > (size_t)ctx->smem_optin)
         return ta_set_err(TA_ERR_TOO_LARGE,
                           "ta_match_greedy: a group with %s%lld ground-truth entities does not fit in shared memory",
                           "", (long long)g_max);
     MatchArgs a{grp_list, grp_dt_off, grp_gt_off, grp_cat, iou_off, iou, n_thr, iou_thrs, n_cfg, cfgs,
                 n_dt, n_gt, dt_attr_a, dt_attr_b, dt_flag, gt_attr_a, gt_attr_b, gt_hp,
-                gt_flag, dt_tpfp, num_gt, dt_match_gt, gt_ignore_out, cpw, nullptr, nullptr, 0};
+                gt_flag, dt_tpfp, num_gt, dt_match_gt, gt_ignore_out, cpw, nullptr, nullptr, 0, iou_cap};
     if (smem > 48 * 1024)
         TA_CUDA(cudaFuncSetAttribute(k_match_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));

@@ -336,7 +336,7 @@ static_assert(PR_CHUNK == 32 * TA_PR_WORDS, "chunk = 8 words of 32 positions");
 //     lane t then holds the TP plane word of threshold t, lane 16 + t the FP plane word.
 // Planes are staged in shared memory cell-major ([cell][16 words]) and written as one 64-byte
 // piece per cell; chunk totals are popcounts.
-__global__ void __launch_bounds__(PR_CHUNK)
+__global__ void __launch_bounds__(PR_CHUNK, 4)
 k_pr_bits(PrArgs a) {
     extern __shared__ uint32_t plane_s[];    // [n_cells][PR_PS]: 16 plane words + 1 pad (bank-conflict-free)
     __shared__ uint32_t rowstage[PR_CHUNK / 32][32];
@@ -349,6 +349,18 @@ k_pr_bits(PrArgs a) {
     uint32_t keep[5], rot[5];
 #pragma unroll
     for (int s = 0; s < 5; ++s) pr_transpose_consts(lane, 16 >> s, keep[s], rot[s]);
+    // compact path: the cells this lane assembles (<= 3 rounds of 32: n_thr + 3 n_cfg <= 31 means
+    // n_cells <= 80) — source lanes of its four operands and its shared-memory slot, fixed for
+    // the whole kernel (the integer divisions stay out of the chunk loop)
+    int src_k[3], src_a[3], soff[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int cell = min(r * 32 + lane, n_cells - 1);
+        const int cfg = cell / n_thr;
+        src_k[r] = cell - cfg * n_thr;
+        src_a[r] = n_thr + cfg;
+        soff[r] = (r * 32 + lane < n_cells) ? cell * PR_PS + warp : -1;
+    }
     // Persistent blocks with a three-deep software pipeline over their chunks: the chunk table
     // entry of chunk c + 3g, the permutation entries of c + 2g and the result words of c + g
     // are in flight while chunk c is transposed (each is a dependent load of the previous one).
@@ -375,18 +387,19 @@ k_pr_bits(PrArgs a) {
 #pragma unroll
             for (int s = 0; s < 5; ++s)
                 x = pr_transpose_apply(x, __shfl_xor_sync(0xffffffffu, x, 16 >> s), keep[s], rot[s]);
-            for (int c0 = 0; c0 < n_cells; c0 += 32) {
-                const int cell = min(c0 + lane, n_cells - 1);
-                const int cfg = cell / n_thr, k = cell - cfg * n_thr;
-                const uint32_t Mk = __shfl_sync(0xffffffffu, x, k);
-                const uint32_t A = __shfl_sync(0xffffffffu, x, n_thr + cfg);
-                const uint32_t B = __shfl_sync(0xffffffffu, x, n_thr + n_cfg + cfg);
-                const uint32_t U = __shfl_sync(0xffffffffu, x, n_thr + 2 * n_cfg + cfg);
-                uint32_t tp, fp;
-                pr_cell_planes(Mk, A, B, U, tp, fp);
-                if (c0 + lane < n_cells) {
-                    plane_s[cell * PR_PS + warp] = tp;
-                    plane_s[cell * PR_PS + TA_PR_WORDS + warp] = fp;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (r * 32 < n_cells) {              // warp-uniform
+                    const uint32_t Mk = __shfl_sync(0xffffffffu, x, src_k[r]);
+                    const uint32_t A = __shfl_sync(0xffffffffu, x, src_a[r]);
+                    const uint32_t B = __shfl_sync(0xffffffffu, x, src_a[r] + n_cfg);
+                    const uint32_t U = __shfl_sync(0xffffffffu, x, src_a[r] + 2 * n_cfg);
+                    uint32_t tp, fp;
+                    pr_cell_planes(Mk, A, B, U, tp, fp);
+                    if (soff[r] >= 0) {
+                        plane_s[soff[r]] = tp;
+                        plane_s[soff[r] + TA_PR_WORDS] = fp;
+                    }
                 }
             }
             uint32_t fm = __ballot_sync(0xffffffffu, full);
@@ -397,11 +410,13 @@ k_pr_bits(PrArgs a) {
                 if (lane == src)
                     for (int q = 0; q < n_cfg; ++q) rowstage[warp][q] = row[q];
                 __syncwarp();
-                for (int cell = lane; cell < n_cells; cell += 32) {
-                    const int cfg = cell / n_thr, k = cell - cfg * n_thr;
-                    const uint32_t rw = rowstage[warp][cfg];
-                    plane_s[cell * PR_PS + warp] |= ((rw >> k) & 1u) << src;
-                    plane_s[cell * PR_PS + TA_PR_WORDS + warp] |= ((rw >> (16 + k)) & 1u) << src;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    if (soff[r] >= 0) {
+                        const uint32_t rw = rowstage[warp][src_a[r] - n_thr];
+                        plane_s[soff[r]] |= ((rw >> src_k[r]) & 1u) << src;
+                        plane_s[soff[r] + TA_PR_WORDS] |= ((rw >> (16 + src_k[r])) & 1u) << src;
+                    }
                 }
             }
         } else {
@@ -437,52 +452,78 @@ k_pr_bits(PrArgs a) {
     }
 }
 
-// One THREAD per (chunk, cell); a warp takes the n_thr cells of ONE range cfg for 32 / n_thr
-// consecutive chunks, so lanes share tk rows and counters (L1 hits) and walk similar numbers of
-// true positives.  Measured alternatives at the bench size: lanes = 32 consecutive cells of one
-// chunk (mixes cfgs whose densities differ 10 x) 0.47 ms; lanes = consecutive chunks of one
-// cell 0.73 ms; lanes = chunks of equal rank inside their categories 0.71 ms.
-// ta_pr_walk_bits visits the cell's true positives only.
+// One THREAD per (group of PR_SEG consecutive chunks, cell).  It walks the group's chunks last to
+// first and CARRIES its state (running counts, suffix-maximum precision, next recall level) from
+// chunk to chunk while they belong to one category, so the per-thread set-up — counter loads and
+// the search for the first recall level — is paid once per run instead of once per chunk.  The
+// best it stores for a chunk is the best of that chunk AND the later chunks of the run: a valid
+// input of k_pr_suffix (every stored value is a maximum over true positives at or after the
+// chunk).  A warp takes the n_thr cells of ONE range cfg for 32 / n_thr consecutive groups, so
+// lanes share tk rows and counters (L1 hits) and walk similar numbers of true positives.
+// Measured alternatives at the bench size (one chunk per thread): lanes = 32 consecutive cells
+// of one chunk 0.47 ms; lanes = consecutive chunks of one cell 0.73 ms; lanes = chunks of equal
+// rank inside their categories 0.71 ms.
+#define PR_SEG 4
+template <int NT, int NC>
 __global__ void __launch_bounds__(128)
-k_pr_envelope_bits(PrArgs a) {
-    // a warp = ONE range cfg, all its thresholds, of 32 / n_thr consecutive chunks: the lanes'
-    // true-positive counts (= trip counts) differ by the threshold only, not by the cfg
-    const uint32_t n_chunks = (uint32_t)a.chunk_start[a.n_cat];
+k_pr_envelope_bits(PrArgs a, int seg) {
+    const int n_thr = NT ? NT : a.n_thr, n_cfg = NC ? NC : a.n_cfg;
+    const int n_chunks = a.chunk_start[a.n_cat];
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = (int)(gid & 31);
-    const int cpw = 32 / a.n_thr;
+    const int cpw = 32 / n_thr;
     const int64_t wg = gid >> 5;
-    const int cfg = (int)(wg % a.n_cfg);
-    const int64_t trip = wg / a.n_cfg;
-    if (lane >= cpw * a.n_thr) return;
-    const int64_t chunk64 = trip * cpw + lane / a.n_thr;
-    if (chunk64 >= (int64_t)n_chunks) return;
-    const int chunk = (int)chunk64;
-    const int b = lane % a.n_thr;
-    const uint32_t cell = (uint32_t)(cfg * a.n_thr + b);
-    const int cat = a.chunk_cat[chunk];
-    if (a.num_gt[(int64_t)cat * a.n_cfg + cfg] == 0) return;
-    const int ch0 = a.chunk_start[cat], ch1 = a.chunk_start[cat + 1];
-    // counts at the END of this chunk = exclusive prefix of the next chunk (category totals
-    // for the last chunk)
-    const uint32_t* nxt = (chunk + 1 < ch1) ? a.chunk_cnt + ((int64_t)(chunk + 1) * a.n_cfg + cfg) * 32
-                                            : a.cat_tot + ((int64_t)cat * a.n_cfg + cfg) * 32;
-    const uint32_t tc = nxt[b], fc = nxt[16 + b];
-    const uint32_t t_begin = a.chunk_cnt[((int64_t)chunk * a.n_cfg + cfg) * 32 + b];
-    unsigned long long* best_out = a.chunk_best + pr_best_idx(a, chunk, (int)cell);
-    if (tc == t_begin) { *best_out = 0ull; return; }          // no TP of this cell in the chunk
-    const int64_t per_t = (int64_t)a.n_cat * a.n_cfg;
-    const uint4* pl = reinterpret_cast<const uint4*>(a.bits + ((int64_t)cell * a.n_chunks_ub + chunk) * 16);
-    uint32_t w[16];
+    const int cfg = (int)(wg % n_cfg);
+    const int64_t trip = wg / n_cfg;
+    if (lane >= cpw * n_thr) return;
+    const int64_t grp = trip * cpw + lane / n_thr;
+    const int b = lane % n_thr;
+    const int64_t c_lo64 = grp * seg;
+    if (c_lo64 >= n_chunks) return;
+    const int c_lo = (int)c_lo64;
+    const int c_hi = min(c_lo + seg, n_chunks) - 1;
+    const int cell = cfg * n_thr + b;
+    const int64_t per_t = (int64_t)a.n_cat * n_cfg;
+    int cat = -1, ch0 = 0;
+    bool live = false;
+    ta_pr_state s;
+    const int32_t* tkp = nullptr;
+    unsigned long long* q = nullptr;
+    for (int c = c_hi; c >= c_lo; --c) {
+        const int c_cat = a.chunk_cat[c];
+        if (c_cat != cat) {                          // a new run: set the state up
+            cat = c_cat;
+            const int64_t cc = (int64_t)cat * n_cfg + cfg;
+            live = a.num_gt[cc] != 0;
+            if (live) {
+                ch0 = a.chunk_start[cat];
+                const int ch1 = a.chunk_start[cat + 1];
+                // counts at the END of this chunk = exclusive prefix of the next chunk (category
+                // totals for the last chunk)
+                const uint32_t* nxt = (c + 1 < ch1) ? a.chunk_cnt + ((int64_t)(c + 1) * n_cfg + cfg) * 32
+                                                    : a.cat_tot + cc * 32;
+                tkp = a.tk + cc * a.n_rec;
+                q = a.ans + ((int64_t)b * per_t + cc) * a.n_rec;
+                ta_pr_state_init(s, nxt[b], nxt[16 + b], tkp, a.n_rec);
+            }
+        }
+        if (!live) continue;
+        unsigned long long* best_out = a.chunk_best + pr_best_idx(a, c, cell);
+        const uint32_t* cnt = a.chunk_cnt + ((int64_t)c * n_cfg + cfg) * 32;
+        if (s.tc == cnt[b]) {                        // no TP of this cell in the chunk
+            s.fc = cnt[16 + b];
+        } else {
+            const uint4* pl = reinterpret_cast<const uint4*>(a.bits + ((int64_t)cell * a.n_chunks_ub + c) * 16);
+            uint32_t w[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint4 v = pl[q];
-        w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            for (int u = 0; u < 4; ++u) {
+                const uint4 v = pl[u];
+                w[4 * u] = v.x; w[4 * u + 1] = v.y; w[4 * u + 2] = v.z; w[4 * u + 3] = v.w;
+            }
+            ta_pr_walk_chunk(s, w, tkp, (uint32_t)(c - ch0), q, (int64_t)1);
+        }
+        *best_out = s.bt ? pr_pack(s.bt, s.bn, 0) : 0ull;
     }
-    const int64_t cc = (int64_t)cat * a.n_cfg + cfg;
-    unsigned long long* q = a.ans + ((int64_t)b * per_t + cc) * a.n_rec;
-    *best_out = ta_pr_walk_bits(w, w + TA_PR_WORDS, (int64_t)1, tc, fc, a.tk + cc * a.n_rec, a.n_rec,
-                                (uint32_t)(chunk - ch0), q, (int64_t)1);
 }
 
 // Exclusive scan of the chunk totals + the tk table, bit-plane path: one block per category,
@@ -533,56 +574,73 @@ k_pr_scan_live(PrArgs a) {
     }
 }
 
-// k_pr_finalize for cell-major answers, tiled: a block owns one threshold and 32 consecutive
-// (category, cfg) cells.  Phase 1 reads the cells' answer rows the way the envelope wrote them
-// (warp per cell, lanes over the recall levels: contiguous), merges the later chunks' best and
-// divides; phase 2 writes the [recall level][cell] tile from shared memory, 256 B per warp.
-// Reads and writes are both coalesced and every entry is independent.  Same values as
-// k_pr_finalize.
-#define PR_TILE_CELLS 32
-#define PR_FIN_WARPS 8
-__global__ void __launch_bounds__(PR_FIN_WARPS * 32)
+// k_pr_finalize for cell-major answers, tiled: a block owns one threshold, PR_FT_CELLS
+// consecutive (category, cfg) cells and PR_FT_K consecutive recall levels.
+//   phase 1  thread = cell: reads its PR_FT_K answers the way the envelope wrote them (128
+//            contiguous bytes), merges each with the best of the later chunks, divides, and
+//            parks the values in shared memory ([level][cell]: conflict-free);
+//   phase 2  every recall level of the tile is ONE contiguous run of PR_FT_CELLS doubles (2 KB) in
+//            precision[T][R][C][cfg]: written with 16-byte stores, a row per warp.
+// Long contiguous writes instead of 256-byte pieces scattered over 101 DRAM pages; every entry
+// is independent.  Same values as k_pr_finalize.
+#define PR_FT_CELLS 256
+#define PR_FT_K 16
+__global__ void __launch_bounds__(PR_FT_CELLS)
 k_pr_finalize_tile(PrArgs a) {
-    extern __shared__ double tile_s[];                    // [n_rec][PR_TILE_CELLS + 1]
+    __shared__ __align__(16) double tile_s[PR_FT_K][PR_FT_CELLS];
     const uint32_t per_t = (uint32_t)a.n_cat * (uint32_t)a.n_cfg;
-    const uint32_t cc0 = blockIdx.x * PR_TILE_CELLS;
-    const int t = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < PR_TILE_CELLS; c += PR_FIN_WARPS) {
-        const uint32_t cc = cc0 + c;
-        if (cc >= per_t) break;
+    const uint32_t cc0 = blockIdx.x * PR_FT_CELLS;
+    const int k0 = blockIdx.y * PR_FT_K;
+    const int t = blockIdx.z;
+    const int nk = min(PR_FT_K, a.n_rec - k0);
+    const uint32_t cc = cc0 + threadIdx.x;
+    if (cc < per_t) {
         const int ngt = a.num_gt[cc];
-        uint32_t tot = 0;
-        const unsigned long long* best = nullptr;
-        if (ngt) {
-            tot = a.cat_tot[(int64_t)cc * 32 + t];
+        if (ngt == 0) {
+#pragma unroll
+            for (int k = 0; k < PR_FT_K; ++k) tile_s[k][threadIdx.x] = -1.0;      // eval.py:522-525
+        } else {
+            const uint32_t tot = a.cat_tot[(int64_t)cc * 32 + t];
             const uint32_t cat = cc / (uint32_t)a.n_cfg, cfg = cc - cat * (uint32_t)a.n_cfg;
-            best = a.chunk_best + pr_best_idx(a, a.chunk_start[cat], (int)(cfg * a.n_thr + t));
-        }
-        const int64_t best_stride = a.best_cell_major ? 1 : (int64_t)a.n_cfg * a.n_thr;
-        const int32_t* tkp = a.tk + (int64_t)cc * a.n_rec;
-        const unsigned long long* ansp = a.ans + ((int64_t)t * per_t + cc) * a.n_rec;
-        for (int k = lane; k < a.n_rec; k += 32) {
-            double v = -1.0;                                       // eval.py:522-525
-            if (ngt) {
-                v = 0.0;                                           // eval.py:565-573
-                if ((uint32_t)max(tkp[k], 1) <= tot) {
+            const unsigned long long* best =
+                a.chunk_best + pr_best_idx(a, a.chunk_start[cat], (int)(cfg * a.n_thr + t));
+            const int64_t best_stride = a.best_cell_major ? 1 : (int64_t)a.n_cfg * a.n_thr;
+            const int32_t* tkp = a.tk + (int64_t)cc * a.n_rec + k0;
+            const unsigned long long* ansp = a.ans + ((int64_t)t * per_t + cc) * a.n_rec + k0;
+            unsigned long long q[PR_FT_K];
+            int32_t need[PR_FT_K];
+#pragma unroll
+            for (int k = 0; k < PR_FT_K; ++k) {
+                need[k] = k < nk ? max(tkp[k], 1) : INT_MAX;
+                q[k] = ((uint32_t)need[k] <= tot) ? ansp[k] : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < PR_FT_K; ++k) {
+                double v = 0.0;                                        // eval.py:565-573
+                if ((uint32_t)need[k] <= tot) {
                     uint32_t qt, qn, ch, bt, bn, dummy;
-                    pr_unpack(ansp[k], qt, qn, ch);
+                    pr_unpack(q[k], qt, qn, ch);
                     pr_unpack(best[(int64_t)ch * best_stride], bt, bn, dummy);
                     if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
                     v = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
                 }
+                tile_s[k][threadIdx.x] = v;
             }
-            tile_s[k * (PR_TILE_CELLS + 1) + c] = v;
         }
     }
     __syncthreads();
-    const uint32_t cc = cc0 + lane;
-    if (cc < per_t) {
-        double* out = a.precision + (int64_t)t * a.n_rec * per_t + cc;
-        for (int k = warp; k < a.n_rec; k += PR_FIN_WARPS)
-            out[(int64_t)k * per_t] = tile_s[k * (PR_TILE_CELLS + 1) + lane];
+    // rows of the tile: PR_FT_CELLS (or fewer at the end) doubles each
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_c = min((uint32_t)PR_FT_CELLS, per_t - cc0);
+    for (int k = warp; k < nk; k += PR_FT_CELLS / 32) {
+        double* out = a.precision + ((int64_t)t * a.n_rec + k0 + k) * per_t + cc0;
+        if ((((uintptr_t)out) & 15) == 0) {
+            for (uint32_t c = 2 * lane; c + 1 < n_c; c += 64)
+                *reinterpret_cast<double2*>(out + c) = *reinterpret_cast<const double2*>(&tile_s[k][c]);
+            if ((n_c & 1) && lane == 0) out[n_c - 1] = tile_s[k][n_c - 1];
+        } else {
+            for (uint32_t c = lane; c < n_c; c += 32) out[c] = tile_s[k][c];
+        }
     }
 }
 
@@ -687,8 +745,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     const size_t n_cells = (size_t)n_cfg * n_thr;
     // the staged planes of one chunk (64 B per cell) and the finalize tile ([n_rec][33] doubles)
     // must fit the default 48 KB of shared memory
-    const int impl = (n_cells * PR_PS * 4 <= 48 * 1024 &&
-                      (size_t)n_rec * (PR_TILE_CELLS + 1) * 8 <= 48 * 1024) ? ta_pr_impl() : 0;
+    const int impl = (n_cells * PR_PS * 4 <= 48 * 1024) ? ta_pr_impl() : 0;
     const size_t o_ccat = take(impl ? (size_t)n_chunks_ub * 4 : 0);
     const size_t o_cp0 = take(impl ? (size_t)n_chunks_ub * 8 : 0);
     const size_t o_cnp = take(impl ? (size_t)n_chunks_ub * 4 : 0);
@@ -737,7 +794,7 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     if (n_chunks_ub > 0 && impl) {
         k_pr_chunks<<<(n_chunks_ub + 255) / 256, 256, 0, st>>>(a);
         if ((rc = ta_check_launch(ctx, "k_pr_chunks"))) return rc;
-        int bits_blocks = ctx->sm_count * 8;           // persistent: 8 CTAs of 256 threads per SM
+        int bits_blocks = ctx->sm_count * 4;           // persistent: 4 CTAs of 256 threads per SM
         if (bits_blocks > n_chunks_ub) bits_blocks = n_chunks_ub;
         k_pr_bits<<<bits_blocks, PR_CHUNK, (size_t)PR_PS * n_cells * 4, st>>>(a);
         if ((rc = ta_check_launch(ctx, "k_pr_bits"))) return rc;
@@ -757,8 +814,13 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     if (n_chunks_ub > 0 && impl) {
         // grid over the upper bound of chunks: the kernel reads the real count on the device
         const int cpw = 32 / n_thr;
-        const int64_t threads = (((int64_t)n_chunks_ub + cpw - 1) / cpw) * n_cfg * 32;
-        k_pr_envelope_bits<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(a);
+        // chunks per thread: runs only pay off when categories span several chunks
+        const int seg = (n_chunks_ub >= 8 * (int64_t)n_cat) ? PR_SEG : 1;
+        const int64_t n_grp = ((int64_t)n_chunks_ub + seg - 1) / seg;
+        const int64_t threads = ((n_grp + cpw - 1) / cpw) * n_cfg * 32;
+        const unsigned eb = (unsigned)((threads + 127) / 128);
+        if (n_thr == 10 && n_cfg == 6) k_pr_envelope_bits<10, 6><<<eb, 128, 0, st>>>(a, seg);
+        else k_pr_envelope_bits<0, 0><<<eb, 128, 0, st>>>(a, seg);
         if ((rc = ta_check_launch(ctx, "k_pr_envelope_bits"))) return rc;
     } else if (n_chunks_ub > 0) {
         int cpb = PR_ENV_MAX_CELLS / n_thr;
@@ -776,8 +838,9 @@ extern "C" int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const 
     if ((rc = ta_check_launch(ctx, "k_pr_suffix"))) return rc;
     const size_t n_prec = (size_t)n_thr * n_rec * n_cat * n_cfg;
     if (impl) {
-        dim3 grid((unsigned)(((size_t)n_cat * n_cfg + PR_TILE_CELLS - 1) / PR_TILE_CELLS), (unsigned)n_thr);
-        k_pr_finalize_tile<<<grid, PR_FIN_WARPS * 32, (size_t)n_rec * (PR_TILE_CELLS + 1) * 8, st>>>(a);
+        dim3 grid((unsigned)(((size_t)n_cat * n_cfg + PR_FT_CELLS - 1) / PR_FT_CELLS),
+                  (unsigned)((n_rec + PR_FT_K - 1) / PR_FT_K), (unsigned)n_thr);
+        k_pr_finalize_tile<<<grid, PR_FT_CELLS, 0, st>>>(a);
         return ta_check_launch(ctx, "k_pr_finalize_tile");
     }
     k_pr_finalize<<<(unsigned)((n_prec + 255) / 256), 256, 0, st>>>(a);
