@@ -820,7 +820,9 @@ k_track_flat(FrameArgs a) {
 // 5-step search over the 33 offsets held one per lane.
 template <int NC>
 __global__ void __launch_bounds__(256)
-k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp) {
+k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp, int gpw) {
+    // gpw = groups per warp (<= 32): 32 for large plans, fewer for small ones so that the work
+    // spreads over more warps (a track plan has a few thousand groups)
     __shared__ ta_range_cfg cfg_s[RR_MAX];
     __shared__ double thr_s[TA_MAX_THRS];
     __shared__ FrameRules rules;
@@ -829,9 +831,9 @@ k_frame_prep(FrameArgs a, int32_t* __restrict__ dt_grp) {
     const uint32_t cfg_all = (n_cfg == 32) ? 0xffffffffu : ((1u << n_cfg) - 1u);
     const int lane = threadIdx.x & 31;
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t grp0 = wid * 32;
+    const int64_t grp0 = wid * gpw;
     if (grp0 >= a.n_groups) return;
-    const int n_in = (int)((grp0 + 32 < a.n_groups) ? 32 : a.n_groups - grp0);
+    const int n_in = (int)((grp0 + gpw < a.n_groups) ? gpw : a.n_groups - grp0);
     const int li = lane < n_in ? lane : n_in;
     const int64_t doff = a.grp_dt_off[grp0 + li], goff = a.grp_gt_off[grp0 + li];
     const int64_t d_end = a.grp_dt_off[grp0 + n_in], g_end = a.grp_gt_off[grp0 + n_in];
@@ -1302,8 +1304,9 @@ extern "C" int ta_match_greedy(ta_ctx* ctx, void* stream, int64_t n_groups,
                     reinterpret_cast<int32_t*>(base + o_flag), reinterpret_cast<int32_t*>(base + o_list),
                     reinterpret_cast<int32_t*>(base + o_flag) + n_groups, rules_g};
         TA_CUDA(cudaMemsetAsync(f.grp_flag, 0, (size_t)n_groups * 4 + 4, st));
-        const int64_t prep_warps = (n_groups + 31) / 32;
-        k_frame_prep<0><<<(unsigned)((prep_warps + 7) / 8), 256, 0, st>>>(f, const_cast<int32_t*>(f.dt_grp));
+        const int gpw = n_groups >= 200000 ? 32 : 4;
+        const int64_t prep_warps = (n_groups + gpw - 1) / gpw;
+        k_frame_prep<0><<<(unsigned)((prep_warps + 7) / 8), 256, 0, st>>>(f, const_cast<int32_t*>(f.dt_grp), gpw);
         if ((rc = ta_check_launch(ctx, "k_frame_prep"))) return rc;
         int64_t blocks = ((n_dt + 31) / 32 + FF_WARPS - 1) / FF_WARPS;
         const int64_t fcap = (int64_t)ctx->sm_count * 16;
@@ -1399,8 +1402,9 @@ extern "C" int ta_frame_sched_build(ta_ctx* ctx, void* stream, int64_t n_groups,
                 nullptr, hdr + 4, nullptr, nullptr,
                 nullptr, nullptr, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr, rules_g};
     a.gt_word_out = reinterpret_cast<uint32_t*>(b + L.o_gtw);
-    const int64_t prep_warps = (n_groups + 31) / 32;
-    k_frame_prep<0><<<(unsigned)((prep_warps + 7) / 8), 256, 0, st>>>(a, nullptr);
+    const int gpw = n_groups >= 200000 ? 32 : 4;
+    const int64_t prep_warps = (n_groups + gpw - 1) / gpw;
+    k_frame_prep<0><<<(unsigned)((prep_warps + 7) / 8), 256, 0, st>>>(a, nullptr, gpw);
     return ta_check_launch(ctx, "k_frame_prep");
 }
 
@@ -1496,10 +1500,11 @@ extern "C" int ta_frame_eval(ta_ctx* ctx, void* stream, int64_t n_groups,
             k_add_counts<<<64, 256, 0, st>>>(reinterpret_cast<const int32_t*>(sb + L.o_numgt), num_gt);
             if ((rc = ta_check_launch(ctx, "k_add_counts"))) return rc;
         } else {
-            const int64_t prep_warps = (n_groups + 31) / 32;
+            const int gpw = n_groups >= 200000 ? 32 : 4;
+            const int64_t prep_warps = (n_groups + gpw - 1) / gpw;
             const unsigned pb = (unsigned)((prep_warps + 7) / 8);
-            if (spec) k_frame_prep<6><<<pb, 256, 0, st>>>(a, nullptr);
-            else k_frame_prep<0><<<pb, 256, 0, st>>>(a, nullptr);
+            if (spec) k_frame_prep<6><<<pb, 256, 0, st>>>(a, nullptr, gpw);
+            else k_frame_prep<0><<<pb, 256, 0, st>>>(a, nullptr, gpw);
             if ((rc = ta_check_launch(ctx, "k_frame_prep"))) return rc;
         }
         if (n_dt > 0) {
