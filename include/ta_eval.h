@@ -70,6 +70,8 @@ const char* ta_last_error(void);
 int         ta_ctx_create(int device, ta_ctx** out);
 int         ta_ctx_destroy(ta_ctx* ctx);
 int         ta_ctx_sm_count(const ta_ctx* ctx);
+/* cudaMemsetAsync(p, 0, bytes) on `stream` (num_gt is ACCUMULATED by the matchers: zero it first) */
+int         ta_zero(ta_ctx* ctx, void* stream, void* p, int64_t bytes);
 /* TA_IOU_3D (tiled kernel) counts the track pairs whose summed intersection exceeds their summed
  * union — the reference asserts i <= u there (eval.py:95).  ta_eval_plan_host returns
  * TA_ERR_ASSERT for them; callers of the staged API read (and reset) the counter here, which

@@ -33,7 +33,7 @@ EXPORTS = [
     "ta_exchange_unique_id", "ta_exchange_create", "ta_exchange_destroy", "ta_exchange_rank",
     "ta_exchange_world", "ta_exchange_gather", "ta_exchange_scatter", "ta_exchange_alltoallv",
     "ta_exchange_allreduce_sum", "ta_exchange_group_begin", "ta_exchange_group_end",
-    "ta_widen_boxes", "ta_ctx_take_assert_count", "ta_ctx_debug_list_count",
+    "ta_widen_boxes", "ta_ctx_take_assert_count", "ta_ctx_debug_list_count", "ta_zero",
 ]
 
 
@@ -118,6 +118,7 @@ def load() -> C.CDLL:
     lib.ta_widen_boxes.argtypes = [P, P, I64, P, P]
     lib.ta_ctx_take_assert_count.argtypes = [P, P, C.POINTER(C.c_int32)]
     lib.ta_ctx_debug_list_count.argtypes = [P, P, C.POINTER(C.c_int32)]
+    lib.ta_zero.argtypes = [P, P, P, I64]
     lib.ta_exchange_group_begin.argtypes = [P]
     lib.ta_exchange_group_end.argtypes = [P]
     lib.ta_rle_iou.argtypes = [P, P, I64, P, I64, P, P, P, P, P, P, P, P, P, P, P, P]

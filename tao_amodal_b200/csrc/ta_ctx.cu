@@ -172,5 +172,16 @@ extern "C" int ta_ctx_debug_list_count(ta_ctx* c, void* stream, int32_t* count) 
     return TA_OK;
 }
 
+// cudaMemsetAsync(p, 0, bytes) on `stream`: callers zero num_gt with it (the counts are
+// accumulated) instead of launching a framework fill kernel.
+extern "C" int ta_zero(ta_ctx* c, void* stream, void* p, int64_t bytes) {
+    if (!c) return ta_set_err(TA_ERR_INVALID, "ta_zero: ctx is NULL");
+    if (bytes < 0 || (bytes > 0 && !p)) return ta_set_err(TA_ERR_INVALID, "ta_zero: bad arguments");
+    if (bytes == 0) return TA_OK;
+    TA_CUDA(cudaSetDevice(c->device));
+    TA_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
+    return TA_OK;
+}
+
 extern "C" int ta_ctx_sm_count(const ta_ctx* c) { return c ? c->sm_count : 0; }
 extern "C" int64_t ta_ctx_launch_count(const ta_ctx* c) { return c ? c->launches : 0; }

@@ -297,7 +297,8 @@ class Engine:
         import torch
         plan = dev.plan
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        dev.t["num_gt"].zero_()
+        _lib.check(self.lib.ta_zero(self._ctx, st, C.c_void_p(dev.t["num_gt"].data_ptr()),
+                                    dev.t["num_gt"].numel() * 4))
         if detail:
             dev.ensure_detail()
         p = dev.ptr
@@ -318,7 +319,8 @@ class Engine:
         plan = dev.plan
         assert plan.kind == "lvis"
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        dev.t["num_gt"].zero_()
+        _lib.check(self.lib.ta_zero(self._ctx, st, C.c_void_p(dev.t["num_gt"].data_ptr()),
+                                    dev.t["num_gt"].numel() * 4))
         if detail:
             dev.ensure_detail()
         p = dev.ptr

@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--cold", action="store_true")
     ap.add_argument("--runs", type=int, default=3)
+    ap.add_argument("--reference", action="store_true",
+                    help="--cold: also time the UNMODIFIED reference CLI (baseline/_ref through "
+                         "oracle/ref_shims.py) on the same two files, fresh process, 1 core")
     args = ap.parse_args()
     from tao_amodal_b200 import synth
     over = {"videos": args.videos} if args.videos else {}
@@ -71,6 +74,23 @@ def main():
                               % (rp, lp, ap_, os.path.join(ROOT, "tools"))],
                              capture_output=True, text=True)
         res["torch_imported_by_cli"] = "NOTORCH" not in chk.stderr
+        if args.reference:
+            # the reference's own script, unmodified, in a fresh interpreter (its JSON parsing,
+            # index building, numba JIT compile and both evaluators included)
+            ref_log = os.path.join(td, "ref.log")
+            code = ("import sys, os; sys.path.insert(0, %r)\n"
+                    "from oracle import ref_bench, ref_shims\n"
+                    "root = ref_bench.find_reference(); ref_shims.REF_ROOT = root\n"
+                    "ref_shims.run_reference_driver(%r, %r, %r)\n" % (ROOT, ap_, rp, ref_log))
+            t0 = time.perf_counter()
+            p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+            res["reference_cold_wall_s"] = time.perf_counter() - t0
+            if p.returncode != 0:
+                res["reference_error"] = p.stderr[-1500:]
+            else:
+                same = open(ref_log).read().replace(ref_log, "") == open(lp).read().replace(lp, "")
+                res["reference_log_identical"] = bool(same)
+                res["speedup_cold_vs_reference"] = res["reference_cold_wall_s"] / res["cold_wall_s"]
         print(json.dumps(res))
         if args.out:
             json.dump(res, open(args.out, "w"), indent=1)
