@@ -518,22 +518,17 @@ def main():
         return out
 
     e2e_steps = max(3, min(args.steps, 10))
-    p_tao, p_lvis = pin(tao_plan), pin(lvis_plan)
     if world == 1:
-        def pinned_out(plan):
-            T, R, Cn, K = 10, 101, len(plan.cat_ids), plan.n_cfg
-            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
-            from tao_amodal_b200.engine import EvalOutput
-            return EvalOutput(precision=mk((T, R, Cn, K), torch.float64),
-                              recall=mk((T, Cn, K), torch.float64),
-                              tp_cnt=mk((T, Cn, K), torch.int64), fp_cnt=mk((T, Cn, K), torch.int64),
-                              num_gt=mk((Cn, K), torch.int32))
-        outs = [pinned_out(tao_plan), pinned_out(lvis_plan)]
+        # transport form of both plans in page-locked memory (ta_host_alloc), built once; one
+        # C call per step: both plans host -> device -> host
+        pack = eng.pack_host([tao_plan, lvis_plan], pinned=True)
+        outs = [pack.new_output(0), pack.new_output(1)]
 
         def e2e_step():
-            eng.evaluate_host_many([p_tao, p_lvis], outs=outs)
+            eng.evaluate_pack(pack, outs)
             return (outs[0].h2d_bytes + outs[1].h2d_bytes, outs[0].d2h_bytes + outs[1].d2h_bytes)
     else:
+        p_tao, p_lvis = pin(tao_plan), pin(lvis_plan)
         # pinned host slices for every owner's results: each rank copies its OWN category block out
         host_part = {id(dv): {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
                               for k, v in pipe.exch[id(dv)].part.items()} for dv in (d_tao, d_lvis)}
@@ -718,7 +713,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "api": ("Engine.evaluate_host_many -> ta_eval_plan_host per plan (pinned host plans -> precision/recall on host)" if world == 1
+                "api": ("Engine.evaluate_pack -> ta_eval_plans_host (both plans in one call: pinned host plans -> precision/recall on host; shared_boxes=%s)" % bool(pack.shared) if world == 1
                         else "per rank: DevicePlan.reload (pinned host plan) + stages + ta_exchange_* + owner-side PR + the owner's slice to its pinned host buffer")},
         "gpu_launches": int(launches),
         "roofline": roofline,

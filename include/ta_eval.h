@@ -23,13 +23,14 @@
 #ifndef TA_EVAL_H
 #define TA_EVAL_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 3
+#define TA_ABI_VERSION 4
 #define TA_MAX_THRS 16   /* IoU thresholds packed as 16 TP bits + 16 FP bits per detection */
 
 typedef enum ta_status {
@@ -225,6 +226,7 @@ int ta_pr_accumulate(ta_ctx* ctx, void* stream, int32_t n_cat, const int64_t* ca
  * Track path when the *_trk_off pointers are non-NULL, frame path (fused) otherwise.   */
 #define TA_PLAN_BOX_F32 1
 #define TA_PLAN_SLOT_U16 2
+#define TA_PLAN_GRP_U16 4
 typedef struct ta_plan_host {
     int64_t n_groups, n_dt, n_gt, n_dt_boxes, n_gt_boxes, n_big;
     int32_t n_cat, n_cfg, n_thr, n_rec, n_slots_max, g_max, iou_mode;
@@ -232,9 +234,17 @@ typedef struct ta_plan_host {
                                                  [N,4] arrays that hold the fp64 coordinates
                                                  exactly (lossless transport: half the PCIe
                                                  bytes); they are widened to fp64 on the device
-                                                 before any arithmetic */
-    const int64_t *grp_dt_off, *grp_gt_off, *iou_off, *cat_dt_off;
-    const int32_t *grp_cat, *acc_perm, *big_list;
+                                                 before any arithmetic.
+                                                 TA_PLAN_GRP_U16: grp_dt_off / grp_gt_off point to
+                                                 uint16 COUNTS [n_groups] (detections / GT of
+                                                 each group, all < 65536) and grp_cat to uint16
+                                                 [n_groups]; the int64 offsets are rebuilt on the
+                                                 device by a prefix sum (6 instead of 20 bytes
+                                                 per group) */
+    const void    *grp_dt_off, *grp_gt_off;   /* int64 [n_groups+1] (see TA_PLAN_GRP_U16) */
+    const int64_t *iou_off, *cat_dt_off;
+    const void    *grp_cat;                   /* int32 [n_groups] (see TA_PLAN_GRP_U16) */
+    const int32_t *acc_perm, *big_list;
     const void    *dt_box, *gt_box;           /* double[N,4], or float[N,4] with TA_PLAN_BOX_F32 */
     const int64_t *dt_trk_off, *gt_trk_off;   /* NULL on the frame path */
     const void    *dt_slot, *gt_slot;         /* int32[N] (uint16[N] with TA_PLAN_SLOT_U16: slots
@@ -245,12 +255,42 @@ typedef struct ta_plan_host {
     const int32_t *gt_hp;
     const double  *iou_thrs, *rec_thrs;
     const ta_range_cfg* cfgs;
+    /* ta_eval_plans_host only: when dt_box_idx is non-NULL this plan's detection boxes are
+     * rows of the dt_box array of plan number dt_box_pool of the same call (the track and the
+     * frame evaluation of one result file hold the same boxes in two orders): dt_box is
+     * ignored, box i of this plan = pool box dt_box_idx[i].  int32 [n_dt_boxes].  A frame-path
+     * pool plan may carry n_dt_boxes > n_dt: its rows from n_dt on are boxes that only the
+     * sharing plan uses.                                                                    */
+    const int32_t *dt_box_idx;
+    int32_t dt_box_pool;
+    int32_t reserved_;
 } ta_plan_host;
 
 int ta_eval_plan_host(ta_ctx* ctx, const ta_plan_host* plan,
                       double* precision, double* recall,
                       int64_t* tp_cnt, int64_t* fp_cnt, int32_t* num_gt,
                       int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* Several plans of one result set in one call — what tools/eval_on_tao_amodal.py:118-151 does
+ * with TaoEval and LVISEval on the same prediction file.  Plan i runs on ctxs[i] (distinct
+ * contexts of one device) and writes outs[i]; results are valid on return.  All host-to-device
+ * copies go through one upload stream in consumption order (shared box pool; then per plan
+ * the matcher's inputs, then accumulate's), so plan i's kernels and download overlap the upload
+ * of plan i+1; put the plan with the larger result tensors first.  h2d_bytes / d2h_bytes:
+ * optional int64 [n_plans].  tp_cnt / fp_cnt / num_gt of an out may be NULL.              */
+typedef struct ta_host_out {
+    double  *precision, *recall;
+    int64_t *tp_cnt, *fp_cnt;
+    int32_t *num_gt;
+} ta_host_out;
+int ta_eval_plans_host(int32_t n_plans, ta_ctx* const* ctxs, const ta_plan_host* const* plans,
+                       const ta_host_out* outs, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* Page-locked host memory for plans and result tensors: with it the copies of
+ * ta_eval_plan(s)_host run asynchronously at full PCIe rate (pageable memory works too, staged
+ * by the driver).  NULL (and ta_last_error) on failure.                                   */
+void* ta_host_alloc(size_t bytes);
+void  ta_host_free(void* p);
 
 /* float [n,4] -> double [n,4] on the device: lossless transport of box coordinates that are
  * exactly representable in float (what TA_PLAN_BOX_F32 does inside ta_eval_plan_host), for

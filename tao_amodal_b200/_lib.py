@@ -28,7 +28,7 @@ IOU_MODES = {"3d_iou": 0, "avg_iou": 1, "imagenetvid": 2, "3d_iou_seq": 3}
 EXPORTS = [
     "ta_abi_version", "ta_last_error", "ta_ctx_create", "ta_ctx_destroy", "ta_ctx_sm_count",
     "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
-    "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host",
+    "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host", "ta_eval_plans_host", "ta_host_alloc", "ta_host_free",
     "ta_rle_iou", "ta_frame_sched_bytes", "ta_frame_sched_build",
     "ta_exchange_unique_id", "ta_exchange_create", "ta_exchange_destroy", "ta_exchange_rank",
     "ta_exchange_world", "ta_exchange_gather", "ta_exchange_scatter", "ta_exchange_alltoallv",
@@ -59,8 +59,14 @@ class PlanHost(C.Structure):
             "grp_dt_off", "grp_gt_off", "iou_off", "cat_dt_off", "grp_cat", "acc_perm", "big_list",
             "dt_box", "gt_box", "dt_trk_off", "gt_trk_off", "dt_slot", "gt_slot",
             "dt_attr_a", "dt_attr_b", "gt_attr_a", "gt_attr_b", "dt_flag", "gt_flag",
-            "gt_hp", "iou_thrs", "rec_thrs", "cfgs")]
+            "gt_hp", "iou_thrs", "rec_thrs", "cfgs", "dt_box_idx")]
+        + [("dt_box_pool", C.c_int32), ("reserved_", C.c_int32)]
     )
+
+
+class HostOut(C.Structure):
+    """struct ta_host_out."""
+    _fields_ = [(n, C.c_void_p) for n in ("precision", "recall", "tp_cnt", "fp_cnt", "num_gt")]
 
 
 class TaEvalError(RuntimeError):
@@ -125,9 +131,15 @@ def load() -> C.CDLL:
     lib.ta_pr_accumulate.argtypes = [P, P, I32, P, P, I64, P, P, P, I32, I32, I32, P, P, P, P, P]
     lib.ta_eval_plan_host.argtypes = [P, C.POINTER(PlanHost), P, P, P, P, P,
                                       C.POINTER(I64), C.POINTER(I64)]
+    lib.ta_eval_plans_host.argtypes = [I32, P, P, P, P, P]
+    lib.ta_host_alloc.argtypes = [C.c_size_t]
+    lib.ta_host_alloc.restype = C.c_void_p
+    lib.ta_host_free.argtypes = [P]
+    lib.ta_host_free.restype = None
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("ta_last_error", "ta_ctx_launch_count", "ta_frame_sched_bytes"):
+        if name not in ("ta_last_error", "ta_ctx_launch_count", "ta_frame_sched_bytes",
+                        "ta_host_alloc", "ta_host_free"):
             fn.restype = C.c_int
     _lib = lib
     return lib

@@ -140,6 +140,7 @@ extern "C" int ta_ctx_destroy(ta_ctx* c) {
     }
     if (c->h_stage) cudaFreeHost(c->h_stage);
     cudaFree(c->d_flags);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return TA_OK;

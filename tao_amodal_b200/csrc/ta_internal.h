@@ -16,6 +16,7 @@ struct ta_ctx {
     int64_t launches;      // kernels launched through this context
     int* d_flags;          // [0]: "intersection > union" counter (eval.py:95)
     cudaStream_t own_stream;
+    cudaStream_t copy_stream;   // uploads of ta_eval_plans_host (created on first use)
     // stream-ordered scratch of ta_pr_accumulate, grown on demand
     void* ws;
     size_t ws_bytes;

@@ -114,12 +114,172 @@ def _ptr(a: Optional[np.ndarray]):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def shared_box_index(pool: EvalPlan, user: EvalPlan, max_extra: float = 0.25):
+    """(idx, extra) such that concat(pool.dt_box, extra)[idx] == user.dt_box: for every detection
+    box of `user` the row of the pool plan's box array that holds the same box; `extra` are the
+    boxes of `user` the pool plan does not have (the two evaluators filter the result file
+    differently), appended to the pool.  None when the plans do not say where their boxes came
+    from or more than max_extra of the pool would be extras.  The identity of the boxes is
+    checked value by value, not assumed."""
+    a, b = pool.dt_box_src, user.dt_box_src
+    if a is None or b is None or a.size == 0 or b.size == 0 or pool.dt_box.shape[0] != a.size:
+        return None
+    n_rows = int(max(a.max(), b.max())) + 1
+    pos = np.full(n_rows, -1, dtype=np.int64)
+    pos[a] = np.arange(a.size)
+    idx = pos[b]
+    missing = np.nonzero(idx < 0)[0]
+    extra = np.zeros((0, 4), dtype=np.float64)
+    if missing.size:
+        msrc, first = np.unique(b[missing], return_index=True)
+        if msrc.size > max_extra * a.size:
+            return None
+        extra = np.ascontiguousarray(user.dt_box[missing[first]])
+        pos[msrc] = a.size + np.arange(msrc.size)
+        idx = pos[b]
+    if a.size + extra.shape[0] >= 2 ** 31:
+        return None
+    step = 1 << 20
+    for i in range(0, idx.size, step):
+        j = idx[i:i + step]
+        own = j < a.size
+        got = np.empty((j.size, 4), dtype=np.float64)
+        got[own] = pool.dt_box[j[own]]
+        got[~own] = extra[j[~own] - a.size]
+        if not np.array_equal(got, user.dt_box[i:i + step]):
+            return None
+    return np.ascontiguousarray(idx.astype(np.int32)), extra
+
+
+class HostPack:
+    """The host-side transport form of the plans of one result set, built once and passed to
+    ``Engine.evaluate_pack`` any number of times (include/ta_eval.h: ta_plan_host):
+
+    * box coordinates as float32 when that is lossless (TA_PLAN_BOX_F32), frame slots as uint16
+      (TA_PLAN_SLOT_U16), group tables as uint16 counts (TA_PLAN_GRP_U16);
+    * with several plans, the track plan's detection boxes as int32 rows of the frame plan's box
+      array (checked value by value; the few boxes only the track plan keeps are appended to
+      that array): the boxes of the result file then cross PCIe once;
+    * the plans ordered so that the one with the larger result tensors goes first (its download
+      overlaps the upload of the next).
+
+    ``pinned=True`` puts every array the C call reads into page-locked memory."""
+
+    def __init__(self, eng: "Engine", plans, iou_mode, iou_thrs, rec_thrs, compress, pinned,
+                 share_boxes):
+        self.eng, self.plans = eng, plans
+        self.n_thr, self.n_rec = len(iou_thrs), len(rec_thrs)
+        self.pinned = pinned
+        hold = eng.host_copy if pinned else np.ascontiguousarray
+        iou_thrs = hold(np.asarray(iou_thrs, dtype=np.float64))
+        rec_thrs = hold(np.asarray(rec_thrs, dtype=np.float64))
+        self.structs, self.keep, self.shared = [], [], {}
+        # plan with the larger result tensors first
+        self.order = sorted(range(len(plans)),
+                            key=lambda k: -len(plans[k].cat_ids) * plans[k].n_cfg)
+        slot_of = {k: s for s, k in enumerate(self.order)}
+        pool_idx = {}
+        if share_boxes and compress and len(plans) > 1:
+            frames = [k for k, p in enumerate(plans) if p.kind == "lvis" and p.masks is None]
+            for k, p in enumerate(plans):
+                if p.kind != "tao" or not frames:
+                    continue
+                if any(v[0] == frames[0] for v in pool_idx.values()):
+                    continue                       # one user per pool
+                got = shared_box_index(plans[frames[0]], p)
+                if got is not None and (lossless_f32_boxes(p) is None) == (
+                        lossless_f32_boxes(plans[frames[0]]) is None):
+                    pool_idx[k] = (frames[0], got[0], got[1])
+        self.shared = {k: v[0] for k, v in pool_idx.items()}
+        extra_of = {v[0]: v[2] for v in pool_idx.values()}
+        for k, plan in enumerate(plans):
+            if plan.masks is not None:
+                raise NotImplementedError("ta_eval_plan_host carries box plans only; use upload() + "
+                                          "evaluate_device() for iou_type='segm'")
+            g_max, n_slots = plan_limits(plan)
+            track = plan.kind == "tao"
+            ph = _lib.PlanHost()
+            ph.n_groups, ph.n_dt, ph.n_gt = plan.n_groups, plan.n_dt, plan.n_gt
+            ph.n_dt_boxes, ph.n_gt_boxes = plan.dt_box.shape[0], plan.gt_box.shape[0]
+            ph.n_cat, ph.n_cfg = len(plan.cat_ids), plan.n_cfg
+            ph.n_thr, ph.n_rec = self.n_thr, self.n_rec
+            ph.n_slots_max, ph.g_max = n_slots, g_max
+            ph.iou_mode = _lib.IOU_MODES[iou_mode]
+            big = None if track else eng.big_list(plan)
+            ph.n_big = 0 if big is None else int(big.size)
+            flags = 0
+            f32 = lossless_f32_boxes(plan) if compress else None
+            dt_box, gt_box = f32 if f32 is not None else (plan.dt_box, plan.gt_box)
+            if f32 is not None:
+                flags |= 1
+            if k in extra_of and extra_of[k].shape[0]:
+                # boxes only the sharing plan uses ride behind this plan's own (rows >= n_dt)
+                dt_box = np.concatenate([dt_box, extra_of[k].astype(dt_box.dtype)])
+                ph.n_dt_boxes = dt_box.shape[0]
+            dt_box_idx = None
+            if k in pool_idx:
+                # the pool's transport format decides how the shared boxes travel
+                dt_box, dt_box_idx = None, pool_idx[k][1]
+                ph.dt_box_pool = slot_of[pool_idx[k][0]]
+            dt_slot, gt_slot = (plan.dt_box_slot, plan.gt_box_slot) if track else (None, None)
+            if track and compress and n_slots <= 65536:
+                dt_slot, gt_slot = plan.dt_box_slot.astype(np.uint16), plan.gt_box_slot.astype(np.uint16)
+                flags |= 2
+            grp_dt, grp_gt, grp_cat = plan.grp_dt_off, plan.grp_gt_off, plan.grp_cat
+            if compress and plan.n_groups:
+                d_cnt, g_cnt = np.diff(plan.grp_dt_off), np.diff(plan.grp_gt_off)
+                if max(int(d_cnt.max()), int(g_cnt.max()), int(plan.grp_cat.max())) < 65536:
+                    grp_dt, grp_gt = d_cnt.astype(np.uint16), g_cnt.astype(np.uint16)
+                    grp_cat = plan.grp_cat.astype(np.uint16)
+                    flags |= 4
+            ph.flags = flags
+            need_iou_off = track or ph.n_big > 0
+            keep = dict(
+                grp_dt_off=grp_dt, grp_gt_off=grp_gt, grp_cat=grp_cat,
+                iou_off=plan.iou_off, cat_dt_off=plan.cat_dt_off, acc_perm=plan.acc_perm,
+                big_list=big if (big is not None and big.size) else None,
+                dt_box=dt_box, gt_box=gt_box, dt_box_idx=dt_box_idx,
+                dt_trk_off=plan.dt_trk_box_off if track else None,
+                gt_trk_off=plan.gt_trk_box_off if track else None,
+                dt_slot=dt_slot, gt_slot=gt_slot,
+                dt_attr_a=plan.dt_attr_a if track else None,
+                dt_attr_b=plan.dt_attr_b if track else None,
+                gt_attr_a=plan.gt_attr_a, gt_attr_b=plan.gt_attr_b if track else None,
+                dt_flag=plan.dt_flag, gt_flag=plan.gt_flag, gt_hp=plan.gt_hp if track else None,
+                cfgs=plan.range_cfgs)
+            for name, v in list(keep.items()):
+                if v is None:
+                    continue
+                if name == "iou_off" and not need_iou_off:
+                    # only its last entry is read (on the host): no copy needed
+                    v = np.ascontiguousarray(v)
+                elif v.dtype.fields is not None:
+                    raw = hold(np.ascontiguousarray(v).view(np.uint8))
+                    v = raw.view(v.dtype)
+                else:
+                    v = hold(v)
+                keep[name] = v
+                setattr(ph, name, _ptr(v))
+            ph.iou_thrs, ph.rec_thrs = _ptr(iou_thrs), _ptr(rec_thrs)
+            keep["iou_thrs"], keep["rec_thrs"] = iou_thrs, rec_thrs
+            self.structs.append(ph)
+            self.keep.append(keep)
+
+    def new_output(self, k: int) -> EvalOutput:
+        plan = self.plans[k]
+        mk = self.eng.host_empty if self.pinned else (lambda shape, dt: np.empty(shape, dtype=dt))
+        T, R, Cn, K = self.n_thr, self.n_rec, len(plan.cat_ids), plan.n_cfg
+        return EvalOutput(precision=mk((T, R, Cn, K), np.float64), recall=mk((T, Cn, K), np.float64),
+                          tp_cnt=mk((T, Cn, K), np.int64), fp_cnt=mk((T, Cn, K), np.int64),
+                          num_gt=mk((Cn, K), np.int32))
+
+
 class Engine:
     """One ta_ctx on one CUDA device."""
 
     def __init__(self, device: int = 0):
         self.lib = _lib.load()
-        if self.lib.ta_abi_version() != 3:
+        if self.lib.ta_abi_version() != 4:
             raise RuntimeError("libta_eval.so ABI version mismatch")
         self.device = int(device)
         h = C.c_void_p()
@@ -175,94 +335,65 @@ class Engine:
         return int(self.lib.ta_ctx_sm_count(self._ctx))
 
     # ------------------------------------------------------------------ host-buffer call
-    def evaluate_host_many(self, plans, outs=None, **kw):
-        """Several plans at once (the CLI's frame + track evaluations): one host thread and one
-        ta_ctx / stream per plan, so the H2D copy of one plan overlaps the kernels and the D2H
-        copy of another.  ctypes releases the GIL during the C calls."""
-        import threading
-        while len(self._extra) < len(plans) - 1:
+    def host_empty(self, shape, dtype) -> np.ndarray:
+        """Uninitialised array in page-locked host memory (ta_host_alloc), freed with the array."""
+        import weakref
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape, dtype=np.int64)) if np.ndim(shape) else int(shape)
+        nbytes = max(1, count * dtype.itemsize)
+        p = self.lib.ta_host_alloc(nbytes)
+        if not p:
+            raise _lib.TaEvalError(_lib.TA_ERR_CUDA, self.lib.ta_last_error().decode())
+        buf = (C.c_ubyte * nbytes).from_address(p)
+        weakref.finalize(buf, self.lib.ta_host_free, C.c_void_p(p))
+        return np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def host_copy(self, a: np.ndarray) -> np.ndarray:
+        out = self.host_empty(a.shape, a.dtype)
+        out[...] = a
+        return out
+
+    def pack_host(self, plans, iou_mode: str = "3d_iou", iou_thrs: np.ndarray = IOU_THRS,
+                  rec_thrs: np.ndarray = REC_THRS, compress: bool = True, pinned: bool = False,
+                  share_boxes: bool = True) -> "HostPack":
+        """Transport form of one or several plans for ta_eval_plans_host (see HostPack)."""
+        return HostPack(self, list(plans), iou_mode, iou_thrs, rec_thrs, compress, pinned,
+                        share_boxes)
+
+    def evaluate_pack(self, pack: "HostPack", outs=None):
+        """ONE C call: every plan of the pack from host memory to its result tensors on the
+        host.  Returns the EvalOutputs in the order the plans were given to pack_host."""
+        n = len(pack.structs)
+        while len(self._extra) < n - 1:
             h = C.c_void_p()
             _lib.check(self.lib.ta_ctx_create(self.device, C.byref(h)))
             self._extra.append(h)
-        ctxs = [self._ctx] + self._extra
-        outs = list(outs) if outs is not None else [None] * len(plans)
-        errs = [None] * len(plans)
-
-        def work(i):
-            try:
-                outs[i] = self.evaluate_host(plans[i], out=outs[i], _ctx=ctxs[i], **kw)
-            except BaseException as e:      # re-raised on the calling thread
-                errs[i] = e
-
-        th = [threading.Thread(target=work, args=(i,)) for i in range(1, len(plans))]
-        for t in th:
-            t.start()
-        work(0)
-        for t in th:
-            t.join()
-        for e in errs:
-            if e is not None:
-                raise e
+        outs = list(outs) if outs is not None else [None] * n
+        for i in range(n):
+            if outs[i] is None:
+                outs[i] = pack.new_output(i)
+        ctxs = (C.c_void_p * n)(*([self._ctx] + self._extra)[:n])
+        plans = (C.c_void_p * n)(*[C.addressof(pack.structs[k]) for k in pack.order])
+        ho = (_lib.HostOut * n)()
+        for slot, k in enumerate(pack.order):
+            o = outs[k]
+            ho[slot].precision, ho[slot].recall = _ptr(o.precision), _ptr(o.recall)
+            ho[slot].tp_cnt, ho[slot].fp_cnt, ho[slot].num_gt = _ptr(o.tp_cnt), _ptr(o.fp_cnt), _ptr(o.num_gt)
+        h2d, d2h = (C.c_int64 * n)(), (C.c_int64 * n)()
+        _lib.check(self.lib.ta_eval_plans_host(n, ctxs, plans, ho, h2d, d2h))
+        for slot, k in enumerate(pack.order):
+            outs[k].h2d_bytes, outs[k].d2h_bytes = int(h2d[slot]), int(d2h[slot])
         return outs
+
+    def evaluate_host_many(self, plans, outs=None, **kw):
+        """Several plans of one result set at once (the CLI's track + frame evaluations)."""
+        return self.evaluate_pack(self.pack_host(plans, **kw), outs)
 
     def evaluate_host(self, plan: EvalPlan, iou_mode: str = "3d_iou",
                       iou_thrs: np.ndarray = IOU_THRS, rec_thrs: np.ndarray = REC_THRS,
-                      out: Optional[EvalOutput] = None, compress_boxes: bool = True,
-                      _ctx=None) -> EvalOutput:
-        if plan.masks is not None:
-            raise NotImplementedError("ta_eval_plan_host carries box plans only; use upload() + "
-                                      "evaluate_device() for iou_type='segm'")
-        n_thr, n_rec, n_cfg, n_cat = len(iou_thrs), len(rec_thrs), plan.n_cfg, len(plan.cat_ids)
-        g_max, n_slots = plan_limits(plan)
-        iou_thrs = np.ascontiguousarray(iou_thrs, dtype=np.float64)
-        rec_thrs = np.ascontiguousarray(rec_thrs, dtype=np.float64)
-        track = plan.kind == "tao"
-        ph = _lib.PlanHost()
-        ph.n_groups, ph.n_dt, ph.n_gt = plan.n_groups, plan.n_dt, plan.n_gt
-        ph.n_dt_boxes, ph.n_gt_boxes = plan.dt_box.shape[0], plan.gt_box.shape[0]
-        ph.n_cat, ph.n_cfg, ph.n_thr, ph.n_rec = n_cat, n_cfg, n_thr, n_rec
-        ph.n_slots_max, ph.g_max = n_slots, g_max
-        ph.iou_mode = _lib.IOU_MODES[iou_mode]
-        big = None if track else self.big_list(plan)
-        ph.n_big = 0 if big is None else int(big.size)
-        f32 = lossless_f32_boxes(plan) if compress_boxes else None
-        ph.flags = 1 if f32 is not None else 0
-        dt_box, gt_box = f32 if f32 is not None else (plan.dt_box, plan.gt_box)
-        dt_slot, gt_slot = (plan.dt_box_slot, plan.gt_box_slot) if track else (None, None)
-        if track and compress_boxes and n_slots <= 65536:
-            u16 = getattr(plan, "_u16_slots", None)
-            if u16 is None:
-                u16 = plan._u16_slots = (np.ascontiguousarray(plan.dt_box_slot.astype(np.uint16)),
-                                         np.ascontiguousarray(plan.gt_box_slot.astype(np.uint16)))
-            dt_slot, gt_slot = u16
-            ph.flags |= 2
-        keep = dict(
-            grp_dt_off=plan.grp_dt_off, grp_gt_off=plan.grp_gt_off, iou_off=plan.iou_off,
-            cat_dt_off=plan.cat_dt_off, grp_cat=plan.grp_cat, acc_perm=plan.acc_perm,
-            big_list=big if (big is not None and big.size) else None,
-            dt_box=dt_box, gt_box=gt_box,
-            dt_trk_off=plan.dt_trk_box_off if track else None,
-            gt_trk_off=plan.gt_trk_box_off if track else None,
-            dt_slot=dt_slot, gt_slot=gt_slot,
-            dt_attr_a=plan.dt_attr_a, dt_attr_b=plan.dt_attr_b,
-            gt_attr_a=plan.gt_attr_a, gt_attr_b=plan.gt_attr_b,
-            dt_flag=plan.dt_flag, gt_flag=plan.gt_flag, gt_hp=plan.gt_hp,
-            iou_thrs=iou_thrs, rec_thrs=rec_thrs, cfgs=plan.range_cfgs)
-        for k, v in keep.items():
-            setattr(ph, k, _ptr(v))
-        if out is None:
-            out = EvalOutput(
-                precision=np.empty((n_thr, n_rec, n_cat, n_cfg), dtype=np.float64),
-                recall=np.empty((n_thr, n_cat, n_cfg), dtype=np.float64),
-                tp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64),
-                fp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64),
-                num_gt=np.empty((n_cat, n_cfg), dtype=np.int32))
-        h2d, d2h = C.c_int64(0), C.c_int64(0)
-        _lib.check(self.lib.ta_eval_plan_host(
-            _ctx or self._ctx, C.byref(ph), _ptr(out.precision), _ptr(out.recall), _ptr(out.tp_cnt),
-            _ptr(out.fp_cnt), _ptr(out.num_gt), C.byref(h2d), C.byref(d2h)))
-        out.h2d_bytes, out.d2h_bytes = int(h2d.value), int(d2h.value)
-        return out
+                      out: Optional[EvalOutput] = None, compress_boxes: bool = True) -> EvalOutput:
+        pack = self.pack_host([plan], iou_mode, iou_thrs, rec_thrs, compress=compress_boxes)
+        return self.evaluate_pack(pack, [out])[0]
 
     # ------------------------------------------------------------------ device-resident path
     def upload(self, plan: EvalPlan, iou_thrs: np.ndarray = IOU_THRS,

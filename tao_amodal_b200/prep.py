@@ -130,6 +130,9 @@ class EvalPlan:
     # lvis, iou_type="segm": run-length masks of the entities (mask.RlePool.export()):
     # {"dt"|"gt": (rle_off int64 [n+1], counts uint32, hw uint32 [n,2], bbox f64 [n,4])}
     masks: Optional[dict] = None
+    # row of the result file (DtColumns) every detection box was taken from: lets the engine see
+    # that two plans of one result file hold the same boxes (engine.shared_box_index)
+    dt_box_src: Optional[np.ndarray] = None
     stats: Dict[str, float] = field(default_factory=dict)
 
     @property
@@ -467,8 +470,8 @@ def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
     if not use_cats:
         cat_ids, n_cat = np.asarray([-1], dtype=np.int64), 1      # eval.py:259-260
 
-    gb_off, gb, gslot = _gather_track_boxes(gt_ent, g_perm)
-    db_off, db, dslot = _gather_track_boxes(dt_ent, d_sel)
+    gb_off, gb, gslot, _ = _gather_track_boxes(gt_ent, g_perm)
+    db_off, db, dslot, db_src = _gather_track_boxes(dt_ent, d_sel)
     cat_grp_off, cat_dt_off = _cat_offsets(n_cat, grp_cat, grp_dt_off)
     dt_score = np.ascontiguousarray(t_score[d_t][d_sel])
 
@@ -492,6 +495,7 @@ def prepare_tao(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
         dt_box=db, gt_box=gb, dt_trk_box_off=db_off, gt_trk_box_off=gb_off,
         dt_box_slot=dslot, gt_box_slot=gslot,
         range_cfgs=tao_range_cfgs(area_rng, time_rng), sentinel=-1,
+        dt_box_src=np.ascontiguousarray(sel[db_src]),
     )
     plan.stats["n_dt_boxes"] = float(db.shape[0])
     plan.stats["n_gt_boxes"] = float(gb.shape[0])
@@ -561,6 +565,7 @@ def _tao_tracks(rows, rank, trk_key, S_frame, S_slot, bbox, area, vis):
         "trk_key": keys, "first_key": first_key, "area_mean": area_mean, "n_anns": n_anns,
         "n_hp": n_hp, "vis_min": vis_min, "box_seg": box_seg,
         "box": bbox[r_sorted[kb]].astype(np.float64), "slot": slot_sorted[kb].astype(np.int32),
+        "src": r_sorted[kb],
     }
 
 
@@ -572,7 +577,8 @@ def _gather_track_boxes(ent, perm):
     np.cumsum(lens, out=off[1:])
     total = int(off[-1])
     idx = np.arange(total, dtype=np.int64) - np.repeat(off[:-1], lens) + np.repeat(seg[:-1][perm], lens)
-    return off, np.ascontiguousarray(ent["box"][idx]), np.ascontiguousarray(ent["slot"][idx])
+    return (off, np.ascontiguousarray(ent["box"][idx]), np.ascontiguousarray(ent["slot"][idx]),
+            ent["src"][idx])
 
 
 # ---- LVIS frame path ---------------------------------------------------------------------
@@ -665,6 +671,7 @@ def prepare_lvis(gt: GtColumns, dt: DtColumns, max_dets: int = MAX_DETS,
         dt_box=np.ascontiguousarray(d_box[d_sel].astype(np.float64)),
         gt_box=np.ascontiguousarray(gt.ann_bbox[g_sel].astype(np.float64)),
         range_cfgs=lvis_range_cfgs(vis_rng), sentinel=0, freq_groups=freq_groups,
+        dt_box_src=np.ascontiguousarray(sel[d_sel]),
     )
     plan.stats["n_dt_boxes"] = float(d_sel.size)
     plan.stats["n_gt_boxes"] = float(g_sel.size)

@@ -148,16 +148,55 @@ def test_lossless_f32_box_transport(eng):
     assert np.array_equal(g["tao_precision"], o.precision.reshape(g["tao_precision"].shape))
 
 
-def test_concurrent_host_calls(eng):
-    """Two plans evaluated concurrently (one ta_ctx / stream / host thread each)."""
+def test_both_plans_in_one_call(eng):
+    """ta_eval_plans_host: the track and the frame plan of one result file in one C call (one
+    ta_ctx / stream each, one upload stream), against the reference goldens, in every transport
+    form: shared box upload, separate boxes, uncompressed, page-locked memory."""
     from conftest import load_golden
-    g = load_golden("edge_mix")
-    tao_plan, lvis_plan = plans_from_json(*golden_inputs(g))
-    for _ in range(3):
-        o_t, o_l = eng.evaluate_host_many([tao_plan, lvis_plan])
-        assert np.array_equal(g["tao_precision"], o_t.precision.reshape(g["tao_precision"].shape))
-        assert np.array_equal(g["lvis_precision"], o_l.precision)
-        assert np.array_equal(g["lvis_tp_cnt"], o_l.tp_cnt)
+    for case in ("edge_mix", "small", "small_ties", "small_float"):
+        g = load_golden(case)
+        tao_plan, lvis_plan = plans_from_json(*golden_inputs(g))
+        variants = [dict(), dict(share_boxes=False), dict(compress=False), dict(pinned=True)]
+        for kw in variants:
+            pack = eng.pack_host([tao_plan, lvis_plan], **kw)
+            if not kw or "pinned" in kw:
+                assert pack.shared == {0: 1}, "the two plans hold the same result boxes"
+                assert pack.structs[0].dt_box_idx and not pack.structs[0].dt_box
+            else:
+                assert not pack.shared
+            for _ in range(2):
+                o_t, o_l = eng.evaluate_pack(pack)
+                assert np.array_equal(g["tao_precision"], o_t.precision.reshape(g["tao_precision"].shape))
+                assert np.array_equal(g["tao_recall"], o_t.recall.reshape(g["tao_recall"].shape))
+                assert np.array_equal(g["lvis_precision"], o_l.precision)
+                assert np.array_equal(g["lvis_tp_cnt"], o_l.tp_cnt)
+                assert np.array_equal(g["lvis_fp_cnt"], o_l.fp_cnt)
+        # bytes over PCIe: sharing + compact tables must not cost more than separate uploads
+        a = eng.evaluate_pack(eng.pack_host([tao_plan, lvis_plan]))
+        b = eng.evaluate_pack(eng.pack_host([tao_plan, lvis_plan], compress=False))
+        assert sum(o.h2d_bytes for o in a) < sum(o.h2d_bytes for o in b)
+        # the order of the plans in the list is the order of the outputs
+        o_l2, o_t2 = eng.evaluate_host_many([lvis_plan, tao_plan])
+        assert np.array_equal(o_l2.precision, a[1].precision) and np.array_equal(o_t2.precision, a[0].precision)
+
+
+def test_group_tables_as_counts(eng):
+    """TA_PLAN_GRP_U16: the device prefix sum over uint16 group sizes reproduces the int64 offsets
+    (sizes that cross several scan blocks; empty groups on either side)."""
+    import ctypes as C
+    import torch
+    from tao_amodal_b200 import _lib
+    from bench import make_workload
+    gt, dt, tao_plan, lvis_plan = make_workload("cfg2", 0, 3)
+    assert lvis_plan.n_groups > 3 * 2048
+    pack = eng.pack_host([lvis_plan])
+    assert pack.structs[0].flags & 4
+    ref = eng.evaluate_device(eng.upload(lvis_plan))
+    out = eng.evaluate_pack(pack)[0]
+    for k in ("precision", "recall", "tp_cnt", "fp_cnt", "num_gt"):
+        assert np.array_equal(getattr(out, k), getattr(ref, k)), k
+    out2 = eng.evaluate_host(lvis_plan, compress_boxes=False)
+    assert np.array_equal(out2.precision, ref.precision)
 
 
 @pytest.mark.parametrize("seed", range(12))
