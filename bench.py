@@ -496,27 +496,6 @@ def main():
         cells_with_gt = [int((single["tao_num_gt"] > 0).sum()), int((single["lvis_num_gt"] > 0).sum())]
 
     # ---- e2e: host buffers (pinned) through the C call(s), H2D + D2H inside the region
-    def pin(plan):
-        import dataclasses
-        rep = {}
-        for f in dataclasses.fields(plan):
-            v = getattr(plan, f.name)
-            if isinstance(v, np.ndarray) and v.size:
-                if v.dtype.fields is not None:
-                    raw = torch.from_numpy(np.ascontiguousarray(v).view(np.uint8)).pin_memory()
-                    rep[f.name] = raw.numpy().view(v.dtype)
-                else:
-                    rep[f.name] = torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy()
-        out = dataclasses.replace(plan, **rep)
-        from tao_amodal_b200.engine import lossless_f32_boxes
-        f32 = lossless_f32_boxes(out)
-        if f32 is not None:      # the transport copies must be pinned too
-            out._f32_boxes = tuple(torch.from_numpy(x).pin_memory().numpy() for x in f32)
-        if plan.kind == "tao" and plan.dt_box_slot.size and int(plan.dt_box_slot.max()) < 65536:
-            out._u16_slots = tuple(torch.from_numpy(np.ascontiguousarray(x.astype(np.uint16))).pin_memory().numpy()
-                                   for x in (plan.dt_box_slot, plan.gt_box_slot))
-        return out
-
     e2e_steps = max(3, min(args.steps, 10))
     if world == 1:
         # transport form of both plans in page-locked memory (ta_host_alloc), built once; one
@@ -528,24 +507,47 @@ def main():
             eng.evaluate_pack(pack, outs)
             return (outs[0].h2d_bytes + outs[1].h2d_bytes, outs[0].d2h_bytes + outs[1].d2h_bytes)
     else:
-        p_tao, p_lvis = pin(tao_plan), pin(lvis_plan)
+        # transport form of both plans in page-locked memory, as at N = 1
+        pack = eng.pack_host([tao_plan, lvis_plan], pinned=True)
         # pinned host slices for every owner's results: each rank copies its OWN category block out
         host_part = {id(dv): {k: torch.empty(v.shape, dtype=v.dtype).pin_memory()
                               for k, v in pipe.exch[id(dv)].part.items()} for dv in (d_tao, d_lvis)}
 
-        copy_out = torch.cuda.Stream()
+        # the resident pass' slices, to check the end-to-end route against; the device slices
+        # are wiped so that only a step that really recomputes them can pass
+        torch.cuda.synchronize()
+        resident_part = {id(dv): {k: v.cpu().clone() for k, v in pipe.exch[id(dv)].part.items()}
+                         for dv in (d_tao, d_lvis)}
+        for dv in (d_tao, d_lvis):
+            for v in pipe.exch[id(dv)].part.values():
+                v.zero_()
+        copy_in, copy_out = torch.cuda.Stream(), torch.cuda.Stream()
+        aux = eng.aux_ctx()       # the upload stream's library calls run beside the main context's
 
         def e2e_step():
-            # pinned host plan -> HBM (boxes as lossless float), local IoU + matching, cross-rank
-            # exchange of the result records, owner-side PR, every owner's slice back to ITS
-            # host (pinned) on a second stream, so the download of the track results overlaps
-            # the upload of the frame plan.  (The exchange's routing tables are part of the
-            # plan, like acc_perm, and stay resident.)
+            # pinned host plans -> HBM on an upload stream (compact transport forms; the frame
+            # plan's boxes first, the track plan takes its boxes from them), local IoU + matching,
+            # cross-rank exchange of the result records, owner-side PR, every owner's slice back
+            # to ITS host (pinned) on a third stream: the track plan's kernels, exchange and
+            # download overlap the upload of the rest of the frame plan.  The frame schedule is
+            # rebuilt from the fresh inputs every step; the exchange's routing tables are part
+            # of the plan, like acc_perm, and stay resident.
             h2d = d2h = 0
             main = torch.cuda.current_stream()
-            for plan, dev in ((p_tao, d_tao), (p_lvis, d_lvis)):
-                h2d += dev.reload(plan)
-                if plan.kind == "tao":
+            ready = {}
+            with torch.cuda.stream(copy_in):
+                shared = bool(pack.shared)
+                if shared:
+                    h2d += d_lvis.reload_pack(pack, 1, only=("dt_box",), ctx=aux)
+                h2d += d_tao.reload_pack(pack, 0, pool=d_lvis if shared else None, ctx=aux)
+                ready[id(d_tao)] = torch.cuda.Event()
+                ready[id(d_tao)].record(copy_in)
+                h2d += d_lvis.reload_pack(pack, 1, skip=("dt_box",) if shared else (), ctx=aux)
+                ready[id(d_lvis)] = torch.cuda.Event()
+                ready[id(d_lvis)].record(copy_in)
+            for dev in (d_tao, d_lvis):
+                main.wait_event(ready[id(dev)])
+                if dev.plan.kind == "tao":
                     eng.stage_iou(dev)
                     eng.stage_match(dev)
                 else:
@@ -570,6 +572,18 @@ def main():
     for _ in range(e2e_steps):
         h2d, d2h = e2e_step()
     e2e_s = time.perf_counter() - t0
+    if world > 1:
+        same = all(torch.equal(host_part[i][k], resident_part[i][k])
+                   for i in host_part for k in host_part[i])
+        flag = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        e2e_same = bool(flag.item())
+        parity["e2e_slices_equal_resident"] = e2e_same
+        if not e2e_same:
+            if rank == 0:
+                sys.stderr.write("PARITY FAILURE: the end-to-end step's result slices differ from the resident pass'\n")
+            dist.destroy_process_group()
+            return 3
     if world == 1:
         # the host-buffer call and the resident route must agree bit for bit
         host_out = {n + "_" + k: getattr(o, k) for n, o in (("tao", outs[0]), ("lvis", outs[1]))
@@ -714,7 +728,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "api": ("Engine.evaluate_pack -> ta_eval_plans_host (both plans in one call: pinned host plans -> precision/recall on host; shared_boxes=%s)" % bool(pack.shared) if world == 1
-                        else "per rank: DevicePlan.reload (pinned host plan) + stages + ta_exchange_* + owner-side PR + the owner's slice to its pinned host buffer")},
+                        else "per rank: DevicePlan.reload_pack (pinned host plans, shared boxes=%s) + stages + ta_exchange_* + owner-side PR + the owner's slice to its pinned host buffer" % bool(pack.shared))},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "parity": parity,

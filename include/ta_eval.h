@@ -297,6 +297,16 @@ void  ta_host_free(void* p);
  * callers that refresh resident plans from host memory. */
 int ta_widen_boxes(ta_ctx* ctx, void* stream, int64_t n, const float* src, double* dst);
 
+/* The device halves of the other compact transport forms of ta_plan_host, for the same callers:
+ * uint16 -> int32 (TA_PLAN_SLOT_U16, the category column of TA_PLAN_GRP_U16); int64 offsets
+ * [n+1] from uint16 counts [n] (TA_PLAN_GRP_U16; scratch comes from the context); dst[i] =
+ * pool[idx[i]] for [.,4] double boxes (dt_box_idx).                                          */
+int ta_widen_u16(ta_ctx* ctx, void* stream, int64_t n, const uint16_t* src, int32_t* dst);
+int ta_offsets_from_counts(ta_ctx* ctx, void* stream, int64_t n, const uint16_t* counts,
+                           int64_t* off);
+int ta_gather_boxes(ta_ctx* ctx, void* stream, int64_t n, const double* pool, const int32_t* idx,
+                    double* dst);
+
 /* ---- multi-GPU exchange (one process per GPU; NCCL over NVLink / NVSwitch) ---------------
  * Videos (and their images) shard across ranks: ta_track_iou / ta_match_greedy / ta_frame_eval
  * run on each rank's own groups with no communication.  accumulate, however, orders all

@@ -28,7 +28,7 @@ IOU_MODES = {"3d_iou": 0, "avg_iou": 1, "imagenetvid": 2, "3d_iou_seq": 3}
 EXPORTS = [
     "ta_abi_version", "ta_last_error", "ta_ctx_create", "ta_ctx_destroy", "ta_ctx_sm_count",
     "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
-    "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host", "ta_eval_plans_host", "ta_host_alloc", "ta_host_free",
+    "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host", "ta_eval_plans_host", "ta_host_alloc", "ta_host_free", "ta_widen_u16", "ta_offsets_from_counts", "ta_gather_boxes",
     "ta_rle_iou", "ta_frame_sched_bytes", "ta_frame_sched_build",
     "ta_exchange_unique_id", "ta_exchange_create", "ta_exchange_destroy", "ta_exchange_rank",
     "ta_exchange_world", "ta_exchange_gather", "ta_exchange_scatter", "ta_exchange_alltoallv",
@@ -132,6 +132,9 @@ def load() -> C.CDLL:
     lib.ta_eval_plan_host.argtypes = [P, C.POINTER(PlanHost), P, P, P, P, P,
                                       C.POINTER(I64), C.POINTER(I64)]
     lib.ta_eval_plans_host.argtypes = [I32, P, P, P, P, P]
+    lib.ta_widen_u16.argtypes = [P, P, I64, P, P]
+    lib.ta_offsets_from_counts.argtypes = [P, P, I64, P, P]
+    lib.ta_gather_boxes.argtypes = [P, P, I64, P, P, P]
     lib.ta_host_alloc.argtypes = [C.c_size_t]
     lib.ta_host_alloc.restype = C.c_void_p
     lib.ta_host_free.argtypes = [P]

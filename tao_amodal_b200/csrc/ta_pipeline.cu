@@ -7,6 +7,7 @@
 // from the stream-ordered pool (cudaMallocAsync; the context sets the pool's release threshold
 // so repeated calls reuse the same pages).
 #include <initializer_list>
+#include <stdlib.h>
 
 #include "ta_internal.h"
 
@@ -133,6 +134,59 @@ extern "C" int ta_widen_boxes(ta_ctx* ctx, void* stream, int64_t n, const float*
     return ta_check_launch(ctx, "k_widen_boxes");
 }
 
+// The device-side halves of the compact transport forms, for callers that keep plans resident
+// and refresh them from host memory (ta_eval_plans_host does the same internally).
+extern "C" int ta_widen_u16(ta_ctx* ctx, void* stream, int64_t n, const uint16_t* src, int32_t* dst) {
+    if (!ctx) return ta_set_err(TA_ERR_INVALID, "ta_widen_u16: ctx is NULL");
+    if (n < 0) return ta_set_err(TA_ERR_INVALID, "ta_widen_u16: negative size");
+    if (n == 0) return TA_OK;
+    TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
+    k_widen_slots<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    return ta_check_launch(ctx, "k_widen_slots");
+}
+
+extern "C" int ta_gather_boxes(ta_ctx* ctx, void* stream, int64_t n, const double* pool,
+                               const int32_t* idx, double* dst) {
+    if (!ctx) return ta_set_err(TA_ERR_INVALID, "ta_gather_boxes: ctx is NULL");
+    if (n < 0) return ta_set_err(TA_ERR_INVALID, "ta_gather_boxes: negative size");
+    if (n == 0) return TA_OK;
+    TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
+    k_gather_boxes<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const double2*)pool, idx, (double2*)dst, n);
+    return ta_check_launch(ctx, "k_gather_boxes");
+}
+
+static int offsets_from_counts(ta_ctx* ctx, cudaStream_t st, int64_t n, const uint16_t* cnt,
+                               int64_t* off, int64_t* part) {
+    int rc;
+    if (n == 0) {
+        TA_CUDA(cudaMemsetAsync(off, 0, 8, st));
+        return TA_OK;
+    }
+    const unsigned nb = (unsigned)((n + SC_B - 1) / SC_B);
+    k_cnt_sums<<<nb, SC_T, 0, st>>>(cnt, n, part);
+    if ((rc = ta_check_launch(ctx, "k_cnt_sums"))) return rc;
+    k_cnt_scan_part<<<1, 1024, 0, st>>>(part, (int)nb);
+    if ((rc = ta_check_launch(ctx, "k_cnt_scan_part"))) return rc;
+    k_cnt_offsets<<<nb, SC_T, 0, st>>>(cnt, n, part, off);
+    return ta_check_launch(ctx, "k_cnt_offsets");
+}
+
+// off[0] = 0, off[i+1] = off[i] + counts[i]: int64 [n+1] from uint16 [n] (TA_PLAN_GRP_U16)
+extern "C" int ta_offsets_from_counts(ta_ctx* ctx, void* stream, int64_t n, const uint16_t* counts,
+                                      int64_t* off) {
+    if (!ctx) return ta_set_err(TA_ERR_INVALID, "ta_offsets_from_counts: ctx is NULL");
+    if (n < 0) return ta_set_err(TA_ERR_INVALID, "ta_offsets_from_counts: negative size");
+    TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
+    void* part = nullptr;
+    int rc = ta_workspace(ctx, (cudaStream_t)stream, (size_t)((n + SC_B - 1) / SC_B + 1) * 8, &part, 1);
+    if (rc != TA_OK) return rc;
+    return offsets_from_counts(ctx, (cudaStream_t)stream, n, counts, off, (int64_t*)part);
+}
+
 // Pinned host memory for plans and results (what makes the copies of ta_eval_plan(s)_host
 // asynchronous) without any other CUDA binding on the caller's side.
 extern "C" void* ta_host_alloc(size_t bytes) {
@@ -189,11 +243,12 @@ struct DevArena {
 };
 
 struct EventSet {
-    cudaEvent_t ev[TA_MAX_PLANS * 6];
+    cudaEvent_t ev[TA_MAX_PLANS * 8 + 1];
     int n = 0;
     ~EventSet() { for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]); }
+    bool timed = false;
     cudaError_t make(cudaEvent_t* e) {
-        cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+        cudaError_t r = cudaEventCreateWithFlags(e, timed ? cudaEventDefault : cudaEventDisableTiming);
         if (r == cudaSuccess) ev[n++] = *e;
         return r;
     }
@@ -221,7 +276,7 @@ struct PlanRun {
          *w_gt_off = nullptr, *w_cat = nullptr, *w_part = nullptr;
     void *d_iou = nullptr, *d_tpfp = nullptr, *d_numgt = nullptr, *d_prec = nullptr, *d_rec = nullptr,
          *d_tp = nullptr, *d_fp = nullptr, *d_word = nullptr;
-    cudaEvent_t ev_alloc, ev_box, ev_in, ev_acc, ev_wide, ev_gath;
+    cudaEvent_t ev_alloc, ev_box, ev_in, ev_acc, ev_wide, ev_gath, ev_kern, ev_done;
     int64_t d2h = 0;
     int bad = 0;
 };
@@ -330,19 +385,7 @@ int plan_widen_dt(PlanRun& r) {
 }
 
 int plan_offsets(PlanRun& r, const uint16_t* cnt, void* off) {
-    const int64_t G = r.pl->n_groups;
-    const unsigned nb = blocks_of(G, SC_B);
-    int rc;
-    if (G == 0) {
-        TA_CUDA(cudaMemsetAsync(off, 0, 8, r.st));
-        return TA_OK;
-    }
-    k_cnt_sums<<<nb, SC_T, 0, r.st>>>(cnt, G, (int64_t*)r.w_part);
-    if ((rc = ta_check_launch(r.ctx, "k_cnt_sums"))) return rc;
-    k_cnt_scan_part<<<1, 1024, 0, r.st>>>((int64_t*)r.w_part, (int)nb);
-    if ((rc = ta_check_launch(r.ctx, "k_cnt_scan_part"))) return rc;
-    k_cnt_offsets<<<nb, SC_T, 0, r.st>>>(cnt, G, (const int64_t*)r.w_part, (int64_t*)off);
-    return ta_check_launch(r.ctx, "k_cnt_offsets");
+    return offsets_from_counts(r.ctx, r.st, r.pl->n_groups, cnt, (int64_t*)off, (int64_t*)r.w_part);
 }
 
 int plan_compute(PlanRun& r, PlanRun* pool) {
@@ -473,6 +516,11 @@ extern "C" int ta_eval_plans_host(int32_t n_plans, ta_ctx* const* ctxs,
     int rc = TA_OK;
     {
         EventSet evs;
+        // TA_PIPE_TRACE=1: timeline of the call on stderr (ms since the first upload)
+        const bool trace = getenv("TA_PIPE_TRACE") != nullptr;
+        evs.timed = trace;
+        cudaEvent_t ev_start;
+        TA_CUDA(evs.make(&ev_start));
         // arenas are declared after the events: they free (stream-ordered) before the events go
         DevArena* arenas[TA_MAX_PLANS] = {nullptr};
         struct ArenaGuard {
@@ -483,12 +531,14 @@ extern "C" int ta_eval_plans_host(int32_t n_plans, ta_ctx* const* ctxs,
             PlanRun& r = run[i];
             ta_begin(r.ctx, r.st);
             arenas[i] = r.ar = new DevArena(r.st);
-            for (cudaEvent_t* e : {&r.ev_alloc, &r.ev_box, &r.ev_in, &r.ev_acc, &r.ev_wide, &r.ev_gath})
+            for (cudaEvent_t* e : {&r.ev_alloc, &r.ev_box, &r.ev_in, &r.ev_acc, &r.ev_wide, &r.ev_gath,
+                                   &r.ev_kern, &r.ev_done})
                 TA_CUDA(evs.make(e));
             rc = plan_alloc(r);
             if (rc == TA_OK) TA_CUDA(cudaStreamWaitEvent(up, r.ev_alloc, 0));
         }
         // uploads, in the order the plans will consume them
+        if (rc == TA_OK) TA_CUDA(cudaEventRecord(ev_start, up));
         for (int i = 0; i < n_plans && rc == TA_OK; ++i)
             if (run[i].is_pool) {
                 TA_CUDA(run[i].ar->flush(ST_BOX, up));
@@ -511,7 +561,9 @@ extern "C" int ta_eval_plans_host(int32_t n_plans, ta_ctx* const* ctxs,
         for (int i = 0; i < n_plans && rc == TA_OK; ++i) {
             PlanRun* pool = plans[i]->dt_box_idx ? &run[plans[i]->dt_box_pool] : nullptr;
             rc = plan_compute(run[i], pool);
+            if (rc == TA_OK && trace) TA_CUDA(cudaEventRecord(run[i].ev_kern, run[i].st));
             if (rc == TA_OK) rc = plan_download(run[i], outs[i]);
+            if (rc == TA_OK && trace) TA_CUDA(cudaEventRecord(run[i].ev_done, run[i].st));
         }
         // a pool's boxes stay until every gather from them has run
         for (int i = 0; i < n_plans && rc == TA_OK; ++i)
@@ -525,6 +577,21 @@ extern "C" int ta_eval_plans_host(int32_t n_plans, ta_ctx* const* ctxs,
         for (int i = 0; i < n_plans; ++i) {
             if (h2d_bytes) h2d_bytes[i] = run[i].ar ? run[i].ar->h2d : 0;
             if (d2h_bytes) d2h_bytes[i] = run[i].d2h;
+        }
+        if (trace && rc == TA_OK) {
+            for (int i = 0; i < n_plans; ++i) cudaStreamSynchronize(run[i].st);
+            for (int i = 0; i < n_plans; ++i) {
+                float t_box = 0, t_in = 0, t_acc = 0, t_k = 0, t_d = 0;
+                if (run[i].is_pool) cudaEventElapsedTime(&t_box, ev_start, run[i].ev_box);
+                cudaEventElapsedTime(&t_in, ev_start, run[i].ev_in);
+                cudaEventElapsedTime(&t_acc, ev_start, run[i].ev_acc);
+                cudaEventElapsedTime(&t_k, ev_start, run[i].ev_kern);
+                cudaEventElapsedTime(&t_d, ev_start, run[i].ev_done);
+                fprintf(stderr, "ta_pipe plan %d (%s): pool boxes up %.2f | inputs up %.2f | accumulate inputs up %.2f | "
+                        "kernels done %.2f | results on host %.2f ms  (h2d %.1f MB, d2h %.1f MB)\n",
+                        i, run[i].track ? "track" : "frame", t_box, t_in, t_acc, t_k, t_d,
+                        run[i].ar->h2d / 1e6, run[i].d2h / 1e6);
+            }
         }
     }   // arena frees are stream-ordered after the kernels
     for (int i = 0; i < n_plans && rc == TA_OK; ++i) rc = plan_read_asserts(run[i]);

@@ -360,6 +360,15 @@ class Engine:
         return HostPack(self, list(plans), iou_mode, iou_thrs, rec_thrs, compress, pinned,
                         share_boxes)
 
+    def aux_ctx(self):
+        """A second ta_ctx of this device, for library calls issued on another stream while the
+        main context is busy (a context's scratch serves one stream at a time)."""
+        if not self._extra:
+            h = C.c_void_p()
+            _lib.check(self.lib.ta_ctx_create(self.device, C.byref(h)))
+            self._extra.append(h)
+        return self._extra[0]
+
     def evaluate_pack(self, pack: "HostPack", outs=None):
         """ONE C call: every plan of the pack from host memory to its result tensors on the
         host.  Returns the EvalOutputs in the order the plans were given to pack_host."""
@@ -628,6 +637,83 @@ class DevicePlan:
                 continue
             self.t[k].copy_(torch.from_numpy(v), non_blocking=True)
             n += v.nbytes
+        return n
+
+    def reload_pack(self, pack: "HostPack", k: int, pool: Optional["DevicePlan"] = None,
+                    only=None, skip=(), ctx=None) -> int:
+        """Refresh the device buffers from plan `k` of a HostPack (the compact transport forms of
+        ta_plan_host: float boxes, uint16 slots and group sizes, detection boxes shared with the
+        plan resident in `pool`), asynchronously on the current stream, and rebuild what depends
+        on them (the frame path's schedule).  `only` / `skip` select columns by name, so that a
+        shared box array can go ahead of the rest; `ctx` is the context to issue the calls on
+        (Engine.aux_ctx() when the current stream is not the one the main context works on).
+        Returns the bytes copied from the host."""
+        import torch
+        eng, lib = self.eng, self.eng.lib
+        keep, flags, plan = pack.keep[k], int(pack.structs[k].flags), self.plan
+        ctx = ctx or eng._ctx
+        assert pack.plans[k] is plan or pack.plans[k].n_dt == plan.n_dt
+        st = C.c_void_p(torch.cuda.current_stream(eng.device).cuda_stream)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        n = 0
+
+        def staged(name, v):
+            nonlocal n
+            t = self.t.get(name + "_stage")
+            if t is None or t.numel() != v.size or t.element_size() != v.itemsize:
+                w = v.view(np.int16) if v.dtype == np.uint16 else v
+                t = self.t[name + "_stage"] = torch.empty(w.shape, dtype=torch.from_numpy(w[:0]).dtype,
+                                                          device=self.dev)
+            t.copy_(torch.from_numpy(v.view(np.int16) if v.dtype == np.uint16 else v), non_blocking=True)
+            n += v.nbytes
+            return t
+
+        for name, v in keep.items():
+            if v is None or name in ("iou_thrs", "rec_thrs") or v.size == 0:
+                continue
+            if (only is not None and name not in only) or name in skip:
+                continue
+            if name == "iou_off" and not (plan.kind == "tao" or self.n_big):
+                continue
+            if name == "dt_box_idx":
+                assert pool is not None, "this plan takes its boxes from another resident plan"
+                _lib.check(lib.ta_gather_boxes(ctx, st, v.size, P(pool.t["dt_box_pool"]),
+                                               P(staged(name, v)), P(self.t["dt_box"])))
+            elif name in ("dt_box", "gt_box"):
+                rows = v.shape[0]
+                dst = self.t[name]
+                if name == "dt_box" and rows != plan.dt_box.shape[0]:
+                    # pool plan: the boxes only the sharing plan uses ride behind this plan's own
+                    big = self.t.get("dt_box_pool")
+                    if big is None or big.shape[0] != rows:
+                        big = self.t["dt_box_pool"] = torch.empty((rows, 4), dtype=torch.float64, device=self.dev)
+                        self.t["dt_box"] = big[:plan.dt_box.shape[0]]
+                        self._refresh()
+                    dst = big
+                elif name == "dt_box":
+                    self.t["dt_box_pool"] = dst
+                if flags & 1:
+                    _lib.check(lib.ta_widen_boxes(ctx, st, rows, P(staged(name, v)), P(dst)))
+                else:
+                    dst.copy_(torch.from_numpy(v), non_blocking=True)
+                    n += v.nbytes
+            elif name in ("dt_slot", "gt_slot") and flags & 2:
+                _lib.check(lib.ta_widen_u16(ctx, st, v.size, P(staged(name, v)), P(self.t[name])))
+            elif name in ("grp_dt_off", "grp_gt_off") and flags & 4:
+                _lib.check(lib.ta_offsets_from_counts(ctx, st, v.size, P(staged(name, v)), P(self.t[name])))
+            elif name == "grp_cat" and flags & 4:
+                _lib.check(lib.ta_widen_u16(ctx, st, v.size, P(staged(name, v)), P(self.t[name])))
+            else:
+                w = v.view(np.uint8) if v.dtype.fields is not None else v
+                self.t[name].copy_(torch.from_numpy(w.view(np.int32) if w.dtype == np.uint32 else w),
+                                   non_blocking=True)
+                n += v.nbytes
+        if "sched" in self.t and only is None:
+            Pk = lambda key: C.c_void_p(self.t[key].data_ptr())
+            _lib.check(lib.ta_frame_sched_build(
+                ctx, st, plan.n_groups, Pk("grp_dt_off"), Pk("grp_gt_off"), Pk("grp_cat"),
+                plan.n_dt, Pk("dt_flag"), plan.n_gt, Pk("gt_attr_a"), Pk("gt_flag"),
+                self.n_cat, plan.n_cfg, Pk("cfgs"), Pk("sched")))
         return n
 
     def ensure_detail(self):

@@ -180,6 +180,32 @@ def test_both_plans_in_one_call(eng):
         assert np.array_equal(o_l2.precision, a[1].precision) and np.array_equal(o_t2.precision, a[0].precision)
 
 
+def test_resident_plans_refreshed_from_a_pack(eng):
+    """DevicePlan.reload_pack: the compact transport forms (float boxes, uint16 slots / group
+    sizes, track boxes gathered from the frame plan's upload) restore wiped device buffers to
+    the exact inputs — the route the multi-GPU end-to-end step takes."""
+    from conftest import load_golden
+    for case in ("edge_mix", "small_float"):
+        g = load_golden(case)
+        tao_plan, lvis_plan = plans_from_json(*golden_inputs(g))
+        d_tao, d_lvis = eng.upload(tao_plan), eng.upload(lvis_plan)
+        pack = eng.pack_host([tao_plan, lvis_plan], pinned=True)
+        assert pack.shared == {0: 1}
+        for rnd in range(2):
+            for dv in (d_tao, d_lvis):
+                for k in dv._input_keys:
+                    if k not in ("iou_thrs", "rec_thrs"):
+                        dv.t[k].zero_()
+            n = d_lvis.reload_pack(pack, 1)
+            n += d_tao.reload_pack(pack, 0, pool=d_lvis)
+            assert n > 0
+            o_t, o_l = eng.evaluate_device(d_tao), eng.evaluate_device(d_lvis)
+            assert np.array_equal(g["tao_precision"], o_t.precision.reshape(g["tao_precision"].shape))
+            assert np.array_equal(g["lvis_precision"], o_l.precision)
+            assert np.array_equal(g["lvis_tp_cnt"], o_l.tp_cnt)
+            assert np.array_equal(g["tao_recall"], o_t.recall.reshape(g["tao_recall"].shape))
+
+
 def test_group_tables_as_counts(eng):
     """TA_PLAN_GRP_U16: the device prefix sum over uint16 group sizes reproduces the int64 offsets
     (sizes that cross several scan blocks; empty groups on either side)."""
