@@ -225,6 +225,8 @@ struct ta_pr_state {
     uint32_t after_tk;      // the level after next_tk, loaded one event ahead (breaks the chain
                             // store -> dependent load -> compare of consecutive recall levels)
     int kq;
+    uint32_t nf;            // the next counted detection ABOVE the walk position is a false positive
+                            // (or the walk started there): a true positive met now ends a TP run
 };
 TA_HD uint32_t ta_pr_tk_at(const int32_t* tk, int k) {
     if (k < 0) return 0u;
@@ -234,6 +236,7 @@ TA_HD uint32_t ta_pr_tk_at(const int32_t* tk, int k) {
 TA_HD void ta_pr_state_init(ta_pr_state& s, uint32_t tc, uint32_t fc, const int32_t* tk, int n_rec) {
     s.tc = tc; s.fc = fc;
     s.bt = 0; s.bn = 1;                  // precision 0: the first true positive always beats it
+    s.nf = 1;
     int lo = -1, hi = n_rec;             // invariant: tk'[lo] <= tc < tk'[hi]
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -244,38 +247,75 @@ TA_HD void ta_pr_state_init(ta_pr_state& s, uint32_t tc, uint32_t fc, const int3
     s.next_tk = ta_pr_tk_at(tk, lo);
     s.after_tk = ta_pr_tk_at(tk, lo - 1);
 }
+// A chunk without true positives of the cell: only the false-positive count moves.
+TA_HD void ta_pr_skip_chunk(ta_pr_state& s, uint32_t fc_before) {
+    if (s.fc != fc_before) s.nf = 1;
+    s.fc = fc_before;
+}
+// The walk visits only the true positives that END a run of true positives (the next counted
+// detection after them is a false positive, or the walk's start): with no false positive in
+// between, precision tc / (tc + fc) only grows from one true positive to the next, so the suffix
+// maximum — and, with the strict comparison below, the very pair (bt, bn) a walk over all true
+// positives keeps — is decided at run ends.  Inside a word the run ends are found at once: adding
+// t << 1 to the complement of m = t | f carries every true positive to the next counted
+// detection, so ((~m + (t << 1)) & m) & f are the false positives that follow a true positive.
+// A recall level is answered lazily: before a candidate with fewer true positives than the level
+// needs is merged (it lies before the level's tk-th true positive), and at the chunk's end.
+#define TA_PR_CANDIDATE(c_, n_)                                                              \
+    do {                                                                                     \
+        const uint32_t cc_ = (c_), nn_ = (n_);                                               \
+        if (next_tk > cc_) {                                                                 \
+            const unsigned long long packed = pr_pack(bt, bn, ch_rel);                       \
+            do {                                                                             \
+                q[kq * q_stride] = packed;                                                   \
+                --kq;                                                                        \
+                next_tk = after_tk;                                                          \
+                after_tk = ta_pr_tk_at(tk, kq - 1);                                          \
+            } while (next_tk > cc_);                                                         \
+        }                                                                                    \
+        /* strict ">" is enough: a tie keeps the later detection's pair, and the only       \
+           value-changing tie, (1,1) vs (k,k), has (1,1) as the candidate (first TP overall) */ \
+        if ((unsigned long long)cc_ * bn > (unsigned long long)bt * nn_) { bt = cc_; bn = nn_; } \
+    } while (0)
 TA_HD void ta_pr_walk_chunk(ta_pr_state& s, const uint32_t* w, const int32_t* tk, uint32_t ch_rel,
                             unsigned long long* q, int64_t q_stride) {
     uint32_t tc = s.tc, fc = s.fc, bt = s.bt, bn = s.bn, next_tk = s.next_tk, after_tk = s.after_tk;
+    uint32_t nf = s.nf;
     int kq = s.kq;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int j = TA_PR_WORDS - 1; j >= 0; --j) {
-        uint32_t t = w[j];
+        const uint32_t t = w[j];
         const uint32_t f = w[TA_PR_WORDS + j];
-        while (t) {
-            const int p = 31 - TA_CLZ(t);
-            t ^= 1u << p;
-            // false positives before position p = count at the word's end - those at >= p
-            const uint32_t n = tc + (fc - (uint32_t)TA_POPC(f >> p));
-            // strict ">" is enough: a tie keeps the later detection's pair, and the only
-            // value-changing tie, (1,1) vs (k,k), has (1,1) as the candidate (first TP overall)
-            if ((unsigned long long)tc * bn > (unsigned long long)bt * n) { bt = tc; bn = n; }
-            if (next_tk == tc) {
-                const unsigned long long packed = pr_pack(bt, bn, ch_rel);
-                do {
-                    q[kq * q_stride] = packed;
-                    --kq;
-                    next_tk = after_tk;
-                    after_tk = ta_pr_tk_at(tk, kq - 1);
-                } while (next_tk == tc);
-            }
-            --tc;
+        const uint32_t m = t | f;
+        if (m == 0) continue;
+        // the word's last counted detection is a true positive and what follows it is not
+        if (nf && (t >> (31 - TA_CLZ(m)))) TA_PR_CANDIDATE(tc, tc + fc);
+        uint32_t cand = ((~m + (t << 1)) & m) & f;
+        while (cand) {
+            const int p = 31 - TA_CLZ(cand);
+            cand ^= 1u << p;
+            // counts just below the false positive at p = the run end's own counts
+            const uint32_t c = tc - (uint32_t)TA_POPC(t >> p);
+            TA_PR_CANDIDATE(c, c + (fc - (uint32_t)TA_POPC(f >> p)));
         }
+        tc -= (uint32_t)TA_POPC(t);
         fc -= (uint32_t)TA_POPC(f);
+        nf = (f & (m & (0u - m))) != 0u;
+    }
+    // recall levels whose tk-th true positive lies in this chunk and before its first run end
+    if (next_tk > tc) {
+        const unsigned long long packed = pr_pack(bt, bn, ch_rel);
+        do {
+            q[kq * q_stride] = packed;
+            --kq;
+            next_tk = after_tk;
+            after_tk = ta_pr_tk_at(tk, kq - 1);
+        } while (next_tk > tc);
     }
     s.tc = tc; s.fc = fc; s.bt = bt; s.bn = bn; s.next_tk = next_tk; s.after_tk = after_tk; s.kq = kq;
+    s.nf = nf;
 }
 // One chunk on its own (tests/hostsim; the kernel carries the state over several chunks)
 TA_HD unsigned long long ta_pr_walk_bits(const uint32_t* T, const uint32_t* F, int64_t stride,

@@ -511,7 +511,7 @@ k_pr_envelope_bits(PrArgs a, int seg) {
         unsigned long long* best_out = a.chunk_best + pr_best_idx(a, c, cell);
         const uint32_t* cnt = a.chunk_cnt + ((int64_t)c * n_cfg + cfg) * 32;
         if (s.tc == cnt[b]) {                        // no TP of this cell in the chunk
-            s.fc = cnt[16 + b];
+            ta_pr_skip_chunk(s, cnt[16 + b]);
         } else {
             const uint4* pl = reinterpret_cast<const uint4*>(a.bits + ((int64_t)cell * a.n_chunks_ub + c) * 16);
             uint32_t w[16];

@@ -240,26 +240,48 @@ static int pr_bits_impl(int32_t n_cat, const int64_t* cat_dt_off, const int32_t*
                 tk[((size_t)cat * n_cfg + cfg) * n_rec + k] = ngt ? (int32_t)ta_min_tp_for_recall(rec_thrs[k], ngt) : 0x7fffffff;
             }
     }
-    // k_pr_envelope_bits
-    for (int chunk = 0; chunk < n_chunks; ++chunk)
+    // k_pr_envelope_bits: one walker per (run of `seg` consecutive chunks, cell), last chunk first,
+    // the state carried from chunk to chunk inside a category (mode 3: seg = 4, as the kernel
+    // does on large inputs)
+    const int seg = mode == 3 ? 4 : 1;
+    for (int c_lo = 0; c_lo < n_chunks; c_lo += seg)
         for (int cell = 0; cell < n_cells; ++cell) {
-            const int cfg = cell / n_thr, b = cell % n_thr, cat = chunk_cat[chunk];
-            if (num_gt[(int64_t)cat * n_cfg + cfg] == 0) continue;
-            const int ch0 = chunk_start[cat], ch1 = chunk_start[cat + 1];
-            const uint32_t* nxt = (chunk + 1 < ch1) ? &chunk_cnt[((size_t)(chunk + 1) * n_cfg + cfg) * 32]
-                                                    : &cat_tot[((size_t)cat * n_cfg + cfg) * 32];
-            const uint32_t tc = nxt[b], fc = nxt[16 + b];
-            const uint32_t t_begin = chunk_cnt[((size_t)chunk * n_cfg + cfg) * 32 + b];
-            unsigned long long* best_out = &chunk_best[(size_t)chunk * n_cells + cell];
-            if (tc == t_begin) { *best_out = 0ull; continue; }
-            const uint32_t* planes = bits.data() + (size_t)chunk * 2 * TA_PR_WORDS * n_cells + cell;
-            const int64_t cc = (int64_t)cat * n_cfg + cfg;
-            // rows: cell-major answers (k_pr_envelope_bits with a.ans), else the precision layout
-            unsigned long long* q = rows ? prec_bits.data() + ((int64_t)b * per_t + cc) * n_rec
-                                         : prec_bits.data() + (int64_t)b * n_rec * per_t + cc;
-            *best_out = ta_pr_walk_bits(planes, planes + (size_t)TA_PR_WORDS * n_cells, n_cells, tc, fc,
-                                        &tk[((size_t)cat * n_cfg + cfg) * n_rec], n_rec, (uint32_t)(chunk - ch0),
-                                        q, rows ? 1 : per_t);
+            const int cfg = cell / n_thr, b = cell % n_thr;
+            const int c_hi = std::min(c_lo + seg, n_chunks) - 1;
+            int cat = -1, ch0 = 0;
+            bool live = false;
+            ta_pr_state st;
+            const int32_t* tkp = nullptr;
+            unsigned long long* q = nullptr;
+            for (int c = c_hi; c >= c_lo; --c) {
+                if (chunk_cat[c] != cat) {
+                    cat = chunk_cat[c];
+                    const int64_t cc = (int64_t)cat * n_cfg + cfg;
+                    live = num_gt[cc] != 0;
+                    if (live) {
+                        ch0 = chunk_start[cat];
+                        const int ch1 = chunk_start[cat + 1];
+                        const uint32_t* nxt = (c + 1 < ch1) ? &chunk_cnt[((size_t)(c + 1) * n_cfg + cfg) * 32]
+                                                            : &cat_tot[((size_t)cat * n_cfg + cfg) * 32];
+                        tkp = &tk[((size_t)cat * n_cfg + cfg) * n_rec];
+                        // rows: cell-major answers (k_pr_envelope_bits with a.ans), else the precision layout
+                        q = rows ? prec_bits.data() + ((int64_t)b * per_t + cc) * n_rec
+                                 : prec_bits.data() + (int64_t)b * n_rec * per_t + cc;
+                        ta_pr_state_init(st, nxt[b], nxt[16 + b], tkp, n_rec);
+                    }
+                }
+                if (!live) continue;
+                const uint32_t* cnt = &chunk_cnt[((size_t)c * n_cfg + cfg) * 32];
+                if (st.tc == cnt[b]) {
+                    ta_pr_skip_chunk(st, cnt[16 + b]);
+                } else {
+                    const uint32_t* planes = bits.data() + (size_t)c * 2 * TA_PR_WORDS * n_cells + cell;
+                    uint32_t w[2 * TA_PR_WORDS];
+                    for (int j = 0; j < 2 * TA_PR_WORDS; ++j) w[j] = planes[(size_t)j * n_cells];
+                    ta_pr_walk_chunk(st, w, tkp, (uint32_t)(c - ch0), q, rows ? 1 : per_t);
+                }
+                chunk_best[(size_t)c * n_cells + cell] = st.bt ? pr_pack(st.bt, st.bn, 0) : 0ull;
+            }
         }
     // k_pr_suffix
     for (int cat = 0; cat < n_cat; ++cat)
@@ -307,6 +329,14 @@ int hs_pr_accumulate_bits_tile(int32_t n_cat, const int64_t* cat_dt_off, const i
                                int64_t* tp_cnt, int64_t* fp_cnt) {
     return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
                         precision, recall, tp_cnt, fp_cnt, 2);
+}
+
+int hs_pr_accumulate_bits_seg(int32_t n_cat, const int64_t* cat_dt_off, const int32_t* acc_perm, int64_t n_dt,
+                              const uint32_t* dt_tpfp, const int32_t* num_gt, int32_t n_thr, int32_t n_cfg,
+                              int32_t n_rec, const double* rec_thrs, double* precision, double* recall,
+                              int64_t* tp_cnt, int64_t* fp_cnt) {
+    return pr_bits_impl(n_cat, cat_dt_off, acc_perm, n_dt, dt_tpfp, num_gt, n_thr, n_cfg, n_rec, rec_thrs,
+                        precision, recall, tp_cnt, fp_cnt, 3);
 }
 
 void hs_transpose32(const uint32_t* in, uint32_t* out) {

@@ -95,7 +95,8 @@ def hostsim_pr(n_cat, cat_dt_off, acc_perm, tpfp, num_gt, n_cfg, iou_thrs=engine
         tp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64),
         fp_cnt=np.empty((n_thr, n_cat, n_cfg), dtype=np.int64), num_gt=num_gt, dt_tpfp=tpfp)
     fn = {"serial": hs.hs_pr_accumulate, "bits": hs.hs_pr_accumulate_bits,
-          "bits_tile": hs.hs_pr_accumulate_bits_tile}[impl]
+          "bits_tile": hs.hs_pr_accumulate_bits_tile,
+          "bits_seg": hs.hs_pr_accumulate_bits_seg}[impl]
     fn.argtypes = [I32, P, P, I64, P, P, I32, I32, I32, P, P, P, P, P]
     fn(n_cat, _p(np.asarray(cat_dt_off, dtype=np.int64)),
        _p(np.asarray(acc_perm, dtype=np.int32)), n_dt, _p(tpfp),

@@ -15,7 +15,7 @@ def _same(a, b):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
 
 
-@pytest.mark.parametrize("impl", ["bits", "bits_tile"])
+@pytest.mark.parametrize("impl", ["bits", "bits_tile", "bits_seg"])
 @pytest.mark.parametrize("seed", range(8))
 def test_random_multi_chunk(seed, impl):
     c = random_pr_case(seed)
@@ -30,6 +30,19 @@ def test_all_or_no_true_positives(tp_rate):
     _same(hostsim_pr(*args, impl="bits"), hostsim_pr(*args, impl="serial"))
 
 
+@pytest.mark.parametrize("tp_rate", [0.02, 0.3, 0.9, 0.995])
+@pytest.mark.parametrize("seed", range(4))
+def test_true_positive_runs_of_every_length(seed, tp_rate):
+    """The walk only visits the true positives that end a run: long categories (many chunks, so
+    that the state is carried over several of them), from almost no to almost only true positives,
+    with ignored detections (neither TP nor FP) in between."""
+    c = random_pr_case(200 + seed, n_cat=3, n_cfg=3, tp_rate=tp_rate, max_len=2600)
+    args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
+    want = hostsim_pr(*args, impl="serial")
+    for impl in ("bits", "bits_tile", "bits_seg"):
+        _same(hostsim_pr(*args, impl=impl), want)
+
+
 def test_track_shape_and_odd_thresholds():
     c = random_pr_case(5, n_cat=5, n_cfg=20, n_thr=10, max_len=700)
     args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
@@ -37,7 +50,7 @@ def test_track_shape_and_odd_thresholds():
     c = random_pr_case(6, n_cat=5, n_cfg=2, n_thr=3, max_len=900)
     args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
     thr, rec = engine.IOU_THRS[:3], np.array([0.0, 0.25, 0.5, 0.5, 0.99, 1.0])
-    for impl in ("bits", "bits_tile"):
+    for impl in ("bits", "bits_tile", "bits_seg"):
         _same(hostsim_pr(*args, iou_thrs=thr, rec_thrs=rec, impl=impl),
               hostsim_pr(*args, iou_thrs=thr, rec_thrs=rec, impl="serial"))
 
@@ -61,7 +74,7 @@ def test_goldens_through_the_bit_plane_emulation(golden):
     gt, res = golden_inputs(golden)
     tao_plan, lvis_plan = plans_from_json(gt, res)
     off_grid = golden["_name"] == "small_float"
-    for impl in ("bits", "bits_tile"):
+    for impl in ("bits", "bits_tile", "bits_seg"):
         compare_with_golden(golden, "tao_", tao_plan, run_hostsim(tao_plan, pr_impl=impl),
                             exact_iou=not off_grid, iou_atol=1e-12)
         compare_with_golden(golden, "lvis_", lvis_plan, run_hostsim(lvis_plan, pr_impl=impl))
