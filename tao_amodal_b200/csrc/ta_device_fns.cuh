@@ -124,13 +124,15 @@ TA_HD int ta_match_one(const double* iou_row, int G, const uint8_t* gt_ig,
 // Smallest TP count t in [0, ngt] with t / ngt >= r (fp64 division as in eval.py:543,561);
 // ngt + 1 when no count reaches r.
 TA_HD int64_t ta_min_tp_for_recall(double r, int32_t ngt) {
+    // 32-bit counts (ngt + 1 <= 2^31 fits): one-instruction int -> double conversions on the GPU
+    const uint32_t top = (uint32_t)ngt + 1u;
     const double n = (double)ngt;
-    double g = r * n;
-    int64_t t = (g <= 0.0) ? 0 : ((g >= n + 1.0) ? (int64_t)ngt + 1 : (int64_t)g);
-    if (t > (int64_t)ngt + 1) t = (int64_t)ngt + 1;
-    while (t > 0 && ((double)(t - 1) / n) >= r) --t;
-    while (t <= (int64_t)ngt && ((double)t / n) < r) ++t;
-    return t;
+    const double g = r * n;
+    uint32_t t = (g <= 0.0) ? 0u : ((g >= n + 1.0) ? top : (uint32_t)g);
+    if (t > top) t = top;
+    while (t > 0u && ((double)(t - 1u) / n) >= r) --t;
+    while (t < top && ((double)t / n) < r) ++t;
+    return (int64_t)t;
 }
 
 // eval.py:550: tp / (fp + tp + np.spacing(1))

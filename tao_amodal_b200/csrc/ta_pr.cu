@@ -585,7 +585,7 @@ k_pr_scan_live(PrArgs a) {
 // is independent.  Same values as k_pr_finalize.
 #define PR_FT_CELLS 256
 #define PR_FT_K 16
-__global__ void __launch_bounds__(PR_FT_CELLS)
+__global__ void __launch_bounds__(PR_FT_CELLS, 3)
 k_pr_finalize_tile(PrArgs a) {
     __shared__ __align__(16) double tile_s[PR_FT_K][PR_FT_CELLS];
     const uint32_t per_t = (uint32_t)a.n_cat * (uint32_t)a.n_cfg;
@@ -622,7 +622,8 @@ k_pr_finalize_tile(PrArgs a) {
                     pr_unpack(q[k], qt, qn, ch);
                     pr_unpack(best[(int64_t)ch * best_stride], bt, bn, dummy);
                     if (pr_better(bt, bn, qt, qn)) { qt = bt; qn = bn; }
-                    v = ta_precision_at((int64_t)qt, (int64_t)(qn - qt));
+                    // ta_precision_at(qt, qn - qt): fp + tp = qn exactly (counts below 2^24)
+                    v = __uint2double_rn(qt) / (__uint2double_rn(qn) + 2.220446049250313e-16);
                 }
                 tile_s[k][threadIdx.x] = v;
             }
