@@ -335,6 +335,37 @@ int ta_exchange_create(ta_ctx* ctx, int32_t rank, int32_t world, const void* id,
 int ta_exchange_destroy(ta_exchange* x);
 int ta_exchange_rank(const ta_exchange* x);
 int ta_exchange_world(const ta_exchange* x);
+
+/* ---- peer windows: the exchange with the library's own kernel over NVLink peer memory --------
+ * A window is a device buffer of this rank that every other rank has mapped (CUDA IPC; one
+ * process per GPU on one NVLink / NVSwitch node).  Per evaluation and plan:
+ *     ta_peer_window_acquire    (stream) wait until every peer has read the previous contents
+ *     ta_peer_window_put ...    (stream) records -> window: TP/FP words or rows in local detection
+ *                               order (an owner's share is one contiguous slice), GT counts
+ *     ta_peer_window_exchange   (stream) ONE kernel: publish the window, wait for each peer's
+ *                               flag, pull this owner's slices from the peers' windows with 16-byte
+ *                               loads, sum the GT counts over all ranks, release the peers
+ * followed by ta_pr_accumulate on what was pulled — the same data movement as
+ * ta_exchange_alltoallv + ta_exchange_allreduce_sum, without an NCCL launch on the step path.
+ * What to pull is fixed per plan (ta_peer_window_set_plan): copies {peer, byte offset in that
+ * peer's window, bytes, local destination} (offsets / sizes multiples of 4) and sums {byte offset,
+ * count, local int32 destination}: dst[i] = sum over all ranks of the int32 at off + 4 i of the
+ * rank's window.  create / destroy / set_plan are collective or synchronising calls outside
+ * the step; NCCL (the communicator of `x`) only carries the IPC handles at creation.
+ * A peer that never arrives makes the waits give up after a few seconds instead of hanging
+ * the GPU; ta_peer_window_check reports that.                                             */
+typedef struct ta_peer_window ta_peer_window;
+typedef struct ta_peer_copy { int32_t peer, reserved_; int64_t src_off, bytes; void* dst; } ta_peer_copy;
+typedef struct ta_peer_sum { int64_t off, count; int32_t* dst; } ta_peer_sum;
+int   ta_peer_window_create(ta_exchange* x, int64_t bytes, ta_peer_window** out);
+int   ta_peer_window_destroy(ta_peer_window* w);
+void* ta_peer_window_ptr(ta_peer_window* w);
+int   ta_peer_window_set_plan(ta_peer_window* w, int32_t n_copy, const ta_peer_copy* copies,
+                              int32_t n_sum, const ta_peer_sum* sums);
+int   ta_peer_window_acquire(ta_peer_window* w, void* stream);
+int   ta_peer_window_put(ta_peer_window* w, void* stream, int64_t off, const void* src, int64_t bytes);
+int   ta_peer_window_exchange(ta_peer_window* w, void* stream);
+int   ta_peer_window_check(ta_peer_window* w, void* stream, int32_t* timed_out);
 int ta_exchange_gather(ta_ctx* ctx, void* stream, int64_t n, int32_t words, const int32_t* index,
                        const uint32_t* src, uint32_t* out);
 int ta_exchange_scatter(ta_ctx* ctx, void* stream, int64_t n, int32_t words, const int32_t* index,

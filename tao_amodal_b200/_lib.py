@@ -29,6 +29,8 @@ EXPORTS = [
     "ta_abi_version", "ta_last_error", "ta_ctx_create", "ta_ctx_destroy", "ta_ctx_sm_count",
     "ta_ctx_launch_count", "ta_track_iou", "ta_box_iou", "ta_match_greedy", "ta_frame_eval",
     "ta_ctx_timing", "ta_ctx_timing_read", "ta_frame_eval_max_gt", "ta_frame_eval_max_dt", "ta_frame_eval_max_pairs", "ta_pr_accumulate", "ta_eval_plan_host", "ta_eval_plans_host", "ta_host_alloc", "ta_host_free", "ta_widen_u16", "ta_offsets_from_counts", "ta_gather_boxes",
+    "ta_peer_window_create", "ta_peer_window_destroy", "ta_peer_window_ptr", "ta_peer_window_set_plan",
+    "ta_peer_window_acquire", "ta_peer_window_put", "ta_peer_window_exchange", "ta_peer_window_check",
     "ta_rle_iou", "ta_frame_sched_bytes", "ta_frame_sched_build",
     "ta_exchange_unique_id", "ta_exchange_create", "ta_exchange_destroy", "ta_exchange_rank",
     "ta_exchange_world", "ta_exchange_gather", "ta_exchange_scatter", "ta_exchange_alltoallv",
@@ -62,6 +64,17 @@ class PlanHost(C.Structure):
             "gt_hp", "iou_thrs", "rec_thrs", "cfgs", "dt_box_idx")]
         + [("dt_box_pool", C.c_int32), ("reserved_", C.c_int32)]
     )
+
+
+class PeerCopy(C.Structure):
+    """struct ta_peer_copy."""
+    _fields_ = [("peer", C.c_int32), ("reserved_", C.c_int32), ("src_off", C.c_int64),
+                ("bytes", C.c_int64), ("dst", C.c_void_p)]
+
+
+class PeerSum(C.Structure):
+    """struct ta_peer_sum."""
+    _fields_ = [("off", C.c_int64), ("count", C.c_int64), ("dst", C.c_void_p)]
 
 
 class HostOut(C.Structure):
@@ -135,6 +148,15 @@ def load() -> C.CDLL:
     lib.ta_widen_u16.argtypes = [P, P, I64, P, P]
     lib.ta_offsets_from_counts.argtypes = [P, P, I64, P, P]
     lib.ta_gather_boxes.argtypes = [P, P, I64, P, P, P]
+    lib.ta_peer_window_create.argtypes = [P, I64, P]
+    lib.ta_peer_window_destroy.argtypes = [P]
+    lib.ta_peer_window_ptr.argtypes = [P]
+    lib.ta_peer_window_ptr.restype = C.c_void_p
+    lib.ta_peer_window_set_plan.argtypes = [P, I32, P, I32, P]
+    lib.ta_peer_window_acquire.argtypes = [P, P]
+    lib.ta_peer_window_put.argtypes = [P, P, I64, P, I64]
+    lib.ta_peer_window_exchange.argtypes = [P, P]
+    lib.ta_peer_window_check.argtypes = [P, P, C.POINTER(I32)]
     lib.ta_host_alloc.argtypes = [C.c_size_t]
     lib.ta_host_alloc.restype = C.c_void_p
     lib.ta_host_free.argtypes = [P]
@@ -142,7 +164,7 @@ def load() -> C.CDLL:
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("ta_last_error", "ta_ctx_launch_count", "ta_frame_sched_bytes",
-                        "ta_host_alloc", "ta_host_free"):
+                        "ta_host_alloc", "ta_host_free", "ta_peer_window_ptr"):
             fn.restype = C.c_int
     _lib = lib
     return lib

@@ -33,6 +33,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi g_nccl;
@@ -54,6 +55,7 @@ int nccl_load() {
     TA_SYM(Send, "ncclSend");
     TA_SYM(Recv, "ncclRecv");
     TA_SYM(AllReduce, "ncclAllReduce");
+    TA_SYM(AllGather, "ncclAllGather");
     TA_SYM(GetErrorString, "ncclGetErrorString");
 #undef TA_SYM
     g_nccl.handle = h;
@@ -223,3 +225,307 @@ extern "C" int ta_exchange_allreduce_sum(ta_exchange* x, void* stream, void* buf
 
 extern "C" int ta_exchange_rank(const ta_exchange* x) { return x ? x->rank : -1; }
 extern "C" int ta_exchange_world(const ta_exchange* x) { return x ? x->world : 0; }
+
+// ---- peer windows: the same exchange with this library's own kernels over NVLink ----------------
+// A window is one cudaMalloc'ed buffer per rank whose CUDA IPC handle every other rank has opened
+// (one process per GPU; NVLink / NVSwitch peer access).  An exchange is then
+//     acquire    wait until every peer has finished reading the window's previous contents
+//     (caller)   write the records into the window (ta_peer_window_put, or kernels writing there)
+//     exchange   ONE kernel: publish the window (epoch flag), wait for each peer's flag, pull this
+//                owner's slices out of the peers' windows with 16-byte loads over NVLink, sum the
+//                GT counts of all ranks, and tell the peers the window has been read
+// i.e. no NCCL launch, no proxy thread and no send-side packing on the step path: the transfer is
+// the owner's loads.  Flags live in the first TA_PW_HDR bytes of the window: [0] ready epoch
+// (written by the owner of the window), [16 + r] the epoch rank r has finished pulling.
+#define TA_PW_HDR 1024
+#define TA_PW_SPIN_LIMIT (1ll << 33)     // clock ticks (a few seconds): a dead peer must not hang the GPU
+
+struct ta_peer_window {
+    ta_exchange* x;
+    int64_t bytes;
+    char* base;                      // this rank's window
+    char* peer[64];                  // every rank's window as mapped here (peer[rank] == base)
+    int64_t peer_bytes[64];          // and its size
+    uint32_t epoch;
+    int n_copy, n_sum;
+    ta_peer_copy* d_copy;
+    ta_peer_sum* d_sum;
+    unsigned int* d_counter;         // blocks that finished pulling (reset by the last one)
+    int* d_err;                      // spin limit hit
+    char** d_peer;
+};
+
+__device__ __forceinline__ uint32_t pw_load_flag(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void pw_store_flag(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool pw_wait(const uint32_t* p, uint32_t epoch, int* err) {
+    const long long t0 = clock64();
+    while ((int32_t)(pw_load_flag(p) - epoch) < 0) {
+        if (clock64() - t0 > TA_PW_SPIN_LIMIT) { atomicExch(err, 1); return false; }
+        __nanosleep(200);
+    }
+    return true;
+}
+
+// wait until every peer has pulled epoch `prev` from this rank's window
+__global__ void k_peer_acquire(const uint32_t* __restrict__ hdr, int world, int me, uint32_t prev, int* err) {
+    const int r = threadIdx.x;
+    if (r < world && r != me) pw_wait(hdr + 16 + r, prev, err);
+}
+
+__global__ void __launch_bounds__(256)
+k_peer_exchange(char* const* __restrict__ peer, int world, int me, uint32_t epoch,
+                const ta_peer_copy* __restrict__ copies, int n_copy,
+                const ta_peer_sum* __restrict__ sums, int n_sum,
+                unsigned int* counter, int* err) {
+    __shared__ int ok_s;
+    // publish: everything written into this window earlier on the stream is visible before the flag
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        pw_store_flag(reinterpret_cast<uint32_t*>(peer[me]), epoch);
+    }
+    uint64_t seen = 1ull << me;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    auto need = [&](int p) -> bool {
+        if ((seen >> p) & 1ull) return true;
+        if (threadIdx.x == 0)
+            ok_s = pw_wait(reinterpret_cast<const uint32_t*>(peer[p]), epoch, err) ? 1 : 0;
+        __syncthreads();
+        const bool ok = ok_s != 0;
+        __syncthreads();
+        seen |= 1ull << p;
+        return ok;
+    };
+    // start with a different peer on every rank: the links fill evenly
+    for (int k = 0; k < n_copy; ++k) {
+        const ta_peer_copy c = copies[(k + (n_copy * me) / max(world, 1)) % n_copy];
+        if (c.bytes <= 0) continue;
+        if (!need(c.peer)) continue;
+        const char* src = peer[c.peer] + c.src_off;
+        char* dst = static_cast<char*>(c.dst);
+        const int64_t n_words = c.bytes >> 2;
+        // head: words before the first 16-byte boundary of the SOURCE
+        const int64_t head = min(n_words, (int64_t)((16 - ((uintptr_t)src & 15)) & 15) >> 2);
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+        if (tid < head) d32[tid] = __ldcv(s32 + tid);
+        const int64_t n_vec = (n_words - head) >> 2;
+        const uint4* s128 = reinterpret_cast<const uint4*>(s32 + head);
+        uint32_t* dv = d32 + head;
+        const bool dst_al = (((uintptr_t)dv) & 15) == 0;
+        int64_t i = tid;
+        for (; i + 3 * nthreads < n_vec; i += 4 * nthreads) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldcv(s128 + i + u * nthreads);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                uint32_t* o = dv + 4 * (i + u * nthreads);
+                if (dst_al) *reinterpret_cast<uint4*>(o) = v[u];
+                else { o[0] = v[u].x; o[1] = v[u].y; o[2] = v[u].z; o[3] = v[u].w; }
+            }
+        }
+        for (; i < n_vec; i += nthreads) {
+            const uint4 v = __ldcv(s128 + i);
+            uint32_t* o = dv + 4 * i;
+            if (dst_al) *reinterpret_cast<uint4*>(o) = v;
+            else { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+        }
+        const int64_t done = head + 4 * n_vec;
+        if (tid < n_words - done) d32[done + tid] = __ldcv(s32 + done + tid);
+    }
+    // sums over all ranks (GT counts): every rank computes the same totals
+    for (int k = 0; k < n_sum; ++k) {
+        const ta_peer_sum q = sums[k];
+        bool ok = true;
+        for (int p = 0; p < world; ++p) ok = need(p) && ok;
+        if (!ok) continue;
+        for (int64_t i = tid; i < q.count; i += nthreads) {
+            int32_t acc = 0;
+            for (int p = 0; p < world; ++p)
+                acc += (int32_t)__ldcv(reinterpret_cast<const uint32_t*>(peer[p] + q.off) + i);
+            q.dst[i] = acc;
+        }
+    }
+    // the last block to finish tells every peer that this rank has read its window
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) {
+            *counter = 0;
+            __threadfence_system();
+            for (int p = 0; p < world; ++p)
+                if (p != me) pw_store_flag(reinterpret_cast<uint32_t*>(peer[p]) + 16 + me, epoch);
+        }
+    }
+}
+
+extern "C" int ta_peer_window_create(ta_exchange* x, int64_t bytes, ta_peer_window** out) {
+    if (!x || !out || bytes < 0) return ta_set_err(TA_ERR_INVALID, "ta_peer_window_create: bad arguments");
+    if (x->world > 64) return ta_set_err(TA_ERR_TOO_LARGE, "ta_peer_window_create: more than 64 ranks");
+    TA_CUDA(cudaSetDevice(x->ctx->device));
+    ta_peer_window* w = new ta_peer_window();
+    memset(w, 0, sizeof(*w));
+    w->x = x;
+    w->bytes = TA_PW_HDR + ((bytes + 255) & ~(int64_t)255);
+    TA_CUDA(cudaMalloc(&w->base, (size_t)w->bytes));
+    TA_CUDA(cudaMemset(w->base, 0, (size_t)w->bytes));
+    TA_CUDA(cudaMalloc(&w->d_counter, 2 * sizeof(int)));
+    TA_CUDA(cudaMemset(w->d_counter, 0, 2 * sizeof(int)));
+    w->d_err = reinterpret_cast<int*>(w->d_counter) + 1;
+    TA_CUDA(cudaDeviceSynchronize());
+    w->peer[x->rank] = w->base;
+    w->peer_bytes[x->rank] = w->bytes;
+    if (x->world > 1) {
+        // every rank's IPC handle and window size through the communicator that already exists
+        struct Card { cudaIpcMemHandle_t h; int64_t bytes; };
+        Card mine;
+        TA_CUDA(cudaIpcGetMemHandle(&mine.h, w->base));
+        mine.bytes = w->bytes;
+        char* d_all = nullptr;
+        const size_t hb = sizeof(Card);
+        TA_CUDA(cudaMalloc(&d_all, hb * (size_t)x->world));
+        TA_CUDA(cudaMemcpy(d_all + hb * (size_t)x->rank, &mine, hb, cudaMemcpyHostToDevice));
+        cudaStream_t st = x->ctx->own_stream;
+        TA_NCCL(g_nccl.AllGather(d_all + hb * (size_t)x->rank, d_all, hb, ncclInt8, x->comm, st));
+        TA_CUDA(cudaStreamSynchronize(st));
+        Card* all = new Card[x->world];
+        TA_CUDA(cudaMemcpy(all, d_all, hb * (size_t)x->world, cudaMemcpyDeviceToHost));
+        cudaFree(d_all);
+        for (int p = 0; p < x->world; ++p) {
+            if (p == x->rank) continue;
+            void* q = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&q, all[p].h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                delete[] all;
+                return ta_set_err(TA_ERR_CUDA, "ta_peer_window_create: cannot map a peer's window (%s)",
+                                  cudaGetErrorString(e));
+            }
+            w->peer[p] = static_cast<char*>(q);
+            w->peer_bytes[p] = all[p].bytes;
+        }
+        delete[] all;
+    }
+    TA_CUDA(cudaMalloc(&w->d_peer, sizeof(char*) * 64));
+    TA_CUDA(cudaMemcpy(w->d_peer, w->peer, sizeof(char*) * 64, cudaMemcpyHostToDevice));
+    w->epoch = 0;
+    *out = w;
+    return TA_OK;
+}
+
+extern "C" void* ta_peer_window_ptr(ta_peer_window* w) { return w ? w->base + TA_PW_HDR : nullptr; }
+
+extern "C" int ta_peer_window_destroy(ta_peer_window* w) {
+    if (!w) return TA_OK;
+    cudaSetDevice(w->x->ctx->device);
+    cudaDeviceSynchronize();
+    for (int p = 0; p < w->x->world; ++p)
+        if (p != w->x->rank && w->peer[p]) cudaIpcCloseMemHandle(w->peer[p]);
+    if (w->d_copy) cudaFree(w->d_copy);
+    if (w->d_sum) cudaFree(w->d_sum);
+    if (w->d_peer) cudaFree(w->d_peer);
+    if (w->d_counter) cudaFree(w->d_counter);
+    if (w->base) cudaFree(w->base);
+    delete w;
+    return TA_OK;
+}
+
+extern "C" int ta_peer_window_set_plan(ta_peer_window* w, int32_t n_copy, const ta_peer_copy* copies,
+                                       int32_t n_sum, const ta_peer_sum* sums) {
+    if (!w || n_copy < 0 || n_sum < 0 || (n_copy && !copies) || (n_sum && !sums))
+        return ta_set_err(TA_ERR_INVALID, "ta_peer_window_set_plan: bad arguments");
+    TA_CUDA(cudaSetDevice(w->x->ctx->device));
+    const int64_t room = w->bytes - TA_PW_HDR;
+    ta_peer_copy* hc = n_copy ? new ta_peer_copy[n_copy] : nullptr;
+    for (int i = 0; i < n_copy; ++i) {
+        hc[i] = copies[i];
+        const ta_peer_copy& c = hc[i];
+        if (c.peer < 0 || c.peer >= w->x->world || c.src_off < 0 || c.bytes < 0 || (c.src_off & 3) ||
+            (c.bytes & 3) || c.src_off + c.bytes > w->peer_bytes[c.peer] - TA_PW_HDR ||
+            (c.bytes && (!c.dst || ((uintptr_t)c.dst & 3)))) {
+            delete[] hc;
+            return ta_set_err(TA_ERR_INVALID, "ta_peer_window_set_plan: copy %s%lld is out of the window or misaligned", "", i);
+        }
+        hc[i].src_off += TA_PW_HDR;
+    }
+    ta_peer_sum* hs = n_sum ? new ta_peer_sum[n_sum] : nullptr;
+    for (int i = 0; i < n_sum; ++i) {
+        hs[i] = sums[i];
+        if (hs[i].off < 0 || (hs[i].off & 3) || hs[i].count < 0 || hs[i].off + 4 * hs[i].count > room ||
+            (hs[i].count && !hs[i].dst)) {
+            delete[] hc;
+            delete[] hs;
+            return ta_set_err(TA_ERR_INVALID, "ta_peer_window_set_plan: sum %s%lld is out of the window", "", i);
+        }
+        hs[i].off += TA_PW_HDR;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (w->d_copy) cudaFree(w->d_copy);
+    if (w->d_sum) cudaFree(w->d_sum);
+    w->d_copy = nullptr;
+    w->d_sum = nullptr;
+    if (e == cudaSuccess && n_copy) e = cudaMalloc(&w->d_copy, sizeof(ta_peer_copy) * n_copy);
+    if (e == cudaSuccess && n_copy) e = cudaMemcpy(w->d_copy, hc, sizeof(ta_peer_copy) * n_copy, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_sum) e = cudaMalloc(&w->d_sum, sizeof(ta_peer_sum) * n_sum);
+    if (e == cudaSuccess && n_sum) e = cudaMemcpy(w->d_sum, hs, sizeof(ta_peer_sum) * n_sum, cudaMemcpyHostToDevice);
+    delete[] hc;
+    delete[] hs;
+    TA_CUDA(e);
+    w->n_copy = n_copy;
+    w->n_sum = n_sum;
+    return TA_OK;
+}
+
+extern "C" int ta_peer_window_acquire(ta_peer_window* w, void* stream) {
+    if (!w) return ta_set_err(TA_ERR_INVALID, "ta_peer_window_acquire: NULL argument");
+    ta_ctx* ctx = w->x->ctx;
+    TA_CUDA(cudaSetDevice(ctx->device));
+    if (w->x->world == 1 || w->epoch == 0) return TA_OK;
+    ta_begin(ctx, (cudaStream_t)stream);
+    k_peer_acquire<<<1, 64, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(w->base), w->x->world,
+                                                      w->x->rank, w->epoch, w->d_err);
+    return ta_check_launch(ctx, "k_peer_acquire");
+}
+
+extern "C" int ta_peer_window_put(ta_peer_window* w, void* stream, int64_t off, const void* src, int64_t bytes) {
+    if (!w || off < 0 || bytes < 0 || off + bytes > w->bytes - TA_PW_HDR || (bytes && !src))
+        return ta_set_err(TA_ERR_INVALID, "ta_peer_window_put: out of the window");
+    TA_CUDA(cudaSetDevice(w->x->ctx->device));
+    if (bytes)
+        TA_CUDA(cudaMemcpyAsync(w->base + TA_PW_HDR + off, src, (size_t)bytes, cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)stream));
+    return TA_OK;
+}
+
+extern "C" int ta_peer_window_exchange(ta_peer_window* w, void* stream) {
+    if (!w) return ta_set_err(TA_ERR_INVALID, "ta_peer_window_exchange: NULL argument");
+    ta_ctx* ctx = w->x->ctx;
+    TA_CUDA(cudaSetDevice(ctx->device));
+    ta_begin(ctx, (cudaStream_t)stream);
+    w->epoch += 1;
+    // every block must be resident (blocks wait for remote flags): two per SM
+    const int blocks = ctx->sm_count * 2;
+    k_peer_exchange<<<blocks, 256, 0, (cudaStream_t)stream>>>(w->d_peer, w->x->world, w->x->rank, w->epoch,
+                                                            w->d_copy, w->n_copy, w->d_sum, w->n_sum,
+                                                            w->d_counter, w->d_err);
+    return ta_check_launch(ctx, "k_peer_exchange");
+}
+
+// 1 when a wait on a peer's flag ran into the spin limit since the last call (a peer died or never
+// entered the exchange: the received data is then incomplete); waits for `stream`.
+extern "C" int ta_peer_window_check(ta_peer_window* w, void* stream, int32_t* timed_out) {
+    if (!w || !timed_out) return ta_set_err(TA_ERR_INVALID, "ta_peer_window_check: NULL argument");
+    TA_CUDA(cudaSetDevice(w->x->ctx->device));
+    int v = 0;
+    TA_CUDA(cudaMemcpyAsync(&v, w->d_err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    TA_CUDA(cudaMemsetAsync(w->d_err, 0, sizeof(int), (cudaStream_t)stream));
+    TA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *timed_out = v;
+    return TA_OK;
+}

@@ -170,6 +170,19 @@ class AbiTransport:
                                                       t.numel(), self._DT[str(t.dtype)]))
         return t
 
+    def peer_window(self, n_bytes: int):
+        """A PeerWindow of n_bytes on every rank (collective), or None when peer access is not
+        available / switched off (TA_XCHG=nccl): the caller then exchanges through NCCL."""
+        import os
+        if os.environ.get("TA_XCHG", "peer") == "nccl":
+            return None
+        try:
+            return PeerWindow(self, n_bytes)
+        except Exception as e:       # noqa: BLE001 - e.g. no peer access between two devices
+            import sys
+            sys.stderr.write("peer windows unavailable (%s): exchanging through NCCL\n" % e)
+            return None
+
     def begin(self):
         from . import _lib
         _lib.check(self.lib.ta_exchange_group_begin(self._h))
@@ -177,6 +190,56 @@ class AbiTransport:
     def end(self):
         from . import _lib
         _lib.check(self.lib.ta_exchange_group_end(self._h))
+
+
+class PeerWindow:
+    """ta_peer_window: a device buffer of this rank that all ranks have mapped (CUDA IPC), and the
+    kernel that pulls an owner's slices out of the peers' windows over NVLink."""
+
+    def __init__(self, tr: AbiTransport, n_bytes: int):
+        from . import _lib
+        self.tr, self.lib = tr, tr.lib
+        h = C.c_void_p()
+        _lib.check(self.lib.ta_peer_window_create(tr._h, int(n_bytes), C.byref(h)))
+        self._h = h
+        self.base = int(self.lib.ta_peer_window_ptr(h))
+        self.n_bytes = int(n_bytes)
+
+    def set_plan(self, copies, sums):
+        """copies: (peer, byte offset in the peer's window, bytes, local device pointer);
+        sums: (byte offset, count, local int32 device pointer)."""
+        from . import _lib
+        cs = (_lib.PeerCopy * max(len(copies), 1))()
+        for i, (peer, off, nb, dst) in enumerate(copies):
+            cs[i].peer, cs[i].src_off, cs[i].bytes, cs[i].dst = int(peer), int(off), int(nb), int(dst)
+        ss = (_lib.PeerSum * max(len(sums), 1))()
+        for i, (off, cnt, dst) in enumerate(sums):
+            ss[i].off, ss[i].count, ss[i].dst = int(off), int(cnt), int(dst)
+        _lib.check(self.lib.ta_peer_window_set_plan(self._h, len(copies), cs, len(sums), ss))
+
+    def acquire(self):
+        from . import _lib
+        _lib.check(self.lib.ta_peer_window_acquire(self._h, self.tr._stream()))
+
+    def put(self, off: int, t, n_bytes: int):
+        from . import _lib
+        _lib.check(self.lib.ta_peer_window_put(self._h, self.tr._stream(), int(off),
+                                               C.c_void_p(t.data_ptr()), int(n_bytes)))
+
+    def exchange(self):
+        from . import _lib
+        _lib.check(self.lib.ta_peer_window_exchange(self._h, self.tr._stream()))
+
+    def timed_out(self) -> bool:
+        from . import _lib
+        v = C.c_int32(0)
+        _lib.check(self.lib.ta_peer_window_check(self._h, self.tr._stream(), C.byref(v)))
+        return bool(v.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ta_peer_window_destroy(self._h)
+            self._h = None
 
 
 # ------------------------------------------------------------------------------ routing
@@ -280,6 +343,42 @@ class DeviceExchange(ExchangePlan):
             nf, nr = max(int(self.flag_idx.numel()), 1), max(int(self.recv_flag_idx.numel()), 1)
             self.send_flag_rows = torch.zeros((nf, K), dtype=torch.int32, device=d)
             self.recv_flag_rows = torch.zeros((nr, K), dtype=torch.int32, device=d)
+        self.window = None
+        if hasattr(tr, "peer_window"):
+            self._open_window()
+
+    def _open_window(self):
+        """Window layout (byte offsets; the first two sections have the same place on every rank):
+        GT counts [C, K] int32 | per-detection records in local order (compact words, or full
+        rows when the plan has no words) | rows of the flagged detections in send order."""
+        tr, dev, K = self.tr, self.dev, self.n_cfg
+        n_dt = dev.plan.n_dt
+        al = lambda v: (int(v) + 255) & ~255
+        rec = 4 if self.compact else 4 * K
+        self.w_numgt = 0
+        self.w_rec = al(self.n_cat * K * 4)
+        self.w_flag = self.w_rec + al(n_dt * rec)
+        nf = int(self.flag_idx.numel()) if self.compact else 0
+        self.window = tr.peer_window(self.w_flag + al(nf * K * 4))
+        if self.window is None:
+            return
+        # where my slices start inside every peer's window: the peer's own offsets, sent to me
+        dt_b = np.asarray(dev.plan.cat_dt_off, dtype=np.int64)[self.bounds]
+        rec_at = tr.counts([self.w_rec + int(dt_b[r]) * rec for r in range(self.world)])
+        copies, r_off = [], 0
+        for p in range(self.world):
+            dst = (self.recv_words if self.compact else self.recv_rows).data_ptr() + r_off * rec
+            copies.append((p, rec_at[p], self.recv_counts[p] * rec, dst))
+            r_off += self.recv_counts[p]
+        if self.compact:
+            f_start = np.concatenate([[0], np.cumsum(self.flag_send)]).astype(np.int64)
+            flag_at = tr.counts([self.w_flag + int(f_start[r]) * K * 4 for r in range(self.world)])
+            f_off = 0
+            for p in range(self.world):
+                copies.append((p, flag_at[p], self.flag_recv[p] * K * 4,
+                               self.recv_flag_rows.data_ptr() + f_off * K * 4))
+                f_off += self.flag_recv[p]
+        self.window.set_plan(copies, [(self.w_numgt, self.n_cat * K, self.num_gt_global.data_ptr())])
 
     def accumulate(self):
         """Exchange + owner-side PR of the matcher outputs currently in dev's buffers."""
@@ -293,7 +392,25 @@ class DeviceExchange(ExchangePlan):
         rows_all = t["dt_tpfp"][:n_dt * K].view(n_dt, K)
         self.num_gt_global.copy_(t["num_gt"])
         use_words = self.compact and dev.words_valid
-        if use_words:
+        if self.window is not None and use_words == self.compact:
+            # the library's own exchange kernel over NVLink peer memory
+            w = self.window
+            w.acquire()
+            w.put(self.w_numgt, t["num_gt"], self.n_cat * K * 4)
+            if use_words:
+                w.put(self.w_rec, t["dt_word"], n_dt * 4)
+                nf = int(self.flag_idx.numel())
+                if nf:
+                    _lib.check(eng.lib.ta_exchange_gather(eng._ctx, st, nf, K, P(self.flag_idx), P(rows_all),
+                                                          C.c_void_p(w.base + self.w_flag)))
+            else:
+                w.put(self.w_rec, rows_all, n_dt * K * 4)
+            w.exchange()
+            nr = int(self.recv_flag_idx.numel()) if use_words else 0
+            if nr:
+                _lib.check(eng.lib.ta_exchange_scatter(eng._ctx, st, nr, K, P(self.recv_flag_idx),
+                                                       P(self.recv_flag_rows), P(self.recv_rows)))
+        elif use_words:
             nf = int(self.flag_idx.numel())
             if nf:
                 _lib.check(eng.lib.ta_exchange_gather(eng._ctx, st, nf, K, P(self.flag_idx),
