@@ -10,7 +10,10 @@
 //     k_xchg_scatter     (frame path) full rows of the few detections the general matcher handled
 //     ncclAllReduce      sum of the non-ignored GT counts  int32 [n_cat][n_cfg]
 // followed by ta_pr_accumulate on the owner's categories; the owners keep (and copy out) their
-// own slices of precision / recall — nothing is gathered on one GPU.
+// own slices of precision / recall — nothing is gathered on one GPU.  The default route does the
+// all-to-all and the all-reduce with ONE kernel of this library over NVLink peer memory instead
+// (peer windows, second half of this file); the NCCL calls stay as the alternative route and
+// carry the setup traffic.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2; an already loaded copy — e.g. the one
 // torch.distributed brought in — is reused), so the library still loads on machines without it
