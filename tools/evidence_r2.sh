@@ -20,6 +20,14 @@ echo "bench rc=$? t=$(el)" >> $S
 timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2_bench_reference_arm.json 2> gpurun_out/r2_bench_reference_arm.err
 echo "reference_arm rc=$? t=$(el)" >> $S
 
+timeout 200 python tools/trace_host_call.py > /dev/null 2> gpurun_out/r2_host_call_trace.txt
+echo "host_call_trace rc=$? t=$(el)" >> $S
+
+for c in cfg2 cfg5; do
+  timeout 300 python tools/bench_cli.py --config $c --cold --out gpurun_out/r2_cli_cold_$c.json > gpurun_out/r2_cli_cold_$c.log 2>&1
+  echo "cli_cold_$c rc=$? t=$(el)" >> $S
+done
+
 timeout 200 python tools/ab_variants.py --out gpurun_out/r2_ab_variants.json > gpurun_out/r2_ab.log 2>&1
 echo "ab rc=$? t=$(el)" >> $S
 tail -3 gpurun_out/r2_ab.log >> $S
