@@ -250,8 +250,10 @@ struct ta_peer_window {
     char* peer[64];                  // every rank's window as mapped here (peer[rank] == base)
     int64_t peer_bytes[64];          // and its size
     uint32_t epoch;
-    int n_copy, n_sum;
-    ta_peer_copy* d_copy;
+    int n_seg, n_words, n_sum;
+    int64_t total_vec;
+    void* d_seg;                     // PwSeg[n_seg]
+    void* d_words;                   // PwWord[n_words]
     ta_peer_sum* d_sum;
     unsigned int* d_counter;         // blocks that finished pulling (reset by the last one)
     int* d_err;                      // spin limit hit
@@ -281,79 +283,85 @@ __global__ void k_peer_acquire(const uint32_t* __restrict__ hdr, int world, int 
     if (r < world && r != me) pw_wait(hdr + 16 + r, prev, err);
 }
 
+// What one exchange pulls, flattened on the host (ta_peer_window_set_plan): every copy is cut into
+// the words before the first 16-byte boundary of its SOURCE, a run of 16-byte vectors, and the
+// words after it.  All vectors of all copies form ONE index space (vec_begin = prefix sums), so a
+// thread keeps PW_UNROLL loads from several peers in flight at once instead of finishing one
+// peer's slice (a few NVLink round trips each) before touching the next.
+struct PwSeg { const uint4* s128; uint32_t* d32; int64_t vec_begin; };
+struct PwWord { const uint32_t* s; uint32_t* d; };
+#define PW_MAX_SEG 160
+#define PW_UNROLL 8
+
 __global__ void __launch_bounds__(256)
 k_peer_exchange(char* const* __restrict__ peer, int world, int me, uint32_t epoch,
-                const ta_peer_copy* __restrict__ copies, int n_copy,
+                const PwSeg* __restrict__ segs, int n_seg, int64_t total_vec,
+                const PwWord* __restrict__ words, int n_words,
                 const ta_peer_sum* __restrict__ sums, int n_sum,
                 unsigned int* counter, int* err) {
+    __shared__ int64_t begin_s[PW_MAX_SEG + 1];
+    __shared__ const uint4* src_s[PW_MAX_SEG];
+    __shared__ uint32_t* dst_s[PW_MAX_SEG];
     __shared__ int ok_s;
     // publish: everything written into this window earlier on the stream is visible before the flag
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         __threadfence_system();
         pw_store_flag(reinterpret_cast<uint32_t*>(peer[me]), epoch);
     }
-    uint64_t seen = 1ull << me;
+    for (int i = threadIdx.x; i < n_seg; i += blockDim.x) {
+        const PwSeg sg = segs[i];
+        begin_s[i] = sg.vec_begin;
+        src_s[i] = sg.s128;
+        dst_s[i] = sg.d32;
+    }
+    if (threadIdx.x == 0) {
+        begin_s[n_seg] = total_vec;
+        ok_s = 1;
+    }
+    __syncthreads();
+    // every peer has published this epoch (one poller per peer and block)
+    if (threadIdx.x < world && threadIdx.x != me)
+        if (!pw_wait(reinterpret_cast<const uint32_t*>(peer[threadIdx.x]), epoch, err)) ok_s = 0;
+    __syncthreads();
+    const bool ok = ok_s != 0;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-    auto need = [&](int p) -> bool {
-        if ((seen >> p) & 1ull) return true;
-        if (threadIdx.x == 0)
-            ok_s = pw_wait(reinterpret_cast<const uint32_t*>(peer[p]), epoch, err) ? 1 : 0;
-        __syncthreads();
-        const bool ok = ok_s != 0;
-        __syncthreads();
-        seen |= 1ull << p;
-        return ok;
-    };
-    // start with a different peer on every rank: the links fill evenly
-    for (int k = 0; k < n_copy; ++k) {
-        const ta_peer_copy c = copies[(k + (n_copy * me) / max(world, 1)) % n_copy];
-        if (c.bytes <= 0) continue;
-        if (!need(c.peer)) continue;
-        const char* src = peer[c.peer] + c.src_off;
-        char* dst = static_cast<char*>(c.dst);
-        const int64_t n_words = c.bytes >> 2;
-        // head: words before the first 16-byte boundary of the SOURCE
-        const int64_t head = min(n_words, (int64_t)((16 - ((uintptr_t)src & 15)) & 15) >> 2);
-        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        if (tid < head) d32[tid] = __ldcv(s32 + tid);
-        const int64_t n_vec = (n_words - head) >> 2;
-        const uint4* s128 = reinterpret_cast<const uint4*>(s32 + head);
-        uint32_t* dv = d32 + head;
-        const bool dst_al = (((uintptr_t)dv) & 15) == 0;
-        int64_t i = tid;
-        for (; i + 3 * nthreads < n_vec; i += 4 * nthreads) {
-            uint4 v[4];
+    if (ok) {
+        for (int64_t i = tid; i < n_words; i += nthreads) *words[i].d = __ldcv(words[i].s);
+        for (int64_t base = tid; base < total_vec; base += PW_UNROLL * nthreads) {
+            uint4 v[PW_UNROLL];
+            uint32_t* o[PW_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = __ldcv(s128 + i + u * nthreads);
+            for (int u = 0; u < PW_UNROLL; ++u) {
+                const int64_t idx = base + u * nthreads;
+                o[u] = nullptr;
+                if (idx < total_vec) {
+                    int lo = 0, hi = n_seg;              // begin_s[lo] <= idx < begin_s[hi]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (begin_s[mid] <= idx) lo = mid; else hi = mid;
+                    }
+                    const int64_t k = idx - begin_s[lo];
+                    v[u] = __ldcv(src_s[lo] + k);
+                    o[u] = dst_s[lo] + 4 * k;
+                }
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                uint32_t* o = dv + 4 * (i + u * nthreads);
-                if (dst_al) *reinterpret_cast<uint4*>(o) = v[u];
-                else { o[0] = v[u].x; o[1] = v[u].y; o[2] = v[u].z; o[3] = v[u].w; }
+            for (int u = 0; u < PW_UNROLL; ++u) {
+                if (!o[u]) continue;
+                if ((((uintptr_t)o[u]) & 15) == 0) *reinterpret_cast<uint4*>(o[u]) = v[u];
+                else { o[u][0] = v[u].x; o[u][1] = v[u].y; o[u][2] = v[u].z; o[u][3] = v[u].w; }
             }
         }
-        for (; i < n_vec; i += nthreads) {
-            const uint4 v = __ldcv(s128 + i);
-            uint32_t* o = dv + 4 * i;
-            if (dst_al) *reinterpret_cast<uint4*>(o) = v;
-            else { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-        }
-        const int64_t done = head + 4 * n_vec;
-        if (tid < n_words - done) d32[done + tid] = __ldcv(s32 + done + tid);
-    }
-    // sums over all ranks (GT counts): every rank computes the same totals
-    for (int k = 0; k < n_sum; ++k) {
-        const ta_peer_sum q = sums[k];
-        bool ok = true;
-        for (int p = 0; p < world; ++p) ok = need(p) && ok;
-        if (!ok) continue;
-        for (int64_t i = tid; i < q.count; i += nthreads) {
-            int32_t acc = 0;
-            for (int p = 0; p < world; ++p)
-                acc += (int32_t)__ldcv(reinterpret_cast<const uint32_t*>(peer[p] + q.off) + i);
-            q.dst[i] = acc;
+        // sums over all ranks (GT counts): every rank computes the same totals
+        for (int k = 0; k < n_sum; ++k) {
+            const ta_peer_sum q = sums[k];
+            for (int64_t i = tid; i < q.count; i += nthreads) {
+                int32_t acc = 0;
+                for (int p = 0; p < world; ++p)
+                    acc += (int32_t)__ldcv(reinterpret_cast<const uint32_t*>(peer[p] + q.off) + i);
+                q.dst[i] = acc;
+            }
         }
     }
     // the last block to finish tells every peer that this rank has read its window
@@ -430,7 +438,8 @@ extern "C" int ta_peer_window_destroy(ta_peer_window* w) {
     cudaDeviceSynchronize();
     for (int p = 0; p < w->x->world; ++p)
         if (p != w->x->rank && w->peer[p]) cudaIpcCloseMemHandle(w->peer[p]);
-    if (w->d_copy) cudaFree(w->d_copy);
+    if (w->d_seg) cudaFree(w->d_seg);
+    if (w->d_words) cudaFree(w->d_words);
     if (w->d_sum) cudaFree(w->d_sum);
     if (w->d_peer) cudaFree(w->d_peer);
     if (w->d_counter) cudaFree(w->d_counter);
@@ -443,44 +452,71 @@ extern "C" int ta_peer_window_set_plan(ta_peer_window* w, int32_t n_copy, const 
                                        int32_t n_sum, const ta_peer_sum* sums) {
     if (!w || n_copy < 0 || n_sum < 0 || (n_copy && !copies) || (n_sum && !sums))
         return ta_set_err(TA_ERR_INVALID, "ta_peer_window_set_plan: bad arguments");
+    if (n_copy > PW_MAX_SEG) return ta_set_err(TA_ERR_TOO_LARGE, "ta_peer_window_set_plan: more than %s%lld copies", "", PW_MAX_SEG);
     TA_CUDA(cudaSetDevice(w->x->ctx->device));
+    const int world = w->x->world, me = w->x->rank;
     const int64_t room = w->bytes - TA_PW_HDR;
-    ta_peer_copy* hc = n_copy ? new ta_peer_copy[n_copy] : nullptr;
     for (int i = 0; i < n_copy; ++i) {
-        hc[i] = copies[i];
-        const ta_peer_copy& c = hc[i];
-        if (c.peer < 0 || c.peer >= w->x->world || c.src_off < 0 || c.bytes < 0 || (c.src_off & 3) ||
+        const ta_peer_copy& c = copies[i];
+        if (c.peer < 0 || c.peer >= world || c.src_off < 0 || c.bytes < 0 || (c.src_off & 3) ||
             (c.bytes & 3) || c.src_off + c.bytes > w->peer_bytes[c.peer] - TA_PW_HDR ||
-            (c.bytes && (!c.dst || ((uintptr_t)c.dst & 3)))) {
-            delete[] hc;
+            (c.bytes && (!c.dst || ((uintptr_t)c.dst & 3))))
             return ta_set_err(TA_ERR_INVALID, "ta_peer_window_set_plan: copy %s%lld is out of the window or misaligned", "", i);
-        }
-        hc[i].src_off += TA_PW_HDR;
     }
-    ta_peer_sum* hs = n_sum ? new ta_peer_sum[n_sum] : nullptr;
-    for (int i = 0; i < n_sum; ++i) {
-        hs[i] = sums[i];
-        if (hs[i].off < 0 || (hs[i].off & 3) || hs[i].count < 0 || hs[i].off + 4 * hs[i].count > room ||
-            (hs[i].count && !hs[i].dst)) {
-            delete[] hc;
-            delete[] hs;
+    for (int i = 0; i < n_sum; ++i)
+        if (sums[i].off < 0 || (sums[i].off & 3) || sums[i].count < 0 || sums[i].off + 4 * sums[i].count > room ||
+            (sums[i].count && !sums[i].dst))
             return ta_set_err(TA_ERR_INVALID, "ta_peer_window_set_plan: sum %s%lld is out of the window", "", i);
+    // segments in the order (peer - me - 1) mod world: at any moment the ranks read from different
+    // peers, so the links fill evenly
+    PwSeg* hs = new PwSeg[n_copy + 1];
+    PwWord* hw = new PwWord[6 * (size_t)n_copy + 1];
+    int n_seg = 0, n_words = 0;
+    int64_t total = 0;
+    for (int step = 0; step < world; ++step) {
+        const int p = (me + 1 + step) % world;
+        for (int i = 0; i < n_copy; ++i) {
+            const ta_peer_copy& c = copies[i];
+            if (c.peer != p || c.bytes == 0) continue;
+            const char* src = w->peer[p] + TA_PW_HDR + c.src_off;
+            const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+            uint32_t* d32 = static_cast<uint32_t*>(c.dst);
+            const int64_t nw = c.bytes >> 2;
+            int64_t head = (int64_t)((16 - ((uintptr_t)src & 15)) & 15) >> 2;
+            if (head > nw) head = nw;
+            const int64_t n_vec = (nw - head) >> 2;
+            for (int64_t k = 0; k < head; ++k) hw[n_words++] = {s32 + k, d32 + k};
+            for (int64_t k = head + 4 * n_vec; k < nw; ++k) hw[n_words++] = {s32 + k, d32 + k};
+            if (n_vec) {
+                hs[n_seg++] = {reinterpret_cast<const uint4*>(s32 + head), d32 + head, total};
+                total += n_vec;
+            }
         }
-        hs[i].off += TA_PW_HDR;
+    }
+    ta_peer_sum* hq = n_sum ? new ta_peer_sum[n_sum] : nullptr;
+    for (int i = 0; i < n_sum; ++i) {
+        hq[i] = sums[i];
+        hq[i].off += TA_PW_HDR;
     }
     cudaError_t e = cudaDeviceSynchronize();
-    if (w->d_copy) cudaFree(w->d_copy);
+    if (w->d_seg) cudaFree(w->d_seg);
+    if (w->d_words) cudaFree(w->d_words);
     if (w->d_sum) cudaFree(w->d_sum);
-    w->d_copy = nullptr;
+    w->d_seg = w->d_words = nullptr;
     w->d_sum = nullptr;
-    if (e == cudaSuccess && n_copy) e = cudaMalloc(&w->d_copy, sizeof(ta_peer_copy) * n_copy);
-    if (e == cudaSuccess && n_copy) e = cudaMemcpy(w->d_copy, hc, sizeof(ta_peer_copy) * n_copy, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_seg) e = cudaMalloc(&w->d_seg, sizeof(PwSeg) * n_seg);
+    if (e == cudaSuccess && n_seg) e = cudaMemcpy(w->d_seg, hs, sizeof(PwSeg) * n_seg, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_words) e = cudaMalloc(&w->d_words, sizeof(PwWord) * n_words);
+    if (e == cudaSuccess && n_words) e = cudaMemcpy(w->d_words, hw, sizeof(PwWord) * n_words, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && n_sum) e = cudaMalloc(&w->d_sum, sizeof(ta_peer_sum) * n_sum);
-    if (e == cudaSuccess && n_sum) e = cudaMemcpy(w->d_sum, hs, sizeof(ta_peer_sum) * n_sum, cudaMemcpyHostToDevice);
-    delete[] hc;
+    if (e == cudaSuccess && n_sum) e = cudaMemcpy(w->d_sum, hq, sizeof(ta_peer_sum) * n_sum, cudaMemcpyHostToDevice);
     delete[] hs;
+    delete[] hw;
+    delete[] hq;
     TA_CUDA(e);
-    w->n_copy = n_copy;
+    w->n_seg = n_seg;
+    w->n_words = n_words;
+    w->total_vec = total;
     w->n_sum = n_sum;
     return TA_OK;
 }
@@ -514,9 +550,10 @@ extern "C" int ta_peer_window_exchange(ta_peer_window* w, void* stream) {
     w->epoch += 1;
     // every block must be resident (blocks wait for remote flags): two per SM
     const int blocks = ctx->sm_count * 2;
-    k_peer_exchange<<<blocks, 256, 0, (cudaStream_t)stream>>>(w->d_peer, w->x->world, w->x->rank, w->epoch,
-                                                            w->d_copy, w->n_copy, w->d_sum, w->n_sum,
-                                                            w->d_counter, w->d_err);
+    k_peer_exchange<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        w->d_peer, w->x->world, w->x->rank, w->epoch, static_cast<const PwSeg*>(w->d_seg), w->n_seg,
+        w->total_vec, static_cast<const PwWord*>(w->d_words), w->n_words, w->d_sum, w->n_sum,
+        w->d_counter, w->d_err);
     return ta_check_launch(ctx, "k_peer_exchange");
 }
 
