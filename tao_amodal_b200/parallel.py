@@ -276,6 +276,47 @@ class ExchangePlan:
         if self.n_loc:
             self.cat_dt_off[1:] = torch.cumsum(cnt_loc[:self.n_loc], 0)
 
+    # ---------------------------------------------------------------------------- peer windows
+    def flag_routing(self, flag_idx: np.ndarray):
+        """(send, recv) counts per rank of the detections `flag_idx` (sorted local indices) whose
+        full rows travel next to the compact words."""
+        b = np.asarray(self.plan.cat_dt_off, dtype=np.int64)[self.bounds]
+        send = [int(v) for v in np.diff(np.searchsorted(flag_idx, b, side="left"))]
+        return send, self.tr.counts(send)
+
+    def window_plan(self, rec_bytes: int, flag=None):
+        """Layout of this rank's peer window and what this owner pulls out of every rank's window
+        (ta_peer_window_set_plan).  Byte offsets; the first two sections sit at the same place on
+        every rank: GT counts [C, K] int32 | one record of rec_bytes per detection in local order
+        (an owner's share is one contiguous slice) | with flag = (send counts, recv counts, row
+        bytes): the rows of the flagged detections in send order.  A rank only knows where ITS
+        slices start inside its own window, so those offsets are exchanged (tr.counts).
+        copies: (peer, byte offset in the peer's window, bytes, "rec" | "flag", byte offset in the
+        owner's receive buffer of that kind)."""
+        al = lambda v: (int(v) + 255) & ~255
+        n_dt = self.plan.n_dt
+        lay = {"numgt": 0, "numgt_count": self.n_cat * self.n_cfg}
+        lay["rec"] = al(lay["numgt_count"] * 4)
+        lay["flag"] = lay["rec"] + al(n_dt * rec_bytes)
+        n_flag = int(sum(flag[0])) if flag else 0
+        row = int(flag[2]) if flag else 0
+        lay["bytes"] = lay["flag"] + al(n_flag * row)
+        dt_b = np.asarray(self.plan.cat_dt_off, dtype=np.int64)[self.bounds]
+        rec_at = self.tr.counts([lay["rec"] + int(dt_b[r]) * rec_bytes for r in range(self.world)])
+        copies, off = [], 0
+        for p in range(self.world):
+            copies.append((p, rec_at[p], self.recv_counts[p] * rec_bytes, "rec", off))
+            off += self.recv_counts[p] * rec_bytes
+        if flag:
+            f_start = np.concatenate([[0], np.cumsum(flag[0])]).astype(np.int64)
+            flag_at = self.tr.counts([lay["flag"] + int(f_start[r]) * row for r in range(self.world)])
+            off = 0
+            for p in range(self.world):
+                copies.append((p, flag_at[p], flag[1][p] * row, "flag", off))
+                off += flag[1][p] * row
+        lay["copies"] = copies
+        return lay
+
     # ---------------------------------------------------------------------------- per step
     def exchange(self, records, out=None):
         """records: [n_dt, ...] in local detection order -> this owner's received records."""
@@ -331,10 +372,7 @@ class DeviceExchange(ExchangePlan):
             eng.stage_frame_eval(dev)
             words = dev.t["dt_word"][:n_dt]
             self.flag_idx = torch.nonzero(words < 0).flatten().to(torch.int32).contiguous()
-            b = np.asarray(dev.plan.cat_dt_off, dtype=np.int64)[self.bounds]
-            pos = np.searchsorted(self.flag_idx.cpu().numpy(), b, side="left")
-            self.flag_send = [int(v) for v in np.diff(pos)]
-            self.flag_recv = tr.counts(self.flag_send)
+            self.flag_send, self.flag_recv = self.flag_routing(self.flag_idx.cpu().numpy())
             self.recv_words = torch.zeros(n, dtype=torch.int32, device=d)
             self.exchange(words, out=self.recv_words)
             self.recv_flag_idx = (torch.nonzero(self.recv_words[:self.n_recv] < 0).flatten()
@@ -348,37 +386,19 @@ class DeviceExchange(ExchangePlan):
             self._open_window()
 
     def _open_window(self):
-        """Window layout (byte offsets; the first two sections have the same place on every rank):
-        GT counts [C, K] int32 | per-detection records in local order (compact words, or full
-        rows when the plan has no words) | rows of the flagged detections in send order."""
-        tr, dev, K = self.tr, self.dev, self.n_cfg
-        n_dt = dev.plan.n_dt
-        al = lambda v: (int(v) + 255) & ~255
+        """The peer window of this plan (ExchangePlan.window_plan) and its pull plan."""
+        tr, K = self.tr, self.n_cfg
         rec = 4 if self.compact else 4 * K
-        self.w_numgt = 0
-        self.w_rec = al(self.n_cat * K * 4)
-        self.w_flag = self.w_rec + al(n_dt * rec)
-        nf = int(self.flag_idx.numel()) if self.compact else 0
-        self.window = tr.peer_window(self.w_flag + al(nf * K * 4))
+        flag = (self.flag_send, self.flag_recv, 4 * K) if self.compact else None
+        lay = self.window_plan(rec, flag)
+        self.w_numgt, self.w_rec, self.w_flag = lay["numgt"], lay["rec"], lay["flag"]
+        self.window = tr.peer_window(lay["bytes"])
         if self.window is None:
             return
-        # where my slices start inside every peer's window: the peer's own offsets, sent to me
-        dt_b = np.asarray(dev.plan.cat_dt_off, dtype=np.int64)[self.bounds]
-        rec_at = tr.counts([self.w_rec + int(dt_b[r]) * rec for r in range(self.world)])
-        copies, r_off = [], 0
-        for p in range(self.world):
-            dst = (self.recv_words if self.compact else self.recv_rows).data_ptr() + r_off * rec
-            copies.append((p, rec_at[p], self.recv_counts[p] * rec, dst))
-            r_off += self.recv_counts[p]
-        if self.compact:
-            f_start = np.concatenate([[0], np.cumsum(self.flag_send)]).astype(np.int64)
-            flag_at = tr.counts([self.w_flag + int(f_start[r]) * K * 4 for r in range(self.world)])
-            f_off = 0
-            for p in range(self.world):
-                copies.append((p, flag_at[p], self.flag_recv[p] * K * 4,
-                               self.recv_flag_rows.data_ptr() + f_off * K * 4))
-                f_off += self.flag_recv[p]
-        self.window.set_plan(copies, [(self.w_numgt, self.n_cat * K, self.num_gt_global.data_ptr())])
+        base = {"rec": (self.recv_words if self.compact else self.recv_rows).data_ptr(),
+                "flag": self.recv_flag_rows.data_ptr() if self.compact else 0}
+        copies = [(p, off, nb, base[kind] + dst) for p, off, nb, kind, dst in lay["copies"]]
+        self.window.set_plan(copies, [(self.w_numgt, lay["numgt_count"], self.num_gt_global.data_ptr())])
 
     def accumulate(self):
         """Exchange + owner-side PR of the matcher outputs currently in dev's buffers."""

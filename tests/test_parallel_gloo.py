@@ -53,6 +53,7 @@ def _worker(rank, world, port, case, kind, q, only_video=None):
         ex = parallel.ExchangePlan(plan, tr, torch.device("cpu"))
         rows = ex.exchange(torch.from_numpy(np.ascontiguousarray(local.dt_tpfp).view(np.int32)))
         num_gt, num_gt_own = ex.global_num_gt(torch.from_numpy(local.num_gt.copy()))
+        _check_peer_window_plans(dist, ex, plan, local, rows, num_gt)
         # owner-side PR through the emulation of the shipped (bit-plane) kernels: categories
         # without detections and owners without categories included
         T, R, K = 10, 101, plan.n_cfg
@@ -84,6 +85,60 @@ def _worker(rank, world, port, case, kind, q, only_video=None):
             q.put(bool(ok))
     finally:
         dist.destroy_process_group()
+
+
+def _check_peer_window_plans(dist, ex, plan, local, rows_nccl, num_gt_sum):
+    """The peer-window route on CPU: every rank fills a window laid out by
+    ExchangePlan.window_plan, the windows are made visible to everybody (an all-gather stands in
+    for the CUDA IPC mapping), and applying the owner's pull plan must reproduce what the
+    all-to-all route delivered — full rows (track path), and words + flagged rows (frame path,
+    with every third local detection flagged)."""
+    import torch
+    K, n_dt = plan.n_cfg, plan.n_dt
+    tpfp = np.ascontiguousarray(local.dt_tpfp).view(np.int32).reshape(n_dt, K)
+
+    def windows_of(lay, fill):
+        w = np.zeros(lay["bytes"], dtype=np.uint8)
+        w[lay["numgt"]:lay["numgt"] + 4 * lay["numgt_count"]] = local.num_gt.astype(np.int32).reshape(-1).view(np.uint8)
+        fill(w)
+        box = [None] * ex.world
+        dist.all_gather_object(box, w)
+        return box
+
+    def pull(lay, wins, sizes):
+        out = {k: np.zeros(n, dtype=np.uint8) for k, n in sizes.items()}
+        for peer, off, nb, kind, dst in lay["copies"]:
+            assert off % 4 == 0 and nb % 4 == 0 and off + nb <= wins[peer].size
+            out[kind][dst:dst + nb] = wins[peer][off:off + nb]
+        tot = sum(w[lay["numgt"]:lay["numgt"] + 4 * lay["numgt_count"]].view(np.int32).astype(np.int64)
+                  for w in wins)
+        return out, tot
+
+    # track-path form: one full row per detection
+    lay = ex.window_plan(4 * K)
+
+    def fill_rows(w):
+        w[lay["rec"]:lay["rec"] + tpfp.nbytes] = tpfp.reshape(-1).view(np.uint8)
+    got, tot = pull(lay, windows_of(lay, fill_rows), {"rec": ex.n_recv * 4 * K})
+    assert np.array_equal(got["rec"].view(np.int32).reshape(-1, K), rows_nccl.numpy().reshape(-1, K))
+    assert np.array_equal(tot, num_gt_sum.numpy().reshape(-1))
+
+    # frame-path form: a 4-byte word per detection + the rows of the flagged ones
+    words = (np.arange(n_dt, dtype=np.int32) * 8 + ex.rank).astype(np.int32)
+    flag_idx = np.arange(0, n_dt, 3, dtype=np.int64)
+    send, recv = ex.flag_routing(flag_idx)
+    lay = ex.window_plan(4, (send, recv, 4 * K))
+    flag_rows = np.ascontiguousarray(tpfp[flag_idx])
+
+    def fill_words(w):
+        w[lay["rec"]:lay["rec"] + words.nbytes] = words.view(np.uint8)
+        w[lay["flag"]:lay["flag"] + flag_rows.nbytes] = flag_rows.reshape(-1).view(np.uint8)
+    got, tot = pull(lay, windows_of(lay, fill_words), {"rec": ex.n_recv * 4, "flag": int(sum(recv)) * 4 * K})
+    want_words = ex.exchange(torch.from_numpy(words)).numpy()
+    assert np.array_equal(got["rec"].view(np.int32), want_words)
+    want_rows = ex.tr.all_to_all(torch.from_numpy(flag_rows), send, recv).numpy()
+    assert np.array_equal(got["flag"].view(np.int32).reshape(-1, K), want_rows.reshape(-1, K))
+    assert np.array_equal(tot, num_gt_sum.numpy().reshape(-1))
 
 
 def _run(world, case, kind, **kw):
