@@ -158,6 +158,20 @@ def _index_of(sorted_keys: np.ndarray, q: np.ndarray) -> np.ndarray:
     """Position of each q in sorted_keys, -1 when absent."""
     if sorted_keys.size == 0:
         return np.full(q.shape, -1, dtype=np.int64)
+    if (q.size >= 4096 and sorted_keys.dtype.kind in "iu" and q.dtype.kind in "iu"):
+        # dense integer keys (ids of images, videos, categories, tracks): a lookup table instead
+        # of a binary search per query
+        lo, hi = int(sorted_keys[0]), int(sorted_keys[-1])
+        span = hi - lo + 1
+        if span <= max(8 * sorted_keys.size, 1 << 16) and span <= (1 << 26):
+            lut = np.full(span, -1, dtype=np.int64)
+            # duplicates: the leftmost position, as searchsorted returns it
+            lut[(sorted_keys[::-1] - lo)] = np.arange(sorted_keys.size - 1, -1, -1, dtype=np.int64)
+            rel = q.astype(np.int64) - lo
+            ok = (rel >= 0) & (rel < span)
+            out = lut[np.where(ok, rel, 0)]
+            out[~ok] = -1
+            return out
     pos = np.searchsorted(sorted_keys, q)
     pos_c = np.minimum(pos, sorted_keys.size - 1)
     return np.where(sorted_keys[pos_c] == q, pos_c, -1).astype(np.int64)
