@@ -34,3 +34,34 @@ def random_pr_case(seed, n_cat=7, n_cfg=6, n_thr=10, max_len=1500, tp_rate=None)
     num_gt[(num_gt == 0) & (tp_tot > 0) & (rng.random((n_cat, n_cfg)) < 0.5)] = 1   # tp > num_gt never happens in
     num_gt = np.maximum(num_gt, np.where(num_gt > 0, tp_tot, 0)).astype(np.int32)   # the evaluators; keep tp <= num_gt
     return dict(n_cat=n_cat, n_cfg=n_cfg, cat_dt_off=cat_dt_off, acc_perm=acc_perm, tpfp=w, num_gt=num_gt)
+
+
+def oracle_pr(c, iou_thrs, rec_thrs):
+    """The case through the ORACLE's accumulate cell (oracle.common.pr_curve, the restatement of
+    tao_amodal/evaluation/tao_amodal/eval.py:508-573 that the reference goldens pin): precision
+    [T, R, C, K], recall / tp_cnt / fp_cnt [T, C, K] in the layouts of ta_pr_accumulate.  A
+    detection's word says per threshold whether it is a true positive (matched, counted), a false
+    positive (unmatched, counted) or ignored."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle.common import pr_curve
+    T, R, C, K = len(iou_thrs), len(rec_thrs), c["n_cat"], c["n_cfg"]
+    prec = -np.ones((T, R, C, K))
+    rec = -np.ones((T, C, K))
+    tp_cnt = np.zeros((T, C, K), dtype=np.int64)
+    fp_cnt = np.zeros((T, C, K), dtype=np.int64)
+    bits = np.arange(T, dtype=np.uint32)[:, None]
+    for cat in range(C):
+        idx = c["acc_perm"][c["cat_dt_off"][cat]:c["cat_dt_off"][cat + 1]]     # descending score
+        for k in range(K):
+            w = c["tpfp"][idx, k].astype(np.uint32)[None, :]
+            tp = ((w >> bits) & 1).astype(bool)
+            fp = ((w >> (16 + bits)) & 1).astype(bool)
+            got = pr_curve(-np.arange(idx.size, dtype=np.float64), np.where(tp, 1, -1), ~(tp | fp),
+                           np.zeros(int(c["num_gt"][cat, k])), -1, rec_thrs)
+            if got is None:
+                continue
+            prec[:, :, cat, k], rec[:, cat, k] = got[0], got[1]
+            tp_cnt[:, cat, k], fp_cnt[:, cat, k] = got[3].sum(1), got[4].sum(1)
+    return prec, rec, tp_cnt, fp_cnt

@@ -289,7 +289,8 @@ def _gpu_pr(eng, c, iou_thrs, rec_thrs, impl):
                                      (101, dict(n_cat=4, n_cfg=3, tp_rate=1.0))])
 def test_pr_accumulate_both_implementations(eng, seed, kw, impl):
     """Position-walk (TA_PR_IMPL=0) and bit-plane (TA_PR_IMPL=1, default) kernels of ta_pr_accumulate on
-    random multi-chunk categories against the plain serial accumulation (tests/hostsim)."""
+    random multi-chunk categories against the plain serial accumulation (tests/hostsim) and the
+    oracle's accumulate cell."""
     from plan_backends import hostsim_pr
     from pr_cases import random_pr_case
     from tao_amodal_b200 import engine
@@ -300,6 +301,13 @@ def test_pr_accumulate_both_implementations(eng, seed, kw, impl):
     assert np.array_equal(ref.recall, rc)
     assert np.array_equal(ref.tp_cnt, tp)
     assert np.array_equal(ref.fp_cnt, fp)
+    if c["tpfp"].shape[0] * c["n_cfg"] <= 200000:
+        # and against the oracle's accumulate cell (oracle.common.pr_curve), not only against the
+        # emulation that shares the device header with the kernels
+        from pr_cases import oracle_pr
+        o_prec, o_rc, o_tp, o_fp = oracle_pr(c, engine.IOU_THRS, engine.REC_THRS)
+        assert np.array_equal(o_prec, prec) and np.array_equal(o_rc, rc)
+        assert np.array_equal(o_tp, tp) and np.array_equal(o_fp, fp)
 
 
 @pytest.mark.parametrize("impl", [0, 1])

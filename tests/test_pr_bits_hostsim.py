@@ -23,6 +23,24 @@ def test_random_multi_chunk(seed, impl):
     _same(hostsim_pr(*args, impl=impl), hostsim_pr(*args, impl="serial"))
 
 
+@pytest.mark.parametrize("seed,kw", [(0, {}), (1, {}), (2, dict(n_cat=5, n_cfg=20, max_len=700)),
+                                     (100, dict(n_cat=4, n_cfg=3, tp_rate=0.0)),
+                                     (101, dict(n_cat=4, n_cfg=3, tp_rate=1.0)),
+                                     (7, dict(n_cat=3, n_cfg=2, tp_rate=0.97, max_len=2600))])
+def test_emulations_match_the_oracle_accumulate_cell(seed, kw):
+    """The random multi-chunk cases against the ORACLE's accumulate cell (not only against the
+    serial emulation built from the same device header): serial and bit-plane emulations."""
+    from pr_cases import oracle_pr
+    c = random_pr_case(seed, **kw)
+    args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
+    prec, rec, tp, fp = oracle_pr(c, engine.IOU_THRS, engine.REC_THRS)
+    for impl in ("serial", "bits_tile", "bits_seg"):
+        out = hostsim_pr(*args, impl=impl)
+        assert np.array_equal(out.precision, prec), impl
+        assert np.array_equal(out.recall, rec), impl
+        assert np.array_equal(out.tp_cnt, tp) and np.array_equal(out.fp_cnt, fp), impl
+
+
 @pytest.mark.parametrize("tp_rate", [0.0, 1.0])
 def test_all_or_no_true_positives(tp_rate):
     c = random_pr_case(100, n_cat=4, n_cfg=3, tp_rate=tp_rate)
