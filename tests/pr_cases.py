@@ -65,3 +65,36 @@ def oracle_pr(c, iou_thrs, rec_thrs):
             prec[:, :, cat, k], rec[:, cat, k] = got[0], got[1]
             tp_cnt[:, cat, k], fp_cnt[:, cat, k] = got[3].sum(1), got[4].sum(1)
     return prec, rec, tp_cnt, fp_cnt
+
+
+def structured_pr_case(patterns, n_cfg=2, n_thr=10, seed=5):
+    """A case from explicit per-category position patterns (0 ignored, 1 true positive, 2 false
+    positive, in descending-score order); higher thresholds lose some true positives, the second
+    cfg is the pattern rotated by three positions."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lens = [len(p) for p in patterns]
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    w = np.zeros((int(off[-1]), n_cfg), dtype=np.uint32)
+    for c, p in enumerate(patterns):
+        p = np.asarray(p)
+        for k in range(n_cfg):
+            for t in range(n_thr):
+                q = p.copy()
+                if t >= 5:
+                    q = np.where((np.arange(len(p)) % (t + 2) == 0) & (q == 1), 2, q)
+                if k == 1:
+                    q = np.roll(q, 3)
+                w[off[c]:off[c + 1], k] |= ((q == 1).astype(np.uint32) << t) | ((q == 2).astype(np.uint32) << (16 + t))
+    tp_tot = np.array([[max(int(((w[off[c]:off[c + 1], k] >> t) & 1).sum()) for t in range(n_thr))
+                        for k in range(n_cfg)] for c in range(len(patterns))], dtype=np.int64)
+    num_gt = (tp_tot + rng.integers(0, 5, tp_tot.shape)).astype(np.int32)
+    return dict(n_cat=len(patterns), n_cfg=n_cfg, cat_dt_off=off,
+                acc_perm=np.arange(int(off[-1]), dtype=np.int32), tpfp=w, num_gt=num_gt)
+
+
+def structured_patterns(L, rng):
+    i = np.arange(L)
+    return [np.ones(L, int), np.full(L, 2), i % 2 + 1, np.where(i < L // 2, 1, 2), np.where(i < L // 2, 2, 1),
+            np.where(i % 32 == 31, 1, np.where(i % 32 == 0, 2, 0)),     # TP ends a word, FP starts the next
+            np.where(i % 256 == 255, 1, 0),                              # a lone TP at every chunk end
+            rng.integers(0, 3, L), np.where(rng.random(L) < 0.05, 2, np.where(rng.random(L) < 0.5, 1, 0))]

@@ -41,6 +41,21 @@ def test_emulations_match_the_oracle_accumulate_cell(seed, kw):
         assert np.array_equal(out.tp_cnt, tp) and np.array_equal(out.fp_cnt, fp), impl
 
 
+@pytest.mark.parametrize("L", [1, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1024, 1300])
+def test_structured_runs_against_the_oracle(L):
+    """Runs of true positives that end at word and chunk boundaries, lone true positives at chunk
+    ends, all-TP / all-FP / alternating lists, lengths around the word and chunk sizes: every
+    emulation of the run-end walk against the oracle's accumulate cell."""
+    from pr_cases import oracle_pr, structured_patterns, structured_pr_case
+    c = structured_pr_case(structured_patterns(L, np.random.Generator(np.random.PCG64(L))))
+    args = (c["n_cat"], c["cat_dt_off"], c["acc_perm"], c["tpfp"], c["num_gt"], c["n_cfg"])
+    prec, rec, tp, fp = oracle_pr(c, engine.IOU_THRS, engine.REC_THRS)
+    for impl in ("serial", "bits", "bits_tile", "bits_seg"):
+        out = hostsim_pr(*args, impl=impl)
+        assert np.array_equal(out.precision, prec) and np.array_equal(out.recall, rec), impl
+        assert np.array_equal(out.tp_cnt, tp) and np.array_equal(out.fp_cnt, fp), impl
+
+
 @pytest.mark.parametrize("tp_rate", [0.0, 1.0])
 def test_all_or_no_true_positives(tp_rate):
     c = random_pr_case(100, n_cat=4, n_cfg=3, tp_rate=tp_rate)
