@@ -352,7 +352,7 @@ int ta_exchange_world(const ta_exchange* x);
  * count, local int32 destination}: dst[i] = sum over all ranks of the int32 at off + 4 i of the
  * rank's window.  create / destroy / set_plan are collective or synchronising calls outside
  * the step; NCCL (the communicator of `x`) only carries the IPC handles at creation.
- * A peer that never arrives makes the waits give up after a few seconds instead of hanging
+ * A peer that never arrives makes the waits give up after about a minute instead of hanging
  * the GPU; ta_peer_window_check reports that.                                             */
 typedef struct ta_peer_window ta_peer_window;
 typedef struct ta_peer_copy { int32_t peer, reserved_; int64_t src_off, bytes; void* dst; } ta_peer_copy;

@@ -241,7 +241,7 @@ extern "C" int ta_exchange_world(const ta_exchange* x) { return x ? x->world : 0
 // the owner's loads.  Flags live in the first TA_PW_HDR bytes of the window: [0] ready epoch
 // (written by the owner of the window), [16 + r] the epoch rank r has finished pulling.
 #define TA_PW_HDR 1024
-#define TA_PW_SPIN_LIMIT (1ll << 33)     // clock ticks (a few seconds): a dead peer must not hang the GPU
+#define TA_PW_SPIN_LIMIT (1ll << 37)     // clock ticks (about a minute): a dead peer must not hang the GPU for good
 
 struct ta_peer_window {
     ta_exchange* x;

@@ -462,6 +462,9 @@ class DeviceExchange(ExchangePlan):
     def to_root(self):
         """Assemble the reference's full tensors in dev.t on rank 0 (API / parity checks)."""
         names = ("precision", "recall", "tp_cnt", "fp_cnt")
+        if self.window is not None and self.window.timed_out():
+            raise RuntimeError("peer exchange: a rank never published its window (a peer process "
+                               "died or did not take part in this evaluation)")
         self.gather_to_root([self.part[k] for k in names], [self.dev.t[k] for k in names])
         self.dev.t["num_gt"].copy_(self.num_gt_global)
 
