@@ -244,6 +244,12 @@ def limit_dets_per_image(image_id: np.ndarray, score: np.ndarray, max_dets: int)
     n = image_id.size
     if max_dets < 0 or n == 0:
         return np.arange(n, dtype=np.int64)
+    # the usual file: every image's rows are one contiguous run and no image is over-full —
+    # the selection is then the identity (checked on the run heads only)
+    head = np.concatenate([[0], np.nonzero(image_id[1:] != image_id[:-1])[0] + 1])
+    if (np.diff(np.concatenate([head, [n]])).max() <= max_dets
+            and np.unique(image_id[head]).size == head.size):
+        return np.arange(n, dtype=np.int64)
     uniq, first, inv, cnt = np.unique(image_id, return_index=True, return_inverse=True,
                                       return_counts=True)
     first_rank = np.empty(uniq.size, dtype=np.int64)
@@ -550,29 +556,15 @@ def _tao_tracks(rows, rank, trk_key, S_frame, S_slot, bbox, area, vis):
     # (dict comprehension, eval.py:322-325)
     slot_sorted = S_slot[rank[order]]
     trk_sorted = inv[order]
-    keep = np.ones(order.size, dtype=bool)
-    same = (trk_sorted[1:] == trk_sorted[:-1]) & (slot_sorted[1:] == slot_sorted[:-1])
-    if same.any():
-        # duplicates of an image need not be adjacent when two images share a frame_index;
-        # re-sort by (track, slot, position) and keep the last of every (track, slot) run
-        o2 = np.lexsort((np.arange(order.size), slot_sorted, trk_sorted))
-        ts, ss = trk_sorted[o2], slot_sorted[o2]
-        last = np.ones(o2.size, dtype=bool)
-        last[:-1] = (ts[1:] != ts[:-1]) | (ss[1:] != ss[:-1])
-        keep[:] = False
-        keep[o2[last]] = True
-    else:
-        # still guard against non-adjacent duplicates
-        o2 = np.lexsort((np.arange(order.size), slot_sorted, trk_sorted))
-        ts, ss = trk_sorted[o2], slot_sorted[o2]
-        dup = (ts[1:] == ts[:-1]) & (ss[1:] == ss[:-1])
-        if dup.any():
-            last = np.ones(o2.size, dtype=bool)
-            last[:-1] = ~dup
-            keep[:] = False
-            keep[o2[last]] = True
-    kb = np.nonzero(keep)[0]
-    kb = kb[np.lexsort((slot_sorted[kb], trk_sorted[kb]))]
+    # one stable sort by (track, slot) — on a single integer key, nearly sorted already — serves
+    # both steps: duplicates of an image need not be adjacent in `order` when two images share a
+    # frame_index, and the kept boxes are wanted in (track, slot) order
+    n_slot = int(slot_sorted.max()) + 1 if slot_sorted.size else 1
+    o2 = np.argsort(trk_sorted.astype(np.int64) * n_slot + slot_sorted, kind="stable")
+    ts, ss = trk_sorted[o2], slot_sorted[o2]
+    last = np.ones(o2.size, dtype=bool)
+    last[:-1] = (ts[1:] != ts[:-1]) | (ss[1:] != ss[:-1])
+    kb = o2[last]                           # the last of every (track, slot) run, in that order
     box_seg = np.zeros(n_trk + 1, dtype=np.int64)
     np.cumsum(np.bincount(trk_sorted[kb], minlength=n_trk), out=box_seg[1:])
     return {
